@@ -1,0 +1,426 @@
+/* oracle/ref_harness.cpp -- drives the UNMODIFIED reference (compiled from
+ * /root/reference/src where it lies, see oracle/Makefile) and records what its
+ * downlink schedulers consume and produce each TTI.  TEST INFRASTRUCTURE ONLY.
+ *
+ * How it observes without touching reference sources:
+ *  - the reference's own scenario function SingleCellWithInterference()
+ *    (scenarios/single-cell-with-interference.h:71) builds the cell, eNB, UEs,
+ *    applications and runs the event loop;
+ *  - an event scheduled at t = 0 swaps the eNB's downlink scheduler for a
+ *    subclass of the reference class (same constructor arguments) whose
+ *    DoSchedule() snapshots inputs, optionally injects CQI through
+ *    ENodeB::UserEquipmentRecord::SetCQI, calls the reference DoSchedule()
+ *    untouched, then snapshots outputs;
+ *  - rand() is defined here, so the two draws of
+ *    downlink-transport-scheduler.cpp:490,511 are known (and reproducible).
+ *
+ * Record format (little endian), consumed by tools/make_golden.py:
+ *   header : char[8] "RSGOLD1\0", int32 algo,S,U,R,rbg_size,  double weight[S], int32 params[S][4], int32 ue_to_slice[U]
+ *   per TTI: int32 marker 0x54544921, int32 tti, double now,
+ *            double avg_before[U], int32 tx_before[U], double last_update[U],
+ *            double state_before[S] (slice_rbs_offset_ or slice_ewma_time_, zeros for PF),
+ *            uint8 cqi[U][R], uint8 active[U], int32 rand2[2],
+ *            int16 rbg_to_ue[G], int32 bits[U], uint8 final_cqi[U],
+ *            int32 target[S], int32 quota[S], int32 nvs_slice,
+ *            double avg_after[U], int32 tx_after[U], uint64 cum_bytes[U], uint64 cum_rbs[U],
+ *            double state_after[S]
+ */
+/* standard headers first, so the access hack below never reaches them */
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <map>
+#include <queue>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#define private public
+#define protected public
+#include "protocolStack/mac/packet-scheduler/packet-scheduler.h"
+#include "protocolStack/mac/packet-scheduler/downlink-transport-scheduler.h"
+#include "protocolStack/mac/packet-scheduler/downlink-nvs-scheduler.h"
+#include "protocolStack/mac/packet-scheduler/downlink-packet-scheduler.h"
+#include "protocolStack/mac/packet-scheduler/dl-pf-packet-scheduler.h"
+#include "flows/radio-bearer.h"
+#undef private
+#undef protected
+
+/* the scenario header is not self-contained: same prelude as src/LTE-Sim.cpp:35-39 */
+#include "TEST/test.h"
+#include "scenarios/simple.h"
+#include "scenarios/single-cell-without-interference.h"
+#include "scenarios/single-cell-with-interference.h"
+#include "protocolStack/mac/enb-mac-entity.h"
+#include "protocolStack/mac/AMCModule.h"
+#include "protocolStack/rrc/rrc-entity.h"
+#include "componentManagers/NetworkManager.h"
+#include "device/ENodeB.h"
+#include "utility/eesm-effective-sinr.h"
+#include "device/UserEquipment.h"
+#include "phy/lte-phy.h"
+#include "protocolStack/protocol-stack.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+/* ---- deterministic rand() replacing libc's for the whole binary ---------- */
+static uint64_t g_rand_state = 0x9E3779B97F4A7C15ull;
+static std::vector<int> g_rand_log;
+static const int32_t* g_rand_script = nullptr; /* [n_ttis][2] */
+static long g_rand_script_len = 0;
+static long g_rand_script_pos = -1;            /* >= 0 while inside a recorded DoSchedule */
+static int g_rand_in_call = 0;
+
+static uint64_t SplitMix64() {
+  uint64_t z = (g_rand_state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+extern "C" int rand(void) {
+  int v;
+  if (g_rand_script && g_rand_script_pos >= 0 && g_rand_in_call < 2 &&
+      g_rand_script_pos * 2 + g_rand_in_call < g_rand_script_len) {
+    v = g_rand_script[g_rand_script_pos * 2 + g_rand_in_call];
+  } else {
+    v = (int)(SplitMix64() % 2147483000ull);
+  }
+  if (g_rand_script_pos >= 0) g_rand_in_call++;
+  g_rand_log.push_back(v);
+  return v;
+}
+extern "C" void srand(unsigned) {}
+
+/* ---- run options ---------------------------------------------------------- */
+struct Options {
+  int algo = 9;
+  std::string config;
+  int n_ttis = 100;
+  std::string out;
+  std::string cqi_file;   /* uint8 [T][U][G], refreshed every TTI */
+  std::string rand_file;  /* int32 [T][2] */
+  int seed = 1;
+  bool timing = false;
+  bool keep_log = false;
+};
+static Options g_opt;
+static FILE* g_out = nullptr;
+static std::vector<uint8_t> g_cqi_script;
+static std::vector<int32_t> g_rand_vec;
+static int g_recorded = 0;
+static double g_sched_seconds = 0;
+static long g_sched_calls = 0;
+static std::stringstream g_capture;
+
+template <typename T>
+static void Put(const T* p, size_t n) {
+  if (g_out) fwrite(p, sizeof(T), n, g_out);
+}
+template <typename T>
+static void Put1(T v) { Put(&v, 1); }
+
+struct Snapshot {
+  int S = 0, U = 0, R = 0, G = 0, rbg = 0;
+};
+
+static ENodeB* TheEnb() { return NetworkManager::Init()->GetENodeBContainer()->at(0); }
+static std::vector<RadioBearer*>* Bearers(PacketScheduler* s) {
+  return s->GetMacEntity()->GetDevice()->GetProtocolStack()->GetRrcEntity()->GetRadioBearerContainer();
+}
+
+/* Shared pre/post logic; the scheduler-specific bits come in through lambdas. */
+template <typename Sched, typename BaseCall, typename StateGet, typename Collect>
+static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to_slice,
+                             const std::vector<double>* weights,
+                             const std::vector<SchedulerAlgoParam>* params, BaseCall base_call,
+                             StateGet state_get, Collect collect) {
+  std::vector<RadioBearer*>* bearers = Bearers(self);
+  const int U = (int)user_to_slice.size();
+  if ((int)bearers->size() != U || g_recorded >= g_opt.n_ttis) {
+    base_call();
+    return;
+  }
+  ENodeB* enb = TheEnb();
+  const int R = (int)enb->GetPhy()->GetBandwidthManager()->GetDlSubChannels().size();
+  const int rbg = get_rbg_size(R);
+  const int G = R / rbg;
+
+  if (g_recorded == 0 && g_out) {
+    const char magic[8] = {'R', 'S', 'G', 'O', 'L', 'D', '1', 0};
+    Put(magic, 8);
+    Put1<int32_t>(g_opt.algo); Put1<int32_t>(S); Put1<int32_t>(U); Put1<int32_t>(R); Put1<int32_t>(rbg);
+    for (int s = 0; s < S; ++s) Put1<double>(weights ? (*weights)[s] : 0.0);
+    for (int s = 0; s < S; ++s) {
+      int32_t p[4] = {0, 0, 1, 1};
+      if (params) { p[0] = (*params)[s].alpha; p[1] = (*params)[s].beta; p[2] = (*params)[s].epsilon; p[3] = (*params)[s].psi; }
+      Put(p, 4);
+    }
+    for (int u = 0; u < U; ++u) Put1<int32_t>(user_to_slice[u]);
+  }
+
+  /* optional CQI injection, one value per RBG repeated over its RBs */
+  if (!g_cqi_script.empty()) {
+    const uint8_t* row = g_cqi_script.data() + (size_t)g_recorded * U * G;
+    for (int u = 0; u < U; ++u) {
+      std::vector<int> v(R);
+      for (int r = 0; r < R; ++r) v[r] = row[(size_t)u * G + std::min(r / rbg, G - 1)];
+      enb->GetUserEquipmentRecord(u)->SetCQI(v);
+    }
+  }
+
+  const double now = Simulator::Init()->Now();
+  std::vector<double> avg_before(U), last_update(U), state_before(S, 0.0);
+  std::vector<int32_t> tx_before(U);
+  for (RadioBearer* b : *bearers) {
+    int u = b->GetUserID();
+    avg_before[u] = b->m_averageTransmissionRate;
+    tx_before[u] = b->m_transmittedBytes;
+    last_update[u] = b->m_lastUpdate;
+  }
+  state_get(state_before);
+  std::vector<uint8_t> cqi((size_t)U * R);
+  for (int u = 0; u < U; ++u) {
+    std::vector<int> v = enb->GetUserEquipmentRecord(u)->GetCQI();
+    for (int r = 0; r < R; ++r) cqi[(size_t)u * R + r] = (uint8_t)v[r];
+  }
+
+  g_rand_log.clear();
+  g_rand_script_pos = g_recorded;
+  g_rand_in_call = 0;
+  g_capture.str(std::string());
+  g_capture.clear();
+  auto t0 = std::chrono::steady_clock::now();
+  base_call();
+  auto t1 = std::chrono::steady_clock::now();
+  g_sched_seconds += std::chrono::duration<double>(t1 - t0).count();
+  g_sched_calls++;
+  g_rand_script_pos = -1;
+
+  int32_t rand2[2] = {0, 0};
+  if (g_rand_log.size() >= 1) rand2[0] = g_rand_log[0];
+  if (g_rand_log.size() >= 2) rand2[1] = g_rand_log[1];
+
+  std::vector<uint8_t> active(U, 0), final_cqi(U, 0);
+  std::vector<int16_t> rbg_to_ue(G, -1);
+  std::vector<int32_t> bits(U, 0), target(S, 0), quota(S, 0);
+  int32_t nvs_slice = -1;
+  collect(active, rbg_to_ue, bits, nvs_slice, rbg);
+
+  /* parse what the reference printed: targets/quotas and final_cqi
+   * (downlink-transport-scheduler.cpp:523-527, 637-649) */
+  {
+    std::string text = g_capture.str();
+    std::istringstream is(text);
+    std::string line;
+    while (std::getline(is, line)) {
+      if (line.compare(0, 9, "slice_id,") == 0) {
+        const char* p = line.c_str();
+        while ((p = strchr(p, '(')) != nullptr) {
+          int i, t, q;
+          if (sscanf(p, "(%d, %d, %d)", &i, &t, &q) == 3 && i >= 0 && i < S) { target[i] = t; quota[i] = q; }
+          ++p;
+        }
+      } else if (line.compare(0, 5, "User(") == 0) {
+        int uid = atoi(line.c_str() + 5);
+        size_t k = line.rfind("final_cqi: ");
+        if (k != std::string::npos && uid >= 0 && uid < U) final_cqi[uid] = (uint8_t)atoi(line.c_str() + k + 11);
+      }
+    }
+  }
+
+  std::vector<double> avg_after(U), state_after(S, 0.0);
+  std::vector<int32_t> tx_after(U);
+  std::vector<uint64_t> cum_bytes(U), cum_rbs(U);
+  for (RadioBearer* b : *bearers) {
+    int u = b->GetUserID();
+    avg_after[u] = b->m_averageTransmissionRate;
+    tx_after[u] = b->m_transmittedBytes;
+    cum_bytes[u] = b->m_cumulativeBytes;
+    cum_rbs[u] = b->m_cumulativeRBs;
+  }
+  state_get(state_after);
+
+  Put1<int32_t>(0x54544921); Put1<int32_t>(g_recorded); Put1<double>(now);
+  Put(avg_before.data(), U); Put(tx_before.data(), U); Put(last_update.data(), U);
+  Put(state_before.data(), S);
+  Put(cqi.data(), cqi.size()); Put(active.data(), U); Put(rand2, 2);
+  Put(rbg_to_ue.data(), G); Put(bits.data(), U); Put(final_cqi.data(), U);
+  Put(target.data(), S); Put(quota.data(), S); Put1<int32_t>(nvs_slice);
+  Put(avg_after.data(), U); Put(tx_after.data(), U); Put(cum_bytes.data(), U); Put(cum_rbs.data(), U);
+  Put(state_after.data(), S);
+  g_recorded++;
+}
+
+template <typename UserList>
+static void CollectUsers(UserList* users, std::vector<uint8_t>& active, std::vector<int16_t>& rbg_to_ue,
+                         std::vector<int32_t>& bits, int rbg) {
+  for (auto* usr : *users) {
+    int id = usr->GetUserID();
+    active[id] = 1;
+    bits[id] = usr->GetAllocatedBits();
+    for (int rb : *usr->GetListOfAllocatedRBs())
+      if (rb % rbg == 0) rbg_to_ue[rb / rbg] = (int16_t)id;
+  }
+}
+
+class ObservedTransport : public DownlinkTransportScheduler {
+ public:
+  ObservedTransport(std::string cfg, int algo) : DownlinkTransportScheduler(cfg, algo) {}
+  void DoSchedule() override {
+    ObservedSchedule(
+        this, num_slices_, user_to_slice_, &slice_weights_, &slice_algo_params_,
+        [this]() { DownlinkTransportScheduler::DoSchedule(); },
+        [this](std::vector<double>& st) { for (int s = 0; s < num_slices_; ++s) st[s] = slice_rbs_offset_[s]; },
+        [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t&, int rbg) {
+          CollectUsers(GetUsersToSchedule(), active, r2u, bits, rbg);
+        });
+  }
+};
+
+class ObservedNvs : public DownlinkNVSScheduler {
+ public:
+  explicit ObservedNvs(std::string cfg) : DownlinkNVSScheduler(cfg, false) {}
+  void DoSchedule() override {
+    ObservedSchedule(
+        this, num_slices_, user_to_slice_, &slice_weights_, &slice_algo_params_,
+        [this]() { DownlinkNVSScheduler::DoSchedule(); },
+        [this](std::vector<double>& st) { for (int s = 0; s < num_slices_; ++s) st[s] = slice_ewma_time_[s]; },
+        [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t& nvs, int rbg) {
+          CollectUsers(GetUsersToSchedule(), active, r2u, bits, rbg);
+          /* only the served slice's users are listed; backlogged bearers are all active */
+          std::fill(active.begin(), active.end(), (uint8_t)1);
+          if (!GetUsersToSchedule()->empty())
+            nvs = user_to_slice_[GetUsersToSchedule()->at(0)->GetUserID()];
+        });
+  }
+};
+
+class ObservedPf : public DL_PF_PacketScheduler {
+ public:
+  explicit ObservedPf(std::string cfg) : DL_PF_PacketScheduler(cfg) {}
+  void DoSchedule() override {
+    ObservedSchedule(
+        this, num_slices_, user_to_slice_, nullptr, nullptr,
+        [this]() { DownlinkPacketScheduler::DoSchedule(); },
+        [](std::vector<double>&) {},
+        [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t&, int rbg) {
+          for (FlowToSchedule* f : *GetFlowsToSchedule()) {
+            int id = f->GetBearer()->GetUserID();
+            active[id] = 1;
+            bits[id] = f->GetAllocatedBits();
+            for (int rb : *f->GetListOfAllocatedRBs())
+              if (rb % rbg == 0) r2u[rb / rbg] = (int16_t)id;
+          }
+        });
+  }
+};
+
+struct Installer {
+  void Install() {
+    ENodeB* enb = TheEnb();
+    EnbMacEntity* mac = (EnbMacEntity*)enb->GetProtocolStack()->GetMacEntity();
+    PacketScheduler* old = mac->GetDownlinkPacketScheduler();
+    PacketScheduler* s = nullptr;
+    switch (g_opt.algo) {
+      case 1: s = new ObservedPf(g_opt.config); break;
+      case 7: s = new ObservedNvs(g_opt.config); break;
+      case 8: s = new ObservedTransport(g_opt.config, 0); break;
+      default: s = new ObservedTransport(g_opt.config, 2); break;
+    }
+    s->SetMacEntity(mac);
+    mac->SetDownlinkPacketScheduler(s);
+    (void)old; /* leaked on purpose: ~DownlinkTransportScheduler throws (packet-scheduler.cpp:53-58,128) */
+  }
+};
+
+static std::vector<uint8_t> ReadAll(const std::string& path) {
+  std::vector<uint8_t> v;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  v.resize(n);
+  if (n && fread(v.data(), 1, n, f) != (size_t)n) { fprintf(stderr, "short read %s\n", path.c_str()); exit(2); }
+  fclose(f);
+  return v;
+}
+
+static int ProbeRowM1() {
+  /* AMCModule.cpp:312-316: TBS(mcs,120) = 5*T[23][itbs] + T[-1][itbs]; TBS(mcs,24) = T[23][itbs] */
+  AMCModule amc;
+  for (int mcs = 0; mcs <= 28; ++mcs)
+    printf("%d %d\n", mcs, amc.GetTBSizeFromMCS(mcs, 120) - 5 * amc.GetTBSizeFromMCS(mcs, 24));
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
+    if (a == "--probe-row-m1") return ProbeRowM1();
+    else if (a == "--algo") g_opt.algo = atoi(next().c_str());
+    else if (a == "--config") g_opt.config = next();
+    else if (a == "--ttis") g_opt.n_ttis = atoi(next().c_str());
+    else if (a == "--out") g_opt.out = next();
+    else if (a == "--cqi") g_opt.cqi_file = next();
+    else if (a == "--rand") g_opt.rand_file = next();
+    else if (a == "--seed") g_opt.seed = atoi(next().c_str());
+    else if (a == "--time") g_opt.timing = true;
+    else if (a == "--keep-log") g_opt.keep_log = true;
+    else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
+  }
+  if (g_opt.config.empty()) {
+    fprintf(stderr, "usage: ref_harness --algo 1|7|8|9 --config cfg.json --ttis N [--out rec.bin] [--cqi cqi.bin] [--rand rand.bin] [--seed k] [--time]\n");
+    return 2;
+  }
+  if (!g_opt.out.empty()) {
+    g_out = fopen(g_opt.out.c_str(), "wb");
+    if (!g_out) { fprintf(stderr, "cannot write %s\n", g_opt.out.c_str()); return 2; }
+  }
+  if (!g_opt.cqi_file.empty()) g_cqi_script = ReadAll(g_opt.cqi_file);
+  if (!g_opt.rand_file.empty()) {
+    std::vector<uint8_t> raw = ReadAll(g_opt.rand_file);
+    g_rand_vec.resize(raw.size() / 4);
+    memcpy(g_rand_vec.data(), raw.data(), g_rand_vec.size() * 4);
+    g_rand_script = g_rand_vec.data();
+    g_rand_script_len = (long)g_rand_vec.size();
+  }
+  g_rand_state ^= (uint64_t)g_opt.seed * 0xD6E8FEB86659FD93ull;
+
+  /* the reference prints per-TTI logs on both streams; capture stdout (parsed
+   * per TTI above) and drop stderr unless asked to keep it */
+  std::streambuf* cout_buf = std::cout.rdbuf(g_capture.rdbuf());
+  std::streambuf* cerr_buf = g_opt.keep_log ? nullptr : std::cerr.rdbuf(nullptr);
+  FILE* devnull = fopen("/dev/null", "w");
+  FILE* saved_stderr = stderr;
+  if (!g_opt.keep_log && devnull) stderr = devnull; /* fprintf(stderr, "all_bytes...") of transport.cpp:374 */
+
+  Simulator* sim = Simulator::Init();
+  Installer inst;
+  sim->Schedule(0.0, &Installer::Install, &inst);
+  double duration = g_opt.n_ttis * 0.001 + 0.0035;
+  int sched_type = g_opt.algo;
+  SingleCellWithInterference(1.0, sched_type, 1, 30, g_opt.seed, duration, g_opt.config);
+
+  stderr = saved_stderr;
+  std::cout.rdbuf(cout_buf);
+  if (cerr_buf) std::cerr.rdbuf(cerr_buf);
+  if (g_out) fclose(g_out);
+  fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_recorded,
+          g_sched_calls, g_sched_seconds);
+  return g_recorded == g_opt.n_ttis ? 0 : 3;
+}

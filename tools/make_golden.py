@@ -1,0 +1,120 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Needs oracle/_ref/ref_harness (``make -C oracle ref``; only possible where
+/root/reference is mounted, i.e. in the build container).  Each case runs the
+reference's own SingleCellWithI scenario with one of its downlink schedulers
+and records, per TTI, everything the scheduler consumed (CQI, EWMA rates,
+slice offsets / NVS credits, the two rand() draws, Now - lastUpdate) and
+produced (RBG->UE map, allocated bits, final CQI, targets/quotas, updated
+state, cumulative bytes/RBs).  The committed fixtures make the parity tests
+runnable where the reference is absent (the GPU box).
+
+Usage: python tools/make_golden.py [--only NAME]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from radiosaber_b200 import workload  # noqa: E402
+from tools import golden_io  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+REF_EXP = "/root/reference/NSDI23-radiosaber-experiments"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SMALL_CFG = {
+    # 5 slices, few UEs: single UEs end up with 15/20/25 RBGs, which exercises the
+    # TransportBlockSizeTable[-1] read of AMCModule.cpp:312-316
+    "slices": [
+        {"n_slices": 2, "weight": 0.3, "video_app": 0, "video_bitrate": 0, "internet_flow": 0, "if_bitrate": 0,
+         "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 3, "weight": 0.1333333333333, "video_app": 0, "video_bitrate": 0, "internet_flow": 0,
+         "if_bitrate": 0, "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 0},
+    ],
+    "ues_per_slice": [2, 1, 3, 1, 2],
+}
+
+FIX20X5 = f"{REF_EXP}/exp-fix20slices/5ues/config-pf.json"
+DIFFW = f"{REF_EXP}/exp-customization/exp-backlogged-20slicesdiffw/config.json"
+MIX20 = f"{REF_EXP}/exp-customization/exp-backlogged-20slices/config.json"
+
+# name, algo, config, n_ttis, cqi source ("trace" = the simulator's own cqi-traces-noise0 ingest,
+# "synth" = injected per-TTI synthetic CQI), seed
+CASES = [
+    ("a9_fix20x5_trace", 9, FIX20X5, 100, "trace", 1),
+    ("a8_fix20x5_trace", 8, FIX20X5, 60, "trace", 1),
+    ("a7_fix20x5_trace", 7, FIX20X5, 60, "trace", 1),
+    ("a1_fix20x5_trace", 1, FIX20X5, 60, "trace", 1),
+    ("a9_fix20x5_synth", 9, FIX20X5, 80, "synth", 2),
+    ("a8_fix20x5_synth", 8, FIX20X5, 40, "synth", 3),
+    ("a7_fix20x5_synth", 7, FIX20X5, 40, "synth", 4),
+    ("a1_fix20x5_synth", 1, FIX20X5, 40, "synth", 5),
+    ("a9_diffw_synth", 9, DIFFW, 40, "synth", 6),
+    ("a8_diffw_synth", 8, DIFFW, 24, "synth", 7),
+    ("a7_mix20_synth", 7, MIX20, 40, "synth", 8),
+    ("a9_small_synth", 9, "SMALL", 120, "synth", 9),
+    ("a8_small_synth", 8, "SMALL", 120, "synth", 10),
+    ("a7_small_synth", 7, "SMALL", 120, "synth", 11),
+    ("a1_small_synth", 1, "SMALL", 120, "synth", 12),
+]
+
+
+def run_case(name, algo, config, n_ttis, source, seed, tmp):
+    if config == "SMALL":
+        config = os.path.join(tmp, "small.json")
+        json.dump(SMALL_CFG, open(config, "w"))
+    cfg = json.load(open(config))
+    n_ues = int(sum(cfg["ues_per_slice"]))
+    n_slices = len(cfg["ues_per_slice"])
+    rec_path = os.path.join(tmp, name + ".bin")
+    cmd = [HARNESS, "--algo", str(algo), "--config", config, "--ttis", str(n_ttis), "--out", rec_path,
+           "--seed", str(seed)]
+    rand2 = workload.synth_rand2(seed, 0, 1, 0, n_ttis, n_slices)[:, 0, :]
+    rand_path = os.path.join(tmp, name + ".rand")
+    rand2.astype("<i4").tofile(rand_path)
+    cmd += ["--rand", rand_path]
+    if source == "synth":
+        cqi = workload.synth_cqi(seed, 0, 1, 0, n_ttis, n_ues, 64)[:, 0]
+        cqi_path = os.path.join(tmp, name + ".cqi")
+        cqi.tofile(cqi_path)
+        cmd += ["--cqi", cqi_path]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    rec = golden_io.compact(golden_io.parse_record_stream(rec_path))
+    assert rec["T"] == n_ttis, (name, rec["T"])
+    if algo in (8, 9):
+        assert (rec["rand2"] == rand2).all(), "scripted rand() values were not the ones consumed"
+    rec["config_json"] = json.dumps(cfg)
+    rec["source"] = source
+    rec["seed"] = seed
+    golden_io.save_npz(os.path.join(GOLDEN, name + ".npz"), rec)
+    print(f"{name}: {out} -> {os.path.getsize(os.path.join(GOLDEN, name + '.npz')) / 1024:.0f} KiB", flush=True)
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    if not os.path.exists(HARNESS):
+        print("oracle/_ref/ref_harness missing: run `make -C oracle ref` first", file=sys.stderr)
+        return 1
+    os.makedirs(GOLDEN, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        for case in CASES:
+            if args.only and case[0] != args.only:
+                continue
+            run_case(*case, tmp)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
