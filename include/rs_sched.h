@@ -1,0 +1,162 @@
+/* include/rs_sched.h -- C ABI of the B200-native downlink RBG scheduler.
+ *
+ * What this replaces.  RadioSaber has no FFI: its "plug-in surface" is the C++
+ * virtual class PacketScheduler (src/protocolStack/mac/packet-scheduler/
+ * packet-scheduler.h:51-174) whose DoSchedule()/RBsAllocation() an ENodeB calls
+ * once per 1 ms TTI (src/device/ENodeB.cpp:438-460).  The four behaviours
+ * reachable from the SingleCellWithI scenario are selected by id
+ * (src/scenarios/single-cell-with-interference.h:94-118):
+ *     1  DL_PF_PacketScheduler            downlink-packet-scheduler.cpp:179-331
+ *     7  DownlinkNVSScheduler(cfg,false)  downlink-nvs-scheduler.cpp:94-142, 275-358
+ *     8  DownlinkTransportScheduler(cfg,0) GreedyByRow   downlink-transport-scheduler.cpp:249-272
+ *     9  DownlinkTransportScheduler(cfg,2) MaximizeCell  downlink-transport-scheduler.cpp:351-376
+ * This library is what a host-side subclass of PacketScheduler binds to (see
+ * INTEGRATION.md and radiosaber_b200/host/rs_gpu_scheduler.h): every entry
+ * point below takes plain pointers and sizes, returns an int status and never
+ * throws.  One handle schedules a BATCH of independent cells (one CTA per
+ * cell); n_cells = 1 is the in-simulator drop-in.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device and
+ * fails with RS_ERR_CUDA otherwise.
+ */
+#ifndef RS_SCHED_H_
+#define RS_SCHED_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK 0
+#define RS_ERR_ARG 1          /* NULL / out-of-range argument */
+#define RS_ERR_UNSUPPORTED 2  /* a configuration the kernels do not cover (message says which) */
+#define RS_ERR_CUDA 3         /* CUDA runtime error (message has the CUDA string) */
+
+#define RS_MAX_SLICES 64      /* (rbg,slice) packs into 6+6 bits of a sort entry */
+#define RS_MAX_RBGS 64        /* one 64-bit RBG mask per UE; 512 RBs / 8 = 64 at 100 MHz */
+
+/* Static description of the cells (identical for every cell of the batch).
+ * Mirrors what the reference's scheduler constructors read from the JSON slice
+ * config (downlink-transport-scheduler.cpp:55-97, downlink-nvs-scheduler.cpp:46-87,
+ * dl-pf-packet-scheduler.cpp:39-57). */
+typedef struct rs_config {
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber */
+  int32_t n_slices;         /* S  <= RS_MAX_SLICES */
+  int32_t n_ues;            /* U; user j == UE id j (flows/application/Application.cpp:72-123) */
+  int32_t n_rbs;            /* 512 for 100 MHz (core/spectrum/bandwidth-manager.cpp:98-102) */
+  int32_t rbg_size;         /* get_rbg_size(): 8 (utility/eesm-effective-sinr.h:82-103) */
+  int32_t cqi_per_rb;       /* 0: cqi[U][G], one value per RBG; 1: cqi[U][n_rbs] */
+  int32_t data_to_transmit; /* bytes queued per bearer; 100000000 = infinite buffer
+                               (downlink-transport-scheduler.cpp:123-125) */
+  int32_t reserved;
+  const double* weight;       /* [S] slice_weights_ */
+  const int32_t* params;      /* [S][4] alpha,beta,epsilon,psi (SchedulerAlgoParam, packet-scheduler.h:31-49) */
+  const int32_t* ue_to_slice; /* [U] user_to_slice_ */
+  const int32_t* tbs_row_m1;  /* [27] TransportBlockSizeTable[-1][*] as the reference's -O0 build reads it
+                                 (AMCModule.cpp:312-316); NULL = the values of the stock build */
+} rs_config;
+
+/* Host (or device, see each call) destinations for one TTI's results; NULL = not wanted. */
+typedef struct rs_outputs {
+  int16_t* rbg_to_ue;    /* [B][G] winner UE id, -1 = RBG left unallocated
+                            (GetListOfAllocatedRBs, downlink-transport-scheduler.cpp:589-601) */
+  int32_t* tbs_bits;     /* [B][U] UpdateAllocatedBits value, 0 if unscheduled (:659) */
+  uint8_t* mcs;          /* [B][U] MCS of the PDCCH records (:661-668), 0xff if unscheduled */
+  uint8_t* final_cqi;    /* [B][U] "final_cqi" of :649, 0 if unscheduled */
+  int32_t* slice_target; /* [B][S] slice_target_rbs (ids 8/9, :463-500) */
+  int32_t* slice_quota;  /* [B][S] slice_quota_rbgs (ids 8/9, :501-521) */
+  int32_t* nvs_slice;    /* [B]    slice served this TTI (id 7, downlink-nvs-scheduler.cpp:94-142) */
+} rs_outputs;
+
+typedef struct rs_handle rs_handle;
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* rs_last_error(void);
+/* Library/ABI version, bumped when a signature changes. */
+int32_t rs_abi_version(void);
+
+/* Replaces the scheduler constructors (ENodeB::SetDLScheduler, ENodeB.cpp:302-391).
+ * Allocates device state for n_cells cells on CUDA device `device` and sets it
+ * to the reference's initial values (average rate 100000.0, radio-bearer.cpp:54;
+ * offsets / NVS credits / byte counters 0). */
+int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle** out);
+void rs_destroy(rs_handle* h);
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*); NULL = the handle's own. */
+int rs_set_stream(rs_handle* h, void* cuda_stream);
+int rs_sync(rs_handle* h);
+
+/* Per-bearer / per-slice state the reference keeps between TTIs (flows/radio-bearer.h:81-85,
+ * downlink-transport-scheduler.h:38, downlink-nvs-scheduler.h:38).  Host arrays, [B][U] / [B][S];
+ * NULL = leave alone / not wanted.  Synchronous. */
+int rs_set_state(rs_handle* h, const double* avg_rate, const int32_t* tx_bytes, const uint64_t* cum_bytes,
+                 const uint64_t* cum_rbs, const double* slice_offset, const double* nvs_ewma);
+int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cum_bytes, uint64_t* cum_rbs,
+                 double* slice_offset, double* nvs_ewma);
+int rs_reset_state(rs_handle* h);
+
+/* One TTI for the whole batch == PacketScheduler::Schedule() (packet-scheduler.cpp:72-90):
+ * UpdateAverageTransmissionRate, SelectFlowsToSchedule, RBsAllocation and the byte accounting of
+ * DoStopSchedule.  HOST buffers in, HOST buffers out, synchronous.
+ *   cqi    [B][U][G] (or [B][U][n_rbs] when cqi_per_rb), values 1..15
+ *   rand2  [B][2]  the two rand() draws of downlink-transport-scheduler.cpp:490,511, each in
+ *                  [0, INT32_MAX - S]; may be NULL for ids 1 and 7
+ *   active [B][U]  1 = bearer has packets (GetDestination()->ACTIVE && HasPackets); NULL = all
+ *   dt     Now - lastUpdate seen by RadioBearer::UpdateAverageTransmissionRate
+ *          (radio-bearer.cpp:138-164); 0 skips the update like the reference does */
+int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
+            const rs_outputs* out);
+
+/* n_ttis consecutive TTIs with every input and output already in DEVICE memory.
+ *   d_cqi   [T][B][U][G]; cqi_tti_stride = bytes between TTIs (0 = the same CQI every TTI)
+ *   d_rand2 [T][B][2]
+ *   d_active [T][B][U] or NULL, active_tti_stride like cqi_tti_stride
+ *   dt      HOST array [T]
+ *   d_out   device pointers, arrays [T][B][...]; NULL members are skipped
+ *   ttis_per_launch  TTIs handled by one kernel launch with the cell state held on chip
+ *                    (<= 0: library default)
+ * Asynchronous on the handle's stream; rs_sync() waits. */
+int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride,
+                  const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
+                  const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch);
+
+/* Same, HOST buffers in and out ([T][B][...]): the library stages them through pinned memory in
+ * chunks and overlaps the copies with the kernels.  Synchronous. */
+int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active,
+                const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
+
+/* Synthetic workload of SURVEY.md section 8(d), generated on the device (bit-identical twin of
+ * radiosaber_b200/workload.py): CQI i.i.d. from the cqi-traces-noise0 histogram, counter-based so
+ * any (cell, tti) shard can be produced on any GPU. d_out: uint8 [n_ttis][B][U][G]. */
+int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t refresh,
+                 uint8_t* d_out);
+/* d_out: int32 [n_ttis][B][2], values in [0, INT32_MAX - S]. */
+int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t* d_out);
+
+/* Per-slice totals over every cell of this handle (what the reference's plotters sum from the
+ * stderr log, NSDI23-radiosaber-experiments/exp-customization/plot_throughput.py:26-56).
+ * stats: uint64 [4][S] = { sum cumulative bytes, sum cumulative RBs, sum q, sum q*q } with
+ * q = a UE's cumulative bytes >> 10 (integers, so any reduction order gives the same bits).
+ * rs_stats_device writes DEVICE memory (feed it to an NCCL reduce); rs_get_stats copies to HOST. */
+int rs_stats_device(rs_handle* h, uint64_t* d_stats);
+int rs_get_stats(rs_handle* h, uint64_t* stats);
+
+/* Introspection for benchmarks and tests. */
+int64_t rs_launch_count(const rs_handle* h);      /* kernels launched by this handle so far */
+int32_t rs_smem_bytes(const rs_handle* h);        /* dynamic shared memory per CTA of the TTI kernel */
+int32_t rs_threads_per_cta(const rs_handle* h);
+int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h); /* U(G+20)+16S+2G+8, SURVEY 8(d) */
+
+/* Device test hook: libstdc++ std::sort order (key descending, comparator of
+ * downlink-transport-scheduler.cpp:357-361) of n_arrays arrays of n 4-bit keys, computed by the same
+ * device routine the RadioSaber path uses.  keys: HOST uint8 [n_arrays][n]; perm_out: HOST int32
+ * [n_arrays][n], perm_out[i] = original index of the element ending at position i.
+ * depth_limit < 0 = the library's 2*floor(log2 n). */
+int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
+                 int32_t* perm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_SCHED_H_ */

@@ -1,0 +1,965 @@
+/* rs_device.cuh -- sm_100a kernels of the per-TTI downlink RBG allocation, one CTA per cell.
+ *
+ * Reference behaviour reproduced (paths under /root/reference/src/protocolStack/mac/packet-scheduler
+ * unless a directory is given; "transport.cpp" = downlink-transport-scheduler.cpp, "nvs.cpp" =
+ * downlink-nvs-scheduler.cpp, "dlps.cpp" = downlink-packet-scheduler.cpp):
+ *   EWMA of the served rate        flows/radio-bearer.cpp:138-164
+ *   scheduling metric              transport.cpp:677-713, nvs.cpp:360-390, dl-pf-packet-scheduler.cpp:128-140
+ *   per-slice enterprise argmax    transport.cpp:543-567
+ *   slice targets / RBG quotas     transport.cpp:463-521
+ *   RadioSaber MaximizeCell        transport.cpp:351-376 (std::sort order)
+ *   Sequential GreedyByRow         transport.cpp:249-272
+ *   NVS slice selection / argmax   nvs.cpp:94-142, 275-311
+ *   No-slicing PF argmax           dlps.cpp:179-271
+ *   EESM -> CQI -> MCS -> TBS      transport.cpp:632-660, utility/eesm-effective-sinr.h:33-46,
+ *                                  protocolStack/mac/AMCModule.cpp:252-317
+ *   byte / RB accounting           transport.cpp:170-199, dl-pf-packet-scheduler.cpp:64-96,
+ *                                  flows/radio-bearer.cpp:100-123
+ *
+ * Everything that decides an assignment is integer or IEEE-754 double arithmetic with explicit
+ * rounding (__dmul_rn/__dadd_rn/__ddiv_rn: no FMA contraction), so results are bit-identical to the
+ * reference's x86-64 build; libm values (pow/exp/log/log10) enter only through tables computed on
+ * the host with glibc (rs_sched.cu).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rs {
+
+constexpr int kThreads = 256;          /* threads per CTA (one CTA = one cell) */
+constexpr int kWarps = kThreads / 32;
+constexpr int kSortThreshold = 16;     /* libstdc++ _S_threshold, bits/stl_algo.h:1848 */
+constexpr int kMStride = 16;           /* metric table row: entries for CQI 0..15 */
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned short kNoUe = 0xffff;
+
+/* ---- tables that are the same for every handle (set once per device) ------------------------- */
+struct ConstTables {
+  double tval[16];   /* exp(-10^(SINR[cqi]/10)), the EESM summand of a CQI (eesm-effective-sinr.h:39-41) */
+  double cut[16];    /* cut[k], k=1..14: largest mean with 10*log10(-log(mean)) >= SINRForCQIIndex[k]
+                        (AMCModule.cpp:252-261 expressed on the EESM mean) */
+};
+__constant__ ConstTables c_tab;
+
+/* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
+struct DevCfg {
+  int algo, S, U, G, R, rbg, cqi_per_rb, data;
+  int n_cells;
+  int n_chunks;            /* metric-table chunks (ranges of slices) */
+  int m_cap;               /* metric-table capacity in UEs */
+  int sort_n;              /* G*S */
+  int sort_depth;          /* 2*floor(log2(G*S)) */
+  int nvs_guard;           /* 1: NVS required-RBs guard can bind (finite data) -> unsupported for now */
+  const int* ue_to_slice;  /* [U] */
+  const int* slice_ptr;    /* [S+1] CSR over UEs sorted by (slice, ue); algo 1: one "slice" = all UEs */
+  const int* slice_ues;    /* [U] */
+  const int* chunk_slice;  /* [n_chunks+1] first slice of each chunk */
+  const double* weight;    /* [S] */
+  const double* epow;      /* [S][16]: pow(eff(c)*180000/1000, epsilon_s) (ids 7/8/9); [1][16] eff*180000 (id 1) */
+  const unsigned char* psi;/* [S] 0/1 */
+  const int* tbs_n;        /* [G+1][16]: GetTBSizeFromMCS(mcs(cqi), k*rbg) */
+  /* state, [B][U] / [B][S] */
+  double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
+  double* offset; double* ewma;
+};
+
+struct RunArgs {
+  const uint8_t* cqi; long long cqi_tti_stride;
+  const int* rand2;
+  const uint8_t* active; long long active_tti_stride;
+  const double* dt;        /* device [T] */
+  int T;
+  short* rbg_to_ue; int* tbs_bits; uint8_t* mcs; uint8_t* final_cqi;
+  int* slice_target; int* slice_quota; int* nvs_slice;
+};
+
+/* ---- shared-memory layout (same function on host and device) --------------------------------- */
+struct Layout {
+  int avg, den, mtab, cumb, cumr, tx, mask, seg, cnt, a, win, posl, posr, wl, wr, pfl, pfr,
+      target, quota, frb, wd, outsl, off, tval, misc, total;
+};
+__host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
+  Layout L;
+  const int n = S * G;
+  const int nw = (n + 31) / 32;
+  int o = 0;
+  L.avg = o;  o += 8 * U;
+  L.den = o;  o += 8 * U;
+  L.mtab = o; o += 8 * kMStride * m_cap;
+  L.cumb = o; o += 8 * U;
+  L.cumr = o; o += 8 * U;
+  L.off = o;  o += 8 * S;
+  L.tval = o; o += 8 * 16;
+  L.tx = o;   o += 4 * U;
+  L.mask = o; o += 8 * U;
+  L.seg = o;  o += 4 * n;
+  L.cnt = o;  o += 4 * 16 * nw;
+  L.wl = o;   o += 4 * (nw + 1);
+  L.wr = o;   o += 4 * (nw + 1);
+  L.target = o; o += 4 * S;
+  L.quota = o;  o += 4 * S;
+  L.frb = o;    o += 4 * S;
+  L.wd = o;     o += 4 * S;
+  L.misc = o;   o += 4 * 16;
+  L.a = o;    o += 2 * n;
+  L.win = o;  o += 2 * n;
+  L.posl = o; o += 2 * n;
+  L.posr = o; o += 2 * n;
+  L.pfl = o;  o += 2 * (nw + 2);
+  L.pfr = o;  o += 2 * (nw + 2);
+  L.outsl = o; o += G;
+  L.total = rs_align(o, 16);
+  return L;
+}
+
+/* ================================================================================================
+ * libstdc++ std::sort (introsort) order of n entries, key = bits 12..15 (descending), payload =
+ * bits 0..11, evaluated level by level over all ranges of one recursion depth at once
+ * (tests/sort_model.py is the executable statement of this formulation).
+ * ============================================================================================== */
+__device__ __forceinline__ bool before(unsigned short x, unsigned short y) { return (x >> 12) > (y >> 12); }
+
+/* std::__partial_sort(first,last,last): __make_heap + __sort_heap (bits/stl_heap.h), comp = before.
+ * Sequential; reached only when the depth limit runs out (never seen on real inputs). */
+__device__ void heap_adjust(unsigned short* f, int hole, int len, unsigned short v) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (before(f[child], f[child - 1])) child--;
+    f[hole] = f[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    f[hole] = f[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && before(f[parent], v)) {
+    f[hole] = f[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  f[hole] = v;
+}
+__device__ void heap_sort(unsigned short* f, int len) {
+  if (len >= 2) {
+    int parent = (len - 2) / 2;
+    while (true) {
+      heap_adjust(f, parent, len, f[parent]);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  int last = len;
+  while (last > 1) {
+    --last;
+    unsigned short v = f[last];
+    f[last] = f[0];
+    heap_adjust(f, 0, last, v);
+  }
+}
+
+/* std::__move_median_to_first(first, first+1, mid, last-1), bits/stl_algo.h:1893-1899 (g++ 13) */
+__device__ __forceinline__ void median_to_first(unsigned short* a, int first, int last) {
+  const int pa = first + 1, pb = first + (last - first) / 2, pc = last - 1;
+  const unsigned short xa = a[pa], xb = a[pb], xc = a[pc];
+  int pick;
+  if (before(xa, xb)) pick = before(xb, xc) ? pb : (before(xa, xc) ? pc : pa);
+  else if (before(xa, xc)) pick = pa;
+  else if (before(xb, xc)) pick = pc;
+  else pick = pb;
+  const unsigned short t = a[first];
+  a[first] = a[pick];
+  a[pick] = t;
+}
+
+__device__ __forceinline__ int prefix_at(const unsigned* w, const unsigned short* pf, int x) {
+  return (int)pf[x >> 5] + __popc(w[x >> 5] & ((1u << (x & 31)) - 1u));
+}
+
+struct SortBufs {
+  unsigned short* a;     /* [n] in: entries in insertion order; scratch afterwards */
+  unsigned short* out;   /* [n] result, sorted (== posr) */
+  unsigned* seg;         /* [n] first | last<<16 of the range an entry is in */
+  unsigned short* posl;  /* [n] */
+  unsigned short* posr;  /* [n] */
+  unsigned* wl;          /* [nw+1] */
+  unsigned* wr;          /* [nw+1] */
+  unsigned short* pfl;   /* [nw+2] */
+  unsigned short* pfr;   /* [nw+2] */
+  unsigned* cnt;         /* [16*nw] */
+  unsigned* misc;        /* [16] */
+};
+
+/* Exclusive prefix over the ballot words of one flag array, by one warp. */
+__device__ __forceinline__ void word_prefix(const unsigned* w, unsigned short* pf, int nw, int lane) {
+  constexpr int WPL = 5; /* 32*5 = 160 >= 129 words (n <= 4096) */
+  int c[WPL];
+  int s = 0;
+#pragma unroll
+  for (int q = 0; q < WPL; ++q) {
+    const int idx = lane * WPL + q;
+    c[q] = (idx < nw) ? __popc(w[idx]) : 0;
+    s += c[q];
+  }
+  int incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int run = incl - s;
+#pragma unroll
+  for (int q = 0; q < WPL; ++q) {
+    const int idx = lane * WPL + q;
+    if (idx <= nw) pf[idx] = (unsigned short)run;
+    run += c[q];
+  }
+}
+
+/* All kThreads threads of the CTA call this. On return b.out[0..n) holds the entries in the order
+ * std::sort leaves them. */
+__device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = (n + 31) >> 5;
+  for (int i = tid; i < n; i += kThreads) b.seg[i] = (unsigned)n << 16;
+  __syncthreads();
+
+  for (int level = 0;; ++level) {
+    /* A: range leaders pick the pivot (or heap-sort when the depth limit is exhausted) */
+    bool any = false;
+    for (int w = warp; w < nw; w += kWarps) {
+      const int i = w * 32 + lane;
+      if (i < n) {
+        const unsigned sg = b.seg[i];
+        const int f = sg & 0xffff, l = sg >> 16;
+        if (l - f > kSortThreshold) {
+          any = true;
+          if (i == f) {
+            if (level >= depth_limit) heap_sort(b.a + f, l - f);
+            else median_to_first(b.a, f, l);
+          }
+        }
+      }
+    }
+    if (!__syncthreads_or(any)) break;
+    if (level >= depth_limit) break;
+
+    /* B: stopper flags of __unguarded_partition: L = "not before pivot", R = "pivot not before" */
+    for (int w = warp; w < nw; w += kWarps) {
+      const int i = w * 32 + lane;
+      bool fl = false, fr = false;
+      if (i < n) {
+        const unsigned sg = b.seg[i];
+        const int f = sg & 0xffff, l = sg >> 16;
+        if (l - f > kSortThreshold && i != f) {
+          const int k = b.a[i] >> 12, p = b.a[f] >> 12;
+          fl = k <= p;
+          fr = k >= p;
+        }
+      }
+      const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
+      if (lane == 0) { b.wl[w] = bl; b.wr[w] = br; }
+    }
+    __syncthreads();
+    /* C: prefix counts over words */
+    if (warp == 0) word_prefix(b.wl, b.pfl, nw, lane);
+    else if (warp == 1) word_prefix(b.wr, b.pfr, nw, lane);
+    __syncthreads();
+    /* D: k-th L stopper from the left / k-th R stopper from the right -> slot first+1+k */
+    for (int w = warp; w < nw; w += kWarps) {
+      const int i = w * 32 + lane;
+      if (i < n) {
+        const unsigned sg = b.seg[i];
+        const int f = sg & 0xffff, l = sg >> 16;
+        if (l - f > kSortThreshold && i != f) {
+          const int k = b.a[i] >> 12, p = b.a[f] >> 12;
+          if (k <= p) b.posl[f + 1 + prefix_at(b.wl, b.pfl, i) - prefix_at(b.wl, b.pfl, f + 1)] = (unsigned short)i;
+          if (k >= p) b.posr[f + 1 + prefix_at(b.wr, b.pfr, l) - prefix_at(b.wr, b.pfr, i + 1)] = (unsigned short)i;
+        }
+      }
+    }
+    __syncthreads();
+    /* E: swap pair k while posL[k] < posR[k]; the first non-swapping k defines the cut */
+    for (int w = warp; w < nw; w += kWarps) {
+      const int j = w * 32 + lane;
+      if (j < n) {
+        const unsigned sg = b.seg[j];
+        const int f = sg & 0xffff, l = sg >> 16;
+        if (l - f > kSortThreshold && j != f) {
+          const int k = j - f - 1;
+          const int nl = prefix_at(b.wl, b.pfl, l) - prefix_at(b.wl, b.pfl, f + 1);
+          const int nr = prefix_at(b.wr, b.pfr, l) - prefix_at(b.wr, b.pfr, f + 1);
+          const bool have_l = k < nl, have_r = k < nr;
+          const int lp = b.posl[j], rp = b.posr[j];
+          const bool sw = have_l && have_r && lp < rp;
+          if (sw) {
+            const unsigned short t = b.a[lp];
+            b.a[lp] = b.a[rp];
+            b.a[rp] = t;
+          } else {
+            bool prev = true;
+            int prev_r = 0x7fffffff;
+            if (k >= 1) {
+              prev_r = b.posr[j - 1];
+              prev = (k - 1 < nl) && (k - 1 < nr) && ((int)b.posl[j - 1] < prev_r);
+            }
+            if (prev) {
+              int cut = have_l ? lp : 0x7fffffff;
+              if (k >= 1 && prev_r < cut) cut = prev_r;
+              b.posl[f] = (unsigned short)cut;   /* slot `first` is never a pair slot: holds the cut */
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    /* F: split every partitioned range at its cut */
+    for (int w = warp; w < nw; w += kWarps) {
+      const int i = w * 32 + lane;
+      if (i < n) {
+        const unsigned sg = b.seg[i];
+        const int f = sg & 0xffff, l = sg >> 16;
+        if (l - f > kSortThreshold) {
+          const int c = b.posl[f];
+          b.seg[i] = (i < c) ? ((unsigned)f | ((unsigned)c << 16)) : ((unsigned)c | ((unsigned)l << 16));
+        }
+      }
+    }
+    /* no barrier: phase A touches seg[] of the thread's own entries and a[], which nobody reads in F */
+  }
+
+  /* __final_insertion_sort == stable sort by key of what is in a[] now: counting sort, 16 keys */
+  for (int q = tid; q < 16 * nw; q += kThreads) b.cnt[q] = 0;
+  __syncthreads();
+  for (int w = warp; w < nw; w += kWarps) {
+    const int i = w * 32 + lane;
+    const bool valid = i < n;
+    const int k = valid ? (b.a[i] >> 12) : 16;
+    const unsigned m = __match_any_sync(kFull, k);
+    const int rk = __popc(m & ((1u << lane) - 1u));
+    if (valid) {
+      b.posl[i] = (unsigned short)rk;
+      if (rk == 0) b.cnt[(15 - k) * nw + w] = __popc(m);
+    }
+  }
+  __syncthreads();
+  { /* exclusive scan of cnt[0..16*nw) in place */
+    const int Q = 16 * nw;
+    const int per = (Q + kThreads - 1) / kThreads;
+    const int q0 = tid * per;
+    int s = 0;
+    for (int q = q0; q < q0 + per && q < Q; ++q) s += (int)b.cnt[q];
+    int incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) b.misc[warp] = (unsigned)incl;
+    __syncthreads();
+    int base = incl - s;
+    for (int w = 0; w < warp; ++w) base += (int)b.misc[w];
+    for (int q = q0; q < q0 + per && q < Q; ++q) {
+      const int c = (int)b.cnt[q];
+      b.cnt[q] = (unsigned)base;
+      base += c;
+    }
+  }
+  __syncthreads();
+  for (int w = warp; w < nw; w += kWarps) {
+    const int i = w * 32 + lane;
+    if (i < n) {
+      const unsigned short e = b.a[i];
+      b.out[b.cnt[(15 - (e >> 12)) * nw + w] + b.posl[i]] = e;
+    }
+  }
+  __syncthreads();
+}
+
+/* ================================================================================================
+ * helpers shared by the four schedulers
+ * ============================================================================================== */
+
+/* RadioBearer::UpdateAverageTransmissionRate, flows/radio-bearer.cpp:138-164 */
+__device__ __forceinline__ double ewma_update(double avg, int tx_bytes, double dt) {
+  const double rate = __ddiv_rn((double)(tx_bytes * 8), dt);
+  const double beta = 0.02;
+  double v = __dadd_rn(__dmul_rn(1 - beta, avg), __dmul_rn(beta, rate));
+  if (v < 1) v = 1;
+  return v;
+}
+
+/* AMCModule::GetCQIFromSinr(GetEesmEffectiveSinr(...)), AMCModule.cpp:252-261 on the EESM mean:
+ * SINRForCQIIndex[k] <= 10*log10(-log(mean))  <=>  mean <= cut[k] (host bisection against glibc). */
+__device__ __forceinline__ int cqi_from_mean(double mean) {
+  /* cut[] decreases with k, so the conditions are nested and the reference's loop is a count */
+  int cqi = 1;
+#pragma unroll
+  for (int k = 1; k <= 14; ++k) cqi += (mean <= c_tab.cut[k]) ? 1 : 0;
+  return cqi;
+}
+
+struct Cell {
+  /* shared-memory views */
+  double* avg; double* den; double* mtab; unsigned long long* cumb; unsigned long long* cumr; double* off;
+  double* tval; int* tx; unsigned* mask; int* target; int* quota; int* frb; int* wd;
+  unsigned short* win; unsigned char* outsl; unsigned* misc;
+  SortBufs sb;
+};
+
+__device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
+  Cell c;
+  c.avg = (double*)(smem + L.avg);
+  c.den = (double*)(smem + L.den);
+  c.mtab = (double*)(smem + L.mtab);
+  c.cumb = (unsigned long long*)(smem + L.cumb);
+  c.cumr = (unsigned long long*)(smem + L.cumr);
+  c.off = (double*)(smem + L.off);
+  c.tval = (double*)(smem + L.tval);
+  c.tx = (int*)(smem + L.tx);
+  c.mask = (unsigned*)(smem + L.mask);
+  c.target = (int*)(smem + L.target);
+  c.quota = (int*)(smem + L.quota);
+  c.frb = (int*)(smem + L.frb);
+  c.wd = (int*)(smem + L.wd);
+  c.win = (unsigned short*)(smem + L.win);
+  c.outsl = (unsigned char*)(smem + L.outsl);
+  c.misc = (unsigned*)(smem + L.misc);
+  c.sb.a = (unsigned short*)(smem + L.a);
+  c.sb.out = (unsigned short*)(smem + L.posr);
+  c.sb.seg = (unsigned*)(smem + L.seg);
+  c.sb.posl = (unsigned short*)(smem + L.posl);
+  c.sb.posr = (unsigned short*)(smem + L.posr);
+  c.sb.wl = (unsigned*)(smem + L.wl);
+  c.sb.wr = (unsigned*)(smem + L.wr);
+  c.sb.pfl = (unsigned short*)(smem + L.pfl);
+  c.sb.pfr = (unsigned short*)(smem + L.pfr);
+  c.sb.cnt = (unsigned*)(smem + L.cnt);
+  c.sb.misc = c.misc;
+  return c;
+}
+
+/* CQI of UE u on the first RB of RBG g (the RB the metric is evaluated on, transport.cpp:536) */
+__device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* cqi, int u, int g) {
+  return d.cqi_per_rb ? (cqi[(size_t)u * d.R + (size_t)g * d.rbg] & 15) : (cqi[(size_t)u * d.G + g] & 15);
+}
+
+/* Slice targets and RBG quotas, transport.cpp:463-521, by one warp (lane s and lane s+32). */
+__device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int lane, int* g_target, int* g_quota) {
+  const int S = d.S;
+  const int nb_rbs = d.G * d.rbg;
+  int tgt[2], wd[2];
+  int sum = 0, nonempty = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    tgt[h] = 0;
+    wd[h] = 0;
+    if (s < S) {
+      wd[h] = c.wd[s];
+      if (wd[h]) tgt[h] = (int)__dadd_rn(__dmul_rn((double)nb_rbs, d.weight[s]), c.off[s]);   /* :475 */
+    }
+    sum += tgt[h];
+    nonempty += wd[h];
+  }
+  sum = __reduce_add_sync(kFull, sum);
+  nonempty = __reduce_add_sync(kFull, nonempty);
+  if (lane == 0) c.misc[14] = (unsigned)nonempty;
+  if (nonempty == 0) return;   /* RBsAllocation only runs with >= 1 user (transport.cpp:152-168) */
+  int extra = nb_rbs - sum;
+  /* first non-empty slice in rotation order k = (i + rand) % S, i = 0..S-1   (:489-500) */
+  const int b0 = r0 % S;
+  int rot[2];
+  unsigned best = 0xffffffffu;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    rot[h] = (s - b0 + S) % S;
+    if (s < S && wd[h]) best = min(best, (unsigned)rot[h]);
+  }
+  best = __reduce_min_sync(kFull, best);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    if (s < S && wd[h]) {
+      tgt[h] += extra / nonempty;
+      if ((unsigned)rot[h] == best) tgt[h] += extra % nonempty;
+    }
+  }
+  /* quotas (:501-521) */
+  int q[2];
+  int qsum = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    q[h] = (s < S) ? tgt[h] / d.rbg : 0;
+    qsum += q[h];
+  }
+  qsum = __reduce_add_sync(kFull, qsum);
+  const int extra_rbgs = d.G - qsum;
+  const int b1 = r1 % S;
+  best = 0xffffffffu;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    rot[h] = (s - b1 + S) % S;
+    if (s < S && wd[h]) best = min(best, (unsigned)rot[h]);
+  }
+  best = __reduce_min_sync(kFull, best);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int s = lane + 32 * h;
+    if (s < S) {
+      if (wd[h]) {
+        q[h] += extra_rbgs / nonempty;
+        if ((unsigned)rot[h] == best) q[h] += extra_rbgs % nonempty;
+      }
+      c.target[s] = tgt[h];
+      c.quota[s] = q[h];
+      if (g_target) g_target[s] = tgt[h];
+      if (g_quota) g_quota[s] = q[h];
+    }
+  }
+}
+
+/* MaximizeCell's first-fit scan over the sorted (rbg,slice) entries, transport.cpp:362-375, by one
+ * warp: 32 entries at a time; inside a chunk the lowest feasible lane is accepted, the others
+ * re-checked against it, until no feasible lane is left. */
+__device__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
+  const int n = d.sort_n;
+  int rem_a = (lane < d.S) ? c.quota[lane] : 0;
+  int rem_b = (lane + 32 < d.S) ? c.quota[lane + 32] : 0;
+  unsigned long long free_mask = (d.G >= 64) ? ~0ull : ((1ull << d.G) - 1ull);
+  for (int base = 0; base < n && free_mask != 0ull; base += 32) {
+    const int i = base + lane;
+    const unsigned e = (i < n) ? sorted[i] : 0u;
+    const int g = (e >> 6) & 63, s = e & 63;
+    const int ra = __shfl_sync(kFull, rem_a, s & 31), rb = __shfl_sync(kFull, rem_b, s & 31);
+    bool feas = (i < n) && ((free_mask >> g) & 1ull) && ((s < 32 ? ra : rb) > 0);
+    unsigned m = __ballot_sync(kFull, feas);
+    while (m) {
+      const int ld = __ffs(m) - 1;
+      const unsigned pe = __shfl_sync(kFull, e, ld);
+      const int pg = (pe >> 6) & 63, ps = pe & 63;
+      if (lane == 0) c.outsl[pg] = (unsigned char)ps;
+      free_mask &= ~(1ull << pg);
+      if (lane == (ps & 31)) { if (ps < 32) rem_a--; else rem_b--; }
+      const int na = __shfl_sync(kFull, rem_a, ps & 31), nb = __shfl_sync(kFull, rem_b, ps & 31);
+      const int nrem = ps < 32 ? na : nb;
+      feas = feas && lane > ld && g != pg && !(s == ps && nrem <= 0);
+      m = __ballot_sync(kFull, feas);
+    }
+  }
+}
+
+/* GreedyByRow, transport.cpp:249-272, by one warp. a[] holds the unsorted (rbg-major) entries. */
+__device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned short* a, int lane) {
+  const int S = d.S;
+  int rem_a = (lane < S) ? c.quota[lane] : 0;
+  int rem_b = (lane + 32 < S) ? c.quota[lane + 32] : 0;
+  for (int g = 0; g < d.G; ++g) {
+    unsigned v = 0;
+    if (lane < S && rem_a > 0) v = ((unsigned)(a[g * S + lane] >> 12) << 8 | (unsigned)(63 - lane)) + 1u;
+    if (lane + 32 < S && rem_b > 0) {
+      const unsigned v2 = ((unsigned)(a[g * S + lane + 32] >> 12) << 8 | (unsigned)(63 - lane - 32)) + 1u;
+      v = max(v, v2);
+    }
+    v = __reduce_max_sync(kFull, v);
+    if (v) {
+      const int ps = 63 - (int)((v - 1u) & 0xffu);
+      if (lane == 0) c.outsl[g] = (unsigned char)ps;
+      if (lane == (ps & 31)) { if (ps < 32) rem_a--; else rem_b--; }
+    }
+  }
+}
+
+/* Link adaptation + accounting for UE u holding the RBGs in mask (transport.cpp:632-660 and 170-199;
+ * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
+__device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* cqi, int u,
+                                            unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc) {
+  int bits = 0, mcs = 0xff, fc = 0;
+  const int nrbg = __popc(m_lo) + __popc(m_hi);
+  if (nrbg > 0) {
+    double sum = 0;
+    unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+    while (m) {
+      const int g = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      if (d.cqi_per_rb) {
+        const uint8_t* p = cqi + (size_t)u * d.R + (size_t)g * d.rbg;
+        for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, c.tval[p[r] & 15]);
+      } else {
+        const double t = c.tval[cqi[(size_t)u * d.G + g] & 15];
+        for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, t);
+      }
+    }
+    const int nrb = nrbg * d.rbg;
+    const double mean = __ddiv_rn(sum, (double)nrb);
+    fc = cqi_from_mean(mean);
+    mcs = 2 * (fc - 1);                        /* MapCQIToMCS, AMCModule.cpp:36-40 */
+    bits = d.tbs_n[nrbg * 16 + fc];
+    const int avail = bits / 8;
+    if (avail > 0) {
+      if (d.algo == 1) {
+        c.tx[u] += avail;
+        c.cumb[u] += (unsigned long long)avail;
+        c.cumr[u] += (unsigned long long)nrb;
+      } else if (d.data > 0) {
+        const int sent = min(avail, d.data);
+        c.tx[u] += sent;
+        c.cumb[u] += (unsigned long long)sent;
+        c.cumr[u] += (unsigned long long)nrb;
+      }
+    }
+  }
+  if (o_bits) o_bits[u] = bits;
+  if (o_mcs) o_mcs[u] = (uint8_t)mcs;
+  if (o_fc) o_fc[u] = (uint8_t)fc;
+}
+
+/* ================================================================================================
+ * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
+ * ============================================================================================== */
+template <int ALGO>
+__global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const RunArgs r) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Layout L = make_layout(d.S, d.U, d.G, d.m_cap);
+  const Cell c = carve(smem, L);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = d.S, U = d.U, G = d.G;
+  const int b = blockIdx.x;
+  if (b >= d.n_cells) return;
+
+  /* cell state -> shared memory */
+  for (int u = tid; u < U; u += kThreads) {
+    const size_t i = (size_t)b * U + u;
+    c.avg[u] = d.avg[i];
+    c.tx[u] = d.tx[i];
+    c.cumb[u] = d.cum_bytes[i];
+    c.cumr[u] = d.cum_rbs[i];
+    c.mask[2 * u] = 0;
+    c.mask[2 * u + 1] = 0;
+  }
+  for (int s = tid; s < S; s += kThreads) {
+    c.off[s] = (ALGO == 7) ? d.ewma[(size_t)b * S + s] : ((ALGO == 1) ? 0.0 : d.offset[(size_t)b * S + s]);
+    c.frb[s] = 0;
+    c.wd[s] = 0;
+    c.target[s] = 0;
+    c.quota[s] = 0;
+  }
+  if (tid < 16) c.tval[tid] = c_tab.tval[tid];
+  for (int g = tid; g < G; g += kThreads) c.outsl[g] = 0xff;
+  __syncthreads();
+
+  for (int t = 0; t < r.T; ++t) {
+    const uint8_t* cqi = r.cqi + (size_t)t * r.cqi_tti_stride +
+                         (size_t)b * U * (d.cqi_per_rb ? d.R : G);
+    const uint8_t* act = r.active ? r.active + (size_t)t * r.active_tti_stride + (size_t)b * U : nullptr;
+    const double dt = r.dt[t];
+    const size_t tb = (size_t)t * d.n_cells + b;
+    short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
+    int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
+    uint8_t* o_mcs = r.mcs ? r.mcs + tb * U : nullptr;
+    uint8_t* o_fc = r.final_cqi ? r.final_cqi + tb * U : nullptr;
+    int* o_tgt = r.slice_target ? r.slice_target + tb * S : nullptr;
+    int* o_quo = r.slice_quota ? r.slice_quota + tb * S : nullptr;
+
+    /* ---- NVS: SelectSliceToServe (nvs.cpp:94-142) runs before the EWMA update ---------------- */
+    int served = -1;
+    if (ALGO == 7) {
+      /* slices with at least one queued bearer */
+      for (int u = tid; u < U; u += kThreads)
+        if ((!act || act[u]) && d.data > 0) c.wd[d.ue_to_slice[u]] = 1;
+      __syncthreads();
+      if (tid == 0) {
+        int slice_id = 0;
+        double max_score = 0;
+        for (int i = 0; i < S; ++i) {
+          if (!c.wd[i]) continue;
+          if (c.off[i] == 0) { slice_id = i; break; }
+          const double score = __ddiv_rn(d.weight[i], c.off[i]);
+          if (score >= max_score) { max_score = score; slice_id = i; }
+        }
+        const double beta = 0.01; /* nvs.h:42 */
+        for (int i = 0; i < S; ++i) {
+          if (!c.wd[i]) continue;
+          double e = __dmul_rn(1 - beta, c.off[i]);
+          if (i == slice_id) e = __dadd_rn(e, __dmul_rn(beta, 1.0));
+          c.off[i] = e;
+        }
+        c.misc[15] = (unsigned)slice_id;
+        if (r.nvs_slice) r.nvs_slice[tb] = slice_id;
+      }
+      __syncthreads();
+      served = (int)c.misc[15];
+    }
+
+    /* ---- P0: EWMA of every bearer; metric denominators; slices with data --------------------- */
+    for (int u = tid; u < U; u += kThreads) {
+      double a = c.avg[u];
+      if (dt != 0) {
+        a = ewma_update(a, c.tx[u], dt);
+        c.avg[u] = a;
+        c.tx[u] = 0;
+      }
+      if (ALGO == 1) {
+        c.den[u] = a;                                             /* dl-pf-packet-scheduler.cpp:128-140 */
+      } else {
+        const int s = d.ue_to_slice[u];
+        /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
+        c.den[u] = d.psi[s] ? __ddiv_rn(__dadd_rn(1.0, a), 1000.0) : 1.0;
+        if ((ALGO == 8 || ALGO == 9) && (!act || act[u])) c.wd[s] = 1;
+      }
+    }
+    __syncthreads();
+
+    if (ALGO == 8 || ALGO == 9) {
+      /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
+      for (int ch = 0; ch < d.n_chunks; ++ch) {
+        const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
+        const int j0 = d.slice_ptr[s0], j1 = d.slice_ptr[s1];
+        if (ch == 0 && warp == kWarps - 1)
+          slice_quotas(d, c, r.rand2[2 * tb], r.rand2[2 * tb + 1], lane, o_tgt, o_quo);
+        for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
+          const int j = j0 + (q >> 4), cq = q & 15;
+          const int u = d.slice_ues[j];
+          c.mtab[q] = cq ? __ddiv_rn(d.epow[d.ue_to_slice[u] * 16 + cq], c.den[u]) : 0.0;
+        }
+        __syncthreads();
+        const bool vec4 = !d.cqi_per_rb && (G % 4 == 0);
+        if (vec4) {
+          const int g4 = G >> 2;
+          const int items = (s1 - s0) * g4;
+          for (int q = tid; q < items; q += kThreads) {
+            const int s = s0 + q / g4, g0 = (q % g4) * 4;
+            double best[4] = {-1.0, -1.0, -1.0, -1.0};
+            int bu[4] = {kNoUe, kNoUe, kNoUe, kNoUe};
+            int bc[4] = {0, 0, 0, 0};
+            for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
+              const int u = d.slice_ues[j];
+              if (act && !act[u]) continue;
+              const unsigned w = *(const unsigned*)(cqi + (size_t)u * G + g0);
+              const double* row = c.mtab + (j - j0) * kMStride;
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                const int cq = (w >> (8 * x)) & 15;
+                const double m = row[cq];
+                if (m > best[x]) { best[x] = m; bu[x] = u; bc[x] = cq; }
+              }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const int g = g0 + x;
+              c.sb.a[g * S + s] = (unsigned short)((bc[x] << 12) | (g << 6) | s);
+              c.win[g * S + s] = (unsigned short)bu[x];
+            }
+          }
+        } else {
+          const int items = (s1 - s0) * G;
+          for (int q = tid; q < items; q += kThreads) {
+            const int s = s0 + q / G, g = q % G;
+            double best = -1.0;
+            int bu = kNoUe, bc = 0;
+            for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
+              const int u = d.slice_ues[j];
+              if (act && !act[u]) continue;
+              const int cq = cqi_first_rb(d, cqi, u, g);
+              const double m = c.mtab[(j - j0) * kMStride + cq];
+              if (m > best) { best = m; bu = u; bc = cq; }
+            }
+            c.sb.a[g * S + s] = (unsigned short)((bc << 12) | (g << 6) | s);
+            c.win[g * S + s] = (unsigned short)bu;
+          }
+        }
+        __syncthreads();
+      }
+
+      /* ---- P3/P4: inter-slice assignment ---------------------------------------------------- */
+      if (ALGO == 9) {
+        sort_desc(c.sb, d.sort_n, d.sort_depth);
+        if (warp == 0) greedy_maxcell(d, c, c.sb.out, lane);
+      } else {
+        if (warp == 0) greedy_by_row(d, c, c.sb.a, lane);
+      }
+      __syncthreads();
+
+      /* ---- P5: RBG -> UE (transport.cpp:589-601) --------------------------------------------- */
+      for (int g = tid; g < G; g += kThreads) {
+        const int sl = c.outsl[g];
+        int ue = -1;
+        if (sl != 0xff) {
+          const unsigned short w = c.win[g * S + sl];
+          if (w != kNoUe) {
+            ue = w;
+            atomicAdd(&c.frb[sl], 1);
+            atomicOr(&c.mask[2 * ue + (g >> 5)], 1u << (g & 31));
+          }
+        }
+        if (o_rbg) o_rbg[g] = (short)ue;
+        c.outsl[g] = 0xff;
+      }
+      __syncthreads();
+      /* slice_rbs_offset_ update (:618-620); only when RBsAllocation ran (>= 1 user) */
+      for (int s = tid; s < S; s += kThreads) {
+        if (c.misc[14]) c.off[s] = (double)(c.target[s] - c.frb[s] * d.rbg);
+        else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
+      }
+    } else if (ALGO == 7) {
+      /* ---- NVS: enterprise argmax over the served slice's users for every RBG (nvs.cpp:275-311) */
+      const int j0 = d.slice_ptr[served], j1 = d.slice_ptr[served + 1];
+      for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
+        const int j = j0 + (q >> 4), cq = q & 15;
+        const int u = d.slice_ues[j];
+        c.mtab[q] = cq ? __ddiv_rn(d.epow[served * 16 + cq], c.den[u]) : 0.0;
+      }
+      __syncthreads();
+      for (int g = tid; g < G; g += kThreads) {
+        double best = -1.0;   /* metrics are >= 0, so this behaves like numeric_limits::lowest() */
+        int bu = -1;
+        for (int j = j0; j < j1; ++j) {
+          const int u = d.slice_ues[j];
+          if (act && !act[u]) continue;
+          if (d.data <= 0) continue;
+          const int cq = cqi_first_rb(d, cqi, u, g);
+          const double m = c.mtab[(j - j0) * kMStride + cq];
+          if (m > best) { best = m; bu = u; }
+        }
+        if (bu >= 0) atomicOr(&c.mask[2 * bu + (g >> 5)], 1u << (g & 31));
+        if (o_rbg) o_rbg[g] = (short)bu;
+      }
+    } else {
+      /* ---- No-slicing PF: per RBG, first flow with the strictly largest metric (dlps.cpp:227-246) */
+      for (int g = warp; g < G; g += kWarps) {
+        double best = 0.0;
+        int bu = 0x7fffffff;
+        for (int u = lane; u < U; u += 32) {
+          if (act && !act[u]) continue;
+          const int cq = cqi_first_rb(d, cqi, u, g);
+          const double m = __ddiv_rn(d.epow[cq], c.den[u]);
+          if (m > best) { best = m; bu = u; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double om = __shfl_xor_sync(kFull, best, o);
+          const int ou = __shfl_xor_sync(kFull, bu, o);
+          if (om > best || (om == best && ou < bu)) { best = om; bu = ou; }
+        }
+        if (lane == 0) {
+          const int ue = (bu == 0x7fffffff) ? -1 : bu;
+          if (ue >= 0) atomicOr(&c.mask[2 * ue + (g >> 5)], 1u << (g & 31));
+          if (o_rbg) o_rbg[g] = (short)ue;
+        }
+      }
+    }
+    __syncthreads();
+
+    /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
+    for (int u = tid; u < U; u += kThreads) {
+      const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
+      finalize_ue(d, c, cqi, u, m_lo, m_hi, o_bits, o_mcs, o_fc);
+      c.mask[2 * u] = 0;
+      c.mask[2 * u + 1] = 0;
+    }
+    for (int s = tid; s < S; s += kThreads) {
+      c.frb[s] = 0;
+      c.wd[s] = 0;
+      c.target[s] = 0;
+      c.quota[s] = 0;
+    }
+    __syncthreads();
+  }
+
+  /* cell state -> HBM */
+  for (int u = tid; u < U; u += kThreads) {
+    const size_t i = (size_t)b * U + u;
+    d.avg[i] = c.avg[u];
+    d.tx[i] = c.tx[u];
+    d.cum_bytes[i] = c.cumb[u];
+    d.cum_rbs[i] = c.cumr[u];
+  }
+  if (ALGO == 7 || ALGO == 8 || ALGO == 9) {
+    double* dst = (ALGO == 7) ? d.ewma : d.offset;
+    for (int s = tid; s < S; s += kThreads) dst[(size_t)b * S + s] = c.off[s];
+  }
+}
+
+/* ---- test hook: the sort alone, one CTA per array --------------------------------------------- */
+__global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* keys, int n, int depth, int* perm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Layout L = make_layout(1, 0, n, 0);   /* S*G == n */
+  const Cell c = carve(smem, L);
+  const uint8_t* k = keys + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += kThreads) c.sb.a[i] = (unsigned short)(((k[i] & 15) << 12) | i);
+  __syncthreads();
+  sort_desc(c.sb, n, depth);
+  for (int i = threadIdx.x; i < n; i += kThreads) perm[(size_t)blockIdx.x * n + i] = c.sb.out[i] & 0xfff;
+}
+
+/* ---- synthetic workload (twin of radiosaber_b200/workload.py) -------------------------------- */
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct CdfTable { unsigned thr[14]; };
+
+__global__ void rs_synth_cqi_kernel(uint8_t* out, unsigned long long key, long long cell0, long long tti0,
+                                    int n_ttis, int n_cells, int U, int G, int refresh, CdfTable cdf) {
+  const size_t total = (size_t)n_ttis * n_cells * U * G;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long rbg = i % G;
+    size_t r = i / G;
+    const unsigned long long ue = r % U; r /= U;
+    const unsigned long long cell = cell0 + (long long)(r % n_cells); r /= n_cells;
+    const unsigned long long epoch = (unsigned long long)(tti0 + (long long)r) / (unsigned long long)refresh;
+    unsigned long long ctr = (epoch << 40) ^ (cell << 20) ^ (ue << 8) ^ rbg;
+    ctr ^= (ue >> 12) * 0xD6E8FEB86659FD93ull;
+    const unsigned u32 = (unsigned)(splitmix64(ctr ^ key) >> 32);
+    int cq = 1;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) cq += (u32 >= cdf.thr[k]);
+    out[i] = (uint8_t)cq;
+  }
+}
+
+__global__ void rs_synth_rand2_kernel(int* out, unsigned long long key, long long cell0, long long tti0,
+                                      int n_ttis, int n_cells, int S) {
+  const size_t total = (size_t)n_ttis * n_cells * 2;
+  const unsigned long long span = (unsigned long long)(2147483647 - S + 1);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long which = i & 1;
+    size_t r = i >> 1;
+    const unsigned long long cell = cell0 + (long long)(r % n_cells);
+    const unsigned long long tti = tti0 + (long long)(r / n_cells);
+    const unsigned long long ctr = (tti << 32) ^ (cell << 1) ^ which;
+    out[i] = (int)((splitmix64(ctr ^ key) >> 11) % span);
+  }
+}
+
+/* ---- per-slice totals: uint64 [4][S] += over cells (integers: order-independent) -------------- */
+__global__ void rs_stats_kernel(const DevCfg d, unsigned long long* stats) {
+  extern __shared__ unsigned long long s_acc[];   /* [4][S] */
+  const int S = d.S;
+  for (int i = threadIdx.x; i < 4 * S; i += blockDim.x) s_acc[i] = 0;
+  __syncthreads();
+  const size_t total = (size_t)d.n_cells * d.U;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = d.ue_to_slice[i % d.U];
+    const unsigned long long by = d.cum_bytes[i], rb = d.cum_rbs[i], q = by >> 10;
+    atomicAdd(&s_acc[0 * S + s], by);
+    atomicAdd(&s_acc[1 * S + s], rb);
+    atomicAdd(&s_acc[2 * S + s], q);
+    atomicAdd(&s_acc[3 * S + s], q * q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * S; i += blockDim.x)
+    if (s_acc[i]) atomicAdd(&stats[i], s_acc[i]);
+}
+
+}  // namespace rs

@@ -1,0 +1,713 @@
+/* rs_sched.cu -- host side of the C ABI declared in include/rs_sched.h.
+ *
+ * Owns the device state of a batch of cells, builds the lookup tables the kernels use (with the
+ * host's glibc, so that every libm value is the one the reference's x86-64 build computes) and
+ * launches the sm_100a kernels of rs_device.cuh.  No CPU implementation of the scheduling path
+ * lives here: without a CUDA device every compute entry point fails with RS_ERR_CUDA.
+ */
+#include "../../include/rs_sched.h"
+#include "rs_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(RS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+  } while (0)
+
+/* ---- AMC tables: standard LTE data (3GPP TS 36.213), same values as AMCModule.cpp:36-231 ------- */
+const double kSinrForCqi[15] = {-4.63, -2.6, -0.12, 2.26, 4.73, 7.53, 8.67, 11.32,
+                                14.24, 15.21, 18.63, 21.32, 23.47, 28.49, 34.6};
+const int kMcsToItbs[29] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 10, 11, 12, 13, 14, 15, 15, 16,
+                            17, 18, 19, 20, 21, 22, 23, 24, 25, 26};
+const int kTbs[110 * 27] = {
+#include "../../include/rs_tbs_36213.inc"
+};
+inline int mcs_from_cqi(int cqi) { return 2 * (cqi - 1); }          /* MapCQIToMCS */
+inline int tbs_row(int row, int itbs, const int32_t* row_m1) {
+  return row < 0 ? row_m1[itbs] : kTbs[row * 27 + itbs];
+}
+/* AMCModule::GetTBSizeFromMCS(mcs, nbRBs), AMCModule.cpp:305-317 incl. the row -1 read */
+int tbs_n(int mcs, int nb_rbs, const int32_t* row_m1) {
+  const int itbs = kMcsToItbs[mcs];
+  if (nb_rbs <= 110) return tbs_row(nb_rbs - 1, itbs, row_m1);
+  return 5 * tbs_row(nb_rbs / 5 - 1, itbs, row_m1) + tbs_row(nb_rbs % 5 - 1, itbs, row_m1);
+}
+/* AMCModule::GetEfficiencyFromCQI, AMCModule.cpp:319-327 */
+double eff_from_cqi(int cqi) {
+  const int bits = kTbs[kMcsToItbs[mcs_from_cqi(cqi)]];
+  volatile double eff = (bits / 0.001) / 180000.;
+  return eff;
+}
+/* The stock -O0 build reads McsToItbs[5..28],0,0,0 for TransportBlockSizeTable[-1] (oracle/_ref probe). */
+void default_row_m1(int32_t* out) {
+  for (int i = 0; i < 27; ++i) out[i] = (i + 5 < 29) ? kMcsToItbs[i + 5] : 0;
+}
+
+/* 10*log10(-log(mean)) as GetEesmEffectiveSinr computes it (eesm-effective-sinr.h:42-44, beta = 1) */
+double eesm_tail(double mean) {
+  volatile double beta = 1;
+  volatile double eff = -beta * log(mean);
+  return 10 * log10(eff);
+}
+
+bool build_const_tables(rs::ConstTables* t, std::string* why) {
+  memset(t, 0, sizeof *t);
+  for (int c = 1; c <= 15; ++c) {
+    volatile double s = pow(10, kSinrForCqi[c - 1] / 10);
+    volatile double beta = 1;
+    t->tval[c] = exp(-s / beta);
+  }
+  t->tval[0] = t->tval[1];
+  for (int k = 1; k <= 14; ++k) {
+    const double thr = kSinrForCqi[k];
+    auto pred = [&](uint64_t bits) {
+      double m;
+      memcpy(&m, &bits, 8);
+      return thr <= eesm_tail(m);
+    };
+    uint64_t lo = 0, hi;             /* pred(lo) true (mean 0 -> +inf dB), pred(hi) false (mean 1 -> -inf dB) */
+    const double one = 1.0;
+    memcpy(&hi, &one, 8);
+    if (!pred(lo) || pred(hi)) { *why = "EESM threshold bracket"; return false; }
+    while (hi - lo > 1) {
+      const uint64_t mid = lo + (hi - lo) / 2;
+      if (pred(mid)) lo = mid; else hi = mid;
+    }
+    /* glibc's log/log10 must be monotone around the cut for the single comparison to be exact */
+    for (uint64_t d = 1; d <= 512; ++d) {
+      if (lo >= d && !pred(lo - d)) { *why = "EESM tail not monotone below a cut"; return false; }
+      if (pred(lo + d)) { *why = "EESM tail not monotone above a cut"; return false; }
+    }
+    memcpy(&t->cut[k], &lo, 8);
+  }
+  for (int k = 2; k <= 14; ++k)
+    if (!(t->cut[k] <= t->cut[k - 1])) { *why = "EESM cuts not ordered"; return false; }
+  return true;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct rs_handle {
+  int device = 0;
+  rs::DevCfg d{};
+  int B = 0, cqi_cols = 0;           /* cqi_cols = G or R */
+  rs::Layout layout{};
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  int64_t launches = 0;
+  int32_t row_m1[27];
+  /* static tables */
+  DevBuf<int> ue_to_slice, slice_ptr, slice_ues, chunk_slice, tbs_n;
+  DevBuf<double> weight, epow;
+  DevBuf<unsigned char> psi;
+  /* state */
+  DevBuf<double> avg, offset, ewma;
+  DevBuf<int> tx;
+  DevBuf<unsigned long long> cum_bytes, cum_rbs;
+  /* per-call scratch */
+  DevBuf<double> dt_dev;
+  double* dt_pinned = nullptr;
+  size_t dt_pinned_n = 0;
+  DevBuf<unsigned long long> stats;
+  /* staging for rs_step / rs_run_host: two slots */
+  struct Slot {
+    DevBuf<uint8_t> cqi, active, mcs, final_cqi;
+    DevBuf<int> rand2, tbs_bits, slice_target, slice_quota, nvs_slice;
+    DevBuf<short> rbg_to_ue;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+  } slot[2];
+};
+
+namespace {
+
+int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
+  const dim3 grid(h->B), block(rs::kThreads);
+  const size_t sm = (size_t)h->layout.total;
+  switch (h->d.algo) {
+    case 1: rs::rs_tti_kernel<1><<<grid, block, sm, h->stream>>>(h->d, a); break;
+    case 7: rs::rs_tti_kernel<7><<<grid, block, sm, h->stream>>>(h->d, a); break;
+    case 8: rs::rs_tti_kernel<8><<<grid, block, sm, h->stream>>>(h->d, a); break;
+    default: rs::rs_tti_kernel<9><<<grid, block, sm, h->stream>>>(h->d, a); break;
+  }
+  CU(cudaGetLastError());
+  h->launches++;
+  return RS_OK;
+}
+
+int set_smem_attr(rs_handle* h) {
+  const int sm = h->layout.total;
+  switch (h->d.algo) {
+    case 1: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
+    case 7: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
+    case 8: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
+    default: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
+  }
+  return RS_OK;
+}
+
+template <typename T>
+int upload(DevBuf<T>& b, const std::vector<T>& v) {
+  CU(b.alloc(v.size()));
+  if (!v.empty()) CU(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return RS_OK;
+}
+
+int ensure_dt(rs_handle* h, const double* dt, int n) {
+  CU(h->dt_dev.alloc((size_t)n));
+  if (h->dt_pinned_n < (size_t)n) {
+    if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
+    h->dt_pinned = nullptr;
+    h->dt_pinned_n = 0;
+    CU(cudaMallocHost((void**)&h->dt_pinned, sizeof(double) * (size_t)n));
+    h->dt_pinned_n = (size_t)n;
+  }
+  /* the previous async copy out of dt_pinned must be over before it is overwritten */
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(h->dt_pinned, dt, sizeof(double) * (size_t)n);
+  CU(cudaMemcpyAsync(h->dt_dev.p, h->dt_pinned, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  return RS_OK;
+}
+
+int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active) {
+  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
+  CU(s.cqi.alloc((size_t)T * B * U * C));
+  CU(s.rand2.alloc((size_t)T * B * 2));
+  if (want_active) CU(s.active.alloc((size_t)T * B * U));
+  if (out) {
+    if (out->rbg_to_ue) CU(s.rbg_to_ue.alloc((size_t)T * B * G));
+    if (out->tbs_bits) CU(s.tbs_bits.alloc((size_t)T * B * U));
+    if (out->mcs) CU(s.mcs.alloc((size_t)T * B * U));
+    if (out->final_cqi) CU(s.final_cqi.alloc((size_t)T * B * U));
+    if (out->slice_target) CU(s.slice_target.alloc((size_t)T * B * S));
+    if (out->slice_quota) CU(s.slice_quota.alloc((size_t)T * B * S));
+    if (out->nvs_slice) CU(s.nvs_slice.alloc((size_t)T * B));
+  }
+  if (!s.in_done) {
+    CU(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+  }
+  return RS_OK;
+}
+
+bool wants(const rs_handle* h, int which) { /* outputs that exist for this scheduler id */
+  const int a = h->d.algo;
+  if (which == 0) return a == 8 || a == 9;   /* slice_target / slice_quota */
+  return a == 7;                             /* nvs_slice */
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rs_last_error(void) { return g_err.c_str(); }
+int32_t rs_abi_version(void) { return 1; }
+
+void rs_destroy(rs_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->ue_to_slice.release(); h->slice_ptr.release(); h->slice_ues.release(); h->chunk_slice.release();
+  h->tbs_n.release(); h->weight.release(); h->epow.release(); h->psi.release();
+  h->avg.release(); h->offset.release(); h->ewma.release(); h->tx.release();
+  h->cum_bytes.release(); h->cum_rbs.release(); h->dt_dev.release(); h->stats.release();
+  for (auto& s : h->slot) {
+    s.cqi.release(); s.active.release(); s.mcs.release(); s.final_cqi.release(); s.rand2.release();
+    s.tbs_bits.release(); s.slice_target.release(); s.slice_quota.release(); s.nvs_slice.release();
+    s.rbg_to_ue.release();
+    if (s.in_done) cudaEventDestroy(s.in_done);
+    if (s.k_done) cudaEventDestroy(s.k_done);
+    if (s.out_done) cudaEventDestroy(s.out_done);
+  }
+  if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
+  delete h;
+}
+
+int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle** out) {
+  if (!cfg || !out || n_cells <= 0) return fail(RS_ERR_ARG, "rs_create: bad argument");
+  *out = nullptr;
+  const int algo = cfg->algo, S = cfg->n_slices, U = cfg->n_ues;
+  if (algo != 1 && algo != 7 && algo != 8 && algo != 9)
+    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber)", algo);
+  if (S < 1 || S > RS_MAX_SLICES) return fail(RS_ERR_UNSUPPORTED, "n_slices %d outside 1..%d", S, RS_MAX_SLICES);
+  if (U < 1 || U > 65000) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..65000", U);
+  if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0)
+    return fail(RS_ERR_UNSUPPORTED, "n_rbs %d must be a positive multiple of rbg_size %d", cfg->n_rbs, cfg->rbg_size);
+  const int G = cfg->n_rbs / cfg->rbg_size;
+  if (G > RS_MAX_RBGS) return fail(RS_ERR_UNSUPPORTED, "%d RBGs > %d", G, RS_MAX_RBGS);
+  if (!cfg->ue_to_slice || (algo != 1 && (!cfg->weight || !cfg->params)))
+    return fail(RS_ERR_ARG, "rs_create: weight/params/ue_to_slice missing");
+  if (cfg->data_to_transmit < 0 || cfg->data_to_transmit > 268435455)
+    return fail(RS_ERR_ARG, "data_to_transmit %d outside 0..2^28-1 (data*8 is an int in the reference)", cfg->data_to_transmit);
+  for (int u = 0; u < U; ++u)
+    if (cfg->ue_to_slice[u] < 0 || cfg->ue_to_slice[u] >= S) return fail(RS_ERR_ARG, "ue_to_slice[%d] out of range", u);
+
+  rs_handle* h = new (std::nothrow) rs_handle;
+  if (!h) return fail(RS_ERR_ARG, "out of memory");
+  h->device = device;
+  h->B = n_cells;
+  if (cfg->tbs_row_m1) memcpy(h->row_m1, cfg->tbs_row_m1, sizeof h->row_m1);
+  else default_row_m1(h->row_m1);
+
+  rs::DevCfg& d = h->d;
+  d.algo = algo; d.S = S; d.U = U; d.G = G; d.R = cfg->n_rbs; d.rbg = cfg->rbg_size;
+  d.cqi_per_rb = cfg->cqi_per_rb ? 1 : 0;
+  d.data = cfg->data_to_transmit;
+  d.n_cells = n_cells;
+  d.sort_n = G * S;
+  { int lg = 0; for (int m = d.sort_n; m > 1; m >>= 1) lg++; d.sort_depth = 2 * lg; }
+  h->cqi_cols = d.cqi_per_rb ? d.R : G;
+
+#define BAIL(code_)            \
+  do {                         \
+    int rc_ = (code_);         \
+    if (rc_ != RS_OK) {        \
+      std::string keep = g_err;\
+      rs_destroy(h);           \
+      g_err = keep;            \
+      return rc_;              \
+    }                          \
+  } while (0)
+
+  /* ---- tables ---- */
+  std::vector<double> epow;
+  std::vector<unsigned char> psi(S, 0);
+  std::vector<double> weight(S, 0.0);
+  int max_tbs = 0;
+  std::vector<int> tbsn((size_t)(G + 1) * 16, 0);
+  for (int k = 1; k <= G; ++k)
+    for (int c = 1; c <= 15; ++c) {
+      tbsn[(size_t)k * 16 + c] = tbs_n(mcs_from_cqi(c), k * d.rbg, h->row_m1);
+      max_tbs = std::max(max_tbs, tbsn[(size_t)k * 16 + c]);
+    }
+  if (algo == 1) {
+    epow.assign(16, 0.0);
+    for (int c = 1; c <= 15; ++c) { volatile double m = eff_from_cqi(c) * 180000.; epow[c] = m; }  /* dl-pf:137 */
+    /* dlps.cpp:264-269: a flow leaves the candidate set once TBS >= data*8; with an infinite buffer never */
+    if ((long long)d.data * 8 <= (long long)max_tbs)
+      BAIL(fail(RS_ERR_UNSUPPORTED, "id 1 with data_to_transmit*8 <= %d bits (flow-satisfied cut-off) is not covered", max_tbs));
+  } else {
+    epow.assign((size_t)S * 16, 0.0);
+    for (int s = 0; s < S; ++s) {
+      const int32_t* p = cfg->params + 4 * s;
+      weight[s] = cfg->weight[s];
+      if (p[3] != 0 && p[3] != 1)
+        BAIL(fail(RS_ERR_UNSUPPORTED, "slice %d: psi=%d; pow(avg, psi) is bit-exact on the device only for psi in {0,1}", s, p[3]));
+      psi[s] = (unsigned char)p[3];
+      for (int c = 1; c <= 15; ++c) {
+        volatile double e = eff_from_cqi(c);
+        volatile double se = e * 180000 / 1000;                       /* transport.cpp:686 */
+        double v = pow(se, p[2]);                                      /* transport.cpp:692 */
+        if (p[0] != 0 && d.data == 0) v = 0.0;                         /* transport.cpp:694-697 */
+        epow[(size_t)s * 16 + c] = v;
+      }
+    }
+    if (algo == 7) {
+      /* nvs.cpp:299-300: allocated RBs < m_requiredRBs = data*8 / TBS1(mcs(wideband CQI)) >= data*8/712 */
+      d.nvs_guard = (d.data > 0 && (long long)d.data * 8 / 712 < (long long)d.R) ? 1 : 0;
+      if (d.nvs_guard)
+        BAIL(fail(RS_ERR_UNSUPPORTED, "id 7 with data_to_transmit=%d: the required-RBs guard can bind; not covered", d.data));
+    }
+  }
+  /* CSR of UEs by slice (ascending UE id inside a slice == the reference's user order) */
+  const int SL = (algo == 1) ? 1 : S;
+  std::vector<int> ptr(SL + 1, 0), ues(U), u2s(cfg->ue_to_slice, cfg->ue_to_slice + U);
+  for (int u = 0; u < U; ++u) ptr[(algo == 1 ? 0 : u2s[u]) + 1]++;
+  for (int s = 0; s < SL; ++s) ptr[s + 1] += ptr[s];
+  { std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int u = 0; u < U; ++u) ues[fill[algo == 1 ? 0 : u2s[u]]++] = u; }
+  int max_slice = 0;
+  for (int s = 0; s < SL; ++s) max_slice = std::max(max_slice, ptr[s + 1] - ptr[s]);
+  /* metric-table chunks: consecutive slices whose UEs fit the table */
+  std::vector<int> chunks;
+  int m_cap = 0;
+  if (algo == 8 || algo == 9) {
+    const int cap = std::max(max_slice, std::min(U, 256));
+    chunks.push_back(0);
+    int cur = 0;
+    for (int s = 0; s < S; ++s) {
+      const int ns = ptr[s + 1] - ptr[s];
+      if (cur + ns > cap) { chunks.push_back(s); cur = 0; }
+      cur += ns;
+      m_cap = std::max(m_cap, cur);
+    }
+    chunks.push_back(S);
+  } else if (algo == 7) {
+    m_cap = max_slice;
+    chunks = {0, S};
+  } else {
+    m_cap = 0;
+    chunks = {0, 1};
+  }
+  d.n_chunks = (int)chunks.size() - 1;
+  d.m_cap = m_cap;
+  h->layout = rs::make_layout(S, U, G, m_cap);
+
+  /* ---- device ---- */
+  {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)));
+    int max_optin = 0;
+    e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e)));
+    if (h->layout.total > max_optin)
+      BAIL(fail(RS_ERR_UNSUPPORTED, "cell needs %d B of shared memory, device allows %d", h->layout.total, max_optin));
+  }
+  rs::ConstTables ct;
+  { std::string why;
+    if (!build_const_tables(&ct, &why)) BAIL(fail(RS_ERR_UNSUPPORTED, "host libm: %s", why.c_str())); }
+  { cudaError_t e = cudaMemcpyToSymbol(rs::c_tab, &ct, sizeof ct);
+    if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e))); }
+  BAIL(set_smem_attr(h));
+  { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking);
+    if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e))); }
+  h->stream = h->own_stream;
+  BAIL(upload(h->ue_to_slice, u2s));
+  BAIL(upload(h->slice_ptr, ptr));
+  BAIL(upload(h->slice_ues, ues));
+  BAIL(upload(h->chunk_slice, chunks));
+  BAIL(upload(h->tbs_n, tbsn));
+  BAIL(upload(h->weight, weight));
+  BAIL(upload(h->epow, epow));
+  BAIL(upload(h->psi, psi));
+  d.ue_to_slice = h->ue_to_slice.p; d.slice_ptr = h->slice_ptr.p; d.slice_ues = h->slice_ues.p;
+  d.chunk_slice = h->chunk_slice.p; d.tbs_n = h->tbs_n.p; d.weight = h->weight.p; d.epow = h->epow.p;
+  d.psi = h->psi.p;
+  const size_t BU = (size_t)n_cells * U, BS = (size_t)n_cells * S;
+  { cudaError_t e = h->avg.alloc(BU);
+    if (e == cudaSuccess) e = h->tx.alloc(BU);
+    if (e == cudaSuccess) e = h->cum_bytes.alloc(BU);
+    if (e == cudaSuccess) e = h->cum_rbs.alloc(BU);
+    if (e == cudaSuccess) e = h->offset.alloc(BS);
+    if (e == cudaSuccess) e = h->ewma.alloc(BS);
+    if (e == cudaSuccess) e = h->stats.alloc((size_t)4 * S);
+    if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaMalloc(state): %s", cudaGetErrorString(e))); }
+  d.avg = h->avg.p; d.tx = h->tx.p; d.cum_bytes = h->cum_bytes.p; d.cum_rbs = h->cum_rbs.p;
+  d.offset = h->offset.p; d.ewma = h->ewma.p;
+  BAIL(rs_reset_state(h));
+#undef BAIL
+  *out = h;
+  return RS_OK;
+}
+
+int rs_set_stream(rs_handle* h, void* cuda_stream) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return RS_OK;
+}
+
+int rs_sync(rs_handle* h) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return RS_OK;
+}
+
+int rs_reset_state(rs_handle* h) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  std::vector<double> avg(BU, 100000.0);   /* m_averageTransmissionRate, radio-bearer.cpp:54 */
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(h->avg.p, avg.data(), BU * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemset(h->tx.p, 0, BU * 4));
+  CU(cudaMemset(h->cum_bytes.p, 0, BU * 8));
+  CU(cudaMemset(h->cum_rbs.p, 0, BU * 8));
+  CU(cudaMemset(h->offset.p, 0, BS * 8));
+  CU(cudaMemset(h->ewma.p, 0, BS * 8));
+  return RS_OK;
+}
+
+int rs_set_state(rs_handle* h, const double* avg_rate, const int32_t* tx_bytes, const uint64_t* cum_bytes,
+                 const uint64_t* cum_rbs, const double* slice_offset, const double* nvs_ewma) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  if (avg_rate) CU(cudaMemcpy(h->avg.p, avg_rate, BU * 8, cudaMemcpyHostToDevice));
+  if (tx_bytes) CU(cudaMemcpy(h->tx.p, tx_bytes, BU * 4, cudaMemcpyHostToDevice));
+  if (cum_bytes) CU(cudaMemcpy(h->cum_bytes.p, cum_bytes, BU * 8, cudaMemcpyHostToDevice));
+  if (cum_rbs) CU(cudaMemcpy(h->cum_rbs.p, cum_rbs, BU * 8, cudaMemcpyHostToDevice));
+  if (slice_offset) CU(cudaMemcpy(h->offset.p, slice_offset, BS * 8, cudaMemcpyHostToDevice));
+  if (nvs_ewma) CU(cudaMemcpy(h->ewma.p, nvs_ewma, BS * 8, cudaMemcpyHostToDevice));
+  return RS_OK;
+}
+
+int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cum_bytes, uint64_t* cum_rbs,
+                 double* slice_offset, double* nvs_ewma) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  if (avg_rate) CU(cudaMemcpy(avg_rate, h->avg.p, BU * 8, cudaMemcpyDeviceToHost));
+  if (tx_bytes) CU(cudaMemcpy(tx_bytes, h->tx.p, BU * 4, cudaMemcpyDeviceToHost));
+  if (cum_bytes) CU(cudaMemcpy(cum_bytes, h->cum_bytes.p, BU * 8, cudaMemcpyDeviceToHost));
+  if (cum_rbs) CU(cudaMemcpy(cum_rbs, h->cum_rbs.p, BU * 8, cudaMemcpyDeviceToHost));
+  if (slice_offset) CU(cudaMemcpy(slice_offset, h->offset.p, BS * 8, cudaMemcpyDeviceToHost));
+  if (nvs_ewma) CU(cudaMemcpy(nvs_ewma, h->ewma.p, BS * 8, cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride,
+                  const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
+                  const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
+  if (!h || !d_cqi || !dt || n_ttis < 0) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
+  if ((h->d.algo == 8 || h->d.algo == 9) && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
+  if (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3)) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
+  if (n_ttis == 0) return RS_OK;
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_dt(h, dt, n_ttis);
+  if (rc != RS_OK) return rc;
+  if (ttis_per_launch <= 0) ttis_per_launch = 16;
+  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
+  for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
+    rs::RunArgs a{};
+    a.T = std::min(ttis_per_launch, n_ttis - t0);
+    a.cqi = d_cqi + (size_t)t0 * cqi_tti_stride;
+    a.cqi_tti_stride = cqi_tti_stride;
+    a.rand2 = d_rand2 ? d_rand2 + (size_t)t0 * B * 2 : nullptr;
+    a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
+    a.active_tti_stride = active_tti_stride;
+    a.dt = h->dt_dev.p + t0;
+    if (d_out) {
+      a.rbg_to_ue = d_out->rbg_to_ue ? d_out->rbg_to_ue + (size_t)t0 * B * G : nullptr;
+      a.tbs_bits = d_out->tbs_bits ? d_out->tbs_bits + (size_t)t0 * B * U : nullptr;
+      a.mcs = d_out->mcs ? d_out->mcs + (size_t)t0 * B * U : nullptr;
+      a.final_cqi = d_out->final_cqi ? d_out->final_cqi + (size_t)t0 * B * U : nullptr;
+      if (wants(h, 0)) {
+        a.slice_target = d_out->slice_target ? d_out->slice_target + (size_t)t0 * B * S : nullptr;
+        a.slice_quota = d_out->slice_quota ? d_out->slice_quota + (size_t)t0 * B * S : nullptr;
+      }
+      if (wants(h, 1)) a.nvs_slice = d_out->nvs_slice ? d_out->nvs_slice + (size_t)t0 * B : nullptr;
+    }
+    rc = launch_ttis(h, a);
+    if (rc != RS_OK) return rc;
+  }
+  return RS_OK;
+}
+
+int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active,
+                const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
+  if (!h || !cqi || !dt || n_ttis < 0) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
+  if ((h->d.algo == 8 || h->d.algo == 9) && !rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
+  if (n_ttis == 0) return RS_OK;
+  CU(cudaSetDevice(h->device));
+  if (ttis_per_launch <= 0) ttis_per_launch = 4;
+  const int TC = std::min(ttis_per_launch, n_ttis);
+  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
+  int rc = ensure_dt(h, dt, n_ttis);
+  if (rc != RS_OK) return rc;
+  for (auto& s : h->slot) { rc = alloc_slot(h, s, TC, out, active != nullptr); if (rc != RS_OK) return rc; }
+  cudaEvent_t dt_ready;
+  CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
+  CU(cudaEventRecord(dt_ready, h->stream));
+  int k = 0;
+  for (int t0 = 0; t0 < n_ttis; t0 += TC, ++k) {
+    rs_handle::Slot& s = h->slot[k & 1];
+    const int T = std::min(TC, n_ttis - t0);
+    /* inputs: the slot's previous kernel must be done with them */
+    if (k >= 2) CU(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
+    CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)t0 * B * U * C, (size_t)T * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
+    if (rand2) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * 2, (size_t)T * B * 2 * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (active) CU(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
+    CU(cudaEventRecord(s.in_done, h->copy_in));
+    /* kernel: inputs in, and the slot's previous outputs drained */
+    CU(cudaStreamWaitEvent(h->stream, s.in_done, 0));
+    if (k >= 2) CU(cudaStreamWaitEvent(h->stream, s.out_done, 0));
+    rs::RunArgs a{};
+    a.T = T;
+    a.cqi = s.cqi.p; a.cqi_tti_stride = (long long)(B * U * C);
+    a.rand2 = rand2 ? s.rand2.p : nullptr;
+    a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
+    a.dt = h->dt_dev.p + t0;
+    if (out) {
+      a.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
+      a.tbs_bits = out->tbs_bits ? s.tbs_bits.p : nullptr;
+      a.mcs = out->mcs ? s.mcs.p : nullptr;
+      a.final_cqi = out->final_cqi ? s.final_cqi.p : nullptr;
+      if (wants(h, 0)) {
+        a.slice_target = out->slice_target ? s.slice_target.p : nullptr;
+        a.slice_quota = out->slice_quota ? s.slice_quota.p : nullptr;
+      }
+      if (wants(h, 1)) a.nvs_slice = out->nvs_slice ? s.nvs_slice.p : nullptr;
+    }
+    rc = launch_ttis(h, a);
+    if (rc != RS_OK) return rc;
+    CU(cudaEventRecord(s.k_done, h->stream));
+    /* outputs */
+    CU(cudaStreamWaitEvent(h->copy_out, s.k_done, 0));
+    if (out) {
+      if (a.rbg_to_ue) CU(cudaMemcpyAsync(out->rbg_to_ue + (size_t)t0 * B * G, s.rbg_to_ue.p, (size_t)T * B * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.tbs_bits) CU(cudaMemcpyAsync(out->tbs_bits + (size_t)t0 * B * U, s.tbs_bits.p, (size_t)T * B * U * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.mcs) CU(cudaMemcpyAsync(out->mcs + (size_t)t0 * B * U, s.mcs.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.final_cqi) CU(cudaMemcpyAsync(out->final_cqi + (size_t)t0 * B * U, s.final_cqi.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.slice_target) CU(cudaMemcpyAsync(out->slice_target + (size_t)t0 * B * S, s.slice_target.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.slice_quota) CU(cudaMemcpyAsync(out->slice_quota + (size_t)t0 * B * S, s.slice_quota.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.nvs_slice) CU(cudaMemcpyAsync(out->nvs_slice + (size_t)t0 * B, s.nvs_slice.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    CU(cudaEventRecord(s.out_done, h->copy_out));
+  }
+  CU(cudaStreamSynchronize(h->copy_out));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->copy_in));
+  cudaEventDestroy(dt_ready);
+  return RS_OK;
+}
+
+int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
+            const rs_outputs* out) {
+  return rs_run_host(h, 1, cqi, rand2, active, &dt, out, 1);
+}
+
+int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t refresh,
+                 uint8_t* d_out) {
+  if (!h || !d_out || n_ttis < 0 || refresh < 1) return fail(RS_ERR_ARG, "rs_synth_cqi: bad argument");
+  if (h->d.cqi_per_rb) return fail(RS_ERR_UNSUPPORTED, "synthetic CQI is one value per RBG");
+  CU(cudaSetDevice(h->device));
+  /* histogram of cqi-traces-noise0; thresholds as in radiosaber_b200/workload.py */
+  static const unsigned long long hist[15] = {19075, 7082, 33860, 261099, 438688, 199446, 518174, 661977,
+                                              237928, 861279, 596358, 355319, 447453, 12000, 153462};
+  unsigned long long total = 0, cum = 0;
+  for (int i = 0; i < 15; ++i) total += hist[i];
+  rs::CdfTable cdf;
+  for (int i = 0; i < 14; ++i) {
+    cum += hist[i];
+    cdf.thr[i] = (unsigned)(unsigned long long)(((double)cum / (double)total) * 4294967296.0);
+  }
+  auto sm64 = [](unsigned long long x) {
+    unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  const unsigned long long key = sm64((seed & 0xFFFFFFFFull) | (0x43514900ull << 32));
+  const size_t total_n = (size_t)n_ttis * h->B * h->d.U * h->d.G;
+  if (total_n == 0) return RS_OK;
+  const int blocks = (int)std::min<size_t>((total_n + 255) / 256, 148 * 16);
+  rs::rs_synth_cqi_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, tti0, n_ttis, h->B, h->d.U, h->d.G,
+                                                         refresh, cdf);
+  CU(cudaGetLastError());
+  h->launches++;
+  return RS_OK;
+}
+
+int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t* d_out) {
+  if (!h || !d_out || n_ttis < 0) return fail(RS_ERR_ARG, "rs_synth_rand2: bad argument");
+  CU(cudaSetDevice(h->device));
+  auto sm64 = [](unsigned long long x) {
+    unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  const unsigned long long key = sm64((seed & 0xFFFFFFFFull) | (0x524E4400ull << 32));
+  const size_t total_n = (size_t)n_ttis * h->B * 2;
+  if (total_n == 0) return RS_OK;
+  const int blocks = (int)std::min<size_t>((total_n + 255) / 256, 148 * 8);
+  rs::rs_synth_rand2_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, tti0, n_ttis, h->B, h->d.S);
+  CU(cudaGetLastError());
+  h->launches++;
+  return RS_OK;
+}
+
+int rs_stats_device(rs_handle* h, uint64_t* d_stats) {
+  if (!h || !d_stats) return fail(RS_ERR_ARG, "rs_stats_device: bad argument");
+  CU(cudaSetDevice(h->device));
+  const int S = h->d.S;
+  CU(cudaMemsetAsync(d_stats, 0, sizeof(uint64_t) * 4 * S, h->stream));
+  const size_t total = (size_t)h->B * h->d.U;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 4);
+  rs::rs_stats_kernel<<<blocks, 256, sizeof(unsigned long long) * 4 * S, h->stream>>>(h->d, (unsigned long long*)d_stats);
+  CU(cudaGetLastError());
+  h->launches++;
+  return RS_OK;
+}
+
+int rs_get_stats(rs_handle* h, uint64_t* stats) {
+  if (!h || !stats) return fail(RS_ERR_ARG, "rs_get_stats: bad argument");
+  int rc = rs_stats_device(h, (uint64_t*)h->stats.p);
+  if (rc != RS_OK) return rc;
+  CU(cudaMemcpyAsync(stats, h->stats.p, sizeof(uint64_t) * 4 * h->d.S, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return RS_OK;
+}
+
+int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
+int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }
+int32_t rs_threads_per_cta(const rs_handle* h) { (void)h; return rs::kThreads; }
+int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h) {
+  if (!h) return 0;
+  const int64_t U = h->d.U, G = h->d.G, S = h->d.S;
+  return U * (G + 20) + 16 * S + 2 * G + 8;
+}
+
+int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
+                 int32_t* perm_out) {
+  if (!keys || !perm_out || n_arrays < 1 || n < 1 || n > 4096) return fail(RS_ERR_ARG, "rs_test_sort: bad argument");
+  CU(cudaSetDevice(device));
+  if (depth_limit < 0) { int lg = 0; for (int m = n; m > 1; m >>= 1) lg++; depth_limit = 2 * lg; }
+  const rs::Layout L = rs::make_layout(1, 0, n, 0);
+  CU(cudaFuncSetAttribute(rs::rs_sort_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  uint8_t* dk = nullptr;
+  int* dp = nullptr;
+  CU(cudaMalloc((void**)&dk, (size_t)n_arrays * n));
+  cudaError_t e = cudaMalloc((void**)&dp, (size_t)n_arrays * n * 4);
+  if (e != cudaSuccess) { cudaFree(dk); return fail(RS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  e = cudaMemcpy(dk, keys, (size_t)n_arrays * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(perm_out, dp, (size_t)n_arrays * n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dk);
+  cudaFree(dp);
+  if (e != cudaSuccess) return fail(RS_ERR_CUDA, "rs_test_sort: %s", cudaGetErrorString(e));
+  return RS_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,304 @@
+"""ctypes binding of the C ABI (include/rs_sched.h -> radiosaber_b200/librs_sched.so).
+
+Host-side mirror of the reference's scheduler plug-in surface for a *batch* of cells: one
+:class:`Scheduler` stands for ``n_cells`` independent ``PacketScheduler`` objects of one kind
+(ids 1 / 7 / 8 / 9, src/scenarios/single-cell-with-interference.h:94-118) built from the same
+slice configuration (:func:`load_slice_config` reads the reference's JSON format,
+downlink-transport-scheduler.cpp:55-97).  ``step()`` is one ``Schedule()`` call
+(packet-scheduler.cpp:72-90) for every cell.
+
+There is no CPU implementation behind this module: if the CUDA library is missing or no GPU is
+present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librs_sched.so")
+_lib = None
+
+# every symbol include/rs_sched.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "rs_last_error", "rs_abi_version", "rs_create", "rs_destroy", "rs_set_stream", "rs_sync",
+    "rs_set_state", "rs_get_state", "rs_reset_state", "rs_step", "rs_run_device", "rs_run_host",
+    "rs_synth_cqi", "rs_synth_rand2", "rs_stats_device", "rs_get_stats", "rs_launch_count",
+    "rs_smem_bytes", "rs_threads_per_cta", "rs_algorithmic_bytes_per_cell_tti", "rs_test_sort",
+)
+
+
+class RsError(RuntimeError):
+    pass
+
+
+class _Cfg(C.Structure):
+    _fields_ = [
+        ("algo", C.c_int32), ("n_slices", C.c_int32), ("n_ues", C.c_int32), ("n_rbs", C.c_int32),
+        ("rbg_size", C.c_int32), ("cqi_per_rb", C.c_int32), ("data_to_transmit", C.c_int32),
+        ("reserved", C.c_int32),
+        ("weight", C.c_void_p), ("params", C.c_void_p), ("ue_to_slice", C.c_void_p), ("tbs_row_m1", C.c_void_p),
+    ]
+
+
+class _Out(C.Structure):
+    _fields_ = [
+        ("rbg_to_ue", C.c_void_p), ("tbs_bits", C.c_void_p), ("mcs", C.c_void_p), ("final_cqi", C.c_void_p),
+        ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
+    ]
+
+
+def lib():
+    """The loaded C ABI library. Raises if it has not been built (``python -c 'import
+    __graft_entry__ as g; g.build()'`` or ``make -C radiosaber_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RsError(f"{LIB_PATH} is missing: build it with `make -C radiosaber_b200/csrc` "
+                          "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.rs_last_error.restype = C.c_char_p
+        L.rs_abi_version.restype = C.c_int32
+        L.rs_create.argtypes = [C.POINTER(_Cfg), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.rs_destroy.argtypes = [C.c_void_p]
+        L.rs_destroy.restype = None
+        L.rs_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.rs_sync.argtypes = [C.c_void_p]
+        L.rs_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.rs_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.rs_reset_state.argtypes = [C.c_void_p]
+        L.rs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(_Out)]
+        L.rs_run_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.POINTER(_Out), C.c_int32]
+        L.rs_run_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(_Out), C.c_int32]
+        L.rs_synth_cqi.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_synth_rand2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+        L.rs_stats_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.rs_launch_count.argtypes = [C.c_void_p]
+        L.rs_launch_count.restype = C.c_int64
+        L.rs_smem_bytes.argtypes = [C.c_void_p]
+        L.rs_smem_bytes.restype = C.c_int32
+        L.rs_threads_per_cta.argtypes = [C.c_void_p]
+        L.rs_threads_per_cta.restype = C.c_int32
+        L.rs_algorithmic_bytes_per_cell_tti.argtypes = [C.c_void_p]
+        L.rs_algorithmic_bytes_per_cell_tti.restype = C.c_int64
+        L.rs_test_sort.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RsError(f"rs error {rc}: {lib().rs_last_error().decode()}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def load_slice_config(path: str):
+    """Parse the reference's JSON slice config into (weight[S], params[S][4], ue_to_slice[U]).
+
+    Same expansion as DownlinkTransportScheduler's constructor (downlink-transport-scheduler.cpp:65-88):
+    each entry of ``slices`` stands for ``n_slices`` slices with one weight and one
+    (alpha, beta, epsilon, psi); ``ues_per_slice[i]`` UEs belong to slice i, UE ids ascending.
+    """
+    with open(path) as f:
+        cfg = json.load(f)
+    weight, params = [], []
+    for grp in cfg["slices"]:
+        for _ in range(int(grp["n_slices"])):
+            weight.append(float(grp["weight"]))
+            params.append([int(grp["algo_alpha"]), int(grp["algo_beta"]), int(grp["algo_epsilon"]),
+                           int(grp["algo_psi"])])
+    ue_to_slice = []
+    for s, n in enumerate(cfg["ues_per_slice"]):
+        ue_to_slice += [s] * int(n)
+    if len(cfg["ues_per_slice"]) != len(weight):
+        raise ValueError("ues_per_slice does not match the number of slices")
+    return (np.asarray(weight, dtype=np.float64), np.asarray(params, dtype=np.int32),
+            np.asarray(ue_to_slice, dtype=np.int32))
+
+
+class Scheduler:
+    """A batch of ``n_cells`` independent cells scheduled on one GPU.
+
+    State (per-bearer EWMA rate and byte counters, per-slice RB offsets / NVS credits) lives in
+    device memory between calls, exactly the members the reference keeps in RadioBearer and in
+    its scheduler objects (flows/radio-bearer.h:81-85, downlink-transport-scheduler.h:38).
+    """
+
+    def __init__(self, algo, weight, params, ue_to_slice, n_cells, n_rbs=512, rbg_size=8, cqi_per_rb=0,
+                 data_to_transmit=100000000, tbs_row_m1=None, device=0):
+        self.algo = int(algo)
+        self.ue_to_slice = np.ascontiguousarray(ue_to_slice, dtype=np.int32)
+        self.U = int(self.ue_to_slice.shape[0])
+        self.weight = np.ascontiguousarray(weight, dtype=np.float64)
+        self.S = int(self.weight.shape[0])
+        self.params = np.ascontiguousarray(params, dtype=np.int32).reshape(self.S, 4)
+        self.B = int(n_cells)
+        self.R = int(n_rbs)
+        self.rbg_size = int(rbg_size)
+        self.G = self.R // self.rbg_size
+        self.cqi_per_rb = int(cqi_per_rb)
+        self.cqi_cols = self.R if self.cqi_per_rb else self.G
+        self.device = int(device)
+        self._row_m1 = None if tbs_row_m1 is None else np.ascontiguousarray(tbs_row_m1, dtype=np.int32)
+        cfg = _Cfg(self.algo, self.S, self.U, self.R, self.rbg_size, self.cqi_per_rb, int(data_to_transmit), 0,
+                   _ptr(self.weight), _ptr(self.params), _ptr(self.ue_to_slice), _ptr(self._row_m1))
+        self._h = C.c_void_p()
+        _check(lib().rs_create(C.byref(cfg), self.B, self.device, C.byref(self._h)))
+
+    @classmethod
+    def from_config(cls, algo, config_path, n_cells, **kw):
+        w, p, u2s = load_slice_config(config_path)
+        return cls(algo, w, p, u2s, n_cells, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().rs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state -------------------------------------------------------------------------------
+    def set_state(self, avg_rate=None, tx_bytes=None, slice_offset=None, nvs_ewma=None, cum_bytes=None,
+                  cum_rbs=None):
+        B, U, S = self.B, self.U, self.S
+
+        def arr(v, dt, shape):
+            return None if v is None else np.ascontiguousarray(np.asarray(v).reshape(shape), dtype=dt)
+
+        a = arr(avg_rate, np.float64, (B, U)); t = arr(tx_bytes, np.int32, (B, U))
+        cb = arr(cum_bytes, np.uint64, (B, U)); cr = arr(cum_rbs, np.uint64, (B, U))
+        so = arr(slice_offset, np.float64, (B, S)); ne = arr(nvs_ewma, np.float64, (B, S))
+        _check(lib().rs_set_state(self._h, _ptr(a), _ptr(t), _ptr(cb), _ptr(cr), _ptr(so), _ptr(ne)))
+
+    def get_state(self):
+        B, U, S = self.B, self.U, self.S
+        st = {"avg_rate": np.empty((B, U), np.float64), "tx_bytes": np.empty((B, U), np.int32),
+              "cum_bytes": np.empty((B, U), np.uint64), "cum_rbs": np.empty((B, U), np.uint64),
+              "slice_offset": np.empty((B, S), np.float64), "nvs_ewma": np.empty((B, S), np.float64)}
+        _check(lib().rs_get_state(self._h, _ptr(st["avg_rate"]), _ptr(st["tx_bytes"]), _ptr(st["cum_bytes"]),
+                                  _ptr(st["cum_rbs"]), _ptr(st["slice_offset"]), _ptr(st["nvs_ewma"])))
+        return st
+
+    def reset_state(self):
+        _check(lib().rs_reset_state(self._h))
+
+    # ---- host-buffer path --------------------------------------------------------------------
+    def _host_outputs(self, T, want_aux):
+        B, U, S, G = self.B, self.U, self.S, self.G
+        lead = (T, B) if T is not None else (B,)
+        out = {"rbg_to_ue": np.empty(lead + (G,), np.int16), "tbs_bits": np.empty(lead + (U,), np.int32),
+               "mcs": np.empty(lead + (U,), np.uint8)}
+        if want_aux:
+            out["final_cqi"] = np.empty(lead + (U,), np.uint8)
+            if self.algo in (8, 9):
+                out["slice_target"] = np.empty(lead + (S,), np.int32)
+                out["slice_quota"] = np.empty(lead + (S,), np.int32)
+            if self.algo == 7:
+                out["nvs_slice"] = np.empty(lead, np.int32)
+        o = _Out(*[_ptr(out.get(k)) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
+                                                "slice_quota", "nvs_slice")])
+        return out, o
+
+    def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False):
+        """One TTI for every cell. cqi: uint8 [B][U][G] (or [B][U][R]); rand2: int32 [B][2]."""
+        B, U = self.B, self.U
+        cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
+        assert cqi.size == B * U * self.cqi_cols, cqi.shape
+        if rand2 is None:
+            rand2 = np.zeros((B, 2), dtype=np.int32)
+        rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, 2)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
+        out, o = self._host_outputs(None, want_aux)
+        _check(lib().rs_step(self._h, _ptr(cqi), _ptr(rand2), _ptr(act), float(dt), C.byref(o)))
+        return out
+
+    def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0):
+        """T TTIs with host arrays [T][B][...]; copies overlap the kernels."""
+        B, U = self.B, self.U
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        T = int(dt.shape[0])
+        cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
+        assert cqi.size == T * B * U * self.cqi_cols, cqi.shape
+        rand2 = None if rand2 is None else np.ascontiguousarray(rand2, dtype=np.int32).reshape(T, B, 2)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
+        out, o = self._host_outputs(T, want_aux)
+        _check(lib().rs_run_host(self._h, T, _ptr(cqi), _ptr(rand2), _ptr(act), _ptr(dt), C.byref(o),
+                                 int(ttis_per_launch)))
+        return out
+
+    # ---- device-resident path (raw device pointers, e.g. torch tensors' data_ptr()) -----------
+    def run_device(self, n_ttis, d_cqi, cqi_tti_stride, d_rand2, dt, d_out=None, d_active=0,
+                   active_tti_stride=0, ttis_per_launch=0):
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        assert dt.shape[0] >= n_ttis
+        o = _Out(*[(d_out or {}).get(k) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
+                                                    "slice_quota", "nvs_slice")])
+        _check(lib().rs_run_device(self._h, int(n_ttis), C.c_void_p(d_cqi), int(cqi_tti_stride),
+                                   C.c_void_p(d_rand2 or None), C.c_void_p(d_active or None),
+                                   int(active_tti_stride), _ptr(dt), C.byref(o), int(ttis_per_launch)))
+
+    def synth_cqi(self, seed, cell0, tti0, n_ttis, refresh, d_out):
+        _check(lib().rs_synth_cqi(self._h, int(seed), int(cell0), int(tti0), int(n_ttis), int(refresh),
+                                  C.c_void_p(d_out)))
+
+    def synth_rand2(self, seed, cell0, tti0, n_ttis, d_out):
+        _check(lib().rs_synth_rand2(self._h, int(seed), int(cell0), int(tti0), int(n_ttis), C.c_void_p(d_out)))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().rs_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
+    def sync(self):
+        _check(lib().rs_sync(self._h))
+
+    def stats_device(self, d_stats):
+        _check(lib().rs_stats_device(self._h, C.c_void_p(d_stats)))
+
+    def get_stats(self):
+        """uint64 [4][S]: sum bytes, sum RBs, sum q, sum q^2 (q = UE cumulative bytes >> 10)."""
+        st = np.empty((4, self.S), dtype=np.uint64)
+        _check(lib().rs_get_stats(self._h, _ptr(st)))
+        return st
+
+    @property
+    def launch_count(self):
+        return int(lib().rs_launch_count(self._h))
+
+    @property
+    def smem_bytes(self):
+        return int(lib().rs_smem_bytes(self._h))
+
+    @property
+    def algorithmic_bytes_per_cell_tti(self):
+        return int(lib().rs_algorithmic_bytes_per_cell_tti(self._h))
+
+
+def test_sort(keys, depth_limit=-1, device=0) -> np.ndarray:
+    """Device std::sort order (key descending) of each row of uint8 keys[n_arrays][n]."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint8)
+    if keys.ndim == 1:
+        keys = keys[None]
+    perm = np.empty(keys.shape, dtype=np.int32)
+    _check(lib().rs_test_sort(int(device), _ptr(keys), keys.shape[0], keys.shape[1], int(depth_limit), _ptr(perm)))
+    return perm
+
+
+def jain_index(stats: np.ndarray, n_ues_per_slice: np.ndarray) -> np.ndarray:
+    """Per-slice Jain fairness (sum q)^2 / (n * sum q^2) from rs_get_stats() totals."""
+    sq = stats[2].astype(np.float64)
+    sqq = stats[3].astype(np.float64)
+    n = np.asarray(n_ues_per_slice, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(sqq > 0, sq * sq / (n * sqq), 0.0)

@@ -1,0 +1,264 @@
+"""GPU: the CUDA path, called through the C ABI, against (a) the golden vectors recorded from the
+unmodified reference and (b) the CPU oracle on the same seeded inputs.  Bit-exact everywhere:
+assignments, TBS, MCS, targets/quotas are integers, and the EWMA rates / offsets / credits are
+IEEE doubles produced by the same operations in the same order (tolerance 0, which is inside the
+1e-9 relative bound BASELINE.json states)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from oracle.pyoracle import OracleScheduler
+from radiosaber_b200 import sched, workload
+from tests.helpers import golden_names, load_golden, replay_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _cqi_keys(rng, shape):
+    p = workload.CQI_HIST.astype(np.float64) / workload.CQI_TOTAL
+    return rng.choice(np.arange(1, 16), size=shape, p=p).astype(np.uint8)
+
+
+# ---- the std::sort emulation on its own ---------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 16, 17, 31, 32, 33, 64, 320, 448, 1280, 1290, 3200, 4096])
+def test_device_sort_matches_std_sort(n):
+    rng = np.random.default_rng(n)
+    rows = [
+        _cqi_keys(rng, n),
+        rng.integers(0, 16, size=n).astype(np.uint8),
+        np.full(n, 7, np.uint8),
+        np.sort(rng.integers(0, 16, size=n)).astype(np.uint8),
+        np.sort(rng.integers(0, 16, size=n))[::-1].astype(np.uint8),
+        np.maximum.reduce(_cqi_keys(rng, (5, n))),
+        (rng.integers(0, 2, size=n) * 15).astype(np.uint8),
+        np.maximum.reduce(_cqi_keys(rng, (40, n))),
+    ]
+    for _ in range(24):
+        rows.append(np.maximum.reduce(_cqi_keys(rng, (int(rng.integers(1, 8)), n))))
+    keys = np.stack(rows)
+    got = sched.test_sort(keys)
+    for i, row in enumerate(keys):
+        want = pyoracle.std_sort_desc(row.astype(np.float64))
+        assert np.array_equal(got[i], want), (n, i)
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 4])
+def test_device_sort_heap_fallback(depth):
+    rng = np.random.default_rng(50 + depth)
+    for n in (17, 100, 1280):
+        keys = rng.integers(0, 16, size=(6, n)).astype(np.uint8)
+        got = sched.test_sort(keys, depth_limit=depth)
+        for i in range(keys.shape[0]):
+            want = pyoracle.introsort_emul_desc(keys[i].astype(np.float64), depth)
+            assert np.array_equal(got[i], want), (n, depth, i)
+
+
+# ---- golden vectors from the unmodified reference ----------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_record(name):
+    rec = load_golden(name)
+    s = sched.Scheduler(int(rec["algo"]), rec["weight"], rec["params"], rec["ue_to_slice"], 1,
+                        n_rbs=int(rec["R"]), rbg_size=int(rec["rbg_size"]), cqi_per_rb=int(rec["cqi_per_rb"]))
+    bad = replay_golden(s, rec)
+    s.close()
+    assert not bad, bad[:10]
+
+
+# ---- batches against the oracle -----------------------------------------------------------------
+def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_active=False, refresh=1):
+    rng = np.random.default_rng(seed)
+    u2s = np.repeat(np.arange(S), ues_per_slice).astype(np.int32)
+    U = len(u2s)
+    G, R = 64, 512
+    o = OracleScheduler(algo, weights, params, u2s, B, cqi_per_rb=cqi_per_rb, n_threads=8)
+    g = sched.Scheduler(algo, weights, params, u2s, B, cqi_per_rb=cqi_per_rb)
+    _, dts = workload.tti_clock(T)
+    for t in range(T):
+        cqi = workload.synth_cqi(seed, 0, B, t, 1, U, G, refresh)[0]
+        if cqi_per_rb:
+            cqi = np.repeat(cqi, 8, axis=-1)
+            noise = rng.integers(-1, 2, size=cqi.shape)
+            cqi = np.clip(cqi.astype(np.int64) + noise, 1, 15).astype(np.uint8)
+        rand2 = workload.synth_rand2(seed, 0, B, t, 1, S)[0]
+        act = None
+        if with_active:
+            act = (rng.random((B, U)) < 0.7).astype(np.uint8)
+            act[0] = 0                     # a cell with nobody to schedule
+            act[1, u2s != 1] = 0           # a cell where only slice 1 has data
+        a = o.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True)
+        b = g.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True)
+        for k in b:
+            assert np.array_equal(a[k], b[k]), (t, k, np.argwhere(a[k] != b[k])[:5])
+        sa, sb = o.get_state(), g.get_state()
+        for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs"):
+            assert np.array_equal(sa[k], sb[k]), (t, k)
+        if algo in (8, 9):
+            assert np.array_equal(sa["slice_offset"], sb["slice_offset"]), t
+        if algo == 7:
+            assert np.array_equal(sa["nvs_ewma"], sb["nvs_ewma"]), t
+    g.close()
+
+
+PF = [0, 0, 1, 1]
+MT = [0, 0, 1, 0]
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+def test_headline_shape_20x5(algo):
+    S = 20
+    _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7])
+def test_mixed_enterprise_schedulers_diff_weights(algo):
+    S = 20
+    w = np.array([0.025] * 10 + [0.075] * 10)
+    p = np.array([MT] * 10 + [PF] * 10, dtype=np.int32)
+    ups = [5, 6, 6, 10, 7, 15, 9, 9, 14, 8, 14, 5, 14, 15, 7, 11, 15, 11, 13, 10]
+    _mk(algo, S, ups, w, p, B=16, seed=20 + algo, T=20)
+
+
+@pytest.mark.parametrize("S,n", [(5, 2), (5, 40), (10, 15), (30, 10), (50, 2), (50, 40), (64, 3), (1, 7), (3, 1)])
+def test_sweep_shapes_radiosaber(S, n):
+    w = 1.0 + (np.arange(S) % 3)
+    w = w / w.sum()
+    p = np.array([PF if s % 2 == 0 else MT for s in range(S)], dtype=np.int32)
+    _mk(9, S, [n] * S, w, p, B=6, seed=S * 100 + n, T=12)
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+def test_inactive_bearers_and_empty_cells(algo):
+    S = 8
+    w = np.full(S, 1.0 / S)
+    _mk(algo, S, [4] * S, w, np.tile(PF, (S, 1)), B=10, seed=300 + algo, T=12, with_active=True)
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+def test_per_rb_cqi_layout(algo):
+    S = 6
+    w = np.full(S, 1.0 / S)
+    _mk(algo, S, [3] * S, w, np.tile(PF, (S, 1)), B=6, seed=400 + algo, T=10, cqi_per_rb=1)
+
+
+def test_epsilon_other_than_one():
+    S = 4
+    p = np.array([[0, 0, 2, 1], [0, 0, 0, 1], [0, 0, 3, 0], [0, 0, 1, 1]], dtype=np.int32)
+    _mk(9, S, [6] * S, np.full(S, 0.25), p, B=8, seed=77, T=10)
+
+
+def test_cqi_held_for_40_ttis():
+    S = 20
+    _mk(9, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=8, seed=5, T=45, refresh=40)
+
+
+# ---- multi-TTI entry points, generators, statistics ---------------------------------------------
+def test_run_host_equals_stepwise_and_oracle():
+    S, B, T = 20, 32, 24
+    u2s = np.repeat(np.arange(S), 5).astype(np.int32)
+    U, G = len(u2s), 64
+    w, p = np.full(S, 0.05), np.tile(PF, (S, 1))
+    cqi = workload.synth_cqi(9, 0, B, 0, T, U, G)
+    rand2 = workload.synth_rand2(9, 0, B, 0, T, S)
+    _, dts = workload.tti_clock(T)
+    o = OracleScheduler(9, w, p, u2s, B, n_threads=8)
+    want = [o.step(cqi[t], rand2[t], dt=float(dts[t])) for t in range(T)]
+    for tpl in (1, 5, 24):
+        g = sched.Scheduler(9, w, p, u2s, B)
+        got = g.run_host(cqi, rand2, dts, ttis_per_launch=tpl)
+        for t in range(T):
+            for k in ("rbg_to_ue", "tbs_bits", "mcs"):
+                assert np.array_equal(got[k][t], want[t][k]), (tpl, t, k)
+        st, so = g.get_state(), o.get_state()
+        for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs", "slice_offset"):
+            assert np.array_equal(st[k], so[k]), (tpl, k)
+        stats = g.get_stats()
+        cb = so["cum_bytes"].reshape(B, S, 5)
+        assert np.array_equal(stats[0], cb.sum(axis=(0, 2)))
+        assert np.array_equal(stats[1], so["cum_rbs"].reshape(B, S, 5).sum(axis=(0, 2)))
+        q = cb >> np.uint64(10)
+        assert np.array_equal(stats[2], q.sum(axis=(0, 2)))
+        assert np.array_equal(stats[3], (q * q).sum(axis=(0, 2)))
+        g.close()
+
+
+def test_device_generators_and_run_device():
+    import torch
+    S, B, T = 20, 40, 12
+    u2s = np.repeat(np.arange(S), 5).astype(np.int32)
+    U, G = len(u2s), 64
+    w, p = np.full(S, 0.05), np.tile(PF, (S, 1))
+    g = sched.Scheduler(9, w, p, u2s, B)
+    d_cqi = torch.empty((T, B, U, G), dtype=torch.uint8, device="cuda")
+    d_r2 = torch.empty((T, B, 2), dtype=torch.int32, device="cuda")
+    g.synth_cqi(3, 100, 7, T, 1, d_cqi.data_ptr())
+    g.synth_rand2(3, 100, 7, T, d_r2.data_ptr())
+    g.sync()
+    cqi = workload.synth_cqi(3, 100, B, 7, T, U, G)
+    rand2 = workload.synth_rand2(3, 100, B, 7, T, S)
+    assert np.array_equal(d_cqi.cpu().numpy(), cqi)
+    assert np.array_equal(d_r2.cpu().numpy(), rand2)
+    d_rbg = torch.empty((T, B, G), dtype=torch.int16, device="cuda")
+    d_bits = torch.empty((T, B, U), dtype=torch.int32, device="cuda")
+    d_mcs = torch.empty((T, B, U), dtype=torch.uint8, device="cuda")
+    _, dts = workload.tti_clock(T)
+    g.run_device(T, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts,
+                 {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr(), "mcs": d_mcs.data_ptr()},
+                 ttis_per_launch=5)
+    g.sync()
+    o = OracleScheduler(9, w, p, u2s, B, n_threads=8)
+    for t in range(T):
+        want = o.step(cqi[t], rand2[t], dt=float(dts[t]))
+        assert np.array_equal(d_rbg[t].cpu().numpy(), want["rbg_to_ue"]), t
+        assert np.array_equal(d_bits[t].cpu().numpy(), want["tbs_bits"]), t
+        assert np.array_equal(d_mcs[t].cpu().numpy(), want["mcs"]), t
+    assert g.launch_count == 2 + 3
+    g.close()
+
+
+def test_full_size_batch_invariants():
+    """BASELINE config #2 size (4096 cells x 20 slices x 5 UEs): properties that need no oracle run,
+    plus an oracle spot check on a few cells."""
+    import torch
+    S, B, T = 20, 4096, 6
+    u2s = np.repeat(np.arange(S), 5).astype(np.int32)
+    U, G = len(u2s), 64
+    w, p = np.full(S, 0.05), np.tile(PF, (S, 1))
+    g = sched.Scheduler(9, w, p, u2s, B)
+    d_cqi = torch.empty((T, B, U, G), dtype=torch.uint8, device="cuda")
+    d_r2 = torch.empty((T, B, 2), dtype=torch.int32, device="cuda")
+    g.synth_cqi(1, 0, 0, T, 1, d_cqi.data_ptr())
+    g.synth_rand2(1, 0, 0, T, d_r2.data_ptr())
+    d_rbg = torch.empty((T, B, G), dtype=torch.int16, device="cuda")
+    d_bits = torch.empty((T, B, U), dtype=torch.int32, device="cuda")
+    d_tgt = torch.empty((T, B, S), dtype=torch.int32, device="cuda")
+    d_quo = torch.empty((T, B, S), dtype=torch.int32, device="cuda")
+    _, dts = workload.tti_clock(T)
+    g.run_device(T, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts,
+                 {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr(),
+                  "slice_target": d_tgt.data_ptr(), "slice_quota": d_quo.data_ptr()})
+    g.sync()
+    rbg = d_rbg.cpu().numpy().astype(np.int64)
+    bits = d_bits.cpu().numpy()
+    tgt, quo = d_tgt.cpu().numpy(), d_quo.cpu().numpy()
+    assert (rbg >= 0).all() and (rbg < U).all()                    # every RBG allocated (backlogged cells)
+    assert (tgt.sum(-1) == 512).all() and (quo.sum(-1) == 64).all()  # targets / quotas are partitions
+    per_slice = np.zeros((T, B, S), dtype=np.int64)
+    np.add.at(per_slice, (np.arange(T)[:, None, None], np.arange(B)[None, :, None], u2s[rbg]), 1)
+    assert (per_slice <= np.maximum(quo, 0)).all()                 # first-fit never exceeds a quota
+    got_ue = np.zeros((T, B, U), dtype=np.int64)
+    np.add.at(got_ue, (np.arange(T)[:, None, None], np.arange(B)[None, :, None], rbg), 1)
+    assert ((bits > 0) == (got_ue > 0)).all()                      # bits iff RBGs
+    st = g.get_state()
+    assert np.array_equal(st["cum_rbs"].astype(np.int64), got_ue.sum(0) * 8)
+    assert np.array_equal(st["cum_bytes"].astype(np.int64), (bits // 8).astype(np.int64).sum(0))
+    # oracle spot check: first and last 8 cells
+    cqi = d_cqi.cpu().numpy()
+    r2 = d_r2.cpu().numpy()
+    for sl in (slice(0, 8), slice(B - 8, B)):
+        o = OracleScheduler(9, w, p, u2s, 8, n_threads=8)
+        for t in range(T):
+            want = o.step(cqi[t, sl], r2[t, sl], dt=float(dts[t]))
+            assert np.array_equal(want["rbg_to_ue"], rbg[t, sl]), t
+            assert np.array_equal(want["tbs_bits"], bits[t, sl]), t
+        assert np.array_equal(o.get_state()["avg_rate"], st["avg_rate"][sl])
+    g.close()
