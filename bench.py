@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py -- scheduled cell-TTIs/s of the per-TTI downlink RBG allocation on B200.
+
+Workload (BASELINE.json configs[1]): a batch of 4096 independent cells per
+GPU, 20 slices x 5 backlogged UEs, 100 MHz = 512 RBs = 64 RBGs, synthetic subband CQI drawn from
+the cqi-traces-noise0 histogram and refreshed every TTI, RadioSaber inter-slice scheduler (id 9)
+with PF enterprise schedulers.  A "step" is `--ttis-per-step` consecutive TTIs of the whole batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path (this repo)
+  python bench.py --impl reference [...]                          # the reference's own CPU scheduler
+
+One JSON line on stdout (rank 0).  `value` = cell-TTIs/s with inputs resident in HBM, timed with
+CUDA events on the launching stream; `e2e` = the same metric through the host-buffer C-ABI call
+(rs_run_host) with the host<->device copies inside the timed region; `roofline` = algorithmic
+bytes of the TTI kernel / its launch time against the measured HBM peak; `cpu_baseline` = the CPU
+oracle port on this box's host cores (a reported baseline, not the target).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from radiosaber_b200 import workload  # noqa: E402
+
+S, UES_PER_SLICE, G, R = 20, 5, 64, 512
+U = S * UES_PER_SLICE
+METRIC = "scheduled cell-TTIs/sec (20 slices x 5 UEs, 100 MHz)"
+UNIT = "cell-TTIs/s"
+SEED = 1
+
+
+def slice_setup():
+    w = np.full(S, 1.0 / S)
+    p = np.tile(np.array([0, 0, 1, 1], dtype=np.int32), (S, 1))   # PF: epsilon 1, psi 1
+    u2s = np.repeat(np.arange(S), UES_PER_SLICE).astype(np.int32)
+    return w, p, u2s
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"{args.cells} cells/GPU x {S} slices x {UES_PER_SLICE} backlogged UEs, 100 MHz "
+                    f"({R} RBs, {G} RBGs), RadioSaber id {args.algo}, PF enterprise schedulers, synthetic CQI "
+                    f"from the cqi-traces-noise0 histogram refreshed every TTI (BASELINE configs[1])",
+        "cells_per_gpu": args.cells, "cells_total": args.cells * n_gpus, "slices": S, "ues": U, "rbgs": G,
+        "scheduler_id": args.algo, "ttis_per_step": args.ttis_per_step, "ttis_per_launch": args.ttis_per_launch,
+        "cqi_refresh_ttis": 1, "seed": SEED,
+        "l2": f"each step streams {args.cells * U * G * args.ttis_per_step / 1e6:.0f} MB of CQI per GPU "
+              "(> 126 MB L2), so no input is L2-resident between timed iterations",
+        "parallelism": f"cells sharded over {n_gpus} GPU(s), no data-path collective; one NCCL reduce of "
+                       "per-slice stats after the timed region",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (nvidia-smi's clocks line via NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline_port(args, budget_s=12.0):
+    """The CPU oracle port (oracle/rs_oracle.cpp) on every host core, on a bounded sample of the
+    same workload.  Test infrastructure used as the checker-side baseline only."""
+    from oracle.pyoracle import OracleScheduler
+    w, p, u2s = slice_setup()
+    cores = os.cpu_count() or 1
+    B = min(args.cells, 64 * cores)
+    o = OracleScheduler(args.algo, w, p, u2s, B, n_threads=cores)
+    _, dts = workload.tti_clock(64)
+    cqi = workload.synth_cqi(SEED, 0, B, 0, 2, U, G)
+    r2 = workload.synth_rand2(SEED, 0, B, 0, 2, S)
+    o.step(cqi[0], r2[0], dt=float(dts[0]))          # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o.step(cqi[n & 1], r2[n & 1], dt=float(dts[1 + (n % 60)]))
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 400:
+            break
+    return {"value": B * n / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{B} cells x {n} TTIs of the same workload, oracle/rs_oracle.cpp -O2, {cores} threads, {el:.1f} s"}
+
+
+def run_reference_arm(args, n_gpus):
+    """`--impl reference`: the UNMODIFIED reference scheduler (DownlinkTransportScheduler::DoSchedule,
+    compiled from the reference sources into oracle/_ref/ref_harness with its own -O0 flags) on the
+    host cores: one single-threaded simulator process per core, one cell each, same slice config,
+    same synthetic CQI / rand() streams.  Falls back to the oracle port if the harness binary is
+    absent."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    cfg = workload_config(args, n_gpus)
+    K, W = args.steps, args.warmup
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "gpu_launches": 0}
+    if os.path.exists(harness):
+        ttis_step = args.ref_ttis_per_step
+        T = (K + W) * ttis_step
+        procs = min(cores, args.ref_procs) if args.ref_procs > 0 else cores
+        with tempfile.TemporaryDirectory() as tmp:
+            json.dump({"slices": [{"n_slices": S, "weight": 1.0 / S, "video_app": 0, "video_bitrate": 0,
+                                   "internet_flow": 0, "if_bitrate": 0, "backlog_flow": 1, "algo_alpha": 0,
+                                   "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1}],
+                       "ues_per_slice": [UES_PER_SLICE] * S}, open(os.path.join(tmp, "cfg.json"), "w"))
+            running = []
+            for pi in range(procs):
+                workload.synth_cqi(SEED, pi, 1, 0, T, U, G)[:, 0].tofile(os.path.join(tmp, f"cqi{pi}.bin"))
+                workload.synth_rand2(SEED, pi, 1, 0, T, S)[:, 0].tofile(os.path.join(tmp, f"rand{pi}.bin"))
+                running.append(subprocess.Popen(
+                    [harness, "--algo", str(args.algo), "--config", os.path.join(tmp, "cfg.json"),
+                     "--ttis", str(T), "--cqi", os.path.join(tmp, f"cqi{pi}.bin"),
+                     "--rand", os.path.join(tmp, f"rand{pi}.bin"), "--time-every", str(ttis_step)],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=tmp))
+            cum = []
+            for pr in running:
+                out, _ = pr.communicate()
+                marks = [json.loads(l) for l in out.splitlines() if l.startswith('{"sched_calls"')]
+                cum.append([m["sched_seconds"] for m in marks][: K + W])
+        cum = np.array([c for c in cum if len(c) == K + W])
+        if cum.size == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "ref_harness produced no timing"}))
+            return
+        # per step: the slowest process defines the step time (all processes run concurrently)
+        steps = np.diff(np.concatenate([np.zeros((cum.shape[0], 1)), cum], axis=1), axis=1)[:, W:]
+        step_s = steps.max(axis=0)
+        total = float(step_s.sum())
+        value = cum.shape[0] * ttis_step * K / total
+        kind, sample = "reference", (f"{cum.shape[0]} single-threaded LTE-Sim processes (one per core) x {ttis_step} TTIs "
+                                     f"per step, 1 cell each; timed region = the reference's DoSchedule "
+                                     f"(EWMA + SelectFlows + RBsAllocation + DoStopSchedule), -O0 as shipped")
+        ms = 1e3 * total / K
+        ncores = int(cum.shape[0])
+    else:
+        base = cpu_baseline_port(args, budget_s=20.0)
+        value, kind, sample, ms, ncores = base["value"], "port", base["sample"], None, base["cores"]
+    line.update({"value": value, "ms_per_step": ms,
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_cuda_arm(args, n_gpus):
+    import torch
+    import torch.distributed as dist
+    from radiosaber_b200 import sched
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    B, TT, K, W = args.cells, args.ttis_per_step, args.steps, args.warmup
+    w, p, u2s = slice_setup()
+    g = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index)
+    stream = torch.cuda.current_stream(dev)
+    g.set_stream(stream.cuda_stream)
+    cell0 = rank * B   # every rank schedules its own Monte-Carlo cells
+
+    # inputs resident in HBM before the timed region: CQI and rand() streams of one step's TTIs
+    d_cqi = torch.empty((TT, B, U, G), dtype=torch.uint8, device=dev)
+    d_r2 = torch.empty((TT, B, 2), dtype=torch.int32, device=dev)
+    g.synth_cqi(SEED, cell0, 0, TT, 1, d_cqi.data_ptr())
+    g.synth_rand2(SEED, cell0, 0, TT, d_r2.data_ptr())
+    d_rbg = torch.empty((TT, B, G), dtype=torch.int16, device=dev)
+    d_bits = torch.empty((TT, B, U), dtype=torch.int32, device=dev)
+    d_mcs = torch.empty((TT, B, U), dtype=torch.uint8, device=dev)
+    outs = {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr(), "mcs": d_mcs.data_ptr()}
+    _, dts = workload.tti_clock((W + K) * TT)
+
+    def step(k):
+        g.run_device(TT, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts[k * TT:(k + 1) * TT], outs,
+                     ttis_per_launch=args.ttis_per_launch)
+
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    launches0 = g.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for k in range(W, W + K):
+        step(k)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = e0.elapsed_time(e1)
+    launches = g.launch_count - launches0
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tl = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+    ms_max = float(tms.item())
+    value = world * B * TT * K / (ms_max * 1e-3)
+
+    # end-of-run per-slice totals: the single NCCL reduce of the north star
+    d_stats = torch.zeros((4, S), dtype=torch.int64, device=dev)
+    g.stats_device(d_stats.data_ptr())
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.reduce(d_stats, dst=0, op=dist.ReduceOp.SUM)
+    stats = d_stats.cpu().numpy().astype(np.uint64)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed) --------
+    TE = args.e2e_ttis
+    h_cqi = torch.empty((TE, B, U, G), dtype=torch.uint8).pin_memory()
+    h_cqi.copy_(d_cqi[:TE].cpu())
+    h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
+    h_r2.copy_(d_r2[:TE].cpu())
+    h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
+    h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
+    h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
+    _, dte = workload.tti_clock(TE)
+
+    def e2e_step():
+        sched._check(sched.lib().rs_run_host(g._h, TE, C.c_void_p(h_cqi.data_ptr()), C.c_void_p(h_r2.data_ptr()),
+                                             None, dte.ctypes.data_as(C.c_void_p), C.byref(o), args.e2e_ttis_per_launch))
+
+    for _ in range(max(1, min(W, 2))):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    KE = max(2, min(K, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        e2e_step()          # synchronous: returns when the results are in host memory
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * TE * KE / float(te.item())
+    h2d = TE * (B * U * G + B * 2 * 4) + TE * 8
+    d2h = TE * (B * G * 2 + B * U * 4 + B * U)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg = g.algorithmic_bytes_per_cell_tti
+        launches_rank0 = K * ((TT + args.ttis_per_launch - 1) // args.ttis_per_launch)
+        launch_ms = ms_max / launches_rank0
+        ttis_launch = min(TT, args.ttis_per_launch)
+        achieved = alg * B * ttis_launch / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "gpu_launches": int(tl.item()),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ttis_per_step": TE, "steps": KE,
+                    "api": "rs_run_host (C ABI, pinned host buffers, copies overlapped with kernels)"},
+            "roofline": {"bound": "hbm", "kernel": f"rs_tti_kernel<{args.algo}>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell_tti": alg, "cell_ttis_per_launch": B * ttis_launch,
+                         "launch_ms": launch_ms,
+                         "note": "path is bound by shared-memory sort/scan and FP64 issue, not HBM (DESIGN.md)"},
+            "clocks": sampler.result(),
+            "smem_bytes_per_cta": g.smem_bytes,
+            "slice_bytes_total": [int(x) for x in stats[0]],
+            "jain_fairness_per_slice_mean": float(np.mean(sched.jain_index(stats, np.full(S, UES_PER_SLICE * B * world)))),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(args)
+        print(json.dumps(line))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cells", type=int, default=4096, help="cells per GPU")
+    ap.add_argument("--algo", type=int, default=9)
+    ap.add_argument("--ttis-per-step", type=int, default=48)
+    ap.add_argument("--ttis-per-launch", type=int, default=16)
+    ap.add_argument("--e2e-ttis", type=int, default=16)
+    ap.add_argument("--e2e-ttis-per-launch", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-ttis-per-step", type=int, default=10)
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: launch ourselves the way the driver does
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                  "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:])
+    n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if args.impl == "reference":
+        run_reference_arm(args, n_gpus)
+    else:
+        run_cuda_arm(args, n_gpus)
+
+
+if __name__ == "__main__":
+    main()

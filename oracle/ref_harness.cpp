@@ -114,6 +114,7 @@ struct Options {
   std::string rand_file;  /* int32 [T][2] */
   int seed = 1;
   bool timing = false;
+  int time_every = 0;     /* print cumulative scheduler seconds every N recorded TTIs */
   bool keep_log = false;
 };
 static Options g_opt;
@@ -207,6 +208,10 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
   auto t1 = std::chrono::steady_clock::now();
   g_sched_seconds += std::chrono::duration<double>(t1 - t0).count();
   g_sched_calls++;
+  if (g_opt.time_every > 0 && g_sched_calls % g_opt.time_every == 0) {
+    fprintf(stdout, "{\"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_sched_calls, g_sched_seconds);
+    fflush(stdout);
+  }
   g_rand_script_pos = -1;
 
   int32_t rand2[2] = {0, 0};
@@ -380,6 +385,7 @@ int main(int argc, char** argv) {
     else if (a == "--rand") g_opt.rand_file = next();
     else if (a == "--seed") g_opt.seed = atoi(next().c_str());
     else if (a == "--time") g_opt.timing = true;
+    else if (a == "--time-every") g_opt.time_every = atoi(next().c_str());
     else if (a == "--keep-log") g_opt.keep_log = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
