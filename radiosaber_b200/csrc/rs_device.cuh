@@ -76,7 +76,7 @@ struct RunArgs {
 
 /* ---- shared-memory layout (same function on host and device) --------------------------------- */
 struct Layout {
-  int avg, den, mtab, cumb, cumr, tx, mask, seg, cnt, a, win, posl, posr, wl, wr, pfl, pfr,
+  int avg, den, mtab, cumb, cumr, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
       target, quota, frb, wd, outsl, off, tval, misc, total;
 };
 __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -94,10 +94,9 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   L.tval = o; o += 8 * 16;
   L.tx = o;   o += 4 * U;
   L.mask = o; o += 8 * U;
-  L.seg = o;  o += 4 * n;
+  L.seg0 = o; o += 4 * (n / 16 + 2);
+  L.seg1 = o; o += 4 * (n / 16 + 2);
   L.cnt = o;  o += 4 * 16 * nw;
-  L.wl = o;   o += 4 * (nw + 1);
-  L.wr = o;   o += 4 * (nw + 1);
   L.target = o; o += 4 * S;
   L.quota = o;  o += 4 * S;
   L.frb = o;    o += 4 * S;
@@ -107,8 +106,6 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   L.win = o;  o += 2 * n;
   L.posl = o; o += 2 * n;
   L.posr = o; o += 2 * n;
-  L.pfl = o;  o += 2 * (nw + 2);
-  L.pfr = o;  o += 2 * (nw + 2);
   L.outsl = o; o += G;
   L.total = rs_align(o, 16);
   return L;
@@ -177,161 +174,104 @@ __device__ __forceinline__ void median_to_first(unsigned short* a, int first, in
   a[pick] = t;
 }
 
-__device__ __forceinline__ int prefix_at(const unsigned* w, const unsigned short* pf, int x) {
-  return (int)pf[x >> 5] + __popc(w[x >> 5] & ((1u << (x & 31)) - 1u));
-}
-
 struct SortBufs {
   unsigned short* a;     /* [n] in: entries in insertion order; scratch afterwards */
   unsigned short* out;   /* [n] result, sorted (== posr) */
-  unsigned* seg;         /* [n] first | last<<16 of the range an entry is in */
   unsigned short* posl;  /* [n] */
   unsigned short* posr;  /* [n] */
-  unsigned* wl;          /* [nw+1] */
-  unsigned* wr;          /* [nw+1] */
-  unsigned short* pfl;   /* [nw+2] */
-  unsigned short* pfr;   /* [nw+2] */
+  unsigned* seg0;        /* [n/16+2] ranges still to partition, ping */
+  unsigned* seg1;        /* [n/16+2] pong */
   unsigned* cnt;         /* [16*nw] */
-  unsigned* misc;        /* [16] */
+  unsigned* misc;        /* [16]: 0..7 warp totals, 8..10 rotating list counters */
 };
 
-/* Exclusive prefix over the ballot words of one flag array, by one warp. */
-__device__ __forceinline__ void word_prefix(const unsigned* w, unsigned short* pf, int nw, int lane) {
-  constexpr int WPL = 5; /* 32*5 = 160 >= 129 words (n <= 4096) */
-  int c[WPL];
-  int s = 0;
-#pragma unroll
-  for (int q = 0; q < WPL; ++q) {
-    const int idx = lane * WPL + q;
-    c[q] = (idx < nw) ? __popc(w[idx]) : 0;
-    s += c[q];
+/* One warp partitions the range [f,l) exactly like std::__unguarded_partition_pivot and returns
+ * the cut.  Stoppers of the left scan (key <= pivot) and of the right scan (key >= pivot) are
+ * listed in slots of the range itself; pair k = (k-th from the left, k-th from the right) is
+ * swapped while the former lies left of the latter. */
+__device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, int lane) {
+  unsigned short* a = b.a;
+  if (lane == 0) median_to_first(a, f, l);
+  __syncwarp();
+  const int p = a[f] >> 12;
+  const int m = l - f - 1, base = f + 1;
+  const unsigned lt = (1u << lane) - 1u;
+  int nl = 0, nr = 0;
+  for (int c0 = 0; c0 < m; c0 += 32) {
+    const int idx = c0 + lane;
+    const bool valid = idx < m;
+    const int k = valid ? (a[base + idx] >> 12) : 0;
+    const bool fl = valid && k <= p, fr = valid && k >= p;
+    const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
+    if (fl) b.posl[base + nl + __popc(bl & lt)] = (unsigned short)(base + idx);
+    if (fr) b.posr[base + nr + __popc(br & lt)] = (unsigned short)(base + idx);
+    nl += __popc(bl);
+    nr += __popc(br);
   }
-  int incl = s;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(kFull, incl, d);
-    if (lane >= d) incl += v;
+  __syncwarp();
+  /* k-th right stopper counted from the right = posr[base + nr - 1 - k] */
+  const int nmin = min(nl, nr);
+  int K = 0;
+  for (int c0 = 0;; c0 += 32) {
+    const int k = c0 + lane;
+    bool sw = false;
+    if (k < nmin) {
+      const int lp = b.posl[base + k], rp = b.posr[base + nr - 1 - k];
+      sw = lp < rp;
+      if (sw) {
+        const unsigned short t = a[lp];
+        a[lp] = a[rp];
+        a[rp] = t;
+      }
+    }
+    const unsigned bs = __ballot_sync(kFull, sw);
+    if (bs != kFull) { K = c0 + __ffs(~bs) - 1; break; }
   }
-  int run = incl - s;
-#pragma unroll
-  for (int q = 0; q < WPL; ++q) {
-    const int idx = lane * WPL + q;
-    if (idx <= nw) pf[idx] = (unsigned short)run;
-    run += c[q];
-  }
+  int cut = (K < nl) ? (int)b.posl[base + K] : 0x7fffffff;
+  if (K >= 1) cut = min(cut, (int)b.posr[base + nr - K]);
+  __syncwarp();
+  return cut;
 }
 
 /* All kThreads threads of the CTA call this. On return b.out[0..n) holds the entries in the order
- * std::sort leaves them. */
+ * std::sort leaves them.  Ranges of one recursion depth are independent, so each level hands the
+ * ranges longer than _S_threshold to the warps, one range per warp at a time. */
 __device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = (n + 31) >> 5;
-  for (int i = tid; i < n; i += kThreads) b.seg[i] = (unsigned)n << 16;
-  __syncthreads();
-
-  for (int level = 0;; ++level) {
-    /* A: range leaders pick the pivot (or heap-sort when the depth limit is exhausted) */
-    bool any = false;
-    for (int w = warp; w < nw; w += kWarps) {
-      const int i = w * 32 + lane;
-      if (i < n) {
-        const unsigned sg = b.seg[i];
-        const int f = sg & 0xffff, l = sg >> 16;
-        if (l - f > kSortThreshold) {
-          any = true;
-          if (i == f) {
-            if (level >= depth_limit) heap_sort(b.a + f, l - f);
-            else median_to_first(b.a, f, l);
-          }
-        }
-      }
-    }
-    if (!__syncthreads_or(any)) break;
-    if (level >= depth_limit) break;
-
-    /* B: stopper flags of __unguarded_partition: L = "not before pivot", R = "pivot not before" */
-    for (int w = warp; w < nw; w += kWarps) {
-      const int i = w * 32 + lane;
-      bool fl = false, fr = false;
-      if (i < n) {
-        const unsigned sg = b.seg[i];
-        const int f = sg & 0xffff, l = sg >> 16;
-        if (l - f > kSortThreshold && i != f) {
-          const int k = b.a[i] >> 12, p = b.a[f] >> 12;
-          fl = k <= p;
-          fr = k >= p;
-        }
-      }
-      const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
-      if (lane == 0) { b.wl[w] = bl; b.wr[w] = br; }
-    }
-    __syncthreads();
-    /* C: prefix counts over words */
-    if (warp == 0) word_prefix(b.wl, b.pfl, nw, lane);
-    else if (warp == 1) word_prefix(b.wr, b.pfr, nw, lane);
-    __syncthreads();
-    /* D: k-th L stopper from the left / k-th R stopper from the right -> slot first+1+k */
-    for (int w = warp; w < nw; w += kWarps) {
-      const int i = w * 32 + lane;
-      if (i < n) {
-        const unsigned sg = b.seg[i];
-        const int f = sg & 0xffff, l = sg >> 16;
-        if (l - f > kSortThreshold && i != f) {
-          const int k = b.a[i] >> 12, p = b.a[f] >> 12;
-          if (k <= p) b.posl[f + 1 + prefix_at(b.wl, b.pfl, i) - prefix_at(b.wl, b.pfl, f + 1)] = (unsigned short)i;
-          if (k >= p) b.posr[f + 1 + prefix_at(b.wr, b.pfr, l) - prefix_at(b.wr, b.pfr, i + 1)] = (unsigned short)i;
-        }
-      }
-    }
-    __syncthreads();
-    /* E: swap pair k while posL[k] < posR[k]; the first non-swapping k defines the cut */
-    for (int w = warp; w < nw; w += kWarps) {
-      const int j = w * 32 + lane;
-      if (j < n) {
-        const unsigned sg = b.seg[j];
-        const int f = sg & 0xffff, l = sg >> 16;
-        if (l - f > kSortThreshold && j != f) {
-          const int k = j - f - 1;
-          const int nl = prefix_at(b.wl, b.pfl, l) - prefix_at(b.wl, b.pfl, f + 1);
-          const int nr = prefix_at(b.wr, b.pfr, l) - prefix_at(b.wr, b.pfr, f + 1);
-          const bool have_l = k < nl, have_r = k < nr;
-          const int lp = b.posl[j], rp = b.posr[j];
-          const bool sw = have_l && have_r && lp < rp;
-          if (sw) {
-            const unsigned short t = b.a[lp];
-            b.a[lp] = b.a[rp];
-            b.a[rp] = t;
-          } else {
-            bool prev = true;
-            int prev_r = 0x7fffffff;
-            if (k >= 1) {
-              prev_r = b.posr[j - 1];
-              prev = (k - 1 < nl) && (k - 1 < nr) && ((int)b.posl[j - 1] < prev_r);
-            }
-            if (prev) {
-              int cut = have_l ? lp : 0x7fffffff;
-              if (k >= 1 && prev_r < cut) cut = prev_r;
-              b.posl[f] = (unsigned short)cut;   /* slot `first` is never a pair slot: holds the cut */
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    /* F: split every partitioned range at its cut */
-    for (int w = warp; w < nw; w += kWarps) {
-      const int i = w * 32 + lane;
-      if (i < n) {
-        const unsigned sg = b.seg[i];
-        const int f = sg & 0xffff, l = sg >> 16;
-        if (l - f > kSortThreshold) {
-          const int c = b.posl[f];
-          b.seg[i] = (i < c) ? ((unsigned)f | ((unsigned)c << 16)) : ((unsigned)c | ((unsigned)l << 16));
-        }
-      }
-    }
-    /* no barrier: phase A touches seg[] of the thread's own entries and a[], which nobody reads in F */
+  if (tid == 0) {
+    b.seg0[0] = (unsigned)n << 16;
+    b.misc[8] = (n > kSortThreshold) ? 1u : 0u;
+    b.misc[9] = 0;
+    b.misc[10] = 0;
   }
+  __syncthreads();
+  for (int level = 0;; ++level) {
+    unsigned* cur = (level & 1) ? b.seg1 : b.seg0;
+    unsigned* nxt = (level & 1) ? b.seg0 : b.seg1;
+    const int c_cur = 8 + level % 3, c_nxt = 8 + (level + 1) % 3, c_old = 8 + (level + 2) % 3;
+    const int nseg = (int)b.misc[c_cur];
+    if (nseg == 0) break;
+    if (level >= depth_limit) {      /* __introsort_loop's depth_limit == 0: heap sort what is left */
+      for (int s = tid; s < nseg; s += kThreads) {
+        const unsigned sg = cur[s];
+        heap_sort(b.a + (sg & 0xffff), (int)(sg >> 16) - (int)(sg & 0xffff));
+      }
+      break;
+    }
+    if (tid == 0) b.misc[c_old] = 0;   /* last read before the previous barrier; next used after this one */
+    for (int s = warp; s < nseg; s += kWarps) {
+      const unsigned sg = cur[s];
+      const int f = sg & 0xffff, l = sg >> 16;
+      const int cut = warp_partition(b, f, l, lane);
+      if (lane == 0) {
+        if (cut - f > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)f | ((unsigned)cut << 16);
+        if (l - cut > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)cut | ((unsigned)l << 16);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
 
   /* __final_insertion_sort == stable sort by key of what is in a[] now: counting sort, 16 keys */
   for (int q = tid; q < 16 * nw; q += kThreads) b.cnt[q] = 0;
@@ -432,13 +372,10 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.misc = (unsigned*)(smem + L.misc);
   c.sb.a = (unsigned short*)(smem + L.a);
   c.sb.out = (unsigned short*)(smem + L.posr);
-  c.sb.seg = (unsigned*)(smem + L.seg);
+  c.sb.seg0 = (unsigned*)(smem + L.seg0);
+  c.sb.seg1 = (unsigned*)(smem + L.seg1);
   c.sb.posl = (unsigned short*)(smem + L.posl);
   c.sb.posr = (unsigned short*)(smem + L.posr);
-  c.sb.wl = (unsigned*)(smem + L.wl);
-  c.sb.wr = (unsigned*)(smem + L.wr);
-  c.sb.pfl = (unsigned short*)(smem + L.pfl);
-  c.sb.pfr = (unsigned short*)(smem + L.pfr);
   c.sb.cnt = (unsigned*)(smem + L.cnt);
   c.sb.misc = c.misc;
   return c;
