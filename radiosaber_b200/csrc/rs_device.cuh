@@ -27,7 +27,10 @@
 
 namespace rs {
 
-constexpr int kThreads = 256;          /* threads per CTA (one CTA = one cell) */
+#ifndef RS_THREADS
+#define RS_THREADS 128
+#endif
+constexpr int kThreads = RS_THREADS;   /* threads per CTA (one CTA = one cell) */
 constexpr int kWarps = kThreads / 32;
 constexpr int kSortThreshold = 16;     /* libstdc++ _S_threshold, bits/stl_algo.h:1848 */
 constexpr int kMStride = 16;           /* metric table row: entries for CQI 0..15 */
@@ -59,6 +62,8 @@ struct DevCfg {
   const double* epow;      /* [S][16]: pow(eff(c)*180000/1000, epsilon_s) (ids 7/8/9); [1][16] eff*180000 (id 1) */
   const unsigned char* psi;/* [S] 0/1 */
   const int* tbs_n;        /* [G+1][16]: GetTBSizeFromMCS(mcs(cqi), k*rbg) */
+  const unsigned short* eq_tab; /* id 9: permutations of all-equal ranges (SortBufs::eq_tab) */
+  int eq_max;
   /* state, [B][U] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
   double* offset; double* ewma;
@@ -183,13 +188,18 @@ struct SortBufs {
   unsigned* seg1;        /* [n/16+2] pong */
   unsigned* cnt;         /* [16*nw] */
   unsigned* misc;        /* [16]: 0..7 warp totals, 8..10 rotating list counters */
+  const unsigned short* eq_tab;  /* all-equal-keys permutations, see eq_offset(); may be null */
+  int eq_max;            /* longest range the table covers */
 };
+
+/* Offset of the permutation for a range of `len` equal keys (len = 17..eq_max) in eq_tab. */
+__host__ __device__ inline size_t eq_offset(int len) { return (size_t)(len - 1) * len / 2 - 136; }
 
 /* One warp partitions the range [f,l) exactly like std::__unguarded_partition_pivot and returns
  * the cut.  Stoppers of the left scan (key <= pivot) and of the right scan (key >= pivot) are
  * listed in slots of the range itself; pair k = (k-th from the left, k-th from the right) is
  * swapped while the former lies left of the latter. */
-__device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, int lane) {
+__device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, int lane, int levels_left) {
   unsigned short* a = b.a;
   if (lane == 0) median_to_first(a, f, l);
   __syncwarp();
@@ -209,6 +219,18 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
     nr += __popc(br);
   }
   __syncwarp();
+  /* Every key equals the pivot: from here on no comparison depends on the data, so what the rest of
+   * the recursion does to this range is a fixed permutation of its length (built on the host by
+   * running the same loop, rs_sched.cu build_eq_table).  Apply it in one gather. */
+  if (nl == m && nr == m && l - f <= b.eq_max && 32 - __clz(l - f) <= levels_left) {
+    const int len = l - f;
+    for (int i = lane; i < len; i += 32) b.posl[f + i] = a[f + i];
+    __syncwarp();
+    const unsigned short* tab = b.eq_tab + eq_offset(len);
+    for (int i = lane; i < len; i += 32) a[f + i] = b.posl[f + tab[i]];
+    __syncwarp();
+    return -1;
+  }
   /* k-th right stopper counted from the right = posr[base + nr - 1 - k] */
   const int nmin = min(nl, nr);
   int K = 0;
@@ -263,8 +285,8 @@ __device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
     for (int s = warp; s < nseg; s += kWarps) {
       const unsigned sg = cur[s];
       const int f = sg & 0xffff, l = sg >> 16;
-      const int cut = warp_partition(b, f, l, lane);
-      if (lane == 0) {
+      const int cut = warp_partition(b, f, l, lane, depth_limit - level);
+      if (lane == 0 && cut >= 0) {
         if (cut - f > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)f | ((unsigned)cut << 16);
         if (l - cut > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)cut | ((unsigned)l << 16);
       }
@@ -378,6 +400,8 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.sb.posr = (unsigned short*)(smem + L.posr);
   c.sb.cnt = (unsigned*)(smem + L.cnt);
   c.sb.misc = c.misc;
+  c.sb.eq_tab = nullptr;
+  c.sb.eq_max = 0;
   return c;
 }
 
@@ -566,7 +590,9 @@ template <int ALGO>
 __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Layout L = make_layout(d.S, d.U, d.G, d.m_cap);
-  const Cell c = carve(smem, L);
+  Cell c = carve(smem, L);
+  c.sb.eq_tab = d.eq_tab;
+  c.sb.eq_max = d.eq_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = d.S, U = d.U, G = d.G;
   const int b = blockIdx.x;
@@ -826,10 +852,13 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
 }
 
 /* ---- test hook: the sort alone, one CTA per array --------------------------------------------- */
-__global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* keys, int n, int depth, int* perm) {
+__global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* keys, int n, int depth, int* perm,
+                                                                const unsigned short* eq_tab, int eq_max) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Layout L = make_layout(1, 0, n, 0);   /* S*G == n */
-  const Cell c = carve(smem, L);
+  Cell c = carve(smem, L);
+  c.sb.eq_tab = eq_tab;
+  c.sb.eq_max = eq_max;
   const uint8_t* k = keys + (size_t)blockIdx.x * n;
   for (int i = threadIdx.x; i < n; i += kThreads) c.sb.a[i] = (unsigned short)(((k[i] & 15) << 12) | i);
   __syncthreads();

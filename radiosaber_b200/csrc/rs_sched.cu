@@ -107,6 +107,41 @@ bool build_const_tables(rs::ConstTables* t, std::string* why) {
   return true;
 }
 
+/* What libstdc++'s __introsort_loop does to a range of `len` EQUAL keys is independent of the data:
+ * __move_median_to_first picks `mid` (every comparison is false, stl_algo.h:1893-1899),
+ * __unguarded_partition stops on every element from both sides, i.e. swaps pair k of
+ * (first+1+k, last-1-k) while the former is left of the latter and returns first+1+(len-1)/2, and
+ * the two halves recurse the same way until they are <= 16 long.  tab[eq_offset(len)+i] = index,
+ * in the range as it is AFTER the first median swap, of the entry that ends at position i. */
+void build_eq_table(int nmax, std::vector<unsigned short>* tab) {
+  tab->assign(nmax >= 17 ? rs::eq_offset(nmax + 1) : 1, 0);
+  std::vector<unsigned short> a(nmax > 0 ? nmax : 1);
+  std::vector<std::pair<int, int>> stack;
+  for (int len = 17; len <= nmax; ++len) {
+    for (int i = 0; i < len; ++i) a[i] = (unsigned short)i;
+    stack.clear();
+    stack.emplace_back(0, len);
+    while (!stack.empty()) {
+      int f = stack.back().first, l = stack.back().second;
+      stack.pop_back();
+      while (l - f > 16) {
+        std::swap(a[f], a[f + (l - f) / 2]);
+        for (int k = 0; f + 1 + k < l - 1 - k; ++k) std::swap(a[f + 1 + k], a[l - 1 - k]);
+        const int cut = f + 1 + (l - f - 1) / 2;
+        stack.emplace_back(cut, l);
+        l = cut;
+      }
+    }
+    unsigned short* out = tab->data() + rs::eq_offset(len);
+    const int mid = len / 2;
+    for (int i = 0; i < len; ++i) {
+      const int x = a[i];
+      out[i] = (unsigned short)(x == 0 ? mid : (x == mid ? 0 : x));
+    }
+  }
+}
+constexpr int kEqMax = 2048;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -138,6 +173,7 @@ struct rs_handle {
   DevBuf<int> ue_to_slice, slice_ptr, slice_ues, chunk_slice, tbs_n;
   DevBuf<double> weight, epow;
   DevBuf<unsigned char> psi;
+  DevBuf<unsigned short> eq_tab;
   /* state */
   DevBuf<double> avg, offset, ewma;
   DevBuf<int> tx;
@@ -246,7 +282,7 @@ void rs_destroy(rs_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ue_to_slice.release(); h->slice_ptr.release(); h->slice_ues.release(); h->chunk_slice.release();
-  h->tbs_n.release(); h->weight.release(); h->epow.release(); h->psi.release();
+  h->tbs_n.release(); h->weight.release(); h->epow.release(); h->psi.release(); h->eq_tab.release();
   h->avg.release(); h->offset.release(); h->ewma.release(); h->tx.release();
   h->cum_bytes.release(); h->cum_rbs.release(); h->dt_dev.release(); h->stats.release();
   for (auto& s : h->slot) {
@@ -413,6 +449,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   BAIL(upload(h->weight, weight));
   BAIL(upload(h->epow, epow));
   BAIL(upload(h->psi, psi));
+  if (algo == 9 && d.sort_n > 16) {
+    std::vector<unsigned short> eq;
+    d.eq_max = std::min(d.sort_n, kEqMax);
+    build_eq_table(d.eq_max, &eq);
+    BAIL(upload(h->eq_tab, eq));
+    d.eq_tab = h->eq_tab.p;
+  }
   d.ue_to_slice = h->ue_to_slice.p; d.slice_ptr = h->slice_ptr.p; d.slice_ues = h->slice_ues.p;
   d.chunk_slice = h->chunk_slice.p; d.tbs_n = h->tbs_n.p; d.weight = h->weight.p; d.epow = h->epow.p;
   d.psi = h->psi.p;
@@ -695,17 +738,27 @@ int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t 
   CU(cudaFuncSetAttribute(rs::rs_sort_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   uint8_t* dk = nullptr;
   int* dp = nullptr;
+  unsigned short* de = nullptr;
+  const int eq_max = std::min(n, kEqMax);
+  if (eq_max >= 17) {
+    std::vector<unsigned short> eq;
+    build_eq_table(eq_max, &eq);
+    CU(cudaMalloc((void**)&de, eq.size() * 2));
+    cudaError_t e0 = cudaMemcpy(de, eq.data(), eq.size() * 2, cudaMemcpyHostToDevice);
+    if (e0 != cudaSuccess) { cudaFree(de); return fail(RS_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e0)); }
+  }
   CU(cudaMalloc((void**)&dk, (size_t)n_arrays * n));
   cudaError_t e = cudaMalloc((void**)&dp, (size_t)n_arrays * n * 4);
   if (e != cudaSuccess) { cudaFree(dk); return fail(RS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
   e = cudaMemcpy(dk, keys, (size_t)n_arrays * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp);
+    rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp, de, de ? eq_max : 0);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(perm_out, dp, (size_t)n_arrays * n * 4, cudaMemcpyDeviceToHost);
   cudaFree(dk);
   cudaFree(dp);
+  if (de) cudaFree(de);
   if (e != cudaSuccess) return fail(RS_ERR_CUDA, "rs_test_sort: %s", cudaGetErrorString(e));
   return RS_OK;
 }

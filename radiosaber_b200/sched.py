@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librs_sched.so")
+LIB_PATH = os.environ.get("RS_SCHED_LIB") or os.path.join(_HERE, "librs_sched.so")
 _lib = None
 
 # every symbol include/rs_sched.h declares (tests check the library exports all of them)

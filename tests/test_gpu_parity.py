@@ -42,6 +42,28 @@ def test_device_sort_matches_std_sort(n):
         assert np.array_equal(got[i], want), (n, i)
 
 
+def test_device_sort_equal_key_ranges():
+    """Ranges of equal keys take the precomputed-permutation shortcut: every length, and mixtures
+    where long equal runs appear only after a few partitions."""
+    rng = np.random.default_rng(99)
+    for n in list(range(17, 140)) + [255, 256, 257, 511, 777, 1024, 1280, 2047, 2048, 2049, 3000, 4096]:
+        keys = np.stack([np.full(n, 9, np.uint8), np.full(n, 0, np.uint8), np.full(n, 15, np.uint8),
+                         rng.choice(np.array([3, 12], dtype=np.uint8), size=n),
+                         rng.choice(np.array([3, 12, 13], dtype=np.uint8), size=n, p=[0.1, 0.8, 0.1])])
+        got = sched.test_sort(keys)
+        for i in range(keys.shape[0]):
+            want = pyoracle.std_sort_desc(keys[i].astype(np.float64))
+            assert np.array_equal(got[i], want), (n, i)
+    # shallow depth limits: the shortcut must step aside when the heap-sort fallback would be reached
+    for depth in (1, 2, 3, 5):
+        for n in (40, 300, 1280):
+            keys = np.stack([np.full(n, 5, np.uint8), rng.choice(np.array([3, 12], dtype=np.uint8), size=n)])
+            got = sched.test_sort(keys, depth_limit=depth)
+            for i in range(keys.shape[0]):
+                want = pyoracle.introsort_emul_desc(keys[i].astype(np.float64), depth)
+                assert np.array_equal(got[i], want), (n, depth, i)
+
+
 @pytest.mark.parametrize("depth", [0, 1, 2, 4])
 def test_device_sort_heap_fallback(depth):
     rng = np.random.default_rng(50 + depth)
