@@ -24,11 +24,21 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace rs {
 
+#ifdef RS_PHASE_TIMING
+#define RS_TICK(k) do { if (threadIdx.x == 0) { long long now_ = clock64(); ph_[k] += now_ - last_; last_ = now_; } } while (0)
+#else
+#define RS_TICK(k) do {} while (0)
+#endif
+
 #ifndef RS_THREADS
 #define RS_THREADS 128
+#endif
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 8
 #endif
 constexpr int kThreads = RS_THREADS;   /* threads per CTA (one CTA = one cell) */
 constexpr int kWarps = kThreads / 32;
@@ -81,10 +91,13 @@ struct RunArgs {
 
 /* ---- shared-memory layout (same function on host and device) --------------------------------- */
 struct Layout {
-  int avg, den, mtab, cumb, cumr, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
+  int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
       target, quota, frb, wd, outsl, off, tval, misc, total;
 };
 __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
+/* The cumulative byte / RB counters stay in HBM (touched only for the few UEs a TTI serves); the
+ * metric table is dead once the sort starts, so it shares the bytes of the sort's slot arrays
+ * when it fits there. */
 __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   Layout L;
   const int n = S * G;
@@ -92,16 +105,20 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   int o = 0;
   L.avg = o;  o += 8 * U;
   L.den = o;  o += 8 * U;
-  L.mtab = o; o += 8 * kMStride * m_cap;
-  L.cumb = o; o += 8 * U;
-  L.cumr = o; o += 8 * U;
   L.off = o;  o += 8 * S;
   L.tval = o; o += 8 * 16;
+  L.posl = o; o += 2 * n;
+  L.posr = o; o += 2 * n;
+  o = rs_align(o, 8);
+  if (8 * kMStride * m_cap <= 4 * n) {
+    L.mtab = L.posl;
+  } else {
+    L.mtab = o; o += 8 * kMStride * m_cap;
+  }
   L.tx = o;   o += 4 * U;
   L.mask = o; o += 8 * U;
   L.seg0 = o; o += 4 * (n / 16 + 2);
   L.seg1 = o; o += 4 * (n / 16 + 2);
-  L.cnt = o;  o += 4 * 16 * nw;
   L.target = o; o += 4 * S;
   L.quota = o;  o += 4 * S;
   L.frb = o;    o += 4 * S;
@@ -109,8 +126,7 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   L.misc = o;   o += 4 * 16;
   L.a = o;    o += 2 * n;
   L.win = o;  o += 2 * n;
-  L.posl = o; o += 2 * n;
-  L.posr = o; o += 2 * n;
+  L.cnt = o;  o += 2 * 16 * nw;
   L.outsl = o; o += G;
   L.total = rs_align(o, 16);
   return L;
@@ -186,7 +202,7 @@ struct SortBufs {
   unsigned short* posr;  /* [n] */
   unsigned* seg0;        /* [n/16+2] ranges still to partition, ping */
   unsigned* seg1;        /* [n/16+2] pong */
-  unsigned* cnt;         /* [16*nw] */
+  unsigned short* cnt;   /* [16*nw] */
   unsigned* misc;        /* [16]: 0..7 warp totals, 8..10 rotating list counters */
   const unsigned short* eq_tab;  /* all-equal-keys permutations, see eq_offset(); may be null */
   int eq_max;            /* longest range the table covers */
@@ -306,7 +322,7 @@ __device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
     const int rk = __popc(m & ((1u << lane) - 1u));
     if (valid) {
       b.posl[i] = (unsigned short)rk;
-      if (rk == 0) b.cnt[(15 - k) * nw + w] = __popc(m);
+      if (rk == 0) b.cnt[(15 - k) * nw + w] = (unsigned short)__popc(m);
     }
   }
   __syncthreads();
@@ -328,7 +344,7 @@ __device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
     for (int w = 0; w < warp; ++w) base += (int)b.misc[w];
     for (int q = q0; q < q0 + per && q < Q; ++q) {
       const int c = (int)b.cnt[q];
-      b.cnt[q] = (unsigned)base;
+      b.cnt[q] = (unsigned short)base;
       base += c;
     }
   }
@@ -368,7 +384,8 @@ __device__ __forceinline__ int cqi_from_mean(double mean) {
 
 struct Cell {
   /* shared-memory views */
-  double* avg; double* den; double* mtab; unsigned long long* cumb; unsigned long long* cumr; double* off;
+  double* avg; double* den; double* mtab; double* off;
+  unsigned long long* cumb; unsigned long long* cumr;   /* this cell's rows of the HBM counters */
   double* tval; int* tx; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
   SortBufs sb;
@@ -379,8 +396,8 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.avg = (double*)(smem + L.avg);
   c.den = (double*)(smem + L.den);
   c.mtab = (double*)(smem + L.mtab);
-  c.cumb = (unsigned long long*)(smem + L.cumb);
-  c.cumr = (unsigned long long*)(smem + L.cumr);
+  c.cumb = nullptr;
+  c.cumr = nullptr;
   c.off = (double*)(smem + L.off);
   c.tval = (double*)(smem + L.tval);
   c.tx = (int*)(smem + L.tx);
@@ -398,7 +415,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.sb.seg1 = (unsigned*)(smem + L.seg1);
   c.sb.posl = (unsigned short*)(smem + L.posl);
   c.sb.posr = (unsigned short*)(smem + L.posr);
-  c.sb.cnt = (unsigned*)(smem + L.cnt);
+  c.sb.cnt = (unsigned short*)(smem + L.cnt);
   c.sb.misc = c.misc;
   c.sb.eq_tab = nullptr;
   c.sb.eq_max = 0;
@@ -587,7 +604,7 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
 template <int ALGO>
-__global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const RunArgs r) {
+__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Layout L = make_layout(d.S, d.U, d.G, d.m_cap);
   Cell c = carve(smem, L);
@@ -597,14 +614,14 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
   const int S = d.S, U = d.U, G = d.G;
   const int b = blockIdx.x;
   if (b >= d.n_cells) return;
+  c.cumb = d.cum_bytes + (size_t)b * U;
+  c.cumr = d.cum_rbs + (size_t)b * U;
 
   /* cell state -> shared memory */
   for (int u = tid; u < U; u += kThreads) {
     const size_t i = (size_t)b * U + u;
     c.avg[u] = d.avg[i];
     c.tx[u] = d.tx[i];
-    c.cumb[u] = d.cum_bytes[i];
-    c.cumr[u] = d.cum_rbs[i];
     c.mask[2 * u] = 0;
     c.mask[2 * u + 1] = 0;
   }
@@ -619,6 +636,10 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
   for (int g = tid; g < G; g += kThreads) c.outsl[g] = 0xff;
   __syncthreads();
 
+#ifdef RS_PHASE_TIMING
+  long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long last_ = clock64();
+#endif
   for (int t = 0; t < r.T; ++t) {
     const uint8_t* cqi = r.cqi + (size_t)t * r.cqi_tti_stride +
                          (size_t)b * U * (d.cqi_per_rb ? d.R : G);
@@ -681,6 +702,7 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
     }
     __syncthreads();
 
+    RS_TICK(0);
     if (ALGO == 8 || ALGO == 9) {
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < d.n_chunks; ++ch) {
@@ -742,15 +764,23 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
         __syncthreads();
       }
 
+      RS_TICK(1);
       /* ---- P3/P4: inter-slice assignment ---------------------------------------------------- */
       if (ALGO == 9) {
+#ifndef RS_SKIP_SORT
         sort_desc(c.sb, d.sort_n, d.sort_depth);
+#endif
+        RS_TICK(2);
+#ifndef RS_SKIP_GREEDY
         if (warp == 0) greedy_maxcell(d, c, c.sb.out, lane);
+#endif
+        RS_TICK(3);
       } else {
         if (warp == 0) greedy_by_row(d, c, c.sb.a, lane);
       }
       __syncthreads();
 
+      RS_TICK(4);
       /* ---- P5: RBG -> UE (transport.cpp:589-601) --------------------------------------------- */
       for (int g = tid; g < G; g += kThreads) {
         const int sl = c.outsl[g];
@@ -821,6 +851,7 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
     }
     __syncthreads();
 
+    RS_TICK(5);
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
@@ -837,13 +868,17 @@ __global__ void __launch_bounds__(kThreads) rs_tti_kernel(const DevCfg d, const 
     __syncthreads();
   }
 
+  RS_TICK(6);
+#ifdef RS_PHASE_TIMING
+  if (threadIdx.x == 0 && (blockIdx.x % 997) == 0)
+    printf("cta %d T %d: p0 %lld argmax %lld sort %lld greedy %lld bar %lld p5 %lld p6 %lld (cycles per TTI)\n", blockIdx.x, r.T,
+           ph_[0] / r.T, ph_[1] / r.T, ph_[2] / r.T, ph_[3] / r.T, ph_[4] / r.T, ph_[5] / r.T, ph_[6] / r.T);
+#endif
   /* cell state -> HBM */
   for (int u = tid; u < U; u += kThreads) {
     const size_t i = (size_t)b * U + u;
     d.avg[i] = c.avg[u];
     d.tx[i] = c.tx[u];
-    d.cum_bytes[i] = c.cumb[u];
-    d.cum_rbs[i] = c.cumr[u];
   }
   if (ALGO == 7 || ALGO == 8 || ALGO == 9) {
     double* dst = (ALGO == 7) ? d.ewma : d.offset;

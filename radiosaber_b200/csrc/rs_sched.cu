@@ -399,7 +399,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   std::vector<int> chunks;
   int m_cap = 0;
   if (algo == 8 || algo == 9) {
-    const int cap = std::max(max_slice, std::min(U, 256));
+    const int cap = std::max(max_slice, std::min(U, 32));   /* small table: more cells resident per SM */
     chunks.push_back(0);
     int cur = 0;
     for (int s = 0; s < S; ++s) {
