@@ -115,6 +115,7 @@ struct Options {
   int seed = 1;
   bool timing = false;
   int time_every = 0;     /* print cumulative scheduler seconds every N recorded TTIs */
+  bool gpu = false;       /* install the product's RsGpuScheduler instead of the reference class */
   bool keep_log = false;
 };
 static Options g_opt;
@@ -333,12 +334,48 @@ class ObservedPf : public DL_PF_PacketScheduler {
   }
 };
 
+#ifdef RS_WITH_GPU_ADAPTOR
+/* The drop-in test: the SAME LTE-Sim scenario, but the eNB's scheduler is the product's host
+ * plug-in (radiosaber_b200/host/rs_gpu_scheduler.h -> C ABI -> CUDA).  Recorded exactly like the
+ * reference classes above, so the two record streams can be compared byte for byte. */
+#include "../radiosaber_b200/host/rs_gpu_scheduler.h"
+class ObservedGpu : public RsGpuScheduler {
+ public:
+  ObservedGpu(std::string cfg, int id) : RsGpuScheduler(cfg, id), id_(id) {}
+  void DoSchedule() override {
+    ObservedSchedule(
+        this, num_slices_, user_to_slice_, &slice_weights_, &slice_algo_params_,
+        [this]() { RsGpuScheduler::DoSchedule(); },
+        [this](std::vector<double>& st) { for (int s = 0; s < num_slices_; ++s) st[s] = slice_state_[s]; },
+        [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t& nvs, int rbg) {
+          CollectUsers(GetUsersToSchedule(), active, r2u, bits, rbg);
+          if (id_ == 7) {
+            std::fill(active.begin(), active.end(), (uint8_t)1);
+            if (!GetUsersToSchedule()->empty())
+              nvs = user_to_slice_[GetUsersToSchedule()->at(0)->GetUserID()];
+          }
+        });
+  }
+ private:
+  int id_;
+};
+#endif
+
 struct Installer {
   void Install() {
     ENodeB* enb = TheEnb();
     EnbMacEntity* mac = (EnbMacEntity*)enb->GetProtocolStack()->GetMacEntity();
     PacketScheduler* old = mac->GetDownlinkPacketScheduler();
     PacketScheduler* s = nullptr;
+#ifdef RS_WITH_GPU_ADAPTOR
+    if (g_opt.gpu) {
+      if (g_opt.algo == 1) { fprintf(stderr, "the host plug-in covers ids 7, 8, 9\n"); exit(2); }
+      s = new ObservedGpu(g_opt.config, g_opt.algo);
+      s->SetMacEntity(mac);
+      mac->SetDownlinkPacketScheduler(s);
+      return;
+    }
+#endif
     switch (g_opt.algo) {
       case 1: s = new ObservedPf(g_opt.config); break;
       case 7: s = new ObservedNvs(g_opt.config); break;
@@ -387,6 +424,7 @@ int main(int argc, char** argv) {
     else if (a == "--time") g_opt.timing = true;
     else if (a == "--time-every") g_opt.time_every = atoi(next().c_str());
     else if (a == "--keep-log") g_opt.keep_log = true;
+    else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   if (g_opt.config.empty()) {

@@ -1,0 +1,53 @@
+"""GPU: the drop-in itself.  oracle/_ref/ref_harness_gpu is the reference's own LTE-Sim
+(SingleCellWithI scenario, unmodified sources) with the product's host plug-in
+(radiosaber_b200/host/rs_gpu_scheduler.h -> C ABI -> CUDA) installed in the eNB instead of the
+reference scheduler class.  It must reproduce, record for record, what the reference classes
+produced on the same CQI / rand() inputs (tests/golden)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.helpers import ROOT, load_golden
+from tools import golden_io
+
+pytestmark = pytest.mark.gpu
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")
+
+CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_small_synth", "a8_fix20x5_synth", "a8_small_synth",
+         "a7_fix20x5_synth", "a7_mix20_synth", "a7_small_synth"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
+    if not os.path.exists(HARNESS):
+        pytest.fail("oracle/_ref/ref_harness_gpu missing: run __graft_entry__.build() where /root/reference is mounted")
+    rec = load_golden(name)
+    S, U, T = int(rec["S"]), int(rec["U"]), int(rec["T"])
+    cfg = {"slices": [], "ues_per_slice": [int((rec["ue_to_slice"] == s).sum()) for s in range(S)]}
+    for s in range(S):
+        a, b, e, p = (int(x) for x in rec["params"][s])
+        cfg["slices"].append({"n_slices": 1, "weight": float(rec["weight"][s]), "video_app": 0, "video_bitrate": 0,
+                              "internet_flow": 0, "if_bitrate": 0, "backlog_flow": 1, "algo_alpha": a,
+                              "algo_beta": b, "algo_epsilon": e, "algo_psi": p})
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg))
+    assert int(rec["cqi_per_rb"]) == 0
+    np.ascontiguousarray(rec["cqi"], dtype=np.uint8).tofile(tmp_path / "cqi.bin")
+    np.ascontiguousarray(rec["rand2"], dtype=np.int32).tofile(tmp_path / "rand.bin")
+    out = tmp_path / "rec.bin"
+    r = subprocess.run([HARNESS, "--gpu", "--algo", str(int(rec["algo"])), "--config", str(tmp_path / "cfg.json"),
+                        "--ttis", str(T), "--cqi", str(tmp_path / "cqi.bin"), "--rand", str(tmp_path / "rand.bin"),
+                        "--out", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
+    got = golden_io.compact(golden_io.parse_record_stream(str(out)))
+    assert int(got["T"]) == T
+    fields = ["rbg_to_ue", "bits", "final_cqi", "avg_before", "avg_after", "tx_after", "cum_bytes", "cum_rbs",
+              "state_before", "state_after", "dt"]
+    if int(rec["algo"]) in (8, 9):
+        fields += ["target", "quota", "rand2"]
+    if int(rec["algo"]) == 7:
+        fields += ["nvs_slice"]
+    for f in fields:
+        assert np.array_equal(np.asarray(got[f]), np.asarray(rec[f])), (name, f)
