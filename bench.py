@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
@@ -205,7 +205,7 @@ def run_reference_arm(args, n_gpus):
 def run_cuda_arm(args, n_gpus):
     import torch
     import torch.distributed as dist
-    from radiosaber_b200 import sched
+    from radiosaber_b200 import sched, shard
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -222,7 +222,7 @@ def run_cuda_arm(args, n_gpus):
     g = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index)
     stream = torch.cuda.current_stream(dev)
     g.set_stream(stream.cuda_stream)
-    cell0 = rank * B   # every rank schedules its own Monte-Carlo cells
+    cell0, _ = shard.shard_cells(B * world, world, rank)   # every rank schedules its own Monte-Carlo cells
 
     # inputs resident in HBM before the timed region: CQI and rand() streams of one step's TTIs
     d_cqi = torch.empty((TT, B, U, G), dtype=torch.uint8, device=dev)
@@ -272,9 +272,8 @@ def run_cuda_arm(args, n_gpus):
     d_stats = torch.zeros((4, S), dtype=torch.int64, device=dev)
     g.stats_device(d_stats.data_ptr())
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.reduce(d_stats, dst=0, op=dist.ReduceOp.SUM)
-    stats = d_stats.cpu().numpy().astype(np.uint64)
+    shard.reduce_stats(d_stats, dst=0)      # NCCL sum-reduce over NVLink (no-op at N=1)
+    stats = d_stats.cpu().numpy().view(np.uint64)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed) --------
     TE = args.e2e_ttis
@@ -347,7 +346,7 @@ def run_cuda_arm(args, n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cells", type=int, default=4096, help="cells per GPU")
