@@ -223,16 +223,26 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
   const int m = l - f - 1, base = f + 1;
   const unsigned lt = (1u << lane) - 1u;
   int nl = 0, nr = 0;
-  for (int c0 = 0; c0 < m; c0 += 32) {
-    const int idx = c0 + lane;
-    const bool valid = idx < m;
-    const int k = valid ? (a[base + idx] >> 12) : 0;
-    const bool fl = valid && k <= p, fr = valid && k >= p;
-    const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
-    if (fl) b.posl[base + nl + __popc(bl & lt)] = (unsigned short)(base + idx);
-    if (fr) b.posr[base + nr + __popc(br & lt)] = (unsigned short)(base + idx);
-    nl += __popc(bl);
-    nr += __popc(br);
+  /* four chunks per trip: the four loads are independent, so their latencies overlap */
+  for (int c0 = 0; c0 < m; c0 += 128) {
+    int k[4];
+    bool v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = c0 + 32 * q + lane;
+      v[q] = idx < m;
+      k[q] = v[q] ? (a[base + idx] >> 12) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = c0 + 32 * q + lane;
+      const bool fl = v[q] && k[q] <= p, fr = v[q] && k[q] >= p;
+      const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
+      if (fl) b.posl[base + nl + __popc(bl & lt)] = (unsigned short)(base + idx);
+      if (fr) b.posr[base + nr + __popc(br & lt)] = (unsigned short)(base + idx);
+      nl += __popc(bl);
+      nr += __popc(br);
+    }
   }
   __syncwarp();
   /* Every key equals the pivot: from here on no comparison depends on the data, so what the rest of
@@ -250,20 +260,36 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
   /* k-th right stopper counted from the right = posr[base + nr - 1 - k] */
   const int nmin = min(nl, nr);
   int K = 0;
-  for (int c0 = 0;; c0 += 32) {
-    const int k = c0 + lane;
-    bool sw = false;
-    if (k < nmin) {
-      const int lp = b.posl[base + k], rp = b.posr[base + nr - 1 - k];
-      sw = lp < rp;
-      if (sw) {
-        const unsigned short t = a[lp];
-        a[lp] = a[rp];
-        a[rp] = t;
+  for (int c0 = 0;; c0 += 64) {   /* two chunks per trip; pairs stop swapping at one k and never resume */
+    bool sw[2];
+    int lp[2], rp[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = c0 + 32 * q + lane;
+      sw[q] = false;
+      lp[q] = 0;
+      rp[q] = 0;
+      if (k < nmin) {
+        lp[q] = b.posl[base + k];
+        rp[q] = b.posr[base + nr - 1 - k];
+        sw[q] = lp[q] < rp[q];
       }
     }
-    const unsigned bs = __ballot_sync(kFull, sw);
-    if (bs != kFull) { K = c0 + __ffs(~bs) - 1; break; }
+    unsigned short t0[2], t1[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      t0[q] = a[lp[q]];
+      t1[q] = a[rp[q]];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (sw[q]) {
+        a[lp[q]] = t1[q];
+        a[rp[q]] = t0[q];
+      }
+    const unsigned bs0 = __ballot_sync(kFull, sw[0]), bs1 = __ballot_sync(kFull, sw[1]);
+    if (bs0 != kFull) { K = c0 + __ffs(~bs0) - 1; break; }
+    if (bs1 != kFull) { K = c0 + 32 + __ffs(~bs1) - 1; break; }
   }
   int cut = (K < nl) ? (int)b.posl[base + K] : 0x7fffffff;
   if (K >= 1) cut = min(cut, (int)b.posr[base + nr - K]);
@@ -274,8 +300,10 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
 /* All kThreads threads of the CTA call this. On return b.out[0..n) holds the entries in the order
  * std::sort leaves them.  Ranges of one recursion depth are independent, so each level hands the
  * ranges longer than _S_threshold to the warps, one range per warp at a time. */
-__device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+/* `rot` rotates which warp takes which range: warp w of every CTA sits on SM sub-partition w % 4, so
+ * without it the single-range levels of all resident cells would pile up on one scheduler. */
+__device__ void sort_desc(const SortBufs& b, int n, int depth_limit, int rot) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = ((tid >> 5) + rot) % kWarps;
   const int nw = (n + 31) >> 5;
   if (tid == 0) {
     b.seg0[0] = (unsigned)n << 16;
@@ -338,10 +366,11 @@ __device__ void sort_desc(const SortBufs& b, int n, int depth_limit) {
       const int v = __shfl_up_sync(kFull, incl, d);
       if (lane >= d) incl += v;
     }
-    if (lane == 31) b.misc[warp] = (unsigned)incl;
+    const int pw = tid >> 5;   /* physical warp: the scan runs over threads in tid order */
+    if (lane == 31) b.misc[pw] = (unsigned)incl;
     __syncthreads();
     int base = incl - s;
-    for (int w = 0; w < warp; ++w) base += (int)b.misc[w];
+    for (int w = 0; w < pw; ++w) base += (int)b.misc[w];
     for (int q = q0; q < q0 + per && q < Q; ++q) {
       const int c = (int)b.cnt[q];
       b.cnt[q] = (unsigned short)base;
@@ -506,32 +535,35 @@ __device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int
 }
 
 /* MaximizeCell's first-fit scan over the sorted (rbg,slice) entries, transport.cpp:362-375, by one
- * warp: 32 entries at a time; inside a chunk the lowest feasible lane is accepted, the others
- * re-checked against it, until no feasible lane is left. */
+ * warp, 32 entries at a time.  Remaining quotas (c.quota) and the RBG->slice map (c.outsl, 0xff =
+ * free) live in shared memory between chunks; inside a chunk every lane keeps the remaining quota
+ * of its own entry's slice in a register, one redux.sync(min) finds the lowest feasible lane and
+ * broadcasts its (rbg,slice), and the other lanes drop out if they lost their RBG or their slice
+ * ran out.  c.quota is consumed (the host-visible quotas were written by slice_quotas). */
 __device__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
   const int n = d.sort_n;
-  int rem_a = (lane < d.S) ? c.quota[lane] : 0;
-  int rem_b = (lane + 32 < d.S) ? c.quota[lane + 32] : 0;
-  unsigned long long free_mask = (d.G >= 64) ? ~0ull : ((1ull << d.G) - 1ull);
-  for (int base = 0; base < n && free_mask != 0ull; base += 32) {
+  int nfree = d.G;
+  for (int base = 0; base < n && nfree > 0; base += 32) {
     const int i = base + lane;
     const unsigned e = (i < n) ? sorted[i] : 0u;
     const int g = (e >> 6) & 63, s = e & 63;
-    const int ra = __shfl_sync(kFull, rem_a, s & 31), rb = __shfl_sync(kFull, rem_b, s & 31);
-    bool feas = (i < n) && ((free_mask >> g) & 1ull) && ((s < 32 ? ra : rb) > 0);
-    unsigned m = __ballot_sync(kFull, feas);
-    while (m) {
-      const int ld = __ffs(m) - 1;
-      const unsigned pe = __shfl_sync(kFull, e, ld);
-      const int pg = (pe >> 6) & 63, ps = pe & 63;
-      if (lane == 0) c.outsl[pg] = (unsigned char)ps;
-      free_mask &= ~(1ull << pg);
-      if (lane == (ps & 31)) { if (ps < 32) rem_a--; else rem_b--; }
-      const int na = __shfl_sync(kFull, rem_a, ps & 31), nb = __shfl_sync(kFull, rem_b, ps & 31);
-      const int nrem = ps < 32 ? na : nb;
-      feas = feas && lane > ld && g != pg && !(s == ps && nrem <= 0);
-      m = __ballot_sync(kFull, feas);
+    int rem = c.quota[s];
+    bool feas = (i < n) && c.outsl[g] == 0xff && rem > 0;
+    unsigned v = feas ? (((unsigned)lane << 12) | (e & 0xfffu)) : 0xffffffffu;
+    unsigned w = __reduce_min_sync(kFull, v);
+    while (w != 0xffffffffu) {
+      const int pg = (w >> 6) & 63, ps = w & 63, ld = (int)(w >> 12);
+      if (s == ps) rem--;
+      if (lane == ld) {
+        c.outsl[pg] = (unsigned char)ps;
+        c.quota[ps] = rem;
+      }
+      nfree--;
+      feas = feas && lane != ld && g != pg && rem > 0;
+      if (!feas) v = 0xffffffffu;
+      w = __reduce_min_sync(kFull, v);
     }
+    __syncwarp();
   }
 }
 
@@ -646,6 +678,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     const uint8_t* act = r.active ? r.active + (size_t)t * r.active_tti_stride + (size_t)b * U : nullptr;
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
+    const int rot = (b + t) % kWarps;   /* which warp plays the single-warp roles this TTI */
     short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
     int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
     uint8_t* o_mcs = r.mcs ? r.mcs + tb * U : nullptr;
@@ -708,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       for (int ch = 0; ch < d.n_chunks; ++ch) {
         const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
         const int j0 = d.slice_ptr[s0], j1 = d.slice_ptr[s1];
-        if (ch == 0 && warp == kWarps - 1)
+        if (ch == 0 && warp == (rot + kWarps - 1) % kWarps)
           slice_quotas(d, c, r.rand2[2 * tb], r.rand2[2 * tb + 1], lane, o_tgt, o_quo);
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
@@ -768,15 +801,15 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       /* ---- P3/P4: inter-slice assignment ---------------------------------------------------- */
       if (ALGO == 9) {
 #ifndef RS_SKIP_SORT
-        sort_desc(c.sb, d.sort_n, d.sort_depth);
+        sort_desc(c.sb, d.sort_n, d.sort_depth, kWarps - rot);
 #endif
         RS_TICK(2);
 #ifndef RS_SKIP_GREEDY
-        if (warp == 0) greedy_maxcell(d, c, c.sb.out, lane);
+        if (warp == rot) greedy_maxcell(d, c, c.sb.out, lane);
 #endif
         RS_TICK(3);
       } else {
-        if (warp == 0) greedy_by_row(d, c, c.sb.a, lane);
+        if (warp == rot) greedy_by_row(d, c, c.sb.a, lane);
       }
       __syncthreads();
 
@@ -897,7 +930,7 @@ __global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* k
   const uint8_t* k = keys + (size_t)blockIdx.x * n;
   for (int i = threadIdx.x; i < n; i += kThreads) c.sb.a[i] = (unsigned short)(((k[i] & 15) << 12) | i);
   __syncthreads();
-  sort_desc(c.sb, n, depth);
+  sort_desc(c.sb, n, depth, blockIdx.x % kWarps);
   for (int i = threadIdx.x; i < n; i += kThreads) perm[(size_t)blockIdx.x * n + i] = c.sb.out[i] & 0xfff;
 }
 
