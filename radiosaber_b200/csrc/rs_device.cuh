@@ -56,8 +56,14 @@ struct ConstTables {
 __constant__ ConstTables c_tab;
 
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
+struct Layout {
+  int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
+      target, quota, frb, wd, outsl, off, tval, misc, total;
+};
+
 struct DevCfg {
   int algo, S, U, G, R, rbg, cqi_per_rb, data;
+  Layout lay;              /* shared-memory offsets, computed once on the host (make_layout) */
   int n_cells;
   int n_chunks;            /* metric-table chunks (ranges of slices) */
   int m_cap;               /* metric-table capacity in UEs */
@@ -90,10 +96,6 @@ struct RunArgs {
 };
 
 /* ---- shared-memory layout (same function on host and device) --------------------------------- */
-struct Layout {
-  int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, total;
-};
 __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
 /* The cumulative byte / RB counters stay in HBM (touched only for the few UEs a TTI serves); the
  * metric table is dead once the sort starts, so it shares the bytes of the sort's slot arrays
@@ -223,8 +225,10 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
   const int m = l - f - 1, base = f + 1;
   const unsigned lt = (1u << lane) - 1u;
   int nl = 0, nr = 0;
-  /* four chunks per trip: the four loads are independent, so their latencies overlap */
-  for (int c0 = 0; c0 < m; c0 += 128) {
+  /* four chunks per trip while the range is long (the four loads are independent, so their
+   * latencies overlap), then one chunk at a time */
+  int c0 = 0;
+  for (; c0 + 96 < m; c0 += 128) {
     int k[4];
     bool v[4];
 #pragma unroll
@@ -243,6 +247,17 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
       nl += __popc(bl);
       nr += __popc(br);
     }
+  }
+  for (; c0 < m; c0 += 32) {
+    const int idx = c0 + lane;
+    const bool valid = idx < m;
+    const int k = valid ? (a[base + idx] >> 12) : 0;
+    const bool fl = valid && k <= p, fr = valid && k >= p;
+    const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
+    if (fl) b.posl[base + nl + __popc(bl & lt)] = (unsigned short)(base + idx);
+    if (fr) b.posr[base + nr + __popc(br & lt)] = (unsigned short)(base + idx);
+    nl += __popc(bl);
+    nr += __popc(br);
   }
   __syncwarp();
   /* Every key equals the pivot: from here on no comparison depends on the data, so what the rest of
@@ -638,8 +653,7 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Layout L = make_layout(d.S, d.U, d.G, d.m_cap);
-  Cell c = carve(smem, L);
+  Cell c = carve(smem, d.lay);
   c.sb.eq_tab = d.eq_tab;
   c.sb.eq_max = d.eq_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -921,9 +935,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
 /* ---- test hook: the sort alone, one CTA per array --------------------------------------------- */
 __global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* keys, int n, int depth, int* perm,
-                                                                const unsigned short* eq_tab, int eq_max) {
+                                                                const unsigned short* eq_tab, int eq_max, const Layout L) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Layout L = make_layout(1, 0, n, 0);   /* S*G == n */
   Cell c = carve(smem, L);
   c.sb.eq_tab = eq_tab;
   c.sb.eq_max = eq_max;

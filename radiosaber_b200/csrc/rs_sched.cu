@@ -419,6 +419,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   d.n_chunks = (int)chunks.size() - 1;
   d.m_cap = m_cap;
   h->layout = rs::make_layout(S, U, G, m_cap);
+  d.lay = h->layout;
 
   /* ---- device ---- */
   {
@@ -752,7 +753,7 @@ int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t 
   if (e != cudaSuccess) { cudaFree(dk); return fail(RS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
   e = cudaMemcpy(dk, keys, (size_t)n_arrays * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp, de, de ? eq_max : 0);
+    rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp, de, de ? eq_max : 0, L);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(perm_out, dp, (size_t)n_arrays * n * 4, cudaMemcpyDeviceToHost);
