@@ -227,7 +227,7 @@ def run_cuda_arm(args, n_gpus):
     # inputs resident in HBM before the timed region: CQI and rand() streams of one step's TTIs
     d_cqi = torch.empty((TT, B, U, G), dtype=torch.uint8, device=dev)
     d_r2 = torch.empty((TT, B, 2), dtype=torch.int32, device=dev)
-    g.synth_cqi(SEED, cell0, 0, TT, 1, d_cqi.data_ptr())
+    g.synth_cqi(SEED, cell0, 0, TT, d_cqi.data_ptr())
     g.synth_rand2(SEED, cell0, 0, TT, d_r2.data_ptr())
     d_rbg = torch.empty((TT, B, G), dtype=torch.int16, device=dev)
     d_bits = torch.empty((TT, B, U), dtype=torch.int32, device=dev)
@@ -276,39 +276,55 @@ def run_cuda_arm(args, n_gpus):
     stats = d_stats.cpu().numpy().view(np.uint64)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed) --------
-    TE = args.e2e_ttis
-    h_cqi = torch.empty((TE, B, U, G), dtype=torch.uint8).pin_memory()
-    h_cqi.copy_(d_cqi[:TE].cpu())
-    h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
-    h_r2.copy_(d_r2[:TE].cpu())
-    h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
-    h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
-    h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
+    # Headline e2e: CQI in the 4-bit wire layout (cqi_per_rb = 2), refreshed every TTI.  Variants:
+    # the u8 layout, and CQI refreshed every 40 TTIs like the reference's CQI_INTERVAL.
     import ctypes as C
-    o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
+    TE = args.e2e_ttis
+    KE = max(2, min(K, args.e2e_steps))
     _, dte = workload.tti_clock(TE)
 
-    def e2e_step():
-        sched._check(sched.lib().rs_run_host(g._h, TE, C.c_void_p(h_cqi.data_ptr()), C.c_void_p(h_r2.data_ptr()),
-                                             None, dte.ctypes.data_as(C.c_void_p), C.byref(o), args.e2e_ttis_per_launch))
+    def e2e_run(layout, refresh):
+        ge = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index, cqi_per_rb=layout)
+        n_slabs = -(-TE // refresh)
+        row = G // 2 if layout == 2 else G
+        d_tmp = torch.empty((n_slabs, B, U, row), dtype=torch.uint8, device=dev)
+        ge.synth_cqi(SEED, cell0, 0, n_slabs, d_tmp.data_ptr())
+        ge.sync()
+        h_cqi = torch.empty((n_slabs, B, U, row), dtype=torch.uint8).pin_memory()
+        h_cqi.copy_(d_tmp)
+        del d_tmp
+        h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
+        h_r2.copy_(d_r2[:TE])
+        h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
+        h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
+        h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
+        o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
 
-    for _ in range(max(1, min(W, 2))):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    KE = max(2, min(K, args.e2e_steps))
-    t0 = time.perf_counter()
-    for _ in range(KE):
-        e2e_step()          # synchronous: returns when the results are in host memory
-    torch.cuda.synchronize(dev)
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * TE * KE / float(te.item())
-    h2d = TE * (B * U * G + B * 2 * 4) + TE * 8
-    d2h = TE * (B * G * 2 + B * U * 4 + B * U)
+        def one():
+            sched._check(sched.lib().rs_run_host(ge._h, TE, C.c_void_p(h_cqi.data_ptr()), refresh,
+                                                 C.c_void_p(h_r2.data_ptr()), None, dte.ctypes.data_as(C.c_void_p),
+                                                 C.byref(o), args.e2e_ttis_per_launch))
+
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            one()          # synchronous: returns when the results are in host memory
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ge.close()
+        h2d = n_slabs * B * U * row + TE * (B * 2 * 4) + TE * 8
+        d2h = TE * (B * G * 2 + B * U * 4 + B * U)
+        return world * B * TE * KE / float(te.item()), h2d, d2h
+
+    e2e_value, h2d, d2h = e2e_run(2, 1)
+    e2e_u8, h2d_u8, _ = e2e_run(0, 1)
+    e2e_r40, h2d_r40, _ = e2e_run(2, 40)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -324,7 +340,10 @@ def run_cuda_arm(args, n_gpus):
             "gpu_launches": int(tl.item()),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ttis_per_step": TE, "steps": KE,
-                    "api": "rs_run_host (C ABI, pinned host buffers, copies overlapped with kernels)"},
+                    "api": "rs_run_host (C ABI, pinned host buffers, copies overlapped with kernels); CQI in the "
+                           "4-bit layout (cqi_per_rb=2), fresh CQI every TTI",
+                    "variants": {"u8_cqi_refresh1": {"value": e2e_u8, "h2d_bytes_per_step": h2d_u8},
+                                 "packed_cqi_refresh40": {"value": e2e_r40, "h2d_bytes_per_step": h2d_r40}}},
             "roofline": {"bound": "hbm", "kernel": f"rs_tti_kernel<{args.algo}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_tti": alg, "cell_ttis_per_launch": B * ttis_launch,
@@ -353,7 +372,7 @@ def main():
     ap.add_argument("--algo", type=int, default=9)
     ap.add_argument("--ttis-per-step", type=int, default=48)
     ap.add_argument("--ttis-per-launch", type=int, default=16)
-    ap.add_argument("--e2e-ttis", type=int, default=16)
+    ap.add_argument("--e2e-ttis", type=int, default=40)
     ap.add_argument("--e2e-ttis-per-launch", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)

@@ -46,7 +46,9 @@ typedef struct rs_config {
   int32_t n_ues;            /* U; user j == UE id j (flows/application/Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (core/spectrum/bandwidth-manager.cpp:98-102) */
   int32_t rbg_size;         /* get_rbg_size(): 8 (utility/eesm-effective-sinr.h:82-103) */
-  int32_t cqi_per_rb;       /* 0: cqi[U][G], one value per RBG; 1: cqi[U][n_rbs] */
+  int32_t cqi_per_rb;       /* CQI layout per UE: 0 = u8 [G], one value per RBG; 1 = u8 [n_rbs], one per RB
+                               (what ENodeB::UserEquipmentRecord::GetCQI holds); 2 = 4-bit [G/2], RBG 2k in the
+                               low and 2k+1 in the high nibble of byte k (a CQI is 4 bits on the air) */
   int32_t data_to_transmit; /* bytes queued per bearer; 100000000 = infinite buffer
                                (downlink-transport-scheduler.cpp:123-125) */
   int32_t reserved;
@@ -99,7 +101,7 @@ int rs_reset_state(rs_handle* h);
 /* One TTI for the whole batch == PacketScheduler::Schedule() (packet-scheduler.cpp:72-90):
  * UpdateAverageTransmissionRate, SelectFlowsToSchedule, RBsAllocation and the byte accounting of
  * DoStopSchedule.  HOST buffers in, HOST buffers out, synchronous.
- *   cqi    [B][U][G] (or [B][U][n_rbs] when cqi_per_rb), values 1..15
+ *   cqi    [B][U][row] with row = G, n_rbs or G/2 bytes by cfg.cqi_per_rb, values 1..15
  *   rand2  [B][2]  the two rand() draws of downlink-transport-scheduler.cpp:490,511, each in
  *                  [0, INT32_MAX - S]; may be NULL for ids 1 and 7
  *   active [B][U]  1 = bearer has packets (GetDestination()->ACTIVE && HasPackets); NULL = all
@@ -109,7 +111,9 @@ int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_
             const rs_outputs* out);
 
 /* n_ttis consecutive TTIs with every input and output already in DEVICE memory.
- *   d_cqi   [T][B][U][G]; cqi_tti_stride = bytes between TTIs (0 = the same CQI every TTI)
+ *   d_cqi   [ceil(T/cqi_refresh)][B][U][row]: TTI t reads slab t / cqi_refresh (the reference refreshes
+ *           CQI every 40 TTIs, enb-mac-entity.cc:38; the headline workload every TTI);
+ *           cqi_tti_stride = bytes between slabs
  *   d_rand2 [T][B][2]
  *   d_active [T][B][U] or NULL, active_tti_stride like cqi_tti_stride
  *   dt      HOST array [T]
@@ -117,20 +121,20 @@ int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_
  *   ttis_per_launch  TTIs handled by one kernel launch with the cell state held on chip
  *                    (<= 0: library default)
  * Asynchronous on the handle's stream; rs_sync() waits. */
-int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride,
+int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                   const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
                   const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch);
 
 /* Same, HOST buffers in and out ([T][B][...]): the library stages them through pinned memory in
  * chunks and overlaps the copies with the kernels.  Synchronous. */
-int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active,
-                const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
+int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
+                const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
 
 /* Synthetic workload of SURVEY.md section 8(d), generated on the device (bit-identical twin of
  * radiosaber_b200/workload.py): CQI i.i.d. from the cqi-traces-noise0 histogram, counter-based so
- * any (cell, tti) shard can be produced on any GPU. d_out: uint8 [n_ttis][B][U][G]. */
-int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t refresh,
-                 uint8_t* d_out);
+ * any (cell, epoch) shard can be produced on any GPU.  d_out: n_slabs slabs [B][U][row] in the handle's
+ * CQI layout (0 or 2); slab j is the CQI of epoch epoch0 + j (epoch = tti / refresh). */
+int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t epoch0, int32_t n_slabs, uint8_t* d_out);
 /* d_out: int32 [n_ttis][B][2], values in [0, INT32_MAX - S]. */
 int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t* d_out);
 

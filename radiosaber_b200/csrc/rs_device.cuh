@@ -62,7 +62,8 @@ struct Layout {
 };
 
 struct DevCfg {
-  int algo, S, U, G, R, rbg, cqi_per_rb, data;
+  int algo, S, U, G, R, rbg, cqi_per_rb, data;   /* cqi_per_rb: 0 u8/RBG, 1 u8/RB, 2 two RBGs per byte */
+  int cqi_row;             /* bytes of CQI per UE: G, R or G/2 */
   Layout lay;              /* shared-memory offsets, computed once on the host (make_layout) */
   int n_cells;
   int n_chunks;            /* metric-table chunks (ranges of slices) */
@@ -86,7 +87,8 @@ struct DevCfg {
 };
 
 struct RunArgs {
-  const uint8_t* cqi; long long cqi_tti_stride;
+  const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
+  int t0, cqi_refresh;
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
   const double* dt;        /* device [T] */
@@ -468,6 +470,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
 
 /* CQI of UE u on the first RB of RBG g (the RB the metric is evaluated on, transport.cpp:536) */
 __device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* cqi, int u, int g) {
+  if (d.cqi_per_rb == 2) return (cqi[(size_t)u * d.cqi_row + (g >> 1)] >> (4 * (g & 1))) & 15;
   return d.cqi_per_rb ? (cqi[(size_t)u * d.R + (size_t)g * d.rbg] & 15) : (cqi[(size_t)u * d.G + g] & 15);
 }
 
@@ -615,11 +618,11 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
     while (m) {
       const int g = __ffsll((long long)m) - 1;
       m &= m - 1;
-      if (d.cqi_per_rb) {
+      if (d.cqi_per_rb == 1) {
         const uint8_t* p = cqi + (size_t)u * d.R + (size_t)g * d.rbg;
         for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, c.tval[p[r] & 15]);
       } else {
-        const double t = c.tval[cqi[(size_t)u * d.G + g] & 15];
+        const double t = c.tval[cqi_first_rb(d, cqi, u, g)];
         for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, t);
       }
     }
@@ -687,8 +690,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   long long last_ = clock64();
 #endif
   for (int t = 0; t < r.T; ++t) {
-    const uint8_t* cqi = r.cqi + (size_t)t * r.cqi_tti_stride +
-                         (size_t)b * U * (d.cqi_per_rb ? d.R : G);
+    const uint8_t* cqi = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride +
+                         (size_t)b * U * d.cqi_row;
     const uint8_t* act = r.active ? r.active + (size_t)t * r.active_tti_stride + (size_t)b * U : nullptr;
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
@@ -763,7 +766,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           c.mtab[q] = cq ? __ddiv_rn(d.epow[d.ue_to_slice[u] * 16 + cq], c.den[u]) : 0.0;
         }
         __syncthreads();
-        const bool vec4 = !d.cqi_per_rb && (G % 4 == 0);
+        const bool vec4 = d.cqi_per_rb != 1 && (G % 4 == 0);
+        const bool nib = d.cqi_per_rb == 2;
         if (vec4) {
           const int g4 = G >> 2;
           const int items = (s1 - s0) * g4;
@@ -775,7 +779,13 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
               const int u = d.slice_ues[j];
               if (act && !act[u]) continue;
-              const unsigned w = *(const unsigned*)(cqi + (size_t)u * G + g0);
+              unsigned w;
+              if (nib) {   /* four nibbles -> one per byte, then the same extraction as the u8 layout */
+                const unsigned h = *(const unsigned short*)(cqi + (size_t)u * d.cqi_row + (g0 >> 1));
+                w = (h & 0xfu) | ((h & 0xf0u) << 4) | ((h & 0xf00u) << 8) | ((h & 0xf000u) << 12);
+              } else {
+                w = *(const unsigned*)(cqi + (size_t)u * G + g0);
+              }
               const double* row = c.mtab + (j - j0) * kMStride;
 #pragma unroll
               for (int x = 0; x < 4; ++x) {
@@ -956,22 +966,35 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 }
 struct CdfTable { unsigned thr[14]; };
 
-__global__ void rs_synth_cqi_kernel(uint8_t* out, unsigned long long key, long long cell0, long long tti0,
-                                    int n_ttis, int n_cells, int U, int G, int refresh, CdfTable cdf) {
-  const size_t total = (size_t)n_ttis * n_cells * U * G;
+__device__ __forceinline__ int synth_one(unsigned long long key, unsigned long long epoch, unsigned long long cell,
+                                         unsigned long long ue, unsigned long long rbg, const CdfTable& cdf) {
+  unsigned long long ctr = (epoch << 40) ^ (cell << 20) ^ (ue << 8) ^ rbg;
+  ctr ^= (ue >> 12) * 0xD6E8FEB86659FD93ull;
+  const unsigned u32 = (unsigned)(splitmix64(ctr ^ key) >> 32);
+  int cq = 1;
+#pragma unroll
+  for (int k = 0; k < 14; ++k) cq += (u32 >= cdf.thr[k]);
+  return cq;
+}
+
+/* n_slabs slabs of [n_cells][U][G] (packed = 0) or [n_cells][U][G/2] (packed = 1, RBG 2k in the low
+ * nibble); slab j holds the CQI of TTI epoch epoch0 + j. */
+__global__ void rs_synth_cqi_kernel(uint8_t* out, unsigned long long key, long long cell0, long long epoch0,
+                                    int n_slabs, int n_cells, int U, int G, int packed, CdfTable cdf) {
+  const int row = packed ? G / 2 : G;
+  const size_t total = (size_t)n_slabs * n_cells * U * row;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const unsigned long long rbg = i % G;
-    size_t r = i / G;
+    const unsigned long long col = i % row;
+    size_t r = i / row;
     const unsigned long long ue = r % U; r /= U;
     const unsigned long long cell = cell0 + (long long)(r % n_cells); r /= n_cells;
-    const unsigned long long epoch = (unsigned long long)(tti0 + (long long)r) / (unsigned long long)refresh;
-    unsigned long long ctr = (epoch << 40) ^ (cell << 20) ^ (ue << 8) ^ rbg;
-    ctr ^= (ue >> 12) * 0xD6E8FEB86659FD93ull;
-    const unsigned u32 = (unsigned)(splitmix64(ctr ^ key) >> 32);
-    int cq = 1;
-#pragma unroll
-    for (int k = 0; k < 14; ++k) cq += (u32 >= cdf.thr[k]);
-    out[i] = (uint8_t)cq;
+    const unsigned long long epoch = (unsigned long long)(epoch0 + (long long)r);
+    if (packed) {
+      const int lo = synth_one(key, epoch, cell, ue, 2 * col, cdf), hi = synth_one(key, epoch, cell, ue, 2 * col + 1, cdf);
+      out[i] = (uint8_t)(lo | (hi << 4));
+    } else {
+      out[i] = (uint8_t)synth_one(key, epoch, cell, ue, col, cdf);
+    }
   }
 }
 

@@ -189,6 +189,7 @@ struct rs_handle {
     DevBuf<int> rand2, tbs_bits, slice_target, slice_quota, nvs_slice;
     DevBuf<short> rbg_to_ue;
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    int slab0 = -1;   /* first CQI slab resident in this slot (rs_run_host with a refresh > 1) */
   } slot[2];
 };
 
@@ -328,12 +329,15 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
 
   rs::DevCfg& d = h->d;
   d.algo = algo; d.S = S; d.U = U; d.G = G; d.R = cfg->n_rbs; d.rbg = cfg->rbg_size;
-  d.cqi_per_rb = cfg->cqi_per_rb ? 1 : 0;
+  if (cfg->cqi_per_rb < 0 || cfg->cqi_per_rb > 2) { delete h; return fail(RS_ERR_ARG, "cqi_per_rb must be 0, 1 or 2"); }
+  if (cfg->cqi_per_rb == 2 && (G % 8) != 0) { delete h; return fail(RS_ERR_UNSUPPORTED, "4-bit CQI layout needs a multiple of 8 RBGs"); }
+  d.cqi_per_rb = cfg->cqi_per_rb;
   d.data = cfg->data_to_transmit;
   d.n_cells = n_cells;
   d.sort_n = G * S;
   { int lg = 0; for (int m = d.sort_n; m > 1; m >>= 1) lg++; d.sort_depth = 2 * lg; }
-  h->cqi_cols = d.cqi_per_rb ? d.R : G;
+  h->cqi_cols = d.cqi_per_rb == 1 ? d.R : (d.cqi_per_rb == 2 ? G / 2 : G);
+  d.cqi_row = h->cqi_cols;
 
 #define BAIL(code_)            \
   do {                         \
@@ -537,10 +541,10 @@ int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cu
   return RS_OK;
 }
 
-int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride,
+int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                   const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
                   const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
-  if (!h || !d_cqi || !dt || n_ttis < 0) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
+  if (!h || !d_cqi || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
   if ((h->d.algo == 8 || h->d.algo == 9) && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
   if (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3)) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
   if (n_ttis == 0) return RS_OK;
@@ -552,8 +556,10 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
     a.T = std::min(ttis_per_launch, n_ttis - t0);
-    a.cqi = d_cqi + (size_t)t0 * cqi_tti_stride;
+    a.cqi = d_cqi;
     a.cqi_tti_stride = cqi_tti_stride;
+    a.t0 = t0;
+    a.cqi_refresh = cqi_refresh;
     a.rand2 = d_rand2 ? d_rand2 + (size_t)t0 * B * 2 : nullptr;
     a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
     a.active_tti_stride = active_tti_stride;
@@ -575,9 +581,9 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
   return RS_OK;
 }
 
-int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active,
-                const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
-  if (!h || !cqi || !dt || n_ttis < 0) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
+int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
+                const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
+  if (!h || !cqi || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
   if ((h->d.algo == 8 || h->d.algo == 9) && !rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
@@ -591,12 +597,19 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t*
   CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
   CU(cudaEventRecord(dt_ready, h->stream));
   int k = 0;
-  for (int t0 = 0; t0 < n_ttis; t0 += TC, ++k) {
+  h->slot[0].slab0 = h->slot[1].slab0 = -1;
+  for (int t0 = 0, T = 0; t0 < n_ttis; t0 += T, ++k) {
     rs_handle::Slot& s = h->slot[k & 1];
-    const int T = std::min(TC, n_ttis - t0);
+    T = std::min(TC, n_ttis - t0);
+    /* a chunk never straddles more CQI slabs than the slot holds: with a refresh > 1 it ends at the
+     * next refresh boundary and needs exactly one slab */
+    if (cqi_refresh > 1) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
+    const int slab0 = t0 / cqi_refresh, n_slabs = (t0 + T - 1) / cqi_refresh - slab0 + 1;
     /* inputs: the slot's previous kernel must be done with them */
     if (k >= 2) CU(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
-    CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)t0 * B * U * C, (size_t)T * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
+    if (!(cqi_refresh > 1 && s.slab0 == slab0))   /* the slab may still be resident from the chunk before last */
+      CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)slab0 * B * U * C, (size_t)n_slabs * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
+    s.slab0 = slab0;
     if (rand2) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * 2, (size_t)T * B * 2 * 4, cudaMemcpyHostToDevice, h->copy_in));
     if (active) CU(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
     CU(cudaEventRecord(s.in_done, h->copy_in));
@@ -606,6 +619,7 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t*
     rs::RunArgs a{};
     a.T = T;
     a.cqi = s.cqi.p; a.cqi_tti_stride = (long long)(B * U * C);
+    a.t0 = t0 - slab0 * cqi_refresh; a.cqi_refresh = cqi_refresh;
     a.rand2 = rand2 ? s.rand2.p : nullptr;
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
     a.dt = h->dt_dev.p + t0;
@@ -645,13 +659,12 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, const int32_t*
 
 int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
             const rs_outputs* out) {
-  return rs_run_host(h, 1, cqi, rand2, active, &dt, out, 1);
+  return rs_run_host(h, 1, cqi, 1, rand2, active, &dt, out, 1);
 }
 
-int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t refresh,
-                 uint8_t* d_out) {
-  if (!h || !d_out || n_ttis < 0 || refresh < 1) return fail(RS_ERR_ARG, "rs_synth_cqi: bad argument");
-  if (h->d.cqi_per_rb) return fail(RS_ERR_UNSUPPORTED, "synthetic CQI is one value per RBG");
+int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t epoch0, int32_t n_slabs, uint8_t* d_out) {
+  if (!h || !d_out || n_slabs < 0) return fail(RS_ERR_ARG, "rs_synth_cqi: bad argument");
+  if (h->d.cqi_per_rb == 1) return fail(RS_ERR_UNSUPPORTED, "synthetic CQI is one value per RBG");
   CU(cudaSetDevice(h->device));
   /* histogram of cqi-traces-noise0; thresholds as in radiosaber_b200/workload.py */
   static const unsigned long long hist[15] = {19075, 7082, 33860, 261099, 438688, 199446, 518174, 661977,
@@ -670,11 +683,11 @@ int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32
     return z ^ (z >> 31);
   };
   const unsigned long long key = sm64((seed & 0xFFFFFFFFull) | (0x43514900ull << 32));
-  const size_t total_n = (size_t)n_ttis * h->B * h->d.U * h->d.G;
+  const size_t total_n = (size_t)n_slabs * h->B * h->d.U * h->cqi_cols;
   if (total_n == 0) return RS_OK;
   const int blocks = (int)std::min<size_t>((total_n + 255) / 256, 148 * 16);
-  rs::rs_synth_cqi_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, tti0, n_ttis, h->B, h->d.U, h->d.G,
-                                                         refresh, cdf);
+  rs::rs_synth_cqi_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, epoch0, n_slabs, h->B, h->d.U, h->d.G,
+                                                         h->d.cqi_per_rb == 2 ? 1 : 0, cdf);
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;

@@ -71,11 +71,11 @@ def lib():
         L.rs_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.rs_reset_state.argtypes = [C.c_void_p]
         L.rs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(_Out)]
-        L.rs_run_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+        L.rs_run_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.POINTER(_Out), C.c_int32]
-        L.rs_run_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        L.rs_run_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(_Out), C.c_int32]
-        L.rs_synth_cqi.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_synth_cqi.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
         L.rs_synth_rand2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
         L.rs_stats_device.argtypes = [C.c_void_p, C.c_void_p]
         L.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -146,7 +146,7 @@ class Scheduler:
         self.rbg_size = int(rbg_size)
         self.G = self.R // self.rbg_size
         self.cqi_per_rb = int(cqi_per_rb)
-        self.cqi_cols = self.R if self.cqi_per_rb else self.G
+        self.cqi_cols = {0: self.G, 1: self.R, 2: self.G // 2}[self.cqi_per_rb]
         self.device = int(device)
         self._row_m1 = None if tbs_row_m1 is None else np.ascontiguousarray(tbs_row_m1, dtype=np.int32)
         cfg = _Cfg(self.algo, self.S, self.U, self.R, self.rbg_size, self.cqi_per_rb, int(data_to_transmit), 0,
@@ -225,34 +225,35 @@ class Scheduler:
         _check(lib().rs_step(self._h, _ptr(cqi), _ptr(rand2), _ptr(act), float(dt), C.byref(o)))
         return out
 
-    def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0):
-        """T TTIs with host arrays [T][B][...]; copies overlap the kernels."""
+    def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0, cqi_refresh=1):
+        """T TTIs with host arrays [T][B][...] (cqi: one slab per cqi_refresh TTIs); copies overlap
+        the kernels."""
         B, U = self.B, self.U
         dt = np.ascontiguousarray(dt, dtype=np.float64)
         T = int(dt.shape[0])
         cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
-        assert cqi.size == T * B * U * self.cqi_cols, cqi.shape
+        assert cqi.size == -(-T // cqi_refresh) * B * U * self.cqi_cols, cqi.shape
         rand2 = None if rand2 is None else np.ascontiguousarray(rand2, dtype=np.int32).reshape(T, B, 2)
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
         out, o = self._host_outputs(T, want_aux)
-        _check(lib().rs_run_host(self._h, T, _ptr(cqi), _ptr(rand2), _ptr(act), _ptr(dt), C.byref(o),
-                                 int(ttis_per_launch)))
+        _check(lib().rs_run_host(self._h, T, _ptr(cqi), int(cqi_refresh), _ptr(rand2), _ptr(act), _ptr(dt),
+                                 C.byref(o), int(ttis_per_launch)))
         return out
 
     # ---- device-resident path (raw device pointers, e.g. torch tensors' data_ptr()) -----------
     def run_device(self, n_ttis, d_cqi, cqi_tti_stride, d_rand2, dt, d_out=None, d_active=0,
-                   active_tti_stride=0, ttis_per_launch=0):
+                   active_tti_stride=0, ttis_per_launch=0, cqi_refresh=1):
         dt = np.ascontiguousarray(dt, dtype=np.float64)
         assert dt.shape[0] >= n_ttis
         o = _Out(*[(d_out or {}).get(k) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
                                                     "slice_quota", "nvs_slice")])
-        _check(lib().rs_run_device(self._h, int(n_ttis), C.c_void_p(d_cqi), int(cqi_tti_stride),
+        _check(lib().rs_run_device(self._h, int(n_ttis), C.c_void_p(d_cqi), int(cqi_tti_stride), int(cqi_refresh),
                                    C.c_void_p(d_rand2 or None), C.c_void_p(d_active or None),
                                    int(active_tti_stride), _ptr(dt), C.byref(o), int(ttis_per_launch)))
 
-    def synth_cqi(self, seed, cell0, tti0, n_ttis, refresh, d_out):
-        _check(lib().rs_synth_cqi(self._h, int(seed), int(cell0), int(tti0), int(n_ttis), int(refresh),
-                                  C.c_void_p(d_out)))
+    def synth_cqi(self, seed, cell0, epoch0, n_slabs, d_out):
+        """n_slabs CQI slabs [B][U][row] for epochs epoch0.. (epoch = tti // refresh) into device memory."""
+        _check(lib().rs_synth_cqi(self._h, int(seed), int(cell0), int(epoch0), int(n_slabs), C.c_void_p(d_out)))
 
     def synth_rand2(self, seed, cell0, tti0, n_ttis, d_out):
         _check(lib().rs_synth_rand2(self._h, int(seed), int(cell0), int(tti0), int(n_ttis), C.c_void_p(d_out)))
@@ -283,6 +284,12 @@ class Scheduler:
     @property
     def algorithmic_bytes_per_cell_tti(self):
         return int(lib().rs_algorithmic_bytes_per_cell_tti(self._h))
+
+
+def pack_cqi(cqi: np.ndarray) -> np.ndarray:
+    """u8 [..., G] (values 1..15) -> the 4-bit layout (cqi_per_rb = 2): [..., G/2], even RBG in the low nibble."""
+    cqi = np.asarray(cqi, dtype=np.uint8)
+    return np.ascontiguousarray(cqi[..., 0::2] | (cqi[..., 1::2] << 4))
 
 
 def test_sort(keys, depth_limit=-1, device=0) -> np.ndarray:

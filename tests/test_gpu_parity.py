@@ -212,7 +212,7 @@ def test_device_generators_and_run_device():
     g = sched.Scheduler(9, w, p, u2s, B)
     d_cqi = torch.empty((T, B, U, G), dtype=torch.uint8, device="cuda")
     d_r2 = torch.empty((T, B, 2), dtype=torch.int32, device="cuda")
-    g.synth_cqi(3, 100, 7, T, 1, d_cqi.data_ptr())
+    g.synth_cqi(3, 100, 7, T, d_cqi.data_ptr())
     g.synth_rand2(3, 100, 7, T, d_r2.data_ptr())
     g.sync()
     cqi = workload.synth_cqi(3, 100, B, 7, T, U, G)
@@ -237,6 +237,44 @@ def test_device_generators_and_run_device():
     g.close()
 
 
+@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+def test_packed_cqi_layout_and_refresh(algo):
+    """4-bit CQI layout (two RBGs per byte) and CQI held for several TTIs, through rs_run_host and
+    rs_run_device with the device generator: same results as the oracle on the unpacked values."""
+    import torch
+    S, B, T, refresh = 20, 24, 23, 5
+    u2s = np.repeat(np.arange(S), 5).astype(np.int32)
+    U, G = len(u2s), 64
+    w, p = np.full(S, 0.05), np.tile(PF, (S, 1))
+    n_slabs = -(-T // refresh)
+    slabs = workload.synth_cqi(11, 50, B, 0, n_slabs, U, G)      # epoch e == "tti" e of the generator
+    rand2 = workload.synth_rand2(11, 50, B, 0, T, S)
+    _, dts = workload.tti_clock(T)
+    o = OracleScheduler(algo, w, p, u2s, B, n_threads=8)
+    want = [o.step(slabs[t // refresh], rand2[t], dt=float(dts[t])) for t in range(T)]
+    # host path, packed
+    g = sched.Scheduler(algo, w, p, u2s, B, cqi_per_rb=2)
+    got = g.run_host(sched.pack_cqi(slabs), rand2, dts, ttis_per_launch=4, cqi_refresh=refresh)
+    for t in range(T):
+        for k in ("rbg_to_ue", "tbs_bits", "mcs"):
+            assert np.array_equal(got[k][t], want[t][k]), (t, k)
+    assert np.array_equal(g.get_state()["avg_rate"], o.get_state()["avg_rate"])
+    # device path: generator writes the packed layout directly
+    g.reset_state()
+    d_cqi = torch.empty((n_slabs, B, U, G // 2), dtype=torch.uint8, device="cuda")
+    d_r2 = torch.from_numpy(rand2).cuda()
+    g.synth_cqi(11, 50, 0, n_slabs, d_cqi.data_ptr())
+    g.sync()
+    assert np.array_equal(d_cqi.cpu().numpy(), sched.pack_cqi(slabs))
+    d_rbg = torch.empty((T, B, G), dtype=torch.int16, device="cuda")
+    g.run_device(T, d_cqi.data_ptr(), B * U * G // 2, d_r2.data_ptr(), dts, {"rbg_to_ue": d_rbg.data_ptr()},
+                 ttis_per_launch=7, cqi_refresh=refresh)
+    g.sync()
+    for t in range(T):
+        assert np.array_equal(d_rbg[t].cpu().numpy(), want[t]["rbg_to_ue"]), t
+    g.close()
+
+
 def test_full_size_batch_invariants():
     """BASELINE config #2 size (4096 cells x 20 slices x 5 UEs): properties that need no oracle run,
     plus an oracle spot check on a few cells."""
@@ -248,7 +286,7 @@ def test_full_size_batch_invariants():
     g = sched.Scheduler(9, w, p, u2s, B)
     d_cqi = torch.empty((T, B, U, G), dtype=torch.uint8, device="cuda")
     d_r2 = torch.empty((T, B, 2), dtype=torch.int32, device="cuda")
-    g.synth_cqi(1, 0, 0, T, 1, d_cqi.data_ptr())
+    g.synth_cqi(1, 0, 0, T, d_cqi.data_ptr())
     g.synth_rand2(1, 0, 0, T, d_r2.data_ptr())
     d_rbg = torch.empty((T, B, G), dtype=torch.int16, device="cuda")
     d_bits = torch.empty((T, B, U), dtype=torch.int32, device="cuda")
