@@ -106,6 +106,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of one TTI-kernel launch from the committed ncu --set full capture
+    (profiles/r01_tti_kernel_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum)."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_tti_kernel_ncu_full.csv")):
+            name, unit, val = line.strip().split(",")[:3]
+            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -345,7 +359,10 @@ def run_cuda_arm(args, n_gpus):
                     "variants": {"u8_cqi_refresh1": {"value": e2e_u8, "h2d_bytes_per_step": h2d_u8},
                                  "packed_cqi_refresh40": {"value": e2e_r40, "h2d_bytes_per_step": h2d_r40}}},
             "roofline": {"bound": "hbm", "kernel": f"rs_tti_kernel<{args.algo}>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_bytes() if (args.cells, ttis_launch) == (4096, 16) else None,
+                         "traffic_note": "DRAM bytes of one launch (65536 cell-TTIs), ncu --set full, profiles/r01_tti_kernel_ncu_full.csv",
+                         "algorithmic_bytes_per_launch": alg * B * ttis_launch, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_tti": alg, "cell_ttis_per_launch": B * ttis_launch,
                          "launch_ms": launch_ms,
                          "note": "path is bound by shared-memory sort/scan and FP64 issue, not HBM (DESIGN.md)"},
