@@ -130,6 +130,48 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
 int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
                 const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
 
+/* ---- trace-driven CQI ingest ---------------------------------------------------------------------
+ * Replaces EnbMacEntity's USE_REAL_TRACE path (src/protocolStack/mac/enb-mac-entity.cc:42-56 and
+ * 160-193): mapping.config gives every UE a trace, ue<trace>.log holds 475 CQI vectors, and each
+ * CQI report (every CQI_INTERVAL = 40 ms) overwrites the UE record's CQI with line
+ * (int)(Now*1000/40) % 475.  Here the traces live in HBM once (4-bit packed when the handle's
+ * layout is 2: 158 x 476 x 32 B = 2.4 MB, L2-resident) and every (cell, UE) replays one of them, so a
+ * trace-driven run streams no CQI at all.
+ *
+ * rs_parse_trace_file / rs_parse_mapping_file / rs_trace_row are host-only helpers (no GPU needed). */
+
+/* out: uint8 [n_rows][n_rbs], the first n_rows lines x n_rbs integers of a ue<id>.log
+ * (enb-mac-entity.cc:169-187). */
+int rs_parse_trace_file(const char* path, int32_t n_rows, int32_t n_rbs, uint8_t* out);
+/* out[k] = trace id on the k-th line of a mapping.config (the uid column is ignored, as in
+ * enb-mac-entity.cc:48-55); at most cap entries are written, *n_out = number of lines.
+ * UE u replays out[u % n] (:164). */
+int rs_parse_mapping_file(const char* path, int32_t* out, int32_t cap, int32_t* n_out);
+/* (int)(Now*1000/CQI_INTERVAL) % n_rows for a report received at simulator time now_seconds
+ * (enb-mac-entity.cc:189-191). */
+int32_t rs_trace_row(double now_seconds, int32_t n_rows);
+
+/* traces   HOST uint8 [n_traces][n_rows][n_rbs], values 1..15 (what rs_parse_trace_file returns);
+ *          converted to the handle's CQI layout (layouts 0 and 2 need one value per RBG, which
+ *          holds for every shipped trace; otherwise RS_ERR_UNSUPPORTED asks for cqi_per_rb = 1)
+ * ue_trace HOST int32 [B][U]: the trace each UE of each cell replays (the reference:
+ *          mapping[u % n_map] for its single cell; a batch gives every cell its own mapping);
+ *          -1 = a UE whose reports never reach the eNB: its record keeps the initial CQI 10. */
+int rs_set_traces(rs_handle* h, const uint8_t* traces, int32_t n_traces, int32_t n_rows, const int32_t* ue_trace);
+
+/* rs_run_device / rs_run_host with the CQI taken from the loaded traces.
+ *   trace_row HOST int32 [T]: the trace line in force at TTI t for every UE (all UEs of a cell report
+ *             in the same TTI: they receive the same downlink burst, phy/ue-lte-phy.cpp:215-232),
+ *             i.e. rs_trace_row(time of the last report); -1 = no report yet (CQI 10 everywhere,
+ *             ENodeB.cpp:207-217)
+ * Everything else as in rs_run_device (device pointers, asynchronous) / rs_run_host (host pointers,
+ * synchronous). */
+int rs_run_traces_device(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* d_rand2,
+                         const uint8_t* d_active, int64_t active_tti_stride, const double* dt,
+                         const rs_outputs* d_out, int32_t ttis_per_launch);
+int rs_run_traces_host(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
+                       const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
+
 /* Synthetic workload of SURVEY.md section 8(d), generated on the device (bit-identical twin of
  * radiosaber_b200/workload.py): CQI i.i.d. from the cqi-traces-noise0 histogram, counter-based so
  * any (cell, epoch) shard can be produced on any GPU.  d_out: n_slabs slabs [B][U][row] in the handle's

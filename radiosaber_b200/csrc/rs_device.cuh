@@ -58,7 +58,7 @@ __constant__ ConstTables c_tab;
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
   int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, total;
+      target, quota, frb, wd, outsl, off, tval, misc, utr, total;
 };
 
 struct DevCfg {
@@ -81,6 +81,12 @@ struct DevCfg {
   const int* tbs_n;        /* [G+1][16]: GetTBSizeFromMCS(mcs(cqi), k*rbg) */
   const unsigned short* eq_tab; /* id 9: permutations of all-equal ranges (SortBufs::eq_tab) */
   int eq_max;
+  /* trace-driven CQI (enb-mac-entity.cc:160-193): [n_traces][trace_rows + 1][cqi_row] in the handle's
+   * CQI layout, row trace_rows = the all-10 vector a UE record holds before its first report
+   * (ENodeB.cpp:207-217); ue_trace_off[b][u] = byte offset of the trace UE u of cell b replays */
+  const uint8_t* trace_tab;
+  const int* ue_trace_off;
+  int trace_rows;
   /* state, [B][U] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
   double* offset; double* ewma;
@@ -89,6 +95,7 @@ struct DevCfg {
 struct RunArgs {
   const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
   int t0, cqi_refresh;
+  const int* trace_row;    /* device [T], trace mode: row of every UE's trace in force at TTI t */
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
   const double* dt;        /* device [T] */
@@ -120,6 +127,7 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
     L.mtab = o; o += 8 * kMStride * m_cap;
   }
   L.tx = o;   o += 4 * U;
+  L.utr = o;  o += 4 * U;
   L.mask = o; o += 8 * U;
   L.seg0 = o; o += 4 * (n / 16 + 2);
   L.seg1 = o; o += 4 * (n / 16 + 2);
@@ -432,7 +440,7 @@ struct Cell {
   /* shared-memory views */
   double* avg; double* den; double* mtab; double* off;
   unsigned long long* cumb; unsigned long long* cumr;   /* this cell's rows of the HBM counters */
-  double* tval; int* tx; unsigned* mask; int* target; int* quota; int* frb; int* wd;
+  double* tval; int* tx; int* utr; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
   SortBufs sb;
 };
@@ -447,6 +455,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.off = (double*)(smem + L.off);
   c.tval = (double*)(smem + L.tval);
   c.tx = (int*)(smem + L.tx);
+  c.utr = (int*)(smem + L.utr);
   c.mask = (unsigned*)(smem + L.mask);
   c.target = (int*)(smem + L.target);
   c.quota = (int*)(smem + L.quota);
@@ -468,10 +477,16 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   return c;
 }
 
-/* CQI of UE u on the first RB of RBG g (the RB the metric is evaluated on, transport.cpp:536) */
-__device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* cqi, int u, int g) {
-  if (d.cqi_per_rb == 2) return (cqi[(size_t)u * d.cqi_row + (g >> 1)] >> (4 * (g & 1))) & 15;
-  return d.cqi_per_rb ? (cqi[(size_t)u * d.R + (size_t)g * d.rbg] & 15) : (cqi[(size_t)u * d.G + g] & 15);
+/* Where UE u's CQI vector of this TTI starts: row u of the [U][cqi_row] slab, or (trace mode) the
+ * current row of the trace the UE replays (cqi then points at that row of trace 0). */
+template <bool TRACE>
+__device__ __forceinline__ const uint8_t* ue_cqi(const DevCfg& d, const Cell& c, const uint8_t* cqi, int u) {
+  return TRACE ? cqi + c.utr[u] : cqi + (size_t)u * d.cqi_row;
+}
+/* CQI on the first RB of RBG g (the RB the metric is evaluated on, transport.cpp:536); p = ue_cqi() */
+__device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* p, int g) {
+  if (d.cqi_per_rb == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
+  return d.cqi_per_rb ? (p[(size_t)g * d.rbg] & 15) : (p[g] & 15);
 }
 
 /* Slice targets and RBG quotas, transport.cpp:463-521, by one warp (lane s and lane s+32). */
@@ -608,7 +623,7 @@ __device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned sho
 
 /* Link adaptation + accounting for UE u holding the RBGs in mask (transport.cpp:632-660 and 170-199;
  * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
-__device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* cqi, int u,
+__device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* row, int u,
                                             unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc) {
   int bits = 0, mcs = 0xff, fc = 0;
   const int nrbg = __popc(m_lo) + __popc(m_hi);
@@ -619,10 +634,10 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
       const int g = __ffsll((long long)m) - 1;
       m &= m - 1;
       if (d.cqi_per_rb == 1) {
-        const uint8_t* p = cqi + (size_t)u * d.R + (size_t)g * d.rbg;
+        const uint8_t* p = row + (size_t)g * d.rbg;
         for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, c.tval[p[r] & 15]);
       } else {
-        const double t = c.tval[cqi_first_rb(d, cqi, u, g)];
+        const double t = c.tval[cqi_first_rb(d, row, g)];
         for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, t);
       }
     }
@@ -653,7 +668,7 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
-template <int ALGO>
+template <int ALGO, bool TRACE>
 __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
   Cell c = carve(smem, d.lay);
@@ -673,6 +688,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     c.tx[u] = d.tx[i];
     c.mask[2 * u] = 0;
     c.mask[2 * u + 1] = 0;
+    if (TRACE) c.utr[u] = d.ue_trace_off[i];
   }
   for (int s = tid; s < S; s += kThreads) {
     c.off[s] = (ALGO == 7) ? d.ewma[(size_t)b * S + s] : ((ALGO == 1) ? 0.0 : d.offset[(size_t)b * S + s]);
@@ -690,8 +706,9 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   long long last_ = clock64();
 #endif
   for (int t = 0; t < r.T; ++t) {
-    const uint8_t* cqi = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride +
-                         (size_t)b * U * d.cqi_row;
+    const uint8_t* cqi = TRACE ? d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row
+                               : r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride +
+                                     (size_t)b * U * d.cqi_row;
     const uint8_t* act = r.active ? r.active + (size_t)t * r.active_tti_stride + (size_t)b * U : nullptr;
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
@@ -780,11 +797,12 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               const int u = d.slice_ues[j];
               if (act && !act[u]) continue;
               unsigned w;
+              const uint8_t* row_u = ue_cqi<TRACE>(d, c, cqi, u);
               if (nib) {   /* four nibbles -> one per byte, then the same extraction as the u8 layout */
-                const unsigned h = *(const unsigned short*)(cqi + (size_t)u * d.cqi_row + (g0 >> 1));
+                const unsigned h = *(const unsigned short*)(row_u + (g0 >> 1));
                 w = (h & 0xfu) | ((h & 0xf0u) << 4) | ((h & 0xf00u) << 8) | ((h & 0xf000u) << 12);
               } else {
-                w = *(const unsigned*)(cqi + (size_t)u * G + g0);
+                w = *(const unsigned*)(row_u + g0);
               }
               const double* row = c.mtab + (j - j0) * kMStride;
 #pragma unroll
@@ -810,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
               const int u = d.slice_ues[j];
               if (act && !act[u]) continue;
-              const int cq = cqi_first_rb(d, cqi, u, g);
+              const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
               const double m = c.mtab[(j - j0) * kMStride + cq];
               if (m > best) { best = m; bu = u; bc = cq; }
             }
@@ -875,7 +893,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           const int u = d.slice_ues[j];
           if (act && !act[u]) continue;
           if (d.data <= 0) continue;
-          const int cq = cqi_first_rb(d, cqi, u, g);
+          const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
           const double m = c.mtab[(j - j0) * kMStride + cq];
           if (m > best) { best = m; bu = u; }
         }
@@ -889,7 +907,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         int bu = 0x7fffffff;
         for (int u = lane; u < U; u += 32) {
           if (act && !act[u]) continue;
-          const int cq = cqi_first_rb(d, cqi, u, g);
+          const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
           const double m = __ddiv_rn(d.epow[cq], c.den[u]);
           if (m > best) { best = m; bu = u; }
         }
@@ -912,7 +930,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, cqi, u, m_lo, m_hi, o_bits, o_mcs, o_fc);
+      finalize_ue(d, c, ue_cqi<TRACE>(d, c, cqi, u), u, m_lo, m_hi, o_bits, o_mcs, o_fc);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;
     }

@@ -182,6 +182,12 @@ struct rs_handle {
   DevBuf<double> dt_dev;
   double* dt_pinned = nullptr;
   size_t dt_pinned_n = 0;
+  /* trace-driven CQI (rs_set_traces) */
+  DevBuf<uint8_t> trace_tab;
+  DevBuf<int> ue_trace_off, trow_dev;
+  int n_traces = 0, trace_rows = 0;
+  int* trow_pinned = nullptr;
+  size_t trow_pinned_n = 0;
   DevBuf<unsigned long long> stats;
   /* staging for rs_step / rs_run_host: two slots */
   struct Slot {
@@ -195,15 +201,21 @@ struct rs_handle {
 
 namespace {
 
+typedef void (*TtiKernel)(const rs::DevCfg, const rs::RunArgs);
+TtiKernel tti_kernel(int algo, bool trace) {
+  switch (algo) {
+    case 1: return trace ? rs::rs_tti_kernel<1, true> : rs::rs_tti_kernel<1, false>;
+    case 7: return trace ? rs::rs_tti_kernel<7, true> : rs::rs_tti_kernel<7, false>;
+    case 8: return trace ? rs::rs_tti_kernel<8, true> : rs::rs_tti_kernel<8, false>;
+    default: return trace ? rs::rs_tti_kernel<9, true> : rs::rs_tti_kernel<9, false>;
+  }
+}
+
+/* a.trace_row != NULL selects the trace-driven instantiation */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
   const dim3 grid(h->B), block(rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
-  switch (h->d.algo) {
-    case 1: rs::rs_tti_kernel<1><<<grid, block, sm, h->stream>>>(h->d, a); break;
-    case 7: rs::rs_tti_kernel<7><<<grid, block, sm, h->stream>>>(h->d, a); break;
-    case 8: rs::rs_tti_kernel<8><<<grid, block, sm, h->stream>>>(h->d, a); break;
-    default: rs::rs_tti_kernel<9><<<grid, block, sm, h->stream>>>(h->d, a); break;
-  }
+  tti_kernel(h->d.algo, a.trace_row != nullptr)<<<grid, block, sm, h->stream>>>(h->d, a);
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;
@@ -211,12 +223,28 @@ int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
 
 int set_smem_attr(rs_handle* h) {
   const int sm = h->layout.total;
-  switch (h->d.algo) {
-    case 1: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
-    case 7: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
-    case 8: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
-    default: CU(cudaFuncSetAttribute(rs::rs_tti_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); break;
+  CU(cudaFuncSetAttribute(tti_kernel(h->d.algo, false), cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CU(cudaFuncSetAttribute(tti_kernel(h->d.algo, true), cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  return RS_OK;
+}
+
+/* the row of every UE's trace in force at each TTI -> device (same staging as dt) */
+int ensure_trow(rs_handle* h, const int32_t* trace_row, int n) {
+  for (int t = 0; t < n; ++t)
+    if (trace_row[t] < -1 || trace_row[t] >= h->trace_rows)
+      return fail(RS_ERR_ARG, "trace_row[%d] = %d outside -1..%d", t, trace_row[t], h->trace_rows - 1);
+  CU(h->trow_dev.alloc((size_t)n));
+  if (h->trow_pinned_n < (size_t)n) {
+    if (h->trow_pinned) cudaFreeHost(h->trow_pinned);
+    h->trow_pinned = nullptr;
+    h->trow_pinned_n = 0;
+    CU(cudaMallocHost((void**)&h->trow_pinned, sizeof(int) * (size_t)n));
+    h->trow_pinned_n = (size_t)n;
   }
+  CU(cudaStreamSynchronize(h->stream));
+  /* -1 = no report received yet: the extra all-10 row behind every trace (ENodeB.cpp:207-217) */
+  for (int t = 0; t < n; ++t) h->trow_pinned[t] = trace_row[t] < 0 ? h->trace_rows : trace_row[t];
+  CU(cudaMemcpyAsync(h->trow_dev.p, h->trow_pinned, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   return RS_OK;
 }
 
@@ -243,9 +271,9 @@ int ensure_dt(rs_handle* h, const double* dt, int n) {
   return RS_OK;
 }
 
-int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active) {
+int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active, bool want_cqi) {
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
-  CU(s.cqi.alloc((size_t)T * B * U * C));
+  if (want_cqi) CU(s.cqi.alloc((size_t)T * B * U * C));
   CU(s.rand2.alloc((size_t)T * B * 2));
   if (want_active) CU(s.active.alloc((size_t)T * B * U));
   if (out) {
@@ -295,6 +323,8 @@ void rs_destroy(rs_handle* h) {
     if (s.out_done) cudaEventDestroy(s.out_done);
   }
   if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
+  if (h->trow_pinned) cudaFreeHost(h->trow_pinned);
+  h->trace_tab.release(); h->ue_trace_off.release(); h->trow_dev.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -541,16 +571,22 @@ int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cu
   return RS_OK;
 }
 
-int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
-                  const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
-                  const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
-  if (!h || !d_cqi || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
+}  /* extern "C" */
+
+namespace {
+/* trace_row == NULL: CQI slabs in device memory; else trace-driven (d_cqi unused) */
+int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
+                    const int32_t* trace_row, const int32_t* d_rand2, const uint8_t* d_active,
+                    int64_t active_tti_stride, const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
+  if (!h || (!d_cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
   if ((h->d.algo == 8 || h->d.algo == 9) && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
-  if (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3)) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
+  if (!trace_row && (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3))) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
+  if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
   int rc = ensure_dt(h, dt, n_ttis);
   if (rc != RS_OK) return rc;
+  if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   if (ttis_per_launch <= 0) ttis_per_launch = 16;
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
@@ -564,6 +600,7 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
     a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
     a.active_tti_stride = active_tti_stride;
     a.dt = h->dt_dev.p + t0;
+    a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
     if (d_out) {
       a.rbg_to_ue = d_out->rbg_to_ue ? d_out->rbg_to_ue + (size_t)t0 * B * G : nullptr;
       a.tbs_bits = d_out->tbs_bits ? d_out->tbs_bits + (size_t)t0 * B * U : nullptr;
@@ -581,18 +618,22 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
   return RS_OK;
 }
 
-int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
-                const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
-  if (!h || !cqi || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
+/* trace_row == NULL: CQI slabs from the host; else trace-driven (cqi unused, nothing but rand2/active goes up) */
+int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* trace_row,
+                  const int32_t* rand2, const uint8_t* active, const double* dt, const rs_outputs* out,
+                  int32_t ttis_per_launch) {
+  if (!h || (!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
   if ((h->d.algo == 8 || h->d.algo == 9) && !rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
+  if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
-  if (ttis_per_launch <= 0) ttis_per_launch = 4;
+  if (ttis_per_launch <= 0) ttis_per_launch = trace_row ? 16 : 4;
   const int TC = std::min(ttis_per_launch, n_ttis);
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   int rc = ensure_dt(h, dt, n_ttis);
   if (rc != RS_OK) return rc;
-  for (auto& s : h->slot) { rc = alloc_slot(h, s, TC, out, active != nullptr); if (rc != RS_OK) return rc; }
+  if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
+  for (auto& s : h->slot) { rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr); if (rc != RS_OK) return rc; }
   cudaEvent_t dt_ready;
   CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
   CU(cudaEventRecord(dt_ready, h->stream));
@@ -603,11 +644,11 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_re
     T = std::min(TC, n_ttis - t0);
     /* a chunk never straddles more CQI slabs than the slot holds: with a refresh > 1 it ends at the
      * next refresh boundary and needs exactly one slab */
-    if (cqi_refresh > 1) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
+    if (cqi_refresh > 1 && !trace_row) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
     const int slab0 = t0 / cqi_refresh, n_slabs = (t0 + T - 1) / cqi_refresh - slab0 + 1;
     /* inputs: the slot's previous kernel must be done with them */
     if (k >= 2) CU(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
-    if (!(cqi_refresh > 1 && s.slab0 == slab0))   /* the slab may still be resident from the chunk before last */
+    if (!trace_row && !(cqi_refresh > 1 && s.slab0 == slab0))   /* the slab may still be resident from the chunk before last */
       CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)slab0 * B * U * C, (size_t)n_slabs * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
     s.slab0 = slab0;
     if (rand2) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * 2, (size_t)T * B * 2 * 4, cudaMemcpyHostToDevice, h->copy_in));
@@ -623,6 +664,7 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_re
     a.rand2 = rand2 ? s.rand2.p : nullptr;
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
     a.dt = h->dt_dev.p + t0;
+    a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
     if (out) {
       a.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
       a.tbs_bits = out->tbs_bits ? s.tbs_bits.p : nullptr;
@@ -654,6 +696,130 @@ int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_re
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaStreamSynchronize(h->copy_in));
   cudaEventDestroy(dt_ready);
+  return RS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
+                  const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
+                  const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
+  if (!d_cqi) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
+  return run_device_impl(h, n_ttis, d_cqi, cqi_tti_stride, cqi_refresh, nullptr, d_rand2, d_active, active_tti_stride,
+                         dt, d_out, ttis_per_launch);
+}
+
+int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
+                const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
+  if (!cqi) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
+  return run_host_impl(h, n_ttis, cqi, cqi_refresh, nullptr, rand2, active, dt, out, ttis_per_launch);
+}
+
+int rs_run_traces_device(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* d_rand2,
+                         const uint8_t* d_active, int64_t active_tti_stride, const double* dt,
+                         const rs_outputs* d_out, int32_t ttis_per_launch) {
+  if (!trace_row) return fail(RS_ERR_ARG, "rs_run_traces_device: bad argument");
+  return run_device_impl(h, n_ttis, nullptr, 0, 1, trace_row, d_rand2, d_active, active_tti_stride, dt, d_out,
+                         ttis_per_launch);
+}
+
+int rs_run_traces_host(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
+                       const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
+  if (!trace_row) return fail(RS_ERR_ARG, "rs_run_traces_host: bad argument");
+  return run_host_impl(h, n_ttis, nullptr, 1, trace_row, rand2, active, dt, out, ttis_per_launch);
+}
+
+/* EnbMacEntity::ReceiveCqiIdealControlMessage under USE_REAL_TRACE, enb-mac-entity.cc:189-191:
+ * int time_stamp = Now()*1000 / CQI_INTERVAL; row = time_stamp % cqi_traces.size() */
+int32_t rs_trace_row(double now_seconds, int32_t n_rows) {
+  if (n_rows <= 0) return -1;
+  volatile double x = now_seconds * 1000;
+  const int time_stamp = (int)(x / 40);
+  return (int32_t)(time_stamp % n_rows);
+}
+
+/* One ue<id>.log as the reference reads it (enb-mac-entity.cc:169-187): n_rows lines, the first n_rbs
+ * integers of each (operator>> semantics: a short or unreadable line repeats the last value read). */
+int rs_parse_trace_file(const char* path, int32_t n_rows, int32_t n_rbs, uint8_t* out) {
+  if (!path || !out || n_rows < 1 || n_rbs < 1) return fail(RS_ERR_ARG, "rs_parse_trace_file: bad argument");
+  FILE* f = fopen(path, "r");
+  if (!f) return fail(RS_ERR_ARG, "cannot open %s", path);
+  std::vector<char> line(1 << 16);
+  int cqi = 0;
+  for (int i = 0; i < n_rows; ++i) {
+    const char* p = "";
+    if (fgets(line.data(), (int)line.size(), f)) p = line.data();
+    for (int j = 0; j < n_rbs; ++j) {
+      char* end = nullptr;
+      const long v = strtol(p, &end, 10);
+      if (end != p) { cqi = (int)v; p = end; }
+      if (cqi < 0 || cqi > 15) { fclose(f); return fail(RS_ERR_ARG, "%s line %d: CQI %d outside 0..15", path, i + 1, cqi); }
+      out[(size_t)i * n_rbs + j] = (uint8_t)cqi;
+    }
+  }
+  fclose(f);
+  return RS_OK;
+}
+
+/* mapping.config as the reference reads it (enb-mac-entity.cc:48-55): pairs "uid tid"; the uid is
+ * ignored, entry k of the map is the k-th tid in file order. */
+int rs_parse_mapping_file(const char* path, int32_t* out, int32_t cap, int32_t* n_out) {
+  if (!path || !n_out || cap < 0 || (cap > 0 && !out)) return fail(RS_ERR_ARG, "rs_parse_mapping_file: bad argument");
+  FILE* f = fopen(path, "r");
+  if (!f) return fail(RS_ERR_ARG, "cannot open %s", path);
+  int uid, tid, n = 0;
+  while (fscanf(f, "%d %d", &uid, &tid) == 2) {
+    if (n < cap) out[n] = tid;
+    n++;
+  }
+  fclose(f);
+  *n_out = n;
+  return RS_OK;
+}
+
+int rs_set_traces(rs_handle* h, const uint8_t* traces, int32_t n_traces, int32_t n_rows, const int32_t* ue_trace) {
+  if (!h || !traces || !ue_trace || n_traces < 1 || n_rows < 1) return fail(RS_ERR_ARG, "rs_set_traces: bad argument");
+  const int R = h->d.R, G = h->d.G, rbg = h->d.rbg, C = h->cqi_cols, lay = h->d.cqi_per_rb;
+  const size_t per_trace = (size_t)(n_rows + 1) * C;
+  if (per_trace * ((size_t)n_traces + 1) > 0x7fffffffull) return fail(RS_ERR_UNSUPPORTED, "trace table larger than 2 GiB");
+  /* pseudo-trace n_traces: CQI 10 on every line, for UEs whose reports never arrive (ue_trace = -1) */
+  std::vector<uint8_t> tab(per_trace * ((size_t)n_traces + 1), (uint8_t)(lay == 2 ? 0xAA : 10));
+  for (int k = 0; k < n_traces; ++k)
+    for (int i = 0; i <= n_rows; ++i) {
+      uint8_t* dst = tab.data() + (size_t)k * per_trace + (size_t)i * C;
+      const uint8_t* src = traces + ((size_t)k * n_rows + i) * R;
+      for (int g = 0; g < G; ++g) {
+        int v0 = 10;   /* row n_rows: UserEquipmentRecord's initial feedback, ENodeB.cpp:207-217 */
+        for (int r = 0; r < rbg; ++r) {
+          const int v = (i < n_rows) ? src[(size_t)g * rbg + r] : 10;
+          if (v < 1 || v > 15) return fail(RS_ERR_ARG, "trace %d row %d RB %d: CQI %d outside 1..15", k, i, g * rbg + r, v);
+          if (r == 0) v0 = v;
+          if (lay == 1) dst[(size_t)g * rbg + r] = (uint8_t)v;
+          else if (v != v0)
+            return fail(RS_ERR_UNSUPPORTED, "trace %d row %d: CQI varies inside RBG %d; create the handle with cqi_per_rb = 1", k, i, g);
+        }
+        if (lay == 0) dst[g] = (uint8_t)v0;
+        else if (lay == 2) dst[g >> 1] = (uint8_t)((g & 1) ? (dst[g >> 1] | (v0 << 4)) : v0);
+      }
+    }
+  const size_t BU = (size_t)h->B * h->d.U;
+  std::vector<int> off(BU);
+  for (size_t i = 0; i < BU; ++i) {
+    if (ue_trace[i] < -1 || ue_trace[i] >= n_traces) return fail(RS_ERR_ARG, "ue_trace[%zu] = %d outside -1..%d", i, ue_trace[i], n_traces - 1);
+    off[i] = (int)((size_t)(ue_trace[i] < 0 ? n_traces : ue_trace[i]) * per_trace);
+  }
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  int rc = upload(h->trace_tab, tab);
+  if (rc != RS_OK) return rc;
+  rc = upload(h->ue_trace_off, off);
+  if (rc != RS_OK) return rc;
+  h->n_traces = n_traces;
+  h->trace_rows = n_rows;
+  h->d.trace_tab = h->trace_tab.p;
+  h->d.ue_trace_off = h->ue_trace_off.p;
+  h->d.trace_rows = n_rows;
   return RS_OK;
 }
 

@@ -28,6 +28,8 @@ ABI_SYMBOLS = (
     "rs_set_state", "rs_get_state", "rs_reset_state", "rs_step", "rs_run_device", "rs_run_host",
     "rs_synth_cqi", "rs_synth_rand2", "rs_stats_device", "rs_get_stats", "rs_launch_count",
     "rs_smem_bytes", "rs_threads_per_cta", "rs_algorithmic_bytes_per_cell_tti", "rs_test_sort",
+    "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
+    "rs_run_traces_device", "rs_run_traces_host",
 )
 
 
@@ -88,6 +90,15 @@ def lib():
         L.rs_algorithmic_bytes_per_cell_tti.argtypes = [C.c_void_p]
         L.rs_algorithmic_bytes_per_cell_tti.restype = C.c_int64
         L.rs_test_sort.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_parse_trace_file.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_parse_mapping_file.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.rs_trace_row.argtypes = [C.c_double, C.c_int32]
+        L.rs_trace_row.restype = C.c_int32
+        L.rs_set_traces.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_run_traces_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.POINTER(_Out), C.c_int32]
+        L.rs_run_traces_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(_Out), C.c_int32]
         _lib = L
     return _lib
 
@@ -251,6 +262,41 @@ class Scheduler:
                                    C.c_void_p(d_rand2 or None), C.c_void_p(d_active or None),
                                    int(active_tti_stride), _ptr(dt), C.byref(o), int(ttis_per_launch)))
 
+    # ---- trace-driven CQI (enb-mac-entity.cc:42-56, 160-193) ----------------------------------
+    def set_traces(self, traces, ue_trace):
+        """traces: uint8 [n_traces][n_rows][n_rbs] (see :func:`load_trace_dir`); ue_trace: int32 [B][U],
+        the trace every UE of every cell replays."""
+        traces = np.ascontiguousarray(traces, dtype=np.uint8)
+        assert traces.ndim == 3 and traces.shape[2] == self.R, traces.shape
+        ue_trace = np.ascontiguousarray(np.broadcast_to(np.asarray(ue_trace, dtype=np.int32), (self.B, self.U)))
+        _check(lib().rs_set_traces(self._h, _ptr(traces), traces.shape[0], traces.shape[1], _ptr(ue_trace)))
+        self.trace_rows = int(traces.shape[1])
+
+    def run_traces_host(self, trace_row, rand2, dt, active=None, want_aux=False, ttis_per_launch=0):
+        """T TTIs with the CQI replayed from the loaded traces; trace_row: int32 [T] (-1 = no report yet)."""
+        B, U = self.B, self.U
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        T = int(dt.shape[0])
+        trace_row = np.ascontiguousarray(trace_row, dtype=np.int32)
+        assert trace_row.shape == (T,)
+        rand2 = None if rand2 is None else np.ascontiguousarray(rand2, dtype=np.int32).reshape(T, B, 2)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
+        out, o = self._host_outputs(T, want_aux)
+        _check(lib().rs_run_traces_host(self._h, T, _ptr(trace_row), _ptr(rand2), _ptr(act), _ptr(dt), C.byref(o),
+                                        int(ttis_per_launch)))
+        return out
+
+    def run_traces_device(self, n_ttis, trace_row, d_rand2, dt, d_out=None, d_active=0, active_tti_stride=0,
+                          ttis_per_launch=0):
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        trace_row = np.ascontiguousarray(trace_row, dtype=np.int32)
+        assert dt.shape[0] >= n_ttis and trace_row.shape[0] >= n_ttis
+        o = _Out(*[(d_out or {}).get(k) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
+                                                    "slice_quota", "nvs_slice")])
+        _check(lib().rs_run_traces_device(self._h, int(n_ttis), _ptr(trace_row), C.c_void_p(d_rand2 or None),
+                                          C.c_void_p(d_active or None), int(active_tti_stride), _ptr(dt),
+                                          C.byref(o), int(ttis_per_launch)))
+
     def synth_cqi(self, seed, cell0, epoch0, n_slabs, d_out):
         """n_slabs CQI slabs [B][U][row] for epochs epoch0.. (epoch = tti // refresh) into device memory."""
         _check(lib().rs_synth_cqi(self._h, int(seed), int(cell0), int(epoch0), int(n_slabs), C.c_void_p(d_out)))
@@ -290,6 +336,53 @@ def pack_cqi(cqi: np.ndarray) -> np.ndarray:
     """u8 [..., G] (values 1..15) -> the 4-bit layout (cqi_per_rb = 2): [..., G/2], even RBG in the low nibble."""
     cqi = np.asarray(cqi, dtype=np.uint8)
     return np.ascontiguousarray(cqi[..., 0::2] | (cqi[..., 1::2] << 4))
+
+
+# ---- trace files (host only; no GPU needed) ---------------------------------------------------------
+TRACE_ROWS = 475      # MAX_TTI_TRACE, enb-mac-entity.cc:40
+CQI_INTERVAL = 40     # enb-mac-entity.cc:38 and the UEs' reporting interval (single-cell-with-interference.h:276-278)
+
+
+def parse_trace_file(path, n_rows=TRACE_ROWS, n_rbs=512) -> np.ndarray:
+    """uint8 [n_rows][n_rbs]: one ue<id>.log as the reference reads it (enb-mac-entity.cc:169-187)."""
+    out = np.empty((n_rows, n_rbs), dtype=np.uint8)
+    _check(lib().rs_parse_trace_file(os.fsencode(path), n_rows, n_rbs, _ptr(out)))
+    return out
+
+
+def parse_mapping_file(path) -> np.ndarray:
+    """int32 [n]: the trace ids of a mapping.config in file order (enb-mac-entity.cc:48-55)."""
+    n = C.c_int32(0)
+    _check(lib().rs_parse_mapping_file(os.fsencode(path), None, 0, C.byref(n)))
+    out = np.empty(n.value, dtype=np.int32)
+    _check(lib().rs_parse_mapping_file(os.fsencode(path), _ptr(out), n.value, C.byref(n)))
+    return out
+
+
+def load_trace_dir(trace_dir, trace_ids=None, n_rows=TRACE_ROWS, n_rbs=512):
+    """(traces uint8 [n][n_rows][n_rbs], ids int32 [n]) for the ue<id>.log files of a cqi-traces directory."""
+    if trace_ids is None:
+        trace_ids = sorted(int(f[2:-4]) for f in os.listdir(trace_dir) if f.startswith("ue") and f.endswith(".log"))
+    ids = np.asarray(list(trace_ids), dtype=np.int32)
+    traces = np.stack([parse_trace_file(os.path.join(trace_dir, f"ue{int(i)}.log"), n_rows, n_rbs) for i in ids])
+    return traces, ids
+
+
+def trace_row(now_seconds, n_rows=TRACE_ROWS) -> int:
+    """(int)(Now*1000/40) % n_rows, enb-mac-entity.cc:189-191."""
+    return int(lib().rs_trace_row(float(now_seconds), int(n_rows)))
+
+
+def trace_rows_for_run(now, first_report_tti=0, interval=CQI_INTERVAL, n_rows=TRACE_ROWS) -> np.ndarray:
+    """int32 [T]: the trace line in force at every TTI of a run whose TTI t happens at now[t] when the
+    UEs report at TTIs first_report_tti, first_report_tti + interval, ... (-1 before the first report)."""
+    now = np.asarray(now, dtype=np.float64)
+    rows = np.full(now.shape[0], -1, dtype=np.int32)
+    for t in range(now.shape[0]):
+        if t >= first_report_tti:
+            last = first_report_tti + (t - first_report_tti) // interval * interval
+            rows[t] = trace_row(now[last], n_rows)
+    return rows
 
 
 def test_sort(keys, depth_limit=-1, device=0) -> np.ndarray:

@@ -59,6 +59,16 @@ def synth_cqi(seed: int, cell0: int, n_cells: int, tti0: int, n_ttis: int, n_ues
     return cqi
 
 
+def histogram_cqi(rng: np.random.Generator, shape) -> np.ndarray:
+    """uint8 array of the given shape, i.i.d. from the same histogram through a numpy generator (synthetic
+    trace files; not the counter-based stream above)."""
+    u32 = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64).astype(np.uint32)
+    cqi = np.ones(u32.shape, dtype=np.uint8)
+    for thr in CQI_CDF32:
+        cqi += (u32 >= thr).astype(np.uint8)
+    return cqi
+
+
 def synth_rand2(seed: int, cell0: int, n_cells: int, tti0: int, n_ttis: int, n_slices: int) -> np.ndarray:
     """int32 [n_ttis][n_cells][2]: the two rand() values of transport.cpp:490,511.
 
