@@ -373,6 +373,14 @@ def run_cuda_arm(args, n_gpus):
         ge.close()
         return world * B * TE * KE / float(te.item()), TE * (B * 2 * 4) + TE * 12
 
+    if args.kernel_only:   # development aid: the device-resident number alone (not a valid bench line)
+        if rank == 0:
+            print(json.dumps({"kernel_only": True, "value": value, "ms_per_step": ms_max / K,
+                              "smem_bytes_per_cta": g.smem_bytes, "clocks": sampler.result()}))
+        g.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_value, h2d, d2h = e2e_run(2, 1)
     e2e_u8, h2d_u8, _ = e2e_run(0, 1)
     e2e_r40, h2d_r40, _ = e2e_run(2, 40)
@@ -435,6 +443,7 @@ def main():
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: launch ourselves the way the driver does

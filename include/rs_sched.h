@@ -201,6 +201,9 @@ int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h); /* U(G+20)+16S+2G
  * depth_limit < 0 = the library's 2*floor(log2 n). */
 int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
                  int32_t* perm_out);
+/* Same, launched `reps` times; *ms_per_launch = mean device time of launches 2..reps (CUDA events). */
+int rs_test_sort_timed(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
+                       int32_t* perm_out, int32_t reps, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

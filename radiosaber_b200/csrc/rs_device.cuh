@@ -58,7 +58,7 @@ __constant__ ConstTables c_tab;
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
   int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, utr, total;
+      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, total;
 };
 
 struct DevCfg {
@@ -95,6 +95,7 @@ struct DevCfg {
 struct RunArgs {
   const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
   int t0, cqi_refresh;
+  int stage;               /* 1: every TTI's CQI is copied to shared memory with cp.async first */
   const int* trace_row;    /* device [T], trace mode: row of every UE's trace in force at TTI t */
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
@@ -109,7 +110,9 @@ __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a *
 /* The cumulative byte / RB counters stay in HBM (touched only for the few UEs a TTI serves); the
  * metric table is dead once the sort starts, so it shares the bytes of the sort's slot arrays
  * when it fits there. */
-__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
+/* cq_bytes: room for one TTI of the cell's CQI ([U][cqi_row], staged with cp.async); 0 = CQI is read
+ * from global memory where it lies. */
+__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0) {
   Layout L;
   const int n = S * G;
   const int nw = (n + 31) / 32;
@@ -140,6 +143,9 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap) {
   L.win = o;  o += 2 * n;
   L.cnt = o;  o += 2 * 16 * nw;
   L.outsl = o; o += G;
+  L.sptr = rs_align(o, 4); o = L.sptr + 4 * (S + 1);
+  L.sues = o; o += 2 * U;
+  L.cq = rs_align(o, 16); o = L.cq + cq_bytes;
   L.total = rs_align(o, 16);
   return L;
 }
@@ -440,7 +446,7 @@ struct Cell {
   /* shared-memory views */
   double* avg; double* den; double* mtab; double* off;
   unsigned long long* cumb; unsigned long long* cumr;   /* this cell's rows of the HBM counters */
-  double* tval; int* tx; int* utr; unsigned* mask; int* target; int* quota; int* frb; int* wd;
+  double* tval; int* tx; int* utr; int* sptr; unsigned short* sues; uint8_t* cq; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
   SortBufs sb;
 };
@@ -456,6 +462,9 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.tval = (double*)(smem + L.tval);
   c.tx = (int*)(smem + L.tx);
   c.utr = (int*)(smem + L.utr);
+  c.sptr = (int*)(smem + L.sptr);
+  c.sues = (unsigned short*)(smem + L.sues);
+  c.cq = smem + L.cq;
   c.mask = (unsigned*)(smem + L.mask);
   c.target = (int*)(smem + L.target);
   c.quota = (int*)(smem + L.quota);
@@ -476,6 +485,14 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.sb.eq_max = 0;
   return c;
 }
+
+/* Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS); both addresses 16-byte aligned */
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 /* Where UE u's CQI vector of this TTI starts: row u of the [U][cqi_row] slab, or (trace mode) the
  * current row of the trace the UE replays (cqi then points at that row of trace 0). */
@@ -699,7 +716,32 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   }
   if (tid < 16) c.tval[tid] = c_tab.tval[tid];
   for (int g = tid; g < G; g += kThreads) c.outsl[g] = 0xff;
+  for (int s = tid; s <= ((ALGO == 1) ? 1 : S); s += kThreads) c.sptr[s] = d.slice_ptr[s];
+  for (int u = tid; u < U; u += kThreads) c.sues[u] = (unsigned short)d.slice_ues[u];
   __syncthreads();
+
+  /* One TTI of this cell's CQI lands in shared memory while P0 runs: rows [U][cqi_row], from the slab or
+   * (trace mode) from the line in force of each UE's trace.  Consecutive TTIs that read the same slab /
+   * line keep what is there. */
+  const bool stage = r.stage != 0;
+  int staged_key = -1;
+  auto cqi_key = [&](int t) { return TRACE ? r.trace_row[t] : (r.t0 + t) / r.cqi_refresh; };
+  auto stage_cqi = [&](int t) {
+    if (TRACE) {
+      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row;
+      const int cpr = d.cqi_row >> 4;
+      for (int q = tid; q < U * cpr; q += kThreads) {
+        const int u = q / cpr, part = (q - u * cpr) << 4;
+        cp_async16(c.cq + u * d.cqi_row + part, base + c.utr[u] + part);
+      }
+    } else {
+      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * d.cqi_row;
+      const int n16 = (U * d.cqi_row) >> 4;
+      for (int q = tid; q < n16; q += kThreads) cp_async16(c.cq + (q << 4), src + ((size_t)q << 4));
+    }
+    cp_async_commit();
+  };
+  if (stage && r.T > 0) { stage_cqi(0); staged_key = cqi_key(0); }
 
 #ifdef RS_PHASE_TIMING
   long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -713,6 +755,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
     const int rot = (b + t) % kWarps;   /* which warp plays the single-warp roles this TTI */
+    auto row_of = [&](int u) -> const uint8_t* { return stage ? c.cq + u * d.cqi_row : ue_cqi<TRACE>(d, c, cqi, u); };
     short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
     int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
     uint8_t* o_mcs = r.mcs ? r.mcs + tb * U : nullptr;
@@ -767,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         if ((ALGO == 8 || ALGO == 9) && (!act || act[u])) c.wd[s] = 1;
       }
     }
+    if (stage) cp_async_wait_all();   /* own copies done; the barrier publishes everybody's */
     __syncthreads();
 
     RS_TICK(0);
@@ -774,12 +818,12 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < d.n_chunks; ++ch) {
         const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
-        const int j0 = d.slice_ptr[s0], j1 = d.slice_ptr[s1];
+        const int j0 = c.sptr[s0], j1 = c.sptr[s1];
         if (ch == 0 && warp == (rot + kWarps - 1) % kWarps)
           slice_quotas(d, c, r.rand2[2 * tb], r.rand2[2 * tb + 1], lane, o_tgt, o_quo);
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
-          const int u = d.slice_ues[j];
+          const int u = c.sues[j];
           c.mtab[q] = cq ? __ddiv_rn(d.epow[d.ue_to_slice[u] * 16 + cq], c.den[u]) : 0.0;
         }
         __syncthreads();
@@ -793,11 +837,11 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             double best[4] = {-1.0, -1.0, -1.0, -1.0};
             int bu[4] = {kNoUe, kNoUe, kNoUe, kNoUe};
             int bc[4] = {0, 0, 0, 0};
-            for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
-              const int u = d.slice_ues[j];
+            for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
+              const int u = c.sues[j];
               if (act && !act[u]) continue;
               unsigned w;
-              const uint8_t* row_u = ue_cqi<TRACE>(d, c, cqi, u);
+              const uint8_t* row_u = row_of(u);
               if (nib) {   /* four nibbles -> one per byte, then the same extraction as the u8 layout */
                 const unsigned h = *(const unsigned short*)(row_u + (g0 >> 1));
                 w = (h & 0xfu) | ((h & 0xf0u) << 4) | ((h & 0xf00u) << 8) | ((h & 0xf000u) << 12);
@@ -825,10 +869,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             const int s = s0 + q / G, g = q % G;
             double best = -1.0;
             int bu = kNoUe, bc = 0;
-            for (int j = d.slice_ptr[s]; j < d.slice_ptr[s + 1]; ++j) {
-              const int u = d.slice_ues[j];
+            for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
+              const int u = c.sues[j];
               if (act && !act[u]) continue;
-              const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
+              const int cq = cqi_first_rb(d, row_of(u), g);
               const double m = c.mtab[(j - j0) * kMStride + cq];
               if (m > best) { best = m; bu = u; bc = cq; }
             }
@@ -879,10 +923,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       }
     } else if (ALGO == 7) {
       /* ---- NVS: enterprise argmax over the served slice's users for every RBG (nvs.cpp:275-311) */
-      const int j0 = d.slice_ptr[served], j1 = d.slice_ptr[served + 1];
+      const int j0 = c.sptr[served], j1 = c.sptr[served + 1];
       for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
         const int j = j0 + (q >> 4), cq = q & 15;
-        const int u = d.slice_ues[j];
+        const int u = c.sues[j];
         c.mtab[q] = cq ? __ddiv_rn(d.epow[served * 16 + cq], c.den[u]) : 0.0;
       }
       __syncthreads();
@@ -890,10 +934,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         double best = -1.0;   /* metrics are >= 0, so this behaves like numeric_limits::lowest() */
         int bu = -1;
         for (int j = j0; j < j1; ++j) {
-          const int u = d.slice_ues[j];
+          const int u = c.sues[j];
           if (act && !act[u]) continue;
           if (d.data <= 0) continue;
-          const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
+          const int cq = cqi_first_rb(d, row_of(u), g);
           const double m = c.mtab[(j - j0) * kMStride + cq];
           if (m > best) { best = m; bu = u; }
         }
@@ -907,7 +951,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         int bu = 0x7fffffff;
         for (int u = lane; u < U; u += 32) {
           if (act && !act[u]) continue;
-          const int cq = cqi_first_rb(d, ue_cqi<TRACE>(d, c, cqi, u), g);
+          const int cq = cqi_first_rb(d, row_of(u), g);
           const double m = __ddiv_rn(d.epow[cq], c.den[u]);
           if (m > best) { best = m; bu = u; }
         }
@@ -930,7 +974,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, ue_cqi<TRACE>(d, c, cqi, u), u, m_lo, m_hi, o_bits, o_mcs, o_fc);
+      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;
     }
@@ -941,6 +985,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       c.quota[s] = 0;
     }
     __syncthreads();
+    if (stage && t + 1 < r.T && cqi_key(t + 1) != staged_key) { stage_cqi(t + 1); staged_key = cqi_key(t + 1); }
   }
 
   RS_TICK(6);

@@ -141,6 +141,9 @@ void build_eq_table(int nmax, std::vector<unsigned short>* tab) {
   }
 }
 constexpr int kEqMax = 2048;
+#ifndef RS_STAGE_MAX_SMEM
+#define RS_STAGE_MAX_SMEM (27 * 1024)   /* staging must leave room for eight cells per SM */
+#endif
 
 template <typename T>
 struct DevBuf {
@@ -186,6 +189,7 @@ struct rs_handle {
   DevBuf<uint8_t> trace_tab;
   DevBuf<int> ue_trace_off, trow_dev;
   int n_traces = 0, trace_rows = 0;
+  bool stage_ok = false;             /* the layout has room for a TTI of CQI (cp.async staging) */
   int* trow_pinned = nullptr;
   size_t trow_pinned_n = 0;
   DevBuf<unsigned long long> stats;
@@ -452,7 +456,14 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   }
   d.n_chunks = (int)chunks.size() - 1;
   d.m_cap = m_cap;
+  /* stage a TTI's CQI in shared memory when the layout is one value per RBG, rows are 16-byte multiples
+   * and the cell still fits eight to an SM */
   h->layout = rs::make_layout(S, U, G, m_cap);
+  h->stage_ok = false;
+  if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
+    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row);
+    if (staged.total <= RS_STAGE_MAX_SMEM) { h->layout = staged; h->stage_ok = true; }
+  }
   d.lay = h->layout;
 
   /* ---- device ---- */
@@ -601,6 +612,7 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.active_tti_stride = active_tti_stride;
     a.dt = h->dt_dev.p + t0;
     a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
     if (d_out) {
       a.rbg_to_ue = d_out->rbg_to_ue ? d_out->rbg_to_ue + (size_t)t0 * B * G : nullptr;
       a.tbs_bits = d_out->tbs_bits ? d_out->tbs_bits + (size_t)t0 * B * U : nullptr;
@@ -665,6 +677,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
     a.dt = h->dt_dev.p + t0;
     a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    a.stage = h->stage_ok ? 1 : 0;   /* slot buffers come from cudaMalloc; B*U*C is a multiple of 16 when stage_ok */
     if (out) {
       a.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
       a.tbs_bits = out->tbs_bits ? s.tbs_bits.p : nullptr;
@@ -911,7 +924,12 @@ int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h) {
 
 int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
                  int32_t* perm_out) {
-  if (!keys || !perm_out || n_arrays < 1 || n < 1 || n > 4096) return fail(RS_ERR_ARG, "rs_test_sort: bad argument");
+  return rs_test_sort_timed(device, keys, n_arrays, n, depth_limit, perm_out, 1, nullptr);
+}
+
+int rs_test_sort_timed(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t n, int32_t depth_limit,
+                       int32_t* perm_out, int32_t reps, float* ms_per_launch) {
+  if (!keys || !perm_out || n_arrays < 1 || n < 1 || n > 4096 || reps < 1) return fail(RS_ERR_ARG, "rs_test_sort: bad argument");
   CU(cudaSetDevice(device));
   if (depth_limit < 0) { int lg = 0; for (int m = n; m > 1; m >>= 1) lg++; depth_limit = 2 * lg; }
   const rs::Layout L = rs::make_layout(1, 0, n, 0);
@@ -932,8 +950,23 @@ int rs_test_sort(int32_t device, const uint8_t* keys, int32_t n_arrays, int32_t 
   if (e != cudaSuccess) { cudaFree(dk); return fail(RS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
   e = cudaMemcpy(dk, keys, (size_t)n_arrays * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
     rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp, de, de ? eq_max : 0, L);
+    cudaEventRecord(e0);
+    for (int r = 1; r < reps; ++r)
+      rs::rs_sort_test_kernel<<<n_arrays, rs::kThreads, L.total>>>(dk, n, depth_limit, dp, de, de ? eq_max : 0, L);
+    cudaEventRecord(e1);
     e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess && ms_per_launch && reps > 1) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_per_launch = ms / (float)(reps - 1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
   }
   if (e == cudaSuccess) e = cudaMemcpy(perm_out, dp, (size_t)n_arrays * n * 4, cudaMemcpyDeviceToHost);
   cudaFree(dk);

@@ -28,6 +28,7 @@ ABI_SYMBOLS = (
     "rs_set_state", "rs_get_state", "rs_reset_state", "rs_step", "rs_run_device", "rs_run_host",
     "rs_synth_cqi", "rs_synth_rand2", "rs_stats_device", "rs_get_stats", "rs_launch_count",
     "rs_smem_bytes", "rs_threads_per_cta", "rs_algorithmic_bytes_per_cell_tti", "rs_test_sort",
+    "rs_test_sort_timed",
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
 )
@@ -90,6 +91,8 @@ def lib():
         L.rs_algorithmic_bytes_per_cell_tti.argtypes = [C.c_void_p]
         L.rs_algorithmic_bytes_per_cell_tti.restype = C.c_int64
         L.rs_test_sort.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.rs_test_sort_timed.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.POINTER(C.c_float)]
         L.rs_parse_trace_file.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
         L.rs_parse_mapping_file.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.rs_trace_row.argtypes = [C.c_double, C.c_int32]
@@ -393,6 +396,16 @@ def test_sort(keys, depth_limit=-1, device=0) -> np.ndarray:
     perm = np.empty(keys.shape, dtype=np.int32)
     _check(lib().rs_test_sort(int(device), _ptr(keys), keys.shape[0], keys.shape[1], int(depth_limit), _ptr(perm)))
     return perm
+
+
+def test_sort_timed(keys, reps=20, depth_limit=-1, device=0):
+    """(perm, ms per launch) of the device sort over all rows of keys (development aid)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint8)
+    perm = np.empty(keys.shape, dtype=np.int32)
+    ms = C.c_float(0)
+    _check(lib().rs_test_sort_timed(int(device), _ptr(keys), keys.shape[0], keys.shape[1], int(depth_limit),
+                                    _ptr(perm), int(reps), C.byref(ms)))
+    return perm, float(ms.value)
 
 
 def jain_index(stats: np.ndarray, n_ues_per_slice: np.ndarray) -> np.ndarray:
