@@ -188,6 +188,32 @@ int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int
 int rs_stats_device(rs_handle* h, uint64_t* d_stats);
 int rs_get_stats(rs_handle* h, uint64_t* stats);
 
+/* ---- log-compatible writer (host only, no GPU needed) ------------------------------------------
+ * The reference's only "output format" is what its schedulers print each TTI and what the paper's
+ * plotters parse (NSDI23-radiosaber-experiments/exp-customization/plot_throughput.py:35-47):
+ *   stdout  "slice_id, target_rbs, quota_rbgs: (i, t, q) ..."   downlink-transport-scheduler.cpp:523-527
+ *           "<ts>" and "User(<u>) allocated RBGS: <g>(<cqi>) ... final_cqi: <c>"   :631-649 (NVS :314-332)
+ *   stderr  "all_bytes: <n>"                                     :366-374 (id 9), :265-270 (id 8)
+ *           "<ts> app: <a> cumu_bytes: <b> cumu_rbs: <r> hol_delay: <d> user: <u> slice: <s>"
+ *                                                                :192-199, nvs :244-251, dl-pf :89-96
+ * An rs_log regenerates that text, byte for byte, for ONE cell of a batch from the results the device
+ * path returns; it keeps the bearer's cumulative byte / RB counters itself.  <ts> is the scheduler's
+ * TTI counter (PacketScheduler::m_ts, packet-scheduler.cpp:292-300: +1 per DoStopSchedule since the eNB
+ * was created, so the first TTI with bearers of a SingleCellWithI run is 100). */
+typedef struct rs_log rs_log;
+int rs_log_create(const rs_config* cfg, rs_log** out);
+void rs_log_destroy(rs_log* lg);
+int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes /*[U]*/, const uint64_t* cum_rbs /*[U]*/);
+int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs);
+/* Appends one TTI of one cell.  cqi [U][row] in cfg's CQI layout; rbg_to_ue [G]; tbs_bits [U];
+ * final_cqi [U] (ids 7/8/9); slice_target / slice_quota [S] (ids 8/9). */
+int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,
+               const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota);
+/* The text accumulated so far (NUL-terminated, owned by the log) and a reset. */
+const char* rs_log_stdout(rs_log* lg, int64_t* len);
+const char* rs_log_stderr(rs_log* lg, int64_t* len);
+void rs_log_clear(rs_log* lg);
+
 /* Introspection for benchmarks and tests. */
 int64_t rs_launch_count(const rs_handle* h);      /* kernels launched by this handle so far */
 int32_t rs_smem_bytes(const rs_handle* h);        /* dynamic shared memory per CTA of the TTI kernel */

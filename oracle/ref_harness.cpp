@@ -117,6 +117,8 @@ struct Options {
   int time_every = 0;     /* print cumulative scheduler seconds every N recorded TTIs */
   bool gpu = false;       /* install the product's RsGpuScheduler instead of the reference class */
   bool keep_log = false;
+  std::string log_out;    /* PREFIX: the reference's own stdout / stderr text of every recorded TTI goes to
+                             PREFIX.stdout / PREFIX.stderr (golden text for the log-writer parity test) */
 };
 static Options g_opt;
 static FILE* g_out = nullptr;
@@ -126,6 +128,12 @@ static int g_recorded = 0;
 static double g_sched_seconds = 0;
 static long g_sched_calls = 0;
 static std::stringstream g_capture;
+static std::stringstream g_cerr_capture;   /* std::cerr while --log-out is active */
+static FILE* g_log_stdout = nullptr;
+static FILE* g_log_stderr = nullptr;
+static char* g_cstderr_buf = nullptr;       /* C stderr (fprintf(stderr, "all_bytes ...")) of the current TTI */
+static size_t g_cstderr_len = 0;
+static FILE* g_cstderr = nullptr;
 
 template <typename T>
 static void Put(const T* p, size_t n) {
@@ -204,9 +212,30 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
   g_rand_in_call = 0;
   g_capture.str(std::string());
   g_capture.clear();
+  FILE* saved_c_stderr = stderr;
+  if (g_log_stderr) {
+    g_cerr_capture.str(std::string());
+    g_cerr_capture.clear();
+    g_cstderr = open_memstream(&g_cstderr_buf, &g_cstderr_len);
+    stderr = g_cstderr;
+  }
   auto t0 = std::chrono::steady_clock::now();
   base_call();
   auto t1 = std::chrono::steady_clock::now();
+  if (g_log_stderr) {
+    /* inside one TTI the C-stream lines (all_bytes, printed from RBsAllocation) come before the
+     * std::cerr lines (DoStopSchedule) */
+    fflush(g_cstderr);
+    stderr = saved_c_stderr;
+    fclose(g_cstderr);
+    fwrite(g_cstderr_buf, 1, g_cstderr_len, g_log_stderr);
+    free(g_cstderr_buf);
+    g_cstderr_buf = nullptr;
+    const std::string e = g_cerr_capture.str();
+    fwrite(e.data(), 1, e.size(), g_log_stderr);
+    const std::string o = g_capture.str();
+    fwrite(o.data(), 1, o.size(), g_log_stdout);
+  }
   g_sched_seconds += std::chrono::duration<double>(t1 - t0).count();
   g_sched_calls++;
   if (g_opt.time_every > 0 && g_sched_calls % g_opt.time_every == 0) {
@@ -424,6 +453,7 @@ int main(int argc, char** argv) {
     else if (a == "--time") g_opt.timing = true;
     else if (a == "--time-every") g_opt.time_every = atoi(next().c_str());
     else if (a == "--keep-log") g_opt.keep_log = true;
+    else if (a == "--log-out") g_opt.log_out = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -448,7 +478,13 @@ int main(int argc, char** argv) {
   /* the reference prints per-TTI logs on both streams; capture stdout (parsed
    * per TTI above) and drop stderr unless asked to keep it */
   std::streambuf* cout_buf = std::cout.rdbuf(g_capture.rdbuf());
-  std::streambuf* cerr_buf = g_opt.keep_log ? nullptr : std::cerr.rdbuf(nullptr);
+  if (!g_opt.log_out.empty()) {
+    g_log_stdout = fopen((g_opt.log_out + ".stdout").c_str(), "w");
+    g_log_stderr = fopen((g_opt.log_out + ".stderr").c_str(), "w");
+    if (!g_log_stdout || !g_log_stderr) { fprintf(stderr, "cannot write the --log-out files\n"); return 2; }
+  }
+  std::streambuf* cerr_buf = g_log_stderr ? std::cerr.rdbuf(g_cerr_capture.rdbuf())
+                                          : (g_opt.keep_log ? nullptr : std::cerr.rdbuf(nullptr));
   FILE* devnull = fopen("/dev/null", "w");
   FILE* saved_stderr = stderr;
   if (!g_opt.keep_log && devnull) stderr = devnull; /* fprintf(stderr, "all_bytes...") of transport.cpp:374 */
@@ -464,6 +500,8 @@ int main(int argc, char** argv) {
   std::cout.rdbuf(cout_buf);
   if (cerr_buf) std::cerr.rdbuf(cerr_buf);
   if (g_out) fclose(g_out);
+  if (g_log_stdout) fclose(g_log_stdout);
+  if (g_log_stderr) fclose(g_log_stderr);
   fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_recorded,
           g_sched_calls, g_sched_seconds);
   return g_recorded == g_opt.n_ttis ? 0 : 3;

@@ -836,6 +836,141 @@ int rs_set_traces(rs_handle* h, const uint8_t* traces, int32_t n_traces, int32_t
   return RS_OK;
 }
 
+/* ---- log-compatible writer (host only) --------------------------------------------------------
+ * Regenerates, from the batch results, the text the reference prints per TTI so that its own plotters
+ * (NSDI23-radiosaber-experiments/ ... /plot_throughput.py:35-47) work unchanged. */
+struct rs_log {
+  int algo = 9, S = 0, U = 0, G = 0, R = 0, rbg = 0, layout = 0, row = 0, data = 0;
+  std::vector<int> u2s;
+  std::vector<uint64_t> cum_bytes, cum_rbs;
+  double eff[16];
+  std::string out, err;
+};
+
+int rs_log_create(const rs_config* cfg, rs_log** out) {
+  if (!cfg || !out || !cfg->ue_to_slice) return fail(RS_ERR_ARG, "rs_log_create: bad argument");
+  if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0 || cfg->n_ues < 1 ||
+      cfg->n_slices < 1 || cfg->cqi_per_rb < 0 || cfg->cqi_per_rb > 2)
+    return fail(RS_ERR_ARG, "rs_log_create: bad configuration");
+  rs_log* lg = new (std::nothrow) rs_log;
+  if (!lg) return fail(RS_ERR_ARG, "out of memory");
+  lg->algo = cfg->algo; lg->S = cfg->n_slices; lg->U = cfg->n_ues; lg->R = cfg->n_rbs; lg->rbg = cfg->rbg_size;
+  lg->G = lg->R / lg->rbg; lg->layout = cfg->cqi_per_rb; lg->data = cfg->data_to_transmit;
+  lg->row = lg->layout == 1 ? lg->R : (lg->layout == 2 ? lg->G / 2 : lg->G);
+  lg->u2s.assign(cfg->ue_to_slice, cfg->ue_to_slice + lg->U);
+  lg->cum_bytes.assign(lg->U, 0);
+  lg->cum_rbs.assign(lg->U, 0);
+  lg->eff[0] = 0.0;
+  for (int c = 1; c <= 15; ++c) lg->eff[c] = eff_from_cqi(c);
+  *out = lg;
+  return RS_OK;
+}
+
+void rs_log_destroy(rs_log* lg) { delete lg; }
+
+int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes, const uint64_t* cum_rbs) {
+  if (!lg) return fail(RS_ERR_ARG, "null log");
+  if (cum_bytes) lg->cum_bytes.assign(cum_bytes, cum_bytes + lg->U);
+  if (cum_rbs) lg->cum_rbs.assign(cum_rbs, cum_rbs + lg->U);
+  return RS_OK;
+}
+
+int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,
+               const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota) {
+  if (!lg || !cqi || !rbg_to_ue || !tbs_bits) return fail(RS_ERR_ARG, "rs_log_tti: bad argument");
+  const int U = lg->U, G = lg->G, S = lg->S, algo = lg->algo;
+  if ((algo == 8 || algo == 9) && (!slice_target || !slice_quota)) return fail(RS_ERR_ARG, "rs_log_tti: ids 8/9 need targets and quotas");
+  if (algo != 1 && !final_cqi) return fail(RS_ERR_ARG, "rs_log_tti: final_cqi missing");
+  char buf[256];
+  auto cqi_at = [&](int u, int g) -> int {   /* CQI on the first RB of RBG g, what :641 prints */
+    const uint8_t* p = cqi + (size_t)u * lg->row;
+    if (lg->layout == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
+    return lg->layout == 1 ? p[(size_t)g * lg->rbg] : p[g];
+  };
+  std::vector<int> n_rbg(U, 0);
+  int scheduled = 0;
+  for (int g = 0; g < G; ++g) {
+    const int u = rbg_to_ue[g];
+    if (u < -1 || u >= U) return fail(RS_ERR_ARG, "rs_log_tti: rbg_to_ue[%d] = %d", g, u);
+    if (u >= 0) { n_rbg[u]++; scheduled++; }
+  }
+  /* RBsAllocation only runs (and prints) when at least one user is schedulable (transport.cpp:152-168);
+   * with every bearer idle nothing is allocated and nothing is printed */
+  bool ran = scheduled > 0;
+  if (!ran && (algo == 8 || algo == 9))
+    for (int s = 0; s < S; ++s) ran = ran || slice_target[s] != 0 || slice_quota[s] != 0;
+  if (ran && algo != 1) {
+    if (algo == 8 || algo == 9) {
+      /* stdout, downlink-transport-scheduler.cpp:523-527 */
+      lg->out += "slice_id, target_rbs, quota_rbgs: ";
+      for (int s = 0; s < S; ++s) {
+        snprintf(buf, sizeof buf, "(%d, %d, %d) ", s, slice_target[s], slice_quota[s]);
+        lg->out += buf;
+      }
+      lg->out += "\n";
+      /* stderr, :366-374 / :265-270: sum over RBGs of the winner's efficiency, in RBG order */
+      double sum_bits = 0;
+      for (int g = 0; g < G; ++g) sum_bits += rbg_to_ue[g] >= 0 ? lg->eff[cqi_at(rbg_to_ue[g], g)] : 0.0;
+      snprintf(buf, sizeof buf, "all_bytes: %.0f\n", sum_bits * 180 / 8 * 4);
+      lg->err += buf;
+    }
+    /* stdout, :631-649 (NVS: downlink-nvs-scheduler.cpp:314-332) */
+    snprintf(buf, sizeof buf, "%llu\n", (unsigned long long)timestamp);
+    lg->out += buf;
+    for (int u = 0; u < U; ++u) {
+      if (!n_rbg[u]) continue;
+      snprintf(buf, sizeof buf, "User(%d) allocated RBGS:", u);
+      lg->out += buf;
+      for (int g = 0; g < G; ++g)
+        if (rbg_to_ue[g] == u) {
+          snprintf(buf, sizeof buf, " %d(%d)", g, cqi_at(u, g));
+          lg->out += buf;
+        }
+      snprintf(buf, sizeof buf, " final_cqi: %d\n", (int)final_cqi[u]);
+      lg->out += buf;
+    }
+  }
+  /* stderr, DoStopSchedule: transport.cpp:177-199, nvs.cpp:226-251, dl-pf-packet-scheduler.cpp:80-96.
+   * Application id == user id and the head-of-line delay of an infinite buffer is 0 in the backlogged
+   * configurations this library covers. */
+  for (int u = 0; u < U; ++u) {
+    const int avail = tbs_bits[u] / 8;
+    if (avail <= 0) continue;
+    int sent = avail;
+    if (algo != 1) {
+      if (lg->data <= 0) continue;
+      sent = std::min(avail, lg->data);
+    }
+    lg->cum_bytes[u] += (uint64_t)sent;
+    lg->cum_rbs[u] += (uint64_t)n_rbg[u] * lg->rbg;
+    snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: 0 user: %d slice: %d\n",
+             (unsigned long long)timestamp, u, (unsigned long long)lg->cum_bytes[u],
+             (unsigned long long)lg->cum_rbs[u], u, lg->u2s[u]);
+    lg->err += buf;
+  }
+  return RS_OK;
+}
+
+const char* rs_log_stdout(rs_log* lg, int64_t* len) {
+  if (!lg) return "";
+  if (len) *len = (int64_t)lg->out.size();
+  return lg->out.c_str();
+}
+const char* rs_log_stderr(rs_log* lg, int64_t* len) {
+  if (!lg) return "";
+  if (len) *len = (int64_t)lg->err.size();
+  return lg->err.c_str();
+}
+void rs_log_clear(rs_log* lg) {
+  if (lg) { lg->out.clear(); lg->err.clear(); }
+}
+int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs) {
+  if (!lg) return fail(RS_ERR_ARG, "null log");
+  if (cum_bytes) memcpy(cum_bytes, lg->cum_bytes.data(), sizeof(uint64_t) * lg->U);
+  if (cum_rbs) memcpy(cum_rbs, lg->cum_rbs.data(), sizeof(uint64_t) * lg->U);
+  return RS_OK;
+}
+
 int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
             const rs_outputs* out) {
   return rs_run_host(h, 1, cqi, 1, rand2, active, &dt, out, 1);

@@ -31,6 +31,8 @@ ABI_SYMBOLS = (
     "rs_test_sort_timed",
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
+    "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti",
+    "rs_log_stdout", "rs_log_stderr", "rs_log_clear",
 )
 
 
@@ -102,6 +104,18 @@ def lib():
                                            C.c_void_p, C.POINTER(_Out), C.c_int32]
         L.rs_run_traces_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(_Out), C.c_int32]
+        L.rs_log_create.argtypes = [C.POINTER(_Cfg), C.POINTER(C.c_void_p)]
+        L.rs_log_destroy.argtypes = [C.c_void_p]
+        L.rs_log_destroy.restype = None
+        L.rs_log_set_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rs_log_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rs_log_tti.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.rs_log_stdout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.rs_log_stdout.restype = C.c_char_p
+        L.rs_log_stderr.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.rs_log_stderr.restype = C.c_char_p
+        L.rs_log_clear.argtypes = [C.c_void_p]
+        L.rs_log_clear.restype = None
         _lib = L
     return _lib
 
@@ -333,6 +347,60 @@ class Scheduler:
     @property
     def algorithmic_bytes_per_cell_tti(self):
         return int(lib().rs_algorithmic_bytes_per_cell_tti(self._h))
+
+
+class LogWriter:
+    """The reference's per-TTI stdout / stderr text for ONE cell, regenerated from batch results
+    (downlink-transport-scheduler.cpp:192-199, 523-527, 631-649; host only)."""
+
+    def __init__(self, algo, ue_to_slice, n_slices, n_rbs=512, rbg_size=8, cqi_per_rb=0,
+                 data_to_transmit=100000000):
+        self._u2s = np.ascontiguousarray(ue_to_slice, dtype=np.int32)
+        self.U, self.S, self.G = int(self._u2s.shape[0]), int(n_slices), int(n_rbs) // int(rbg_size)
+        cfg = _Cfg(int(algo), self.S, self.U, int(n_rbs), int(rbg_size), int(cqi_per_rb), int(data_to_transmit), 0,
+                   None, None, _ptr(self._u2s), None)
+        self._h = C.c_void_p()
+        _check(lib().rs_log_create(C.byref(cfg), C.byref(self._h)))
+
+    def tti(self, timestamp, cqi, rbg_to_ue, tbs_bits, final_cqi=None, slice_target=None, slice_quota=None):
+        a = [np.ascontiguousarray(cqi, dtype=np.uint8), np.ascontiguousarray(rbg_to_ue, dtype=np.int16),
+             np.ascontiguousarray(tbs_bits, dtype=np.int32),
+             None if final_cqi is None else np.ascontiguousarray(final_cqi, dtype=np.uint8),
+             None if slice_target is None else np.ascontiguousarray(slice_target, dtype=np.int32),
+             None if slice_quota is None else np.ascontiguousarray(slice_quota, dtype=np.int32)]
+        _check(lib().rs_log_tti(self._h, int(timestamp), *[_ptr(x) for x in a]))
+
+    def set_counters(self, cum_bytes=None, cum_rbs=None):
+        cb = None if cum_bytes is None else np.ascontiguousarray(cum_bytes, dtype=np.uint64)
+        cr = None if cum_rbs is None else np.ascontiguousarray(cum_rbs, dtype=np.uint64)
+        _check(lib().rs_log_set_counters(self._h, _ptr(cb), _ptr(cr)))
+
+    def counters(self):
+        cb, cr = np.empty(self.U, np.uint64), np.empty(self.U, np.uint64)
+        _check(lib().rs_log_get_counters(self._h, _ptr(cb), _ptr(cr)))
+        return cb, cr
+
+    @property
+    def stdout(self) -> str:
+        return lib().rs_log_stdout(self._h, None).decode()
+
+    @property
+    def stderr(self) -> str:
+        return lib().rs_log_stderr(self._h, None).decode()
+
+    def clear(self):
+        lib().rs_log_clear(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rs_log_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_cqi(cqi: np.ndarray) -> np.ndarray:

@@ -1,0 +1,98 @@
+"""Log-compatible writer: the text the reference's schedulers print per TTI, regenerated
+from batch results, against the unmodified reference's own output (tests/golden/logs/, captured by
+oracle/ref_harness.cpp --log-out through tools/make_golden_logs.py).  Host-only code: runs without a GPU;
+the GPU test feeds it with what the CUDA path returns."""
+import os
+
+import numpy as np
+import pytest
+
+from radiosaber_b200 import sched
+from tests.helpers import GOLDEN, load_golden
+
+LOGS = os.path.join(GOLDEN, "logs")
+CASES = sorted(f[:-7] for f in os.listdir(LOGS) if f.endswith(".stdout"))
+FIRST_TS = 100   # PacketScheduler::m_ts at the first TTI with bearers (applications start at 0.1 s)
+
+
+def _ref_text(name):
+    return (open(os.path.join(LOGS, name + ".stdout")).read(), open(os.path.join(LOGS, name + ".stderr")).read())
+
+
+def _n_ttis(name, rec):
+    out, err = _ref_text(name)
+    if int(rec["algo"]) == 1:
+        return len({l.split()[0] for l in err.splitlines()})
+    return sum(1 for l in out.splitlines() if l.strip().isdigit())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_writer_reproduces_reference_text_from_reference_results(name):
+    rec = load_golden(name)
+    algo = int(rec["algo"])
+    T = _n_ttis(name, rec)
+    assert T >= 4
+    lw = sched.LogWriter(algo, rec["ue_to_slice"], int(rec["S"]), cqi_per_rb=int(rec["cqi_per_rb"]))
+    for t in range(T):
+        lw.tti(FIRST_TS + t, rec["cqi"][t], rec["rbg_to_ue"][t], rec["bits"][t], rec["final_cqi"][t],
+               rec["target"][t] if algo in (8, 9) else None, rec["quota"][t] if algo in (8, 9) else None)
+    out, err = _ref_text(name)
+    assert lw.stdout == out
+    assert lw.stderr == err
+    cb, cr = lw.counters()
+    assert np.array_equal(cb, rec["cum_bytes"][T - 1]) and np.array_equal(cr, rec["cum_rbs"][T - 1])
+    lw.clear()
+    assert lw.stdout == "" and lw.stderr == ""
+
+
+def test_writer_layouts_agree():
+    rec = load_golden("a9_fix20x5_synth")
+    texts = []
+    for layout in (0, 1, 2):
+        lw = sched.LogWriter(9, rec["ue_to_slice"], int(rec["S"]), cqi_per_rb=layout)
+        cqi = rec["cqi"][0]
+        c = {0: cqi, 1: np.repeat(cqi, 8, axis=1), 2: sched.pack_cqi(cqi)}[layout]
+        lw.tti(100, c, rec["rbg_to_ue"][0], rec["bits"][0], rec["final_cqi"][0], rec["target"][0], rec["quota"][0])
+        texts.append((lw.stdout, lw.stderr))
+    assert texts[0] == texts[1] == texts[2]
+
+
+def test_plotter_style_parse_of_stderr():
+    """The fields plot_throughput.py:35-47 reads (ts, app, cumu_bytes, cumu_rbs, slice) round-trip."""
+    rec = load_golden("a8_fix20x5_synth")
+    lw = sched.LogWriter(8, rec["ue_to_slice"], int(rec["S"]))
+    for t in range(4):
+        lw.tti(100 + t, rec["cqi"][t], rec["rbg_to_ue"][t], rec["bits"][t], rec["final_cqi"][t], rec["target"][t],
+               rec["quota"][t])
+    last = {}
+    for line in lw.stderr.splitlines():
+        w = line.split()
+        if len(w) > 2 and w[1] == "app:":
+            last[int(w[2])] = (int(w[4]), int(w[6]), int(w[12]))
+    for u, (b, r, s) in last.items():
+        assert b == int(rec["cum_bytes"][3][u]) and r == int(rec["cum_rbs"][3][u]) and s == int(rec["ue_to_slice"][u])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_results_reproduce_reference_text(name):
+    """End to end: CUDA path -> results -> writer == the reference's own log text."""
+    rec = load_golden(name)
+    algo = int(rec["algo"])
+    T = _n_ttis(name, rec)
+    g = sched.Scheduler(algo, rec["weight"], rec["params"], rec["ue_to_slice"], 1, cqi_per_rb=int(rec["cqi_per_rb"]))
+    g.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
+                slice_offset=rec["state_before"][0][None] if algo in (8, 9) else None,
+                nvs_ewma=rec["state_before"][0][None] if algo == 7 else None)
+    res = g.run_host(rec["cqi"][:T, None], rec["rand2"][:T, None, :], rec["dt"][:T], want_aux=True)
+    lw = sched.LogWriter(algo, rec["ue_to_slice"], int(rec["S"]), cqi_per_rb=int(rec["cqi_per_rb"]))
+    for t in range(T):
+        lw.tti(FIRST_TS + t, rec["cqi"][t], res["rbg_to_ue"][t, 0], res["tbs_bits"][t, 0], res["final_cqi"][t, 0],
+               res["slice_target"][t, 0] if algo in (8, 9) else None,
+               res["slice_quota"][t, 0] if algo in (8, 9) else None)
+    out, err = _ref_text(name)
+    assert lw.stdout == out and lw.stderr == err
+    st = g.get_state()
+    cb, cr = lw.counters()
+    assert np.array_equal(cb, st["cum_bytes"][0]) and np.array_equal(cr, st["cum_rbs"][0])
+    g.close()
