@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -456,13 +457,18 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   }
   d.n_chunks = (int)chunks.size() - 1;
   d.m_cap = m_cap;
-  /* stage a TTI's CQI in shared memory when the layout is one value per RBG, rows are 16-byte multiples
-   * and the cell still fits eight to an SM */
+  /* Stage a TTI's CQI in shared memory (cp.async) when the layout is one value per RBG, rows are 16-byte
+   * multiples and the staged cell does not cost occupancy the batch could use: eight cells per SM for
+   * big batches, fewer when there are not that many cells per SM to begin with. */
   h->layout = rs::make_layout(S, U, G, m_cap);
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
     const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row);
-    if (staged.total <= RS_STAGE_MAX_SMEM) { h->layout = staged; h->stage_ok = true; }
+    const int kSmemPerSm = 227 * 1024, kSms = 148;
+    const int fit = kSmemPerSm / (staged.total + 1024);
+    const int floor_fit = 2;   /* big cells: two staged cells per SM beat more unstaged ones (tools/sweep_bench.py) */
+    const int wanted = std::min(floor_fit, (n_cells + kSms - 1) / kSms);
+    if (staged.total <= RS_STAGE_MAX_SMEM || (fit >= 1 && fit >= wanted)) { h->layout = staged; h->stage_ok = true; }
   }
   d.lay = h->layout;
 
