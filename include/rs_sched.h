@@ -10,6 +10,7 @@
  *     7  DownlinkNVSScheduler(cfg,false)  downlink-nvs-scheduler.cpp:94-142, 275-358
  *     8  DownlinkTransportScheduler(cfg,0) GreedyByRow   downlink-transport-scheduler.cpp:249-272
  *     9  DownlinkTransportScheduler(cfg,2) MaximizeCell  downlink-transport-scheduler.cpp:351-376
+ *    11  DownlinkNVSScheduler(cfg,true)   downlink-nvs-scheduler.cpp:405-528 (300-sample non-greedy PF)
  * This library is what a host-side subclass of PacketScheduler binds to (see
  * INTEGRATION.md and radiosaber_b200/host/rs_gpu_scheduler.h): every entry
  * point below takes plain pointers and sizes, returns an int status and never
@@ -41,7 +42,7 @@ extern "C" {
  * config (downlink-transport-scheduler.cpp:55-97, downlink-nvs-scheduler.cpp:46-87,
  * dl-pf-packet-scheduler.cpp:39-57). */
 typedef struct rs_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 11 NVS non-greedy */
   int32_t n_slices;         /* S  <= RS_MAX_SLICES */
   int32_t n_ues;            /* U; user j == UE id j (flows/application/Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (core/spectrum/bandwidth-manager.cpp:98-102) */
@@ -102,8 +103,11 @@ int rs_reset_state(rs_handle* h);
  * UpdateAverageTransmissionRate, SelectFlowsToSchedule, RBsAllocation and the byte accounting of
  * DoStopSchedule.  HOST buffers in, HOST buffers out, synchronous.
  *   cqi    [B][U][row] with row = G, n_rbs or G/2 bytes by cfg.cqi_per_rb, values 1..15
- *   rand2  [B][2]  the two rand() draws of downlink-transport-scheduler.cpp:490,511, each in
- *                  [0, INT32_MAX - S]; may be NULL for ids 1 and 7
+ *   rand2  [B][n]  the rand() values the scheduler draws this TTI, in call order, n =
+ *                  rs_rand_draws_per_cell_tti(): ids 8/9 n = 2, the two draws of
+ *                  downlink-transport-scheduler.cpp:490,511, each in [0, INT32_MAX - S]; id 11 n = 300 x the
+ *                  largest slice, sample-major over the served slice's users
+ *                  (downlink-nvs-scheduler.cpp:437-446 takes each value % 4); NULL for ids 1 and 7
  *   active [B][U]  1 = bearer has packets (GetDestination()->ACTIVE && HasPackets); NULL = all
  *   dt     Now - lastUpdate seen by RadioBearer::UpdateAverageTransmissionRate
  *          (radio-bearer.cpp:138-164); 0 skips the update like the reference does */
@@ -114,7 +118,7 @@ int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_
  *   d_cqi   [ceil(T/cqi_refresh)][B][U][row]: TTI t reads slab t / cqi_refresh (the reference refreshes
  *           CQI every 40 TTIs, enb-mac-entity.cc:38; the headline workload every TTI);
  *           cqi_tti_stride = bytes between slabs
- *   d_rand2 [T][B][2]
+ *   d_rand2 [T][B][n], n = rs_rand_draws_per_cell_tti()
  *   d_active [T][B][U] or NULL, active_tti_stride like cqi_tti_stride
  *   dt      HOST array [T]
  *   d_out   device pointers, arrays [T][B][...]; NULL members are skipped
@@ -177,7 +181,7 @@ int rs_run_traces_host(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, c
  * any (cell, epoch) shard can be produced on any GPU.  d_out: n_slabs slabs [B][U][row] in the handle's
  * CQI layout (0 or 2); slab j is the CQI of epoch epoch0 + j (epoch = tti / refresh). */
 int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t epoch0, int32_t n_slabs, uint8_t* d_out);
-/* d_out: int32 [n_ttis][B][2], values in [0, INT32_MAX - S]. */
+/* d_out: int32 [n_ttis][B][n], n = max(2, rs_rand_draws_per_cell_tti()), values in [0, INT32_MAX - S]. */
 int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int32_t n_ttis, int32_t* d_out);
 
 /* Per-slice totals over every cell of this handle (what the reference's plotters sum from the
@@ -215,6 +219,7 @@ const char* rs_log_stderr(rs_log* lg, int64_t* len);
 void rs_log_clear(rs_log* lg);
 
 /* Introspection for benchmarks and tests. */
+int32_t rs_rand_draws_per_cell_tti(const rs_handle* h);   /* int32 values per cell in rand2 (0, 2 or 300 x largest slice) */
 int64_t rs_launch_count(const rs_handle* h);      /* kernels launched by this handle so far */
 int32_t rs_smem_bytes(const rs_handle* h);        /* dynamic shared memory per CTA of the TTI kernel */
 int32_t rs_threads_per_cta(const rs_handle* h);

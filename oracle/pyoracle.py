@@ -33,6 +33,7 @@ class _Io(C.Structure):
         ("cqi", C.c_void_p), ("active", C.c_void_p), ("rand2", C.c_void_p), ("dt", C.c_double),
         ("rbg_to_ue", C.c_void_p), ("tbs_bits", C.c_void_p), ("mcs", C.c_void_p), ("final_cqi", C.c_void_p),
         ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
+        ("rand_stride", C.c_int32),
     ]
 
 
@@ -123,7 +124,7 @@ class OracleScheduler:
         assert cqi.size == B * U * (self.R if self.cqi_per_rb else G), cqi.shape
         if rand2 is None:
             rand2 = np.zeros((B, 2), dtype=np.int32)
-        rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, 2)
+        rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, -1)   # [B][2]; id 11: [B][300 * users]
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
         out = {
             "rbg_to_ue": np.empty((B, G), dtype=np.int16),
@@ -142,7 +143,8 @@ class OracleScheduler:
                  _ptr(self.slice_offset), _ptr(self.nvs_ewma),
                  _ptr(cqi), _ptr(act), _ptr(rand2), float(dt),
                  _ptr(out["rbg_to_ue"]), _ptr(out["tbs_bits"]), _ptr(out["mcs"]), _ptr(aux.get("final_cqi")),
-                 _ptr(aux.get("slice_target")), _ptr(aux.get("slice_quota")), _ptr(aux.get("nvs_slice")))
+                 _ptr(aux.get("slice_target")), _ptr(aux.get("slice_quota")), _ptr(aux.get("nvs_slice")),
+                 int(rand2.shape[1]))
         rc = lib().rso_step(C.byref(self._cfg), B, C.byref(io), self.n_threads)
         if rc != 0:
             raise RuntimeError(f"rso_step failed: {rc}")

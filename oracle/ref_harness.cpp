@@ -117,6 +117,8 @@ struct Options {
   int time_every = 0;     /* print cumulative scheduler seconds every N recorded TTIs */
   bool gpu = false;       /* install the product's RsGpuScheduler instead of the reference class */
   bool keep_log = false;
+  std::string rand_log;   /* every rand() value drawn inside each recorded DoSchedule: int32 n, int32 v[n] per TTI
+                             (id 11 draws 300 x users of them, downlink-nvs-scheduler.cpp:437-446) */
   std::string log_out;    /* PREFIX: the reference's own stdout / stderr text of every recorded TTI goes to
                              PREFIX.stdout / PREFIX.stderr (golden text for the log-writer parity test) */
 };
@@ -129,6 +131,7 @@ static double g_sched_seconds = 0;
 static long g_sched_calls = 0;
 static std::stringstream g_capture;
 static std::stringstream g_cerr_capture;   /* std::cerr while --log-out is active */
+static FILE* g_rand_log_file = nullptr;
 static FILE* g_log_stdout = nullptr;
 static FILE* g_log_stderr = nullptr;
 static char* g_cstderr_buf = nullptr;       /* C stderr (fprintf(stderr, "all_bytes ...")) of the current TTI */
@@ -247,6 +250,11 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
   int32_t rand2[2] = {0, 0};
   if (g_rand_log.size() >= 1) rand2[0] = g_rand_log[0];
   if (g_rand_log.size() >= 2) rand2[1] = g_rand_log[1];
+  if (g_rand_log_file) {
+    const int32_t n = (int32_t)g_rand_log.size();
+    fwrite(&n, 4, 1, g_rand_log_file);
+    for (int v : g_rand_log) { const int32_t x = v; fwrite(&x, 4, 1, g_rand_log_file); }
+  }
 
   std::vector<uint8_t> active(U, 0), final_cqi(U, 0);
   std::vector<int16_t> rbg_to_ue(G, -1);
@@ -327,7 +335,7 @@ class ObservedTransport : public DownlinkTransportScheduler {
 
 class ObservedNvs : public DownlinkNVSScheduler {
  public:
-  explicit ObservedNvs(std::string cfg) : DownlinkNVSScheduler(cfg, false) {}
+  explicit ObservedNvs(std::string cfg, bool nongreedy = false) : DownlinkNVSScheduler(cfg, nongreedy) {}
   void DoSchedule() override {
     ObservedSchedule(
         this, num_slices_, user_to_slice_, &slice_weights_, &slice_algo_params_,
@@ -408,6 +416,7 @@ struct Installer {
     switch (g_opt.algo) {
       case 1: s = new ObservedPf(g_opt.config); break;
       case 7: s = new ObservedNvs(g_opt.config); break;
+      case 11: s = new ObservedNvs(g_opt.config, true); break;   /* DLScheduler_NVS_NONGREEDY, ENodeB.cpp:351-355 */
       case 8: s = new ObservedTransport(g_opt.config, 0); break;
       default: s = new ObservedTransport(g_opt.config, 2); break;
     }
@@ -454,6 +463,7 @@ int main(int argc, char** argv) {
     else if (a == "--time-every") g_opt.time_every = atoi(next().c_str());
     else if (a == "--keep-log") g_opt.keep_log = true;
     else if (a == "--log-out") g_opt.log_out = next();
+    else if (a == "--rand-log") g_opt.rand_log = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -466,6 +476,10 @@ int main(int argc, char** argv) {
     if (!g_out) { fprintf(stderr, "cannot write %s\n", g_opt.out.c_str()); return 2; }
   }
   if (!g_opt.cqi_file.empty()) g_cqi_script = ReadAll(g_opt.cqi_file);
+  if (!g_opt.rand_log.empty()) {
+    g_rand_log_file = fopen(g_opt.rand_log.c_str(), "wb");
+    if (!g_rand_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.rand_log.c_str()); return 2; }
+  }
   if (!g_opt.rand_file.empty()) {
     std::vector<uint8_t> raw = ReadAll(g_opt.rand_file);
     g_rand_vec.resize(raw.size() / 4);
@@ -500,6 +514,7 @@ int main(int argc, char** argv) {
   std::cout.rdbuf(cout_buf);
   if (cerr_buf) std::cerr.rdbuf(cerr_buf);
   if (g_out) fclose(g_out);
+  if (g_rand_log_file) fclose(g_rand_log_file);
   if (g_log_stdout) fclose(g_log_stdout);
   if (g_log_stderr) fclose(g_log_stderr);
   fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_recorded,

@@ -158,7 +158,7 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
       usr.cqi[r] = q;
       usr.eff[r] = EffFromCqi(q);
     }
-    if (cfg->dead_work || cfg->algo == 7) {
+    if (cfg->dead_work || cfg->algo == 7 || cfg->algo == 11) {
       std::vector<double> sinrs;
       for (int r = 0; r < R; ++r) sinrs.push_back(SinrFromCqi(usr.cqi[r]));
       usr.wide_cqi = CqiFromSinr(Eesm(sinrs));
@@ -380,7 +380,77 @@ void StepTransport(const CellView& c, const int32_t* row_m1) {
   for (const User& usr : users) AccountUser(c, usr);
 }
 
-/* DownlinkNVSScheduler::DoSchedule, nvs.cpp:196-218 (greedy variant, id 7). */
+/* DownlinkNVSScheduler::AssignRBsGivenMCS, nvs.cpp:489-528: per RBG the first user with the strictly
+ * largest metric, where a user counts only on RBGs whose CQI reaches its assigned MCS (the reference
+ * calls the assigned CQI level "mcs"); returns the sum of the winning metrics. */
+double AssignRbsGivenMcs(const CellView& c, const std::vector<User>& users, const std::vector<int>& assigned_mcs,
+                         std::vector<int>& rbgs_assignment) {
+  const int rbg_size = c.cfg->rbg_size;
+  const int nb_rbgs = (int)rbgs_assignment.size();
+  double pf_metric = 0;
+  for (int i = 0; i < nb_rbgs; i++) {
+    double highest_metric = -1;
+    for (size_t index = 0; index < users.size(); ++index) {
+      int cqi = users[index].cqi[i * rbg_size];
+      double metric = 0;
+      if (assigned_mcs[index] <= cqi) {
+        double sEff = EffFromCqi(assigned_mcs[index]);
+        /* UserToSchedule::GetAverageTransmissionRate, ps.cpp:423-433: 1 + sum of the bearers' rates */
+        double sum_rate = 1;
+        sum_rate += c.avg[users[index].id];
+        metric = sEff * 180000 / sum_rate;
+      }
+      if (highest_metric < metric) {
+        highest_metric = metric;
+        rbgs_assignment[i] = (int)index;
+      }
+    }
+    pf_metric += highest_metric;
+  }
+  return pf_metric;
+}
+
+/* DownlinkNVSScheduler::RBsAllocationNonGreedyPF, nvs.cpp:405-452 (id 11): 300 random per-user CQI
+ * back-offs (rand() % 4 below the user's best RBG), keep the first sample with the largest metric sum.
+ * draws = the rand() values in call order, 300 x users.size() of them. */
+void AllocateNonGreedy(const CellView& c, std::vector<User>& users, const int32_t* draws) {
+  const int rbg_size = c.cfg->rbg_size;
+  int nb_rbs = c.cfg->n_rbs;
+  nb_rbs = nb_rbs - (nb_rbs % rbg_size);
+  const int nb_rbgs = nb_rbs / rbg_size;
+  std::vector<int> user_highest_cqi;
+  for (const User& usr : users) {
+    int highest_cqi = 0;
+    for (int i = 0; i < nb_rbgs; i++) {
+      int cqi = usr.cqi[i * rbg_size];
+      if (highest_cqi < cqi) highest_cqi = cqi;
+    }
+    user_highest_cqi.push_back(highest_cqi);
+  }
+  std::vector<int> best_rbgs_assignment;
+  double highest_pf_metric = 0;
+  const int cqi_search_range = 4;
+  const int num_sample = 300;
+  size_t pos = 0;
+  for (int i = 0; i < num_sample; i++) {
+    std::vector<int> assigned_mcs;
+    std::vector<int> rbgs_assignment(nb_rbgs, -1);
+    for (size_t k = 0; k < user_highest_cqi.size(); k++)
+      assigned_mcs.push_back(std::max(user_highest_cqi[k] - draws[pos++] % cqi_search_range, 1));
+    double pf_metric = AssignRbsGivenMcs(c, users, assigned_mcs, rbgs_assignment);
+    if (highest_pf_metric < pf_metric) {
+      highest_pf_metric = pf_metric;
+      best_rbgs_assignment = rbgs_assignment;
+    }
+  }
+  for (size_t rbg_id = 0; rbg_id < best_rbgs_assignment.size(); rbg_id++) {
+    User& usr = users[best_rbgs_assignment[rbg_id]];
+    for (int j = (int)rbg_id * rbg_size; j < (int)(rbg_id + 1) * rbg_size; ++j) usr.rbs.push_back(j);
+    if (c.rbg_to_ue) c.rbg_to_ue[rbg_id] = (int16_t)usr.id;
+  }
+}
+
+/* DownlinkNVSScheduler::DoSchedule, nvs.cpp:196-218 (id 7; id 11 = the non-greedy variant). */
 void StepNvs(const CellView& c, const int32_t* row_m1) {
   const rso_config* cfg = c.cfg;
   const int S = cfg->n_slices, rbg_size = cfg->rbg_size;
@@ -416,6 +486,13 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   UpdateAverages(c);
   std::vector<User> users = SelectUsers(c, slice_id);
   if (users.empty()) return;
+
+  if (cfg->algo == 11) {
+    AllocateNonGreedy(c, users, c.rand2);
+    for (User& usr : users) FinalizeUser(c, usr, row_m1);
+    for (const User& usr : users) AccountUser(c, usr);
+    return;
+  }
 
   /* RBsAllocation, nvs.cpp:275-358 */
   int nb_rbs = cfg->n_rbs;
@@ -511,7 +588,7 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   c.ewma = io->nvs_ewma ? io->nvs_ewma + (size_t)b * S : nullptr;
   c.cqi = io->cqi + (size_t)b * cqi_stride;
   c.active = io->active ? io->active + (size_t)b * U : nullptr;
-  c.rand2 = io->rand2 ? io->rand2 + (size_t)b * 2 : nullptr;
+  c.rand2 = io->rand2 ? io->rand2 + (size_t)b * (io->rand_stride > 0 ? io->rand_stride : 2) : nullptr;
   c.dt = io->dt;
   c.rbg_to_ue = io->rbg_to_ue ? io->rbg_to_ue + (size_t)b * G : nullptr;
   c.tbs_bits = io->tbs_bits ? io->tbs_bits + (size_t)b * U : nullptr;
@@ -523,7 +600,7 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   ClearOutputs(c);
   switch (cfg->algo) {
     case 1: StepPf(c, row_m1); break;
-    case 7: StepNvs(c, row_m1); break;
+    case 7: case 11: StepNvs(c, row_m1); break;
     default: StepTransport(c, row_m1); break;
   }
 }
@@ -615,9 +692,10 @@ extern "C" {
 
 int rso_step(const rso_config* cfg, int32_t n_cells, rso_io* io, int32_t n_threads) {
   if (!cfg || !io || n_cells < 0) return 1;
-  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 8 && cfg->algo != 9) return 2;
+  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 8 && cfg->algo != 9 && cfg->algo != 11) return 2;
   if ((cfg->algo == 8 || cfg->algo == 9) && (!io->rand2 || !io->slice_offset)) return 3;
-  if (cfg->algo == 7 && !io->nvs_ewma) return 3;
+  if ((cfg->algo == 7 || cfg->algo == 11) && !io->nvs_ewma) return 3;
+  if (cfg->algo == 11 && (!io->rand2 || io->rand_stride < 300)) return 3;
   int32_t row_m1[27];
   if (cfg->tbs_row_m1) std::memcpy(row_m1, cfg->tbs_row_m1, sizeof(row_m1));
   else DefaultRowM1(row_m1);

@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 typedef struct rso_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber (single-cell-with-interference.h:94-118) */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 11 NVS non-greedy (single-cell-with-interference.h:94-118) */
   int32_t n_slices;         /* S */
   int32_t n_ues;            /* U; user j == UE id j (Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (bandwidth-manager.cpp:98-102) */
@@ -59,7 +59,9 @@ typedef struct rso_io {
   uint8_t* final_cqi;    /* [B][U] "final_cqi" of transport.cpp:649, 0 if unscheduled */
   int32_t* slice_target; /* [B][S] slice_target_rbs (ids 8/9) */
   int32_t* slice_quota;  /* [B][S] slice_quota_rbgs (ids 8/9) */
-  int32_t* nvs_slice;    /* [B] slice served (id 7) */
+  int32_t* nvs_slice;    /* [B] slice served (ids 7/11) */
+  int32_t rand_stride;   /* int32 values per cell in rand2: 0 or 2 for ids 8/9; id 11: >= 300 x the users of a
+                            slice, the rand() draws of nvs.cpp:437-446 in call order */
 } rso_io;
 
 /* One TTI for n_cells cells, n_threads host threads (cells are independent). */

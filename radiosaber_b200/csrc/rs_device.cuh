@@ -58,7 +58,7 @@ __constant__ ConstTables c_tab;
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
   int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, total;
+      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, ng_hc, ng_list, ng_mcs, ng_red, total;
 };
 
 struct DevCfg {
@@ -87,6 +87,8 @@ struct DevCfg {
   const uint8_t* trace_tab;
   const int* ue_trace_off;
   int trace_rows;
+  int rand_stride;         /* int32 rand() draws per cell-TTI in RunArgs::rand2: 2 (ids 8/9), 300 x max UEs per slice (id 11) */
+  int ng_ues;              /* id 11: largest slice */
   /* state, [B][U] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
   double* offset; double* ewma;
@@ -112,7 +114,8 @@ __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a *
  * when it fits there. */
 /* cq_bytes: room for one TTI of the cell's CQI ([U][cqi_row], staged with cp.async); 0 = CQI is read
  * from global memory where it lies. */
-__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0) {
+/* ng_ues: id 11 only, the largest number of UEs in a slice (scratch of the 300-sample search). */
+__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0) {
   Layout L;
   const int n = S * G;
   const int nw = (n + 31) / 32;
@@ -146,6 +149,10 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   L.sptr = rs_align(o, 4); o = L.sptr + 4 * (S + 1);
   L.sues = o; o += 2 * U;
   L.cq = rs_align(o, 16); o = L.cq + cq_bytes;
+  L.ng_red = rs_align(o, 8); o = L.ng_red + (ng_ues ? 16 * (RS_THREADS / 32) : 0);
+  L.ng_list = o; o += 2 * ng_ues;
+  L.ng_hc = o;   o += ng_ues;
+  L.ng_mcs = o;  o += ng_ues * RS_THREADS;
   L.total = rs_align(o, 16);
   return L;
 }
@@ -448,6 +455,7 @@ struct Cell {
   unsigned long long* cumb; unsigned long long* cumr;   /* this cell's rows of the HBM counters */
   double* tval; int* tx; int* utr; int* sptr; unsigned short* sues; uint8_t* cq; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
+  unsigned short* ng_list; unsigned char* ng_hc; unsigned char* ng_mcs; unsigned char* ng_red;
   SortBufs sb;
 };
 
@@ -465,6 +473,10 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.sptr = (int*)(smem + L.sptr);
   c.sues = (unsigned short*)(smem + L.sues);
   c.cq = smem + L.cq;
+  c.ng_list = (unsigned short*)(smem + L.ng_list);
+  c.ng_hc = smem + L.ng_hc;
+  c.ng_mcs = smem + L.ng_mcs;
+  c.ng_red = smem + L.ng_red;
   c.mask = (unsigned*)(smem + L.mask);
   c.target = (int*)(smem + L.target);
   c.quota = (int*)(smem + L.quota);
@@ -694,6 +706,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = d.S, U = d.U, G = d.G;
   const int b = blockIdx.x;
+  constexpr bool NVS = ALGO == 7 || ALGO == 11;   /* DownlinkNVSScheduler, greedy and non-greedy */
   if (b >= d.n_cells) return;
   c.cumb = d.cum_bytes + (size_t)b * U;
   c.cumr = d.cum_rbs + (size_t)b * U;
@@ -708,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     if (TRACE) c.utr[u] = d.ue_trace_off[i];
   }
   for (int s = tid; s < S; s += kThreads) {
-    c.off[s] = (ALGO == 7) ? d.ewma[(size_t)b * S + s] : ((ALGO == 1) ? 0.0 : d.offset[(size_t)b * S + s]);
+    c.off[s] = NVS ? d.ewma[(size_t)b * S + s] : ((ALGO == 1) ? 0.0 : d.offset[(size_t)b * S + s]);
     c.frb[s] = 0;
     c.wd[s] = 0;
     c.target[s] = 0;
@@ -765,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
     /* ---- NVS: SelectSliceToServe (nvs.cpp:94-142) runs before the EWMA update ---------------- */
     int served = -1;
-    if (ALGO == 7) {
+    if (NVS) {
       /* slices with at least one queued bearer */
       for (int u = tid; u < U; u += kThreads)
         if ((!act || act[u]) && d.data > 0) c.wd[d.ue_to_slice[u]] = 1;
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
         const int j0 = c.sptr[s0], j1 = c.sptr[s1];
         if (ch == 0 && warp == (rot + kWarps - 1) % kWarps)
-          slice_quotas(d, c, r.rand2[2 * tb], r.rand2[2 * tb + 1], lane, o_tgt, o_quo);
+          slice_quotas(d, c, r.rand2[tb * d.rand_stride], r.rand2[tb * d.rand_stride + 1], lane, o_tgt, o_quo);
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
           const int u = c.sues[j];
@@ -921,6 +934,88 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         if (c.misc[14]) c.off[s] = (double)(c.target[s] - c.frb[s] * d.rbg);
         else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
       }
+    } else if (ALGO == 11) {
+      /* ---- NVS non-greedy (RBsAllocationNonGreedyPF + AssignRBsGivenMCS, nvs.cpp:405-528): 300 samples
+       * of per-user CQI back-offs, one sample per thread at a time; the first sample with the largest
+       * sum over RBGs of the winning PF metric is kept. */
+      const int j0 = c.sptr[served], j1 = c.sptr[served + 1];
+      if (warp == 0) {   /* the users the reference lists: bearers of the served slice with packets, in order */
+        int cnt = 0;
+        for (int jb = j0; jb < j1; jb += 32) {
+          const int j = jb + lane;
+          const int u = j < j1 ? c.sues[j] : 0;
+          const bool in = j < j1 && (!act || act[u]) && d.data > 0;
+          const unsigned bal = __ballot_sync(kFull, in);
+          if (in) c.ng_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)u;
+          cnt += __popc(bal);
+        }
+        if (lane == 0) c.misc[13] = (unsigned)cnt;
+      }
+      __syncthreads();
+      const int Ua = (int)c.misc[13];
+      for (int q = tid; q < Ua; q += kThreads) {   /* user_highest_cqi, nvs.cpp:416-425 */
+        const uint8_t* row = row_of(c.ng_list[q]);
+        int hc = 0;
+        for (int g = 0; g < G; ++g) hc = max(hc, cqi_first_rb(d, row, g));
+        c.ng_hc[q] = (unsigned char)hc;
+      }
+      for (int q = tid; q < Ua * kMStride; q += kThreads) {   /* sEff * 180000 / (1 + avg), nvs.cpp:512-513 */
+        const int cq = q & 15;
+        c.mtab[q] = cq ? __ddiv_rn(d.epow[cq], __dadd_rn(1.0, c.avg[c.ng_list[q >> 4]])) : 0.0;
+      }
+      __syncthreads();
+      const int* draws = r.rand2 + tb * d.rand_stride;
+      unsigned char* my = c.ng_mcs + tid * d.ng_ues;
+      double best_pf = 0.0;
+      int best_i = 0x7fffffff;
+      if (Ua > 0) {
+        for (int i = tid; i < 300; i += kThreads) {
+          for (int q = 0; q < Ua; ++q) my[q] = (unsigned char)max((int)c.ng_hc[q] - draws[i * Ua + q] % 4, 1);
+          double pf = 0.0;
+          for (int g = 0; g < G; ++g) {
+            double highest = -1.0;
+            for (int q = 0; q < Ua; ++q) {
+              const int mcs = my[q];
+              const double m = (mcs <= cqi_first_rb(d, row_of(c.ng_list[q]), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
+              if (highest < m) highest = m;
+            }
+            pf = __dadd_rn(pf, highest);
+          }
+          if (best_pf < pf) { best_pf = pf; best_i = i; }   /* this thread's samples come in increasing order */
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double op = __shfl_xor_sync(kFull, best_pf, o);
+        const int oi = __shfl_xor_sync(kFull, best_i, o);
+        if (op > best_pf || (op == best_pf && oi < best_i)) { best_pf = op; best_i = oi; }
+      }
+      if (lane == 0) {
+        ((double*)c.ng_red)[warp] = best_pf;
+        ((int*)(c.ng_red + 8 * kWarps))[warp] = best_i;
+      }
+      __syncthreads();
+      best_pf = ((double*)c.ng_red)[0];
+      best_i = ((int*)(c.ng_red + 8 * kWarps))[0];
+      for (int w = 1; w < kWarps; ++w) {
+        const double op = ((double*)c.ng_red)[w];
+        const int oi = ((int*)(c.ng_red + 8 * kWarps))[w];
+        if (op > best_pf || (op == best_pf && oi < best_i)) { best_pf = op; best_i = oi; }
+      }
+      for (int g = tid; g < G; g += kThreads) {   /* the winning sample's assignment, nvs.cpp:453-460 */
+        int bu = -1;
+        if (best_i != 0x7fffffff) {
+          double highest = -1.0;
+          for (int q = 0; q < Ua; ++q) {
+            const int mcs = max((int)c.ng_hc[q] - draws[best_i * Ua + q] % 4, 1);
+            const int u = c.ng_list[q];
+            const double m = (mcs <= cqi_first_rb(d, row_of(u), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
+            if (highest < m) { highest = m; bu = u; }
+          }
+        }
+        if (bu >= 0) atomicOr(&c.mask[2 * bu + (g >> 5)], 1u << (g & 31));
+        if (o_rbg) o_rbg[g] = (short)bu;
+      }
     } else if (ALGO == 7) {
       /* ---- NVS: enterprise argmax over the served slice's users for every RBG (nvs.cpp:275-311) */
       const int j0 = c.sptr[served], j1 = c.sptr[served + 1];
@@ -1000,8 +1095,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     d.avg[i] = c.avg[u];
     d.tx[i] = c.tx[u];
   }
-  if (ALGO == 7 || ALGO == 8 || ALGO == 9) {
-    double* dst = (ALGO == 7) ? d.ewma : d.offset;
+  if (NVS || ALGO == 8 || ALGO == 9) {
+    double* dst = NVS ? d.ewma : d.offset;
     for (int s = tid; s < S; s += kThreads) dst[(size_t)b * S + s] = c.off[s];
   }
 }
@@ -1061,16 +1156,18 @@ __global__ void rs_synth_cqi_kernel(uint8_t* out, unsigned long long key, long l
   }
 }
 
+/* stride draws per (tti, cell): 2 for ids 8/9 (the original packing of the counter), more for id 11 */
 __global__ void rs_synth_rand2_kernel(int* out, unsigned long long key, long long cell0, long long tti0,
-                                      int n_ttis, int n_cells, int S) {
-  const size_t total = (size_t)n_ttis * n_cells * 2;
+                                      int n_ttis, int n_cells, int S, int stride) {
+  const size_t total = (size_t)n_ttis * n_cells * stride;
   const unsigned long long span = (unsigned long long)(2147483647 - S + 1);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const unsigned long long which = i & 1;
-    size_t r = i >> 1;
+    const unsigned long long which = i % stride;
+    size_t r = i / stride;
     const unsigned long long cell = cell0 + (long long)(r % n_cells);
     const unsigned long long tti = tti0 + (long long)(r / n_cells);
-    const unsigned long long ctr = (tti << 32) ^ (cell << 1) ^ which;
+    const unsigned long long ctr = stride == 2 ? ((tti << 32) ^ (cell << 1) ^ which)
+                                               : ((tti << 40) ^ (cell << 16) ^ which ^ 0x5EA4C4000000ull);
     out[i] = (int)((splitmix64(ctr ^ key) >> 11) % span);
   }
 }

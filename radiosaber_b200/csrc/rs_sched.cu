@@ -211,6 +211,7 @@ TtiKernel tti_kernel(int algo, bool trace) {
   switch (algo) {
     case 1: return trace ? rs::rs_tti_kernel<1, true> : rs::rs_tti_kernel<1, false>;
     case 7: return trace ? rs::rs_tti_kernel<7, true> : rs::rs_tti_kernel<7, false>;
+    case 11: return trace ? rs::rs_tti_kernel<11, true> : rs::rs_tti_kernel<11, false>;
     case 8: return trace ? rs::rs_tti_kernel<8, true> : rs::rs_tti_kernel<8, false>;
     default: return trace ? rs::rs_tti_kernel<9, true> : rs::rs_tti_kernel<9, false>;
   }
@@ -279,7 +280,7 @@ int ensure_dt(rs_handle* h, const double* dt, int n) {
 int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active, bool want_cqi) {
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   if (want_cqi) CU(s.cqi.alloc((size_t)T * B * U * C));
-  CU(s.rand2.alloc((size_t)T * B * 2));
+  CU(s.rand2.alloc((size_t)T * B * std::max(h->d.rand_stride, 1)));
   if (want_active) CU(s.active.alloc((size_t)T * B * U));
   if (out) {
     if (out->rbg_to_ue) CU(s.rbg_to_ue.alloc((size_t)T * B * G));
@@ -301,7 +302,7 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
 bool wants(const rs_handle* h, int which) { /* outputs that exist for this scheduler id */
   const int a = h->d.algo;
   if (which == 0) return a == 8 || a == 9;   /* slice_target / slice_quota */
-  return a == 7;                             /* nvs_slice */
+  return a == 7 || a == 11;                  /* nvs_slice */
 }
 
 }  // namespace
@@ -340,8 +341,8 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   if (!cfg || !out || n_cells <= 0) return fail(RS_ERR_ARG, "rs_create: bad argument");
   *out = nullptr;
   const int algo = cfg->algo, S = cfg->n_slices, U = cfg->n_ues;
-  if (algo != 1 && algo != 7 && algo != 8 && algo != 9)
-    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber)", algo);
+  if (algo != 1 && algo != 7 && algo != 8 && algo != 9 && algo != 11)
+    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 11 (NVS non-greedy)", algo);
   if (S < 1 || S > RS_MAX_SLICES) return fail(RS_ERR_UNSUPPORTED, "n_slices %d outside 1..%d", S, RS_MAX_SLICES);
   if (U < 1 || U > 65000) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..65000", U);
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0)
@@ -396,11 +397,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
       tbsn[(size_t)k * 16 + c] = tbs_n(mcs_from_cqi(c), k * d.rbg, h->row_m1);
       max_tbs = std::max(max_tbs, tbsn[(size_t)k * 16 + c]);
     }
-  if (algo == 1) {
+  if (algo == 1 || algo == 11) {
     epow.assign(16, 0.0);
     for (int c = 1; c <= 15; ++c) { volatile double m = eff_from_cqi(c) * 180000.; epow[c] = m; }  /* dl-pf:137 */
     /* dlps.cpp:264-269: a flow leaves the candidate set once TBS >= data*8; with an infinite buffer never */
-    if ((long long)d.data * 8 <= (long long)max_tbs)
+    if (algo == 11) {
+      for (int s = 0; s < S; ++s) weight[s] = cfg->weight[s];
+    } else if ((long long)d.data * 8 <= (long long)max_tbs)
       BAIL(fail(RS_ERR_UNSUPPORTED, "id 1 with data_to_transmit*8 <= %d bits (flow-satisfied cut-off) is not covered", max_tbs));
   } else {
     epow.assign((size_t)S * 16, 0.0);
@@ -448,7 +451,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
       m_cap = std::max(m_cap, cur);
     }
     chunks.push_back(S);
-  } else if (algo == 7) {
+  } else if (algo == 7 || algo == 11) {
     m_cap = max_slice;
     chunks = {0, S};
   } else {
@@ -460,10 +463,14 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   /* Stage a TTI's CQI in shared memory (cp.async) when the layout is one value per RBG, rows are 16-byte
    * multiples and the staged cell does not cost occupancy the batch could use: eight cells per SM for
    * big batches, fewer when there are not that many cells per SM to begin with. */
-  h->layout = rs::make_layout(S, U, G, m_cap);
+  d.ng_ues = (algo == 11) ? max_slice : 0;
+  /* rand() draws a TTI consumes per cell: transport.cpp:490,511 (ids 8/9); nvs.cpp:437-446 draws
+   * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
+  d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9) ? 2 : 0);
+  h->layout = rs::make_layout(S, U, G, m_cap, 0, d.ng_ues);
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
-    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row);
+    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues);
     const int kSmemPerSm = 227 * 1024, kSms = 148;
     const int fit = kSmemPerSm / (staged.total + 1024);
     const int floor_fit = 2;   /* big cells: two staged cells per SM beat more unstaged ones (tools/sweep_bench.py) */
@@ -596,7 +603,7 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
                     const int32_t* trace_row, const int32_t* d_rand2, const uint8_t* d_active,
                     int64_t active_tti_stride, const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
   if (!h || (!d_cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
-  if ((h->d.algo == 8 || h->d.algo == 9) && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
+  if (h->d.rand_stride > 0 && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (!trace_row && (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3))) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
@@ -613,7 +620,7 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.cqi_tti_stride = cqi_tti_stride;
     a.t0 = t0;
     a.cqi_refresh = cqi_refresh;
-    a.rand2 = d_rand2 ? d_rand2 + (size_t)t0 * B * 2 : nullptr;
+    a.rand2 = (d_rand2 && h->d.rand_stride) ? d_rand2 + (size_t)t0 * B * h->d.rand_stride : nullptr;
     a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
     a.active_tti_stride = active_tti_stride;
     a.dt = h->dt_dev.p + t0;
@@ -641,7 +648,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
                   const int32_t* rand2, const uint8_t* active, const double* dt, const rs_outputs* out,
                   int32_t ttis_per_launch) {
   if (!h || (!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
-  if ((h->d.algo == 8 || h->d.algo == 9) && !rand2) return fail(RS_ERR_ARG, "ids 8/9 need rand2");
+  if (h->d.rand_stride > 0 && !rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
@@ -669,7 +676,8 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     if (!trace_row && !(cqi_refresh > 1 && s.slab0 == slab0))   /* the slab may still be resident from the chunk before last */
       CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)slab0 * B * U * C, (size_t)n_slabs * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
     s.slab0 = slab0;
-    if (rand2) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * 2, (size_t)T * B * 2 * 4, cudaMemcpyHostToDevice, h->copy_in));
+    const size_t RS = (size_t)h->d.rand_stride;
+    if (rand2 && RS) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * RS, (size_t)T * B * RS * 4, cudaMemcpyHostToDevice, h->copy_in));
     if (active) CU(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
     CU(cudaEventRecord(s.in_done, h->copy_in));
     /* kernel: inputs in, and the slot's previous outputs drained */
@@ -679,7 +687,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     a.T = T;
     a.cqi = s.cqi.p; a.cqi_tti_stride = (long long)(B * U * C);
     a.t0 = t0 - slab0 * cqi_refresh; a.cqi_refresh = cqi_refresh;
-    a.rand2 = rand2 ? s.rand2.p : nullptr;
+    a.rand2 = (rand2 && RS) ? s.rand2.p : nullptr;
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
     a.dt = h->dt_dev.p + t0;
     a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
@@ -1023,10 +1031,11 @@ int rs_synth_rand2(rs_handle* h, uint64_t seed, int64_t cell0, int64_t tti0, int
     return z ^ (z >> 31);
   };
   const unsigned long long key = sm64((seed & 0xFFFFFFFFull) | (0x524E4400ull << 32));
-  const size_t total_n = (size_t)n_ttis * h->B * 2;
+  const int stride = std::max(h->d.rand_stride, 2);
+  const size_t total_n = (size_t)n_ttis * h->B * stride;
   if (total_n == 0) return RS_OK;
   const int blocks = (int)std::min<size_t>((total_n + 255) / 256, 148 * 8);
-  rs::rs_synth_rand2_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, tti0, n_ttis, h->B, h->d.S);
+  rs::rs_synth_rand2_kernel<<<blocks, 256, 0, h->stream>>>(d_out, key, cell0, tti0, n_ttis, h->B, h->d.S, stride);
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;
@@ -1054,6 +1063,7 @@ int rs_get_stats(rs_handle* h, uint64_t* stats) {
   return RS_OK;
 }
 
+int32_t rs_rand_draws_per_cell_tti(const rs_handle* h) { return h ? h->d.rand_stride : 0; }
 int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
 int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }
 int32_t rs_threads_per_cta(const rs_handle* h) { (void)h; return rs::kThreads; }

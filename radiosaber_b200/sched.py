@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "rs_set_state", "rs_get_state", "rs_reset_state", "rs_step", "rs_run_device", "rs_run_host",
     "rs_synth_cqi", "rs_synth_rand2", "rs_stats_device", "rs_get_stats", "rs_launch_count",
     "rs_smem_bytes", "rs_threads_per_cta", "rs_algorithmic_bytes_per_cell_tti", "rs_test_sort",
-    "rs_test_sort_timed",
+    "rs_test_sort_timed", "rs_rand_draws_per_cell_tti",
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti",
@@ -84,6 +84,8 @@ def lib():
         L.rs_synth_rand2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
         L.rs_stats_device.argtypes = [C.c_void_p, C.c_void_p]
         L.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.rs_rand_draws_per_cell_tti.argtypes = [C.c_void_p]
+        L.rs_rand_draws_per_cell_tti.restype = C.c_int32
         L.rs_launch_count.argtypes = [C.c_void_p]
         L.rs_launch_count.restype = C.c_int64
         L.rs_smem_bytes.argtypes = [C.c_void_p]
@@ -181,6 +183,8 @@ class Scheduler:
                    _ptr(self.weight), _ptr(self.params), _ptr(self.ue_to_slice), _ptr(self._row_m1))
         self._h = C.c_void_p()
         _check(lib().rs_create(C.byref(cfg), self.B, self.device, C.byref(self._h)))
+        # rand() draws per cell-TTI the scheduler consumes: 0 (ids 1/7), 2 (ids 8/9), 300 x largest slice (id 11)
+        self.rand_stride = int(lib().rs_rand_draws_per_cell_tti(self._h))
 
     @classmethod
     def from_config(cls, algo, config_path, n_cells, **kw):
@@ -234,20 +238,30 @@ class Scheduler:
             if self.algo in (8, 9):
                 out["slice_target"] = np.empty(lead + (S,), np.int32)
                 out["slice_quota"] = np.empty(lead + (S,), np.int32)
-            if self.algo == 7:
+            if self.algo in (7, 11):
                 out["nvs_slice"] = np.empty(lead, np.int32)
         o = _Out(*[_ptr(out.get(k)) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
                                                 "slice_quota", "nvs_slice")])
         return out, o
+
+    def _draws(self, rand2, lead):
+        """rand() draws as int32 lead + (rand_stride,); a wider array (recorded draws padded to the largest
+        TTI) is cut or zero-padded to the stride; ids without draws get a dummy."""
+        n = max(self.rand_stride, 2)
+        if rand2 is None:
+            return np.zeros(lead + (n,), dtype=np.int32)
+        r = np.asarray(rand2, dtype=np.int32)
+        r = r.reshape(lead + (-1,))
+        if r.shape[-1] < n:
+            r = np.concatenate([r, np.zeros(lead + (n - r.shape[-1],), dtype=np.int32)], axis=-1)
+        return np.ascontiguousarray(r[..., :n])
 
     def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False):
         """One TTI for every cell. cqi: uint8 [B][U][G] (or [B][U][R]); rand2: int32 [B][2]."""
         B, U = self.B, self.U
         cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
         assert cqi.size == B * U * self.cqi_cols, cqi.shape
-        if rand2 is None:
-            rand2 = np.zeros((B, 2), dtype=np.int32)
-        rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, 2)
+        rand2 = self._draws(rand2, (B,))
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
         out, o = self._host_outputs(None, want_aux)
         _check(lib().rs_step(self._h, _ptr(cqi), _ptr(rand2), _ptr(act), float(dt), C.byref(o)))
@@ -261,7 +275,7 @@ class Scheduler:
         T = int(dt.shape[0])
         cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
         assert cqi.size == -(-T // cqi_refresh) * B * U * self.cqi_cols, cqi.shape
-        rand2 = None if rand2 is None else np.ascontiguousarray(rand2, dtype=np.int32).reshape(T, B, 2)
+        rand2 = None if rand2 is None else self._draws(rand2, (T, B))
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
         out, o = self._host_outputs(T, want_aux)
         _check(lib().rs_run_host(self._h, T, _ptr(cqi), int(cqi_refresh), _ptr(rand2), _ptr(act), _ptr(dt),
@@ -296,7 +310,7 @@ class Scheduler:
         T = int(dt.shape[0])
         trace_row = np.ascontiguousarray(trace_row, dtype=np.int32)
         assert trace_row.shape == (T,)
-        rand2 = None if rand2 is None else np.ascontiguousarray(rand2, dtype=np.int32).reshape(T, B, 2)
+        rand2 = None if rand2 is None else self._draws(rand2, (T, B))
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
         out, o = self._host_outputs(T, want_aux)
         _check(lib().rs_run_traces_host(self._h, T, _ptr(trace_row), _ptr(rand2), _ptr(act), _ptr(dt), C.byref(o),

@@ -86,6 +86,23 @@ def synth_rand2(seed: int, cell0: int, n_cells: int, tti0: int, n_ttis: int, n_s
     return ((h >> np.uint64(11)) % span).astype(np.int32)
 
 
+def synth_rand_draws(seed: int, cell0: int, n_cells: int, tti0: int, n_ttis: int, n_slices: int, stride: int) -> np.ndarray:
+    """int32 [n_ttis][n_cells][stride]: the rand() values a scheduler draws per cell-TTI.  stride 2 is
+    :func:`synth_rand2`; wider strides (id 11: 300 x the largest slice, downlink-nvs-scheduler.cpp:437-446)
+    pack the counter differently.  Twin of ``rs_synth_rand2`` in the C ABI."""
+    if stride == 2:
+        return synth_rand2(seed, cell0, n_cells, tti0, n_ttis, n_slices)
+    key = _key(seed, DOMAIN_RAND)
+    tti = np.arange(tti0, tti0 + n_ttis, dtype=np.uint64)[:, None, None]
+    cell = np.arange(cell0, cell0 + n_cells, dtype=np.uint64)[None, :, None]
+    which = np.arange(stride, dtype=np.uint64)[None, None, :]
+    with np.errstate(over="ignore"):
+        ctr = (tti << np.uint64(40)) ^ (cell << np.uint64(16)) ^ which ^ np.uint64(0x5EA4C4000000)
+        h = splitmix64(ctr ^ key)
+    span = np.uint64(2147483647 - n_slices + 1)
+    return ((h >> np.uint64(11)) % span).astype(np.int32)
+
+
 def tti_clock(n_ttis: int, start: float = 0.1):
     """The reference's TTI clock: FrameManager re-schedules itself every 0.001 s and the
     simulator accumulates ``t += 0.001`` in double (simulator.cc:116-126), applications start at

@@ -27,9 +27,11 @@ def replay_golden(sched, rec, check_final_cqi=True):
     bad = []
     sched.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
                     slice_offset=rec["state_before"][0][None] if algo in (8, 9) else None,
-                    nvs_ewma=rec["state_before"][0][None] if algo == 7 else None)
+                    nvs_ewma=rec["state_before"][0][None] if algo in (7, 11) else None)
     for t in range(T):
-        out = sched.step(rec["cqi"][t][None], rec["rand2"][t][None], dt=float(rec["dt"][t]), want_aux=True)
+        # id 11: every rand() value of the 300-sample search (downlink-nvs-scheduler.cpp:437-446)
+        draws = rec["rand_ng"][t][None] if algo == 11 else rec["rand2"][t][None]
+        out = sched.step(rec["cqi"][t][None], draws, dt=float(rec["dt"][t]), want_aux=True)
         st = sched.get_state()
 
         def chk(field, a, b):
@@ -49,7 +51,7 @@ def replay_golden(sched, rec, check_final_cqi=True):
                 chk("slice_target", out["slice_target"][0], rec["target"][t])
                 chk("slice_quota", out["slice_quota"][0], rec["quota"][t])
             chk("slice_offset", st["slice_offset"][0], rec["state_after"][t])
-        if algo == 7:
+        if algo in (7, 11):
             chk("nvs_ewma", st["nvs_ewma"][0], rec["state_after"][t])
             if "nvs_slice" in out:
                 chk("nvs_slice", out["nvs_slice"][0], rec["nvs_slice"][t])

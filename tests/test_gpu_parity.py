@@ -101,7 +101,7 @@ def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_
             cqi = np.repeat(cqi, 8, axis=-1)
             noise = rng.integers(-1, 2, size=cqi.shape)
             cqi = np.clip(cqi.astype(np.int64) + noise, 1, 15).astype(np.uint8)
-        rand2 = workload.synth_rand2(seed, 0, B, t, 1, S)[0]
+        rand2 = workload.synth_rand_draws(seed, 0, B, t, 1, S, max(g.rand_stride, 2))[0]
         act = None
         if with_active:
             act = (rng.random((B, U)) < 0.7).astype(np.uint8)
@@ -116,7 +116,7 @@ def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_
             assert np.array_equal(sa[k], sb[k]), (t, k)
         if algo in (8, 9):
             assert np.array_equal(sa["slice_offset"], sb["slice_offset"]), t
-        if algo == 7:
+        if algo in (7, 11):
             assert np.array_equal(sa["nvs_ewma"], sb["nvs_ewma"]), t
     g.close()
 
@@ -125,7 +125,7 @@ PF = [0, 0, 1, 1]
 MT = [0, 0, 1, 0]
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
 def test_headline_shape_20x5(algo):
     S = 20
     _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
@@ -148,14 +148,14 @@ def test_sweep_shapes_radiosaber(S, n):
     _mk(9, S, [n] * S, w, p, B=6, seed=S * 100 + n, T=12)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
 def test_inactive_bearers_and_empty_cells(algo):
     S = 8
     w = np.full(S, 1.0 / S)
     _mk(algo, S, [4] * S, w, np.tile(PF, (S, 1)), B=10, seed=300 + algo, T=12, with_active=True)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
 def test_per_rb_cqi_layout(algo):
     S = 6
     w = np.full(S, 1.0 / S)
@@ -234,6 +234,45 @@ def test_device_generators_and_run_device():
         assert np.array_equal(d_bits[t].cpu().numpy(), want["tbs_bits"]), t
         assert np.array_equal(d_mcs[t].cpu().numpy(), want["mcs"]), t
     assert g.launch_count == 2 + 3
+    g.close()
+
+
+def test_nvs_nongreedy_device_draws_and_run_device():
+    """id 11: the device generator of the 300 x users rand() draws equals its numpy twin, and rs_run_device
+    over several launches equals the oracle fed with the same draws."""
+    import torch
+    S, B, T = 6, 33, 9
+    ues = [5, 3, 7, 1, 4, 2]
+    u2s = np.repeat(np.arange(S), ues).astype(np.int32)
+    U, G = len(u2s), 64
+    w = np.array([0.3, 0.1, 0.2, 0.1, 0.2, 0.1])
+    p = np.tile(PF, (S, 1))
+    g = sched.Scheduler(11, w, p, u2s, B, cqi_per_rb=2)
+    n = g.rand_stride
+    assert n == 300 * 7
+    d_cqi = torch.empty((T, B, U, G // 2), dtype=torch.uint8, device="cuda")
+    d_r = torch.empty((T, B, n), dtype=torch.int32, device="cuda")
+    g.synth_cqi(5, 10, 0, T, d_cqi.data_ptr())
+    g.synth_rand2(5, 10, 0, T, d_r.data_ptr())
+    g.sync()
+    draws = workload.synth_rand_draws(5, 10, B, 0, T, S, n)
+    assert np.array_equal(d_r.cpu().numpy(), draws)
+    cqi = workload.synth_cqi(5, 10, B, 0, T, U, G)
+    d_rbg = torch.empty((T, B, G), dtype=torch.int16, device="cuda")
+    d_bits = torch.empty((T, B, U), dtype=torch.int32, device="cuda")
+    d_nvs = torch.empty((T, B), dtype=torch.int32, device="cuda")
+    _, dts = workload.tti_clock(T)
+    g.run_device(T, d_cqi.data_ptr(), B * U * G // 2, d_r.data_ptr(), dts,
+                 {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr(), "nvs_slice": d_nvs.data_ptr()},
+                 ttis_per_launch=4)
+    g.sync()
+    o = OracleScheduler(11, w, p, u2s, B, n_threads=8)
+    for t in range(T):
+        want = o.step(cqi[t], draws[t], dt=float(dts[t]), want_aux=True)
+        assert np.array_equal(d_nvs[t].cpu().numpy(), want["nvs_slice"]), t
+        assert np.array_equal(d_rbg[t].cpu().numpy(), want["rbg_to_ue"]), t
+        assert np.array_equal(d_bits[t].cpu().numpy(), want["tbs_bits"]), t
+    assert np.array_equal(g.get_state()["avg_rate"], o.get_state()["avg_rate"])
     g.close()
 
 

@@ -66,6 +66,11 @@ CASES = [
     ("a8_small_synth", 8, "SMALL", 120, "synth", 10),
     ("a7_small_synth", 7, "SMALL", 120, "synth", 11),
     ("a1_small_synth", 1, "SMALL", 120, "synth", 12),
+    # id 11 (NVS non-greedy, downlink-nvs-scheduler.cpp:405-528): the records also hold every rand() value the
+    # 300-sample search drew (rand_ng), read back through ref_harness --rand-log
+    ("a11_fix20x5_synth", 11, FIX20X5, 24, "synth", 13),
+    ("a11_small_synth", 11, "SMALL", 60, "synth", 14),
+    ("a11_fix20x5_trace", 11, FIX20X5, 12, "trace", 1),
 ]
 
 
@@ -88,9 +93,23 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
         cqi_path = os.path.join(tmp, name + ".cqi")
         cqi.tofile(cqi_path)
         cmd += ["--cqi", cqi_path]
+    rlog_path = os.path.join(tmp, name + ".rlog")
+    if algo == 11:
+        cmd += ["--rand-log", rlog_path]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     rec = golden_io.compact(golden_io.parse_record_stream(rec_path))
     assert rec["T"] == n_ttis, (name, rec["T"])
+    if algo == 11:
+        raw = np.fromfile(rlog_path, dtype="<i4")
+        draws, pos = [], 0
+        for _ in range(n_ttis):
+            k = int(raw[pos])
+            draws.append(raw[pos + 1:pos + 1 + k])
+            pos += 1 + k
+        assert pos == len(raw)
+        width = max(len(d) for d in draws)
+        rec["rand_ng_n"] = np.array([len(d) for d in draws], dtype=np.int32)
+        rec["rand_ng"] = np.stack([np.pad(d, (0, width - len(d))) for d in draws]).astype(np.int32)
     if algo in (8, 9):
         assert (rec["rand2"] == rand2).all(), "scripted rand() values were not the ones consumed"
     rec["config_json"] = json.dumps(cfg)
