@@ -10,6 +10,7 @@
  *     7  DownlinkNVSScheduler(cfg,false)  downlink-nvs-scheduler.cpp:94-142, 275-358
  *     8  DownlinkTransportScheduler(cfg,0) GreedyByRow   downlink-transport-scheduler.cpp:249-272
  *     9  DownlinkTransportScheduler(cfg,2) MaximizeCell  downlink-transport-scheduler.cpp:351-376
+ *    10  DownlinkTransportScheduler(cfg,4) UpperBound    downlink-transport-scheduler.cpp:223-246
  *    11  DownlinkNVSScheduler(cfg,true)   downlink-nvs-scheduler.cpp:405-528 (300-sample non-greedy PF)
  * This library is what a host-side subclass of PacketScheduler binds to (see
  * INTEGRATION.md and radiosaber_b200/host/rs_gpu_scheduler.h): every entry
@@ -42,7 +43,7 @@ extern "C" {
  * config (downlink-transport-scheduler.cpp:55-97, downlink-nvs-scheduler.cpp:46-87,
  * dl-pf-packet-scheduler.cpp:39-57). */
 typedef struct rs_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 11 NVS non-greedy */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy */
   int32_t n_slices;         /* S  <= RS_MAX_SLICES */
   int32_t n_ues;            /* U; user j == UE id j (flows/application/Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (core/spectrum/bandwidth-manager.cpp:98-102) */
@@ -69,7 +70,14 @@ typedef struct rs_outputs {
   uint8_t* final_cqi;    /* [B][U] "final_cqi" of :649, 0 if unscheduled */
   int32_t* slice_target; /* [B][S] slice_target_rbs (ids 8/9, :463-500) */
   int32_t* slice_quota;  /* [B][S] slice_quota_rbgs (ids 8/9, :501-521) */
-  int32_t* nvs_slice;    /* [B]    slice served this TTI (id 7, downlink-nvs-scheduler.cpp:94-142) */
+  int32_t* nvs_slice;    /* [B]    slice served this TTI (ids 7/11, downlink-nvs-scheduler.cpp:94-142) */
+  /* id 10 (UpperBound, downlink-transport-scheduler.cpp:223-246, 603-616) grants an RBG to every slice that
+   * ranks it among its own best quota RBGs, so the grants are a list: slice-major, each slice's grants in
+   * the order of its std::sort (the order the RBs are appended to the winners' lists).  For id 10
+   * rbg_to_ue[g] is the highest user id holding RBG g. */
+  int32_t* alloc_n;      /* [B]     number of (user, RBG) grants; entries past 2G are dropped */
+  int16_t* alloc_ue;     /* [B][2G] user of grant e, -1 past alloc_n */
+  int16_t* alloc_rbg;    /* [B][2G] RBG of grant e */
 } rs_outputs;
 
 typedef struct rs_handle rs_handle;

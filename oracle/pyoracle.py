@@ -33,6 +33,7 @@ class _Io(C.Structure):
         ("cqi", C.c_void_p), ("active", C.c_void_p), ("rand2", C.c_void_p), ("dt", C.c_double),
         ("rbg_to_ue", C.c_void_p), ("tbs_bits", C.c_void_p), ("mcs", C.c_void_p), ("final_cqi", C.c_void_p),
         ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
+        ("alloc_n", C.c_void_p), ("alloc_ue", C.c_void_p), ("alloc_rbg", C.c_void_p),
         ("rand_stride", C.c_int32),
     ]
 
@@ -139,11 +140,15 @@ class OracleScheduler:
                 "slice_quota": np.empty((B, S), dtype=np.int32),
                 "nvs_slice": np.empty((B,), dtype=np.int32),
             }
+            if self.algo == 10:
+                aux.update({"alloc_n": np.empty((B,), dtype=np.int32), "alloc_ue": np.empty((B, 2 * G), dtype=np.int16),
+                            "alloc_rbg": np.empty((B, 2 * G), dtype=np.int16)})
         io = _Io(_ptr(self.avg_rate), _ptr(self.tx_bytes), _ptr(self.cum_bytes), _ptr(self.cum_rbs),
                  _ptr(self.slice_offset), _ptr(self.nvs_ewma),
                  _ptr(cqi), _ptr(act), _ptr(rand2), float(dt),
                  _ptr(out["rbg_to_ue"]), _ptr(out["tbs_bits"]), _ptr(out["mcs"]), _ptr(aux.get("final_cqi")),
                  _ptr(aux.get("slice_target")), _ptr(aux.get("slice_quota")), _ptr(aux.get("nvs_slice")),
+                 _ptr(aux.get("alloc_n")), _ptr(aux.get("alloc_ue")), _ptr(aux.get("alloc_rbg")),
                  int(rand2.shape[1]))
         rc = lib().rso_step(C.byref(self._cfg), B, C.byref(io), self.n_threads)
         if rc != 0:

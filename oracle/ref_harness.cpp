@@ -119,6 +119,8 @@ struct Options {
   bool keep_log = false;
   std::string rand_log;   /* every rand() value drawn inside each recorded DoSchedule: int32 n, int32 v[n] per TTI
                              (id 11 draws 300 x users of them, downlink-nvs-scheduler.cpp:437-446) */
+  std::string alloc_log;  /* every (user, RBG) grant of each recorded TTI in the order of the users' RB lists: int32 n,
+                             int16 (ue, rbg)[n] per TTI (id 10 books an RBG to several slices, which rbg_to_ue[G] cannot hold) */
   std::string log_out;    /* PREFIX: the reference's own stdout / stderr text of every recorded TTI goes to
                              PREFIX.stdout / PREFIX.stderr (golden text for the log-writer parity test) */
 };
@@ -132,6 +134,7 @@ static long g_sched_calls = 0;
 static std::stringstream g_capture;
 static std::stringstream g_cerr_capture;   /* std::cerr while --log-out is active */
 static FILE* g_rand_log_file = nullptr;
+static FILE* g_alloc_log_file = nullptr;
 static FILE* g_log_stdout = nullptr;
 static FILE* g_log_stderr = nullptr;
 static char* g_cstderr_buf = nullptr;       /* C stderr (fprintf(stderr, "all_bytes ...")) of the current TTI */
@@ -310,12 +313,22 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
 template <typename UserList>
 static void CollectUsers(UserList* users, std::vector<uint8_t>& active, std::vector<int16_t>& rbg_to_ue,
                          std::vector<int32_t>& bits, int rbg) {
+  std::vector<int16_t> grants;
   for (auto* usr : *users) {
     int id = usr->GetUserID();
     active[id] = 1;
     bits[id] = usr->GetAllocatedBits();
     for (int rb : *usr->GetListOfAllocatedRBs())
-      if (rb % rbg == 0) rbg_to_ue[rb / rbg] = (int16_t)id;
+      if (rb % rbg == 0) {
+        rbg_to_ue[rb / rbg] = (int16_t)id;
+        grants.push_back((int16_t)id);
+        grants.push_back((int16_t)(rb / rbg));
+      }
+  }
+  if (g_alloc_log_file) {
+    const int32_t n = (int32_t)(grants.size() / 2);
+    fwrite(&n, 4, 1, g_alloc_log_file);
+    fwrite(grants.data(), 2, grants.size(), g_alloc_log_file);
   }
 }
 
@@ -418,6 +431,7 @@ struct Installer {
       case 7: s = new ObservedNvs(g_opt.config); break;
       case 11: s = new ObservedNvs(g_opt.config, true); break;   /* DLScheduler_NVS_NONGREEDY, ENodeB.cpp:351-355 */
       case 8: s = new ObservedTransport(g_opt.config, 0); break;
+      case 10: s = new ObservedTransport(g_opt.config, 4); break;   /* DLScheduler_UpperBound, ENodeB.cpp:381-385 */
       default: s = new ObservedTransport(g_opt.config, 2); break;
     }
     s->SetMacEntity(mac);
@@ -464,6 +478,7 @@ int main(int argc, char** argv) {
     else if (a == "--keep-log") g_opt.keep_log = true;
     else if (a == "--log-out") g_opt.log_out = next();
     else if (a == "--rand-log") g_opt.rand_log = next();
+    else if (a == "--alloc-log") g_opt.alloc_log = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -476,6 +491,10 @@ int main(int argc, char** argv) {
     if (!g_out) { fprintf(stderr, "cannot write %s\n", g_opt.out.c_str()); return 2; }
   }
   if (!g_opt.cqi_file.empty()) g_cqi_script = ReadAll(g_opt.cqi_file);
+  if (!g_opt.alloc_log.empty()) {
+    g_alloc_log_file = fopen(g_opt.alloc_log.c_str(), "wb");
+    if (!g_alloc_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.alloc_log.c_str()); return 2; }
+  }
   if (!g_opt.rand_log.empty()) {
     g_rand_log_file = fopen(g_opt.rand_log.c_str(), "wb");
     if (!g_rand_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.rand_log.c_str()); return 2; }
@@ -515,6 +534,7 @@ int main(int argc, char** argv) {
   if (cerr_buf) std::cerr.rdbuf(cerr_buf);
   if (g_out) fclose(g_out);
   if (g_rand_log_file) fclose(g_rand_log_file);
+  if (g_alloc_log_file) fclose(g_alloc_log_file);
   if (g_log_stdout) fclose(g_log_stdout);
   if (g_log_stderr) fclose(g_log_stderr);
   fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_recorded,

@@ -122,6 +122,9 @@ struct CellView {
   int32_t* target;
   int32_t* quota;
   int32_t* nvs_slice;
+  int32_t* alloc_n;
+  int16_t* alloc_ue;
+  int16_t* alloc_rbg;
 };
 
 /* RadioBearer::UpdateAverageTransmissionRate, flows/radio-bearer.cpp:138-164,
@@ -283,6 +286,8 @@ void ClearOutputs(const CellView& c) {
   if (c.target) std::fill(c.target, c.target + cfg->n_slices, 0);
   if (c.quota) std::fill(c.quota, c.quota + cfg->n_slices, 0);
   if (c.nvs_slice) *c.nvs_slice = -1;
+  if (c.alloc_n) *c.alloc_n = 0;
+  if (c.alloc_ue) { std::fill(c.alloc_ue, c.alloc_ue + 2 * G, (int16_t)-1); std::fill(c.alloc_rbg, c.alloc_rbg + 2 * G, (int16_t)-1); }
 }
 
 /* DownlinkTransportScheduler::DoSchedule, transport.cpp:152-168, ids 8 and 9. */
@@ -360,6 +365,38 @@ void StepTransport(const CellView& c, const int32_t* row_m1) {
         se[i][sl] = users[j].eff[i * rbg_size];
       }
     }
+  }
+
+  if (cfg->algo == 10) {
+    /* UpperBound, transport.cpp:223-246: every slice with a positive quota takes its own best quota RBGs
+     * (the real std::sort of (rbg, eff) pairs), so an RBG can be granted to several slices; then
+     * :603-616: the winners' RB lists are appended in that sorted order. */
+    int n_alloc = 0;
+    for (int j = 0; j < S; ++j) {
+      if (quota[j] <= 0) continue;
+      std::vector<std::pair<int, double>> sorted_cqi;
+      for (int i = 0; i < G; ++i) sorted_cqi.emplace_back(i, se[i][j]);
+      std::sort(sorted_cqi.begin(), sorted_cqi.end(),
+                [](std::pair<int, double> a, std::pair<int, double> b) { return a.second > b.second; });
+      for (int k = 0; k < quota[j] && k < G; ++k) {   /* k >= G would read past the vector in the reference */
+        const int rbg = sorted_cqi[k].first;
+        const int uindex = user_index[rbg][j];
+        if (uindex < 0) continue;             /* assert in the reference */
+        final_rbgs[j] += 1;
+        for (int r = rbg * rbg_size; r < (rbg + 1) * rbg_size; ++r) users[uindex].rbs.push_back(r);
+        if (c.alloc_ue && n_alloc < 2 * G) { c.alloc_ue[n_alloc] = (int16_t)users[uindex].id; c.alloc_rbg[n_alloc] = (int16_t)rbg; }
+        n_alloc++;
+      }
+    }
+    if (c.alloc_n) *c.alloc_n = n_alloc;
+    if (c.rbg_to_ue)   /* what a single-valued map can say: the highest user id holding the RBG */
+      for (const User& usr : users)
+        for (int r : usr.rbs)
+          if (r % rbg_size == 0) c.rbg_to_ue[r / rbg_size] = (int16_t)usr.id;
+    for (int i = 0; i < S; ++i) c.offset[i] = target[i] - final_rbgs[i] * rbg_size;
+    for (User& usr : users) FinalizeUser(c, usr, row_m1);
+    for (const User& usr : users) AccountUser(c, usr);
+    return;
   }
 
   std::vector<int> rbg_to_slice =           /* :569-586 */
@@ -597,6 +634,9 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   c.target = io->slice_target ? io->slice_target + (size_t)b * S : nullptr;
   c.quota = io->slice_quota ? io->slice_quota + (size_t)b * S : nullptr;
   c.nvs_slice = io->nvs_slice ? io->nvs_slice + b : nullptr;
+  c.alloc_n = io->alloc_n ? io->alloc_n + b : nullptr;
+  c.alloc_ue = (io->alloc_ue && io->alloc_rbg) ? io->alloc_ue + (size_t)b * 2 * G : nullptr;
+  c.alloc_rbg = (io->alloc_ue && io->alloc_rbg) ? io->alloc_rbg + (size_t)b * 2 * G : nullptr;
   ClearOutputs(c);
   switch (cfg->algo) {
     case 1: StepPf(c, row_m1); break;
@@ -692,8 +732,8 @@ extern "C" {
 
 int rso_step(const rso_config* cfg, int32_t n_cells, rso_io* io, int32_t n_threads) {
   if (!cfg || !io || n_cells < 0) return 1;
-  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 8 && cfg->algo != 9 && cfg->algo != 11) return 2;
-  if ((cfg->algo == 8 || cfg->algo == 9) && (!io->rand2 || !io->slice_offset)) return 3;
+  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 8 && cfg->algo != 9 && cfg->algo != 10 && cfg->algo != 11) return 2;
+  if ((cfg->algo == 8 || cfg->algo == 9 || cfg->algo == 10) && (!io->rand2 || !io->slice_offset)) return 3;
   if ((cfg->algo == 7 || cfg->algo == 11) && !io->nvs_ewma) return 3;
   if (cfg->algo == 11 && (!io->rand2 || io->rand_stride < 300)) return 3;
   int32_t row_m1[27];

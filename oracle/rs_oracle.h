@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 typedef struct rso_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 11 NVS non-greedy (single-cell-with-interference.h:94-118) */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy (single-cell-with-interference.h:94-118) */
   int32_t n_slices;         /* S */
   int32_t n_ues;            /* U; user j == UE id j (Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (bandwidth-manager.cpp:98-102) */
@@ -60,6 +60,9 @@ typedef struct rso_io {
   int32_t* slice_target; /* [B][S] slice_target_rbs (ids 8/9) */
   int32_t* slice_quota;  /* [B][S] slice_quota_rbgs (ids 8/9) */
   int32_t* nvs_slice;    /* [B] slice served (ids 7/11) */
+  int32_t* alloc_n;      /* [B] id 10: number of (user, RBG) grants (an RBG can go to several slices) */
+  int16_t* alloc_ue;     /* [B][2G] id 10: user of grant e, slice-major, each slice's grants in its sorted order; -1 past n */
+  int16_t* alloc_rbg;    /* [B][2G] id 10: RBG of grant e */
   int32_t rand_stride;   /* int32 values per cell in rand2: 0 or 2 for ids 8/9; id 11: >= 300 x the users of a
                             slice, the rand() draws of nvs.cpp:437-446 in call order */
 } rso_io;

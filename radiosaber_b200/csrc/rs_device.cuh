@@ -89,6 +89,7 @@ struct DevCfg {
   int trace_rows;
   int rand_stride;         /* int32 rand() draws per cell-TTI in RunArgs::rand2: 2 (ids 8/9), 300 x max UEs per slice (id 11) */
   int ng_ues;              /* id 11: largest slice */
+  int sort_depth_g;        /* id 10: 2*floor(log2(G)), the depth limit of a per-slice sort of G entries */
   /* state, [B][U] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
   double* offset; double* ewma;
@@ -105,6 +106,7 @@ struct RunArgs {
   int T;
   short* rbg_to_ue; int* tbs_bits; uint8_t* mcs; uint8_t* final_cqi;
   int* slice_target; int* slice_quota; int* nvs_slice;
+  int* alloc_n; short* alloc_ue; short* alloc_rbg;   /* id 10: [T][B], [T][B][2G], [T][B][2G] */
 };
 
 /* ---- shared-memory layout (same function on host and device) --------------------------------- */
@@ -115,9 +117,12 @@ __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a *
 /* cq_bytes: room for one TTI of the cell's CQI ([U][cqi_row], staged with cp.async); 0 = CQI is read
  * from global memory where it lies. */
 /* ng_ues: id 11 only, the largest number of UEs in a slice (scratch of the 300-sample search). */
-__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0) {
+/* min_sort_n: id 10 sorts one slice's G entries at a time and parks the grants next to them: it needs
+ * the slot arrays at least 8 G entries long whatever S is. */
+__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
+                                              int min_sort_n = 0) {
   Layout L;
-  const int n = S * G;
+  const int n = (S * G > min_sort_n) ? S * G : min_sort_n;
   const int nw = (n + 31) / 32;
   int o = 0;
   L.avg = o;  o += 8 * U;
@@ -653,12 +658,17 @@ __device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned sho
 /* Link adaptation + accounting for UE u holding the RBGs in mask (transport.cpp:632-660 and 170-199;
  * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
 __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* row, int u,
-                                            unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc) {
+                                            unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc,
+                                            const double* presum = nullptr) {
   int bits = 0, mcs = 0xff, fc = 0;
   const int nrbg = __popc(m_lo) + __popc(m_hi);
   if (nrbg > 0) {
     double sum = 0;
     unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+    if (presum) {   /* id 10: the RB list is not in RBG order; the caller summed it in list order */
+      sum = presum[u];
+      m = 0;
+    }
     while (m) {
       const int g = __ffsll((long long)m) - 1;
       m &= m - 1;
@@ -820,14 +830,14 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         const int s = d.ue_to_slice[u];
         /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
         c.den[u] = d.psi[s] ? __ddiv_rn(__dadd_rn(1.0, a), 1000.0) : 1.0;
-        if ((ALGO == 8 || ALGO == 9) && (!act || act[u])) c.wd[s] = 1;
+        if ((ALGO == 8 || ALGO == 9 || ALGO == 10) && (!act || act[u])) c.wd[s] = 1;
       }
     }
     if (stage) cp_async_wait_all();   /* own copies done; the barrier publishes everybody's */
     __syncthreads();
 
     RS_TICK(0);
-    if (ALGO == 8 || ALGO == 9) {
+    if (ALGO == 8 || ALGO == 9 || ALGO == 10) {
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < d.n_chunks; ++ch) {
         const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
@@ -898,7 +908,79 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
       RS_TICK(1);
       /* ---- P3/P4: inter-slice assignment ---------------------------------------------------- */
-      if (ALGO == 9) {
+      if (ALGO == 10) {
+        /* UpperBound (transport.cpp:223-246, 603-616): every slice with a positive quota takes the first
+         * quota entries of ITS OWN std::sort of the G (rbg, efficiency) pairs, so an RBG can be granted
+         * to several slices.  One sort of G entries per slice, by the whole CTA; the grants are parked in
+         * shared memory (slice-major, sorted order) next to the sort buffers. */
+        SortBufs s2 = c.sb;
+        s2.a = c.sb.posl;
+        s2.posl = c.sb.posl + G;
+        s2.posr = c.sb.posl + 2 * G;
+        s2.out = s2.posr;
+        unsigned short* g_ue = c.sb.posl + 4 * G;    /* [2G] */
+        unsigned short* g_rbg = c.sb.posl + 6 * G;   /* [2G] */
+        int base = 0;
+        for (int s = 0; s < S; ++s) {
+          const int q = min(c.quota[s], G);
+          if (q <= 0) { if (tid == 0) c.frb[s] = 0; continue; }
+          for (int i = tid; i < G; i += kThreads) s2.a[i] = (unsigned short)((c.sb.a[i * S + s] & 0xf000u) | (unsigned)i);
+          __syncthreads();
+          sort_desc(s2, G, d.sort_depth_g, kWarps - rot);
+          for (int k = tid; k < q; k += kThreads) {
+            const int g = s2.out[k] & 0xfff;
+            if (base + k < 2 * G) {
+              g_ue[base + k] = c.win[g * S + s];
+              g_rbg[base + k] = (unsigned short)g;
+            }
+          }
+          if (tid == 0) { c.frb[s] = q; c.wd[s] = base; }   /* wd is free once the quotas exist: first grant of the slice */
+          base += q;
+          __syncthreads();
+        }
+        const int n_grants = min(base, 2 * G);
+        for (int u = tid; u < U; u += kThreads) c.den[u] = 0.0;   /* the metric denominators are dead: EESM sums */
+        __syncthreads();
+        /* per slice, in grant order: the winner's RB list grows by the RBG's RBs (EESM summand per RB) */
+        for (int s = tid; s < S; s += kThreads) {
+          const int q = c.frb[s], b0 = c.wd[s];
+          int cnt = 0;
+          for (int k = 0; k < q && b0 + k < 2 * G; ++k) {
+            const int ue = g_ue[b0 + k], g = g_rbg[b0 + k];
+            if (ue == kNoUe) continue;
+            cnt++;
+            double sum = c.den[ue];
+            const uint8_t* row = row_of(ue);
+            if (d.cqi_per_rb == 1) {
+              const uint8_t* p = row + (size_t)g * d.rbg;
+              for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+            } else {
+              const double tv = c.tval[cqi_first_rb(d, row, g)];
+              for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+            }
+            c.den[ue] = sum;
+            c.mask[2 * ue + (g >> 5)] |= 1u << (g & 31);   /* a UE belongs to one slice: no other thread touches it */
+          }
+          c.frb[s] = cnt;
+          if (c.misc[14]) c.off[s] = (double)(c.target[s] - cnt * d.rbg);   /* :618-620 */
+          else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
+        }
+        __syncthreads();
+        short* o_au = r.alloc_ue ? r.alloc_ue + tb * 2 * G : nullptr;
+        short* o_ar = r.alloc_rbg ? r.alloc_rbg + tb * 2 * G : nullptr;
+        for (int e = tid; e < 2 * G; e += kThreads) {
+          const bool in = e < n_grants && g_ue[e] != kNoUe;
+          if (o_au) o_au[e] = in ? (short)g_ue[e] : (short)-1;
+          if (o_ar) o_ar[e] = in ? (short)g_rbg[e] : (short)-1;
+        }
+        if (tid == 0 && r.alloc_n) r.alloc_n[tb] = base;
+        for (int g = tid; g < G; g += kThreads) {   /* single-valued view: the highest UE id holding the RBG */
+          int ue = -1;
+          for (int e = 0; e < n_grants; ++e)
+            if (g_rbg[e] == g && g_ue[e] != kNoUe) ue = max(ue, (int)g_ue[e]);
+          if (o_rbg) o_rbg[g] = (short)ue;
+        }
+      } else if (ALGO == 9) {
 #ifndef RS_SKIP_SORT
         sort_desc(c.sb, d.sort_n, d.sort_depth, kWarps - rot);
 #endif
@@ -914,6 +996,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
       RS_TICK(4);
       /* ---- P5: RBG -> UE (transport.cpp:589-601) --------------------------------------------- */
+      if (ALGO != 10)
       for (int g = tid; g < G; g += kThreads) {
         const int sl = c.outsl[g];
         int ue = -1;
@@ -930,6 +1013,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       }
       __syncthreads();
       /* slice_rbs_offset_ update (:618-620); only when RBsAllocation ran (>= 1 user) */
+      if (ALGO != 10)
       for (int s = tid; s < S; s += kThreads) {
         if (c.misc[14]) c.off[s] = (double)(c.target[s] - c.frb[s] * d.rbg);
         else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
@@ -1069,7 +1153,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc);
+      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, ALGO == 10 ? c.den : nullptr);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;
     }
@@ -1095,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     d.avg[i] = c.avg[u];
     d.tx[i] = c.tx[u];
   }
-  if (NVS || ALGO == 8 || ALGO == 9) {
+  if (NVS || ALGO == 8 || ALGO == 9 || ALGO == 10) {
     double* dst = NVS ? d.ewma : d.offset;
     for (int s = tid; s < S; s += kThreads) dst[(size_t)b * S + s] = c.off[s];
   }

@@ -198,7 +198,8 @@ struct rs_handle {
   struct Slot {
     DevBuf<uint8_t> cqi, active, mcs, final_cqi;
     DevBuf<int> rand2, tbs_bits, slice_target, slice_quota, nvs_slice;
-    DevBuf<short> rbg_to_ue;
+    DevBuf<short> rbg_to_ue, alloc_ue, alloc_rbg;
+    DevBuf<int> alloc_n;
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
     int slab0 = -1;   /* first CQI slab resident in this slot (rs_run_host with a refresh > 1) */
   } slot[2];
@@ -211,6 +212,7 @@ TtiKernel tti_kernel(int algo, bool trace) {
   switch (algo) {
     case 1: return trace ? rs::rs_tti_kernel<1, true> : rs::rs_tti_kernel<1, false>;
     case 7: return trace ? rs::rs_tti_kernel<7, true> : rs::rs_tti_kernel<7, false>;
+    case 10: return trace ? rs::rs_tti_kernel<10, true> : rs::rs_tti_kernel<10, false>;
     case 11: return trace ? rs::rs_tti_kernel<11, true> : rs::rs_tti_kernel<11, false>;
     case 8: return trace ? rs::rs_tti_kernel<8, true> : rs::rs_tti_kernel<8, false>;
     default: return trace ? rs::rs_tti_kernel<9, true> : rs::rs_tti_kernel<9, false>;
@@ -290,6 +292,11 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
     if (out->slice_target) CU(s.slice_target.alloc((size_t)T * B * S));
     if (out->slice_quota) CU(s.slice_quota.alloc((size_t)T * B * S));
     if (out->nvs_slice) CU(s.nvs_slice.alloc((size_t)T * B));
+    if (h->d.algo == 10) {
+      if (out->alloc_n) CU(s.alloc_n.alloc((size_t)T * B));
+      if (out->alloc_ue) CU(s.alloc_ue.alloc((size_t)T * B * 2 * G));
+      if (out->alloc_rbg) CU(s.alloc_rbg.alloc((size_t)T * B * 2 * G));
+    }
   }
   if (!s.in_done) {
     CU(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
@@ -301,7 +308,7 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
 
 bool wants(const rs_handle* h, int which) { /* outputs that exist for this scheduler id */
   const int a = h->d.algo;
-  if (which == 0) return a == 8 || a == 9;   /* slice_target / slice_quota */
+  if (which == 0) return a == 8 || a == 9 || a == 10;   /* slice_target / slice_quota */
   return a == 7 || a == 11;                  /* nvs_slice */
 }
 
@@ -310,7 +317,7 @@ bool wants(const rs_handle* h, int which) { /* outputs that exist for this sched
 extern "C" {
 
 const char* rs_last_error(void) { return g_err.c_str(); }
-int32_t rs_abi_version(void) { return 1; }
+int32_t rs_abi_version(void) { return 2; }
 
 void rs_destroy(rs_handle* h) {
   if (!h) return;
@@ -323,7 +330,7 @@ void rs_destroy(rs_handle* h) {
   for (auto& s : h->slot) {
     s.cqi.release(); s.active.release(); s.mcs.release(); s.final_cqi.release(); s.rand2.release();
     s.tbs_bits.release(); s.slice_target.release(); s.slice_quota.release(); s.nvs_slice.release();
-    s.rbg_to_ue.release();
+    s.rbg_to_ue.release(); s.alloc_ue.release(); s.alloc_rbg.release(); s.alloc_n.release();
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.k_done) cudaEventDestroy(s.k_done);
     if (s.out_done) cudaEventDestroy(s.out_done);
@@ -341,8 +348,8 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   if (!cfg || !out || n_cells <= 0) return fail(RS_ERR_ARG, "rs_create: bad argument");
   *out = nullptr;
   const int algo = cfg->algo, S = cfg->n_slices, U = cfg->n_ues;
-  if (algo != 1 && algo != 7 && algo != 8 && algo != 9 && algo != 11)
-    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 11 (NVS non-greedy)", algo);
+  if (algo != 1 && algo != 7 && algo != 8 && algo != 9 && algo != 10 && algo != 11)
+    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 10 (UpperBound), 11 (NVS non-greedy)", algo);
   if (S < 1 || S > RS_MAX_SLICES) return fail(RS_ERR_UNSUPPORTED, "n_slices %d outside 1..%d", S, RS_MAX_SLICES);
   if (U < 1 || U > 65000) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..65000", U);
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0)
@@ -440,7 +447,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   /* metric-table chunks: consecutive slices whose UEs fit the table */
   std::vector<int> chunks;
   int m_cap = 0;
-  if (algo == 8 || algo == 9) {
+  if (algo == 8 || algo == 9 || algo == 10) {
     const int cap = std::max(max_slice, std::min(U, 32));   /* small table: more cells resident per SM */
     chunks.push_back(0);
     int cur = 0;
@@ -466,11 +473,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   d.ng_ues = (algo == 11) ? max_slice : 0;
   /* rand() draws a TTI consumes per cell: transport.cpp:490,511 (ids 8/9); nvs.cpp:437-446 draws
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
-  d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9) ? 2 : 0);
-  h->layout = rs::make_layout(S, U, G, m_cap, 0, d.ng_ues);
+  d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9 || algo == 10) ? 2 : 0);
+  const int min_sort_n = (algo == 10) ? 8 * G : 0;
+  { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
+  h->layout = rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
-    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues);
+    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
     const int kSmemPerSm = 227 * 1024, kSms = 148;
     const int fit = kSmemPerSm / (staged.total + 1024);
     const int floor_fit = 2;   /* big cells: two staged cells per SM beat more unstaged ones (tools/sweep_bench.py) */
@@ -508,9 +517,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   BAIL(upload(h->weight, weight));
   BAIL(upload(h->epow, epow));
   BAIL(upload(h->psi, psi));
-  if (algo == 9 && d.sort_n > 16) {
+  if ((algo == 9 && d.sort_n > 16) || (algo == 10 && G > 16)) {
     std::vector<unsigned short> eq;
-    d.eq_max = std::min(d.sort_n, kEqMax);
+    d.eq_max = std::min(algo == 10 ? G : d.sort_n, kEqMax);
     build_eq_table(d.eq_max, &eq);
     BAIL(upload(h->eq_tab, eq));
     d.eq_tab = h->eq_tab.p;
@@ -636,6 +645,11 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
         a.slice_quota = d_out->slice_quota ? d_out->slice_quota + (size_t)t0 * B * S : nullptr;
       }
       if (wants(h, 1)) a.nvs_slice = d_out->nvs_slice ? d_out->nvs_slice + (size_t)t0 * B : nullptr;
+      if (h->d.algo == 10) {
+        a.alloc_n = d_out->alloc_n ? d_out->alloc_n + (size_t)t0 * B : nullptr;
+        a.alloc_ue = d_out->alloc_ue ? d_out->alloc_ue + (size_t)t0 * B * 2 * G : nullptr;
+        a.alloc_rbg = d_out->alloc_rbg ? d_out->alloc_rbg + (size_t)t0 * B * 2 * G : nullptr;
+      }
     }
     rc = launch_ttis(h, a);
     if (rc != RS_OK) return rc;
@@ -702,6 +716,11 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
         a.slice_quota = out->slice_quota ? s.slice_quota.p : nullptr;
       }
       if (wants(h, 1)) a.nvs_slice = out->nvs_slice ? s.nvs_slice.p : nullptr;
+      if (h->d.algo == 10) {
+        a.alloc_n = out->alloc_n ? s.alloc_n.p : nullptr;
+        a.alloc_ue = out->alloc_ue ? s.alloc_ue.p : nullptr;
+        a.alloc_rbg = out->alloc_rbg ? s.alloc_rbg.p : nullptr;
+      }
     }
     rc = launch_ttis(h, a);
     if (rc != RS_OK) return rc;
@@ -716,6 +735,9 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
       if (a.slice_target) CU(cudaMemcpyAsync(out->slice_target + (size_t)t0 * B * S, s.slice_target.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
       if (a.slice_quota) CU(cudaMemcpyAsync(out->slice_quota + (size_t)t0 * B * S, s.slice_quota.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
       if (a.nvs_slice) CU(cudaMemcpyAsync(out->nvs_slice + (size_t)t0 * B, s.nvs_slice.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_n) CU(cudaMemcpyAsync(out->alloc_n + (size_t)t0 * B, s.alloc_n.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_ue) CU(cudaMemcpyAsync(out->alloc_ue + (size_t)t0 * B * 2 * G, s.alloc_ue.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_rbg) CU(cudaMemcpyAsync(out->alloc_rbg + (size_t)t0 * B * 2 * G, s.alloc_rbg.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
     }
     CU(cudaEventRecord(s.out_done, h->copy_out));
   }
@@ -863,6 +885,8 @@ struct rs_log {
 
 int rs_log_create(const rs_config* cfg, rs_log** out) {
   if (!cfg || !out || !cfg->ue_to_slice) return fail(RS_ERR_ARG, "rs_log_create: bad argument");
+  if (cfg->algo == 10)
+    return fail(RS_ERR_UNSUPPORTED, "rs_log: id 10 prints each user's RBGs in grant order, which the single-valued rbg_to_ue cannot carry");
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0 || cfg->n_ues < 1 ||
       cfg->n_slices < 1 || cfg->cqi_per_rb < 0 || cfg->cqi_per_rb > 2)
     return fail(RS_ERR_ARG, "rs_log_create: bad configuration");

@@ -242,7 +242,7 @@ class RsGpuScheduler : public PacketScheduler {
     std::vector<double> state(slice_state_);
     Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, id_ == 7 ? nullptr : state.data(),
                        id_ == 7 ? state.data() : nullptr), "rs_set_state");
-    rs_outputs out;
+    rs_outputs out = {};
     int32_t nvs_slice = -1;
     out.rbg_to_ue = rbg_to_ue_.data();
     out.tbs_bits = bits_.data();

@@ -53,6 +53,7 @@ class _Out(C.Structure):
     _fields_ = [
         ("rbg_to_ue", C.c_void_p), ("tbs_bits", C.c_void_p), ("mcs", C.c_void_p), ("final_cqi", C.c_void_p),
         ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
+        ("alloc_n", C.c_void_p), ("alloc_ue", C.c_void_p), ("alloc_rbg", C.c_void_p),
     ]
 
 
@@ -235,13 +236,17 @@ class Scheduler:
                "mcs": np.empty(lead + (U,), np.uint8)}
         if want_aux:
             out["final_cqi"] = np.empty(lead + (U,), np.uint8)
-            if self.algo in (8, 9):
+            if self.algo == 10:
+                out["alloc_n"] = np.empty(lead, np.int32)
+                out["alloc_ue"] = np.empty(lead + (2 * G,), np.int16)
+                out["alloc_rbg"] = np.empty(lead + (2 * G,), np.int16)
+            if self.algo in (8, 9, 10):
                 out["slice_target"] = np.empty(lead + (S,), np.int32)
                 out["slice_quota"] = np.empty(lead + (S,), np.int32)
             if self.algo in (7, 11):
                 out["nvs_slice"] = np.empty(lead, np.int32)
         o = _Out(*[_ptr(out.get(k)) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
-                                                "slice_quota", "nvs_slice")])
+                                                "slice_quota", "nvs_slice", "alloc_n", "alloc_ue", "alloc_rbg")])
         return out, o
 
     def _draws(self, rand2, lead):
@@ -288,7 +293,7 @@ class Scheduler:
         dt = np.ascontiguousarray(dt, dtype=np.float64)
         assert dt.shape[0] >= n_ttis
         o = _Out(*[(d_out or {}).get(k) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
-                                                    "slice_quota", "nvs_slice")])
+                                                    "slice_quota", "nvs_slice", "alloc_n", "alloc_ue", "alloc_rbg")])
         _check(lib().rs_run_device(self._h, int(n_ttis), C.c_void_p(d_cqi), int(cqi_tti_stride), int(cqi_refresh),
                                    C.c_void_p(d_rand2 or None), C.c_void_p(d_active or None),
                                    int(active_tti_stride), _ptr(dt), C.byref(o), int(ttis_per_launch)))
@@ -323,7 +328,7 @@ class Scheduler:
         trace_row = np.ascontiguousarray(trace_row, dtype=np.int32)
         assert dt.shape[0] >= n_ttis and trace_row.shape[0] >= n_ttis
         o = _Out(*[(d_out or {}).get(k) for k in ("rbg_to_ue", "tbs_bits", "mcs", "final_cqi", "slice_target",
-                                                    "slice_quota", "nvs_slice")])
+                                                    "slice_quota", "nvs_slice", "alloc_n", "alloc_ue", "alloc_rbg")])
         _check(lib().rs_run_traces_device(self._h, int(n_ttis), _ptr(trace_row), C.c_void_p(d_rand2 or None),
                                           C.c_void_p(d_active or None), int(active_tti_stride), _ptr(dt),
                                           C.byref(o), int(ttis_per_launch)))

@@ -19,6 +19,14 @@ def load_golden(name):
     return golden_io.load_npz(os.path.join(GOLDEN, name + ".npz"))
 
 
+def grants_by_user(ue, rbg):
+    """{user: [RBGs in grant order]} from parallel grant arrays."""
+    d = {}
+    for u, g in zip(np.asarray(ue).tolist(), np.asarray(rbg).tolist()):
+        d.setdefault(u, []).append(g)
+    return d
+
+
 def replay_golden(sched, rec, check_final_cqi=True):
     """Drive a 1-cell scheduler (oracle or CUDA, same python surface) through a golden record,
     chaining its own state, and compare every TTI with what the reference produced.
@@ -26,7 +34,7 @@ def replay_golden(sched, rec, check_final_cqi=True):
     algo, T = int(rec["algo"]), int(rec["T"])
     bad = []
     sched.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
-                    slice_offset=rec["state_before"][0][None] if algo in (8, 9) else None,
+                    slice_offset=rec["state_before"][0][None] if algo in (8, 9, 10) else None,
                     nvs_ewma=rec["state_before"][0][None] if algo in (7, 11) else None)
     for t in range(T):
         # id 11: every rand() value of the 300-sample search (downlink-nvs-scheduler.cpp:437-446)
@@ -39,6 +47,12 @@ def replay_golden(sched, rec, check_final_cqi=True):
                 bad.append((t, field))
 
         chk("rbg_to_ue", out["rbg_to_ue"][0], rec["rbg_to_ue"][t])
+        if algo == 10:   # every (user, RBG) grant, per user in the order of the user's RB list
+            n, m = int(out["alloc_n"][0]), int(rec["alloc_n"][t])
+            got = grants_by_user(out["alloc_ue"][0][:n], out["alloc_rbg"][0][:n])
+            want = grants_by_user(rec["alloc_ue"][t][:m], rec["alloc_rbg"][t][:m])
+            if n != m or got != want:
+                bad.append((t, "grants"))
         chk("tbs_bits", out["tbs_bits"][0], rec["bits"][t])
         if check_final_cqi and algo != 1 and "final_cqi" in out:  # PF prints no final_cqi line
             chk("final_cqi", out["final_cqi"][0], rec["final_cqi"][t])
@@ -46,7 +60,7 @@ def replay_golden(sched, rec, check_final_cqi=True):
         chk("tx_bytes", st["tx_bytes"][0], rec["tx_after"][t])
         chk("cum_bytes", st["cum_bytes"][0], rec["cum_bytes"][t])
         chk("cum_rbs", st["cum_rbs"][0], rec["cum_rbs"][t])
-        if algo in (8, 9):
+        if algo in (8, 9, 10):
             if "slice_target" in out:
                 chk("slice_target", out["slice_target"][0], rec["target"][t])
                 chk("slice_quota", out["slice_quota"][0], rec["quota"][t])

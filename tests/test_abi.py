@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(sched.LIB_PATH)
     for name in _declared_symbols():
         assert hasattr(L, name), name
-    assert sched.lib().rs_abi_version() == 1
+    assert sched.lib().rs_abi_version() == 2
 
 
 def test_create_rejects_bad_configs_without_touching_the_gpu():
@@ -39,7 +39,7 @@ def test_create_rejects_bad_configs_without_touching_the_gpu():
         sched.Scheduler(9, w, p, u2s, 1)
     p[1, 3] = 1
     with pytest.raises(sched.RsError, match="scheduler id"):
-        sched.Scheduler(10, w, p, u2s, 1)
+        sched.Scheduler(12, w, p, u2s, 1)
     with pytest.raises(sched.RsError, match="multiple"):
         sched.Scheduler(9, w, p, u2s, 1, n_rbs=25, rbg_size=2)
     with pytest.raises(sched.RsError, match="n_slices"):

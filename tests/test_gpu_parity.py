@@ -114,7 +114,7 @@ def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_
         sa, sb = o.get_state(), g.get_state()
         for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs"):
             assert np.array_equal(sa[k], sb[k]), (t, k)
-        if algo in (8, 9):
+        if algo in (8, 9, 10):
             assert np.array_equal(sa["slice_offset"], sb["slice_offset"]), t
         if algo in (7, 11):
             assert np.array_equal(sa["nvs_ewma"], sb["nvs_ewma"]), t
@@ -125,13 +125,13 @@ PF = [0, 0, 1, 1]
 MT = [0, 0, 1, 0]
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
 def test_headline_shape_20x5(algo):
     S = 20
     _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7])
+@pytest.mark.parametrize("algo", [9, 8, 7, 10])
 def test_mixed_enterprise_schedulers_diff_weights(algo):
     S = 20
     w = np.array([0.025] * 10 + [0.075] * 10)
@@ -148,14 +148,14 @@ def test_sweep_shapes_radiosaber(S, n):
     _mk(9, S, [n] * S, w, p, B=6, seed=S * 100 + n, T=12)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
 def test_inactive_bearers_and_empty_cells(algo):
     S = 8
     w = np.full(S, 1.0 / S)
     _mk(algo, S, [4] * S, w, np.tile(PF, (S, 1)), B=10, seed=300 + algo, T=12, with_active=True)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
 def test_per_rb_cqi_layout(algo):
     S = 6
     w = np.full(S, 1.0 / S)

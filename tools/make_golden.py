@@ -71,6 +71,12 @@ CASES = [
     ("a11_fix20x5_synth", 11, FIX20X5, 24, "synth", 13),
     ("a11_small_synth", 11, "SMALL", 60, "synth", 14),
     ("a11_fix20x5_trace", 11, FIX20X5, 12, "trace", 1),
+    # id 10 (UpperBound, downlink-transport-scheduler.cpp:223-246): an RBG may go to several slices, so the
+    # records also hold every (user, RBG) grant in the order of the users' RB lists (ref_harness --alloc-log)
+    ("a10_fix20x5_synth", 10, FIX20X5, 40, "synth", 15),
+    ("a10_diffw_synth", 10, DIFFW, 24, "synth", 16),
+    ("a10_small_synth", 10, "SMALL", 80, "synth", 17),
+    ("a10_fix20x5_trace", 10, FIX20X5, 30, "trace", 1),
 ]
 
 
@@ -96,6 +102,9 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
     rlog_path = os.path.join(tmp, name + ".rlog")
     if algo == 11:
         cmd += ["--rand-log", rlog_path]
+    alog_path = os.path.join(tmp, name + ".alog")
+    if algo == 10:
+        cmd += ["--alloc-log", alog_path]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     rec = golden_io.compact(golden_io.parse_record_stream(rec_path))
     assert rec["T"] == n_ttis, (name, rec["T"])
@@ -110,7 +119,23 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
         width = max(len(d) for d in draws)
         rec["rand_ng_n"] = np.array([len(d) for d in draws], dtype=np.int32)
         rec["rand_ng"] = np.stack([np.pad(d, (0, width - len(d))) for d in draws]).astype(np.int32)
-    if algo in (8, 9):
+    if algo == 10:
+        raw = np.fromfile(alog_path, dtype="<i2")
+        G = int(rec["G"])
+        ue = np.full((n_ttis, 2 * G), -1, dtype=np.int16)
+        rb = np.full((n_ttis, 2 * G), -1, dtype=np.int16)
+        cnt = np.zeros(n_ttis, dtype=np.int32)
+        pos = 0
+        for t in range(n_ttis):
+            k = int(raw[pos]) | (int(raw[pos + 1]) << 16)
+            pos += 2
+            pairs = raw[pos:pos + 2 * k].reshape(k, 2)
+            pos += 2 * k
+            cnt[t] = k
+            ue[t, :k], rb[t, :k] = pairs[:, 0], pairs[:, 1]
+        assert pos == len(raw) and cnt.max() <= 2 * G
+        rec["alloc_n"], rec["alloc_ue"], rec["alloc_rbg"] = cnt, ue, rb
+    if algo in (8, 9, 10):
         assert (rec["rand2"] == rand2).all(), "scripted rand() values were not the ones consumed"
     rec["config_json"] = json.dumps(cfg)
     rec["source"] = source

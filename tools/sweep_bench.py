@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE.json configs[2] and configs[3] on one GPU (device-resident inputs, CUDA events):
 
-  configs[2]: the 4096-cell 20 x 5 batch under ids 1 / 7 / 8 / 9 (and 11, NVS non-greedy) with PF enterprise schedulers and with the
+  configs[2]: the 4096-cell 20 x 5 batch under ids 1 / 7 / 8 / 9 (and 10 UpperBound, 11 NVS non-greedy) with PF enterprise schedulers and with the
               Sec 6.2-style mix (per-slice parameters cycling PF (eps 1, psi 1) / MT == max-CI (eps 1, psi 0))
   configs[3]: slices x UEs-per-slice sweep, weights proportional to 1 + (s mod 3), RadioSaber (9), the batch
               size chosen so that cells x UEs ~ 409 600
@@ -88,9 +88,9 @@ def main():
         pf = np.tile(np.array([0, 0, 1, 1], dtype=np.int32), (S, 1))
         mix = pf.copy()
         mix[1::2, 3] = 0      # every other slice MT (max-CI): eps 1, psi 0
-        for algo in (9, 8, 7, 1, 11):
+        for algo in (9, 8, 7, 1, 11, 10):
             emit(measure(algo, w, pf, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF"))
-            if algo not in (1, 11):
+            if algo not in (1, 11, 10):
                 emit(measure(algo, w, mix, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF/MT mix"))
     if args.only in (None, "sweep"):
         for S in (5, 10, 15, 20, 30, 40, 50):
