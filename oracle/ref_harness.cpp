@@ -419,7 +419,10 @@ struct Installer {
     PacketScheduler* s = nullptr;
 #ifdef RS_WITH_GPU_ADAPTOR
     if (g_opt.gpu) {
-      if (g_opt.algo == 1) { fprintf(stderr, "the host plug-in covers ids 7, 8, 9\n"); exit(2); }
+      if (g_opt.algo != 1 && g_opt.algo != 7 && g_opt.algo != 8 && g_opt.algo != 9) {
+        fprintf(stderr, "the host plug-in covers ids 1, 7, 8, 9\n");
+        exit(2);
+      }
       s = new ObservedGpu(g_opt.config, g_opt.algo);
       s->SetMacEntity(mac);
       mac->SetDownlinkPacketScheduler(s);

@@ -4,6 +4,8 @@
  * the arguments the reference's schedulers take, installed by ENodeB::SetDLScheduler
  * (src/device/ENodeB.cpp:302-391; the three-line change is in INTEGRATION.md):
  *
+ *     case ENodeB::DLScheduler_TYPE_PROPORTIONAL_FAIR:   // id 1
+ *       scheduler = new RsGpuScheduler(config_fname, 1);   // was DL_PF_PacketScheduler(config_fname)
  *     case ENodeB::DLScheduler_MAXCELL:      // id 9
  *       scheduler = new RsGpuScheduler(config_fname, 9);   // was DownlinkTransportScheduler(config_fname, 2)
  *
@@ -62,9 +64,13 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<SchedulerAlgoParam> slice_algo_params_;
   std::vector<double> slice_state_; /* slice_rbs_offset_ (ids 8/9) or slice_ewma_time_ (id 7) */
 
-  /* scheduler_id: 7 NVS, 8 Sequential, 9 RadioSaber (single-cell-with-interference.h:99-110) */
+  /* scheduler_id: 1 No-Slicing PF, 7 NVS, 8 Sequential, 9 RadioSaber (single-cell-with-interference.h:95-110).
+   * Id 1 replaces DL_PF_PacketScheduler(config_fname) (ENodeB.cpp:309-313); that class schedules flows
+   * (FlowToSchedule, one per bearer), which for the one-bearer-per-UE backlogged configurations is the same
+   * list as the users kept here. */
   RsGpuScheduler(std::string config_fname, int scheduler_id) : id_(scheduler_id) {
-    if (id_ != 7 && id_ != 8 && id_ != 9) throw std::runtime_error("RsGpuScheduler: scheduler id must be 7, 8 or 9");
+    if (id_ != 1 && id_ != 7 && id_ != 8 && id_ != 9)
+      throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8 or 9");
     std::ifstream ifs(config_fname);
     if (!ifs.is_open()) throw std::runtime_error("Fail to open configuration file.");
     Json::Reader reader;
@@ -215,6 +221,8 @@ class RsGpuScheduler : public PacketScheduler {
       UserToSchedule* user = nullptr;
       for (auto u = users->begin(); u != users->end(); ++u)
         if ((*u)->GetUserID() == uid) user = *u;
+      if (user && id_ == 1)
+        throw std::runtime_error("RsGpuScheduler: id 1 schedules flows; two bearers on one UE are not covered");
       if (!user) {
         user = new UserToSchedule(uid, bearer->GetDestination());
         std::vector<int> cqi = enb->GetUserEquipmentRecord(bearer->GetDestination()->GetIDNetworkNode())->GetCQI();
@@ -240,7 +248,7 @@ class RsGpuScheduler : public PacketScheduler {
       rand2[1] = rand();
     }
     std::vector<double> state(slice_state_);
-    Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, id_ == 7 ? nullptr : state.data(),
+    Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, (id_ == 8 || id_ == 9) ? state.data() : nullptr,
                        id_ == 7 ? state.data() : nullptr), "rs_set_state");
     rs_outputs out = {};
     int32_t nvs_slice = -1;
@@ -253,7 +261,7 @@ class RsGpuScheduler : public PacketScheduler {
     out.nvs_slice = &nvs_slice;
     /* dt = 0: the EWMA was applied by the bearers themselves a few lines up */
     Check(rs_step(h_, cqi_.data(), rand2, active_.data(), 0.0, &out), "rs_step");
-    Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, id_ == 7 ? nullptr : slice_state_.data(),
+    Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, (id_ == 8 || id_ == 9) ? slice_state_.data() : nullptr,
                        id_ == 7 ? slice_state_.data() : nullptr), "rs_get_state");
 
     UsersToSchedule* users = GetUsersToSchedule();
@@ -261,7 +269,7 @@ class RsGpuScheduler : public PacketScheduler {
       for (auto it = users->begin(); it != users->end();) {
         if (user_to_slice_[(*it)->GetUserID()] != nvs_slice) { delete *it; it = users->erase(it); } else ++it;
       }
-    } else { /* the reference's log line, :523-527 */
+    } else if (id_ != 1) { /* the reference's log line, :523-527 */
       std::cout << "slice_id, target_rbs, quota_rbgs: ";
       for (int i = 0; i < S; ++i) std::cout << "(" << i << ", " << target_[i] << ", " << quota_[i] << ") ";
       std::cout << std::endl;
@@ -274,16 +282,18 @@ class RsGpuScheduler : public PacketScheduler {
       for (int r = g * rbg_size_; r < (g + 1) * rbg_size_; ++r) by_id[ue]->GetListOfAllocatedRBs()->push_back(r);
     }
     PdcchMapIdealControlMessage* pdcch = new PdcchMapIdealControlMessage();
-    std::cout << GetTimeStamp() << std::endl;
+    if (id_ != 1) std::cout << GetTimeStamp() << std::endl;   /* DownlinkPacketScheduler::RBsAllocation prints nothing */
     for (auto it = users->begin(); it != users->end(); ++it) {
       UserToSchedule* ue = *it;
       std::vector<int>* rbs = ue->GetListOfAllocatedRBs();
       if (rbs->empty()) continue;
-      std::cout << "User(" << ue->GetUserID() << ") allocated RBGS:";
-      for (size_t i = 0; i < rbs->size(); i++)
-        if (rbs->at(i) % rbg_size_ == 0)
-          std::cout << " " << rbs->at(i) / rbg_size_ << "(" << ue->GetCqiFeedbacks().at(rbs->at(i)) << ")";
-      std::cout << " final_cqi: " << (int)final_cqi_[ue->GetUserID()] << std::endl;
+      if (id_ != 1) {
+        std::cout << "User(" << ue->GetUserID() << ") allocated RBGS:";
+        for (size_t i = 0; i < rbs->size(); i++)
+          if (rbs->at(i) % rbg_size_ == 0)
+            std::cout << " " << rbs->at(i) / rbg_size_ << "(" << ue->GetCqiFeedbacks().at(rbs->at(i)) << ")";
+        std::cout << " final_cqi: " << (int)final_cqi_[ue->GetUserID()] << std::endl;
+      }
       ue->UpdateAllocatedBits(bits_[ue->GetUserID()]);
       for (size_t i = 0; i < rbs->size(); i++)
         pdcch->AddNewRecord(PdcchMapIdealControlMessage::DOWNLINK, rbs->at(i), ue->GetUserNode(), mcs_[ue->GetUserID()]);
