@@ -16,7 +16,7 @@ from tools import golden_io
 pytestmark = pytest.mark.gpu
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")
 
-CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_small_synth", "a8_fix20x5_synth", "a8_small_synth",
+CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_diffw_trace", "a9_small_synth", "a8_fix20x5_synth", "a8_small_synth",
          "a7_fix20x5_synth", "a7_mix20_synth", "a7_small_synth", "a1_fix20x5_synth", "a1_small_synth"]
 
 

@@ -15,7 +15,8 @@ from tests.helpers import GOLDEN, load_golden
 
 FIX = os.path.join(GOLDEN, "traces", "trace_subset.npz")
 REF_TRACES = "/root/reference/cqi-traces-noise0"
-TRACE_GOLDENS = ["a9_fix20x5_trace", "a8_fix20x5_trace", "a7_fix20x5_trace", "a1_fix20x5_trace"]
+TRACE_GOLDENS = ["a9_fix20x5_trace", "a8_fix20x5_trace", "a7_fix20x5_trace", "a1_fix20x5_trace", "a9_diffw_trace",
+                 "a10_fix20x5_trace", "a11_fix20x5_trace"]
 
 
 def _fixture():
@@ -112,10 +113,11 @@ def test_cuda_trace_run_matches_reference_record(name, layout):
     g = sched.Scheduler(algo, rec["weight"], rec["params"], rec["ue_to_slice"], 1, cqi_per_rb=layout)
     g.set_traces(np.repeat(rows, 8, axis=2), _ue_trace_slots(mapping, slot, U, rec)[None])
     g.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
-                slice_offset=rec["state_before"][0][None] if algo in (8, 9) else None,
-                nvs_ewma=rec["state_before"][0][None] if algo == 7 else None)
+                slice_offset=rec["state_before"][0][None] if algo in (8, 9, 10) else None,
+                nvs_ewma=rec["state_before"][0][None] if algo in (7, 11) else None)
     tr = sched.trace_rows_for_run(rec["now"], 0)
-    out = g.run_traces_host(tr, rec["rand2"][:, None, :], rec["dt"], want_aux=True, ttis_per_launch=7)
+    draws = rec["rand_ng"] if algo == 11 else rec["rand2"]
+    out = g.run_traces_host(tr, draws[:, None, :], rec["dt"], want_aux=True, ttis_per_launch=7)
     assert np.array_equal(out["rbg_to_ue"][:, 0], rec["rbg_to_ue"])
     assert np.array_equal(out["tbs_bits"][:, 0], rec["bits"])
     if algo != 1:

@@ -60,6 +60,9 @@ CASES = [
     ("a7_fix20x5_synth", 7, FIX20X5, 40, "synth", 4),
     ("a1_fix20x5_synth", 1, FIX20X5, 40, "synth", 5),
     ("a9_diffw_synth", 9, DIFFW, 40, "synth", 6),
+    # BASELINE.json configs[0]: SingleCellWithI, scheduler 9, exp-backlogged-20slicesdiffw, real CQI traces
+    # through mapping1.config (204 UEs)
+    ("a9_diffw_trace", 9, DIFFW, 45, "trace", 1),
     ("a8_diffw_synth", 8, DIFFW, 24, "synth", 7),
     ("a7_mix20_synth", 7, MIX20, 40, "synth", 8),
     ("a9_small_synth", 9, "SMALL", 120, "synth", 9),
