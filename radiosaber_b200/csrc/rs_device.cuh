@@ -21,12 +21,16 @@
  * reference's x86-64 build; libm values (pow/exp/log/log10) enter only through tables computed on
  * the host with glibc (rs_sched.cu).
  */
-#pragma once
+/* No include guard: rs_sched.cu includes this file twice, once per CTA width (RS_NS = the namespace,
+ * RS_THREADS = threads per cell, RS_MIN_BLOCKS = cells per SM the register budget must allow). */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
 
-namespace rs {
+#ifndef RS_NS
+#define RS_NS rs
+#endif
+namespace RS_NS {
 
 #ifdef RS_PHASE_TIMING
 #define RS_TICK(k) do { if (threadIdx.x == 0) { long long now_ = clock64(); ph_[k] += now_ - last_; last_ = now_; } } while (0)
@@ -146,7 +150,7 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   L.quota = o;  o += 4 * S;
   L.frb = o;    o += 4 * S;
   L.wd = o;     o += 4 * S;
-  L.misc = o;   o += 4 * 16;
+  L.misc = o;   o += 4 * 48;
   L.a = o;    o += 2 * n;
   L.win = o;  o += 2 * n;
   L.cnt = o;  o += 2 * 16 * nw;
@@ -233,7 +237,7 @@ struct SortBufs {
   unsigned* seg0;        /* [n/16+2] ranges still to partition, ping */
   unsigned* seg1;        /* [n/16+2] pong */
   unsigned short* cnt;   /* [16*nw] */
-  unsigned* misc;        /* [16]: 0..7 warp totals, 8..10 rotating list counters */
+  unsigned* misc;        /* [48]: 8..10 rotating list counters, 13..15 per-TTI scalars of the kernel, 16.. warp totals */
   const unsigned short* eq_tab;  /* all-equal-keys permutations, see eq_offset(); may be null */
   int eq_max;            /* longest range the table covers */
 };
@@ -410,10 +414,10 @@ __device__ void sort_desc(const SortBufs& b, int n, int depth_limit, int rot) {
       if (lane >= d) incl += v;
     }
     const int pw = tid >> 5;   /* physical warp: the scan runs over threads in tid order */
-    if (lane == 31) b.misc[pw] = (unsigned)incl;
+    if (lane == 31) b.misc[16 + pw] = (unsigned)incl;
     __syncthreads();
     int base = incl - s;
-    for (int w = 0; w < pw; ++w) base += (int)b.misc[w];
+    for (int w = 0; w < pw; ++w) base += (int)b.misc[16 + w];
     for (int q = q0; q < q0 + per && q < Q; ++q) {
       const int c = (int)b.cnt[q];
       b.cnt[q] = (unsigned short)base;
@@ -850,7 +854,9 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           c.mtab[q] = cq ? __ddiv_rn(d.epow[d.ue_to_slice[u] * 16 + cq], c.den[u]) : 0.0;
         }
         __syncthreads();
-        const bool vec4 = d.cqi_per_rb != 1 && (G % 4 == 0);
+        /* four RBGs per item (one 32-bit CQI load per UE) while that still gives every thread an item;
+         * fewer, bigger slices on a wide CTA go one RBG per item */
+        const bool vec4 = d.cqi_per_rb != 1 && (G % 4 == 0) && (kThreads <= 128 || (s1 - s0) * (G >> 2) >= kThreads);
         const bool nib = d.cqi_per_rb == 2;
         if (vec4) {
           const int g4 = G >> 2;
@@ -1185,6 +1191,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   }
 }
 
+#ifndef RS_CORE_ONLY
 /* ---- test hook: the sort alone, one CTA per array --------------------------------------------- */
 __global__ void __launch_bounds__(kThreads) rs_sort_test_kernel(const uint8_t* keys, int n, int depth, int* perm,
                                                                 const unsigned short* eq_tab, int eq_max, const Layout L) {
@@ -1276,4 +1283,6 @@ __global__ void rs_stats_kernel(const DevCfg d, unsigned long long* stats) {
     if (s_acc[i]) atomicAdd(&stats[i], s_acc[i]);
 }
 
-}  // namespace rs
+#endif  /* RS_CORE_ONLY */
+
+}  // namespace RS_NS

@@ -6,7 +6,24 @@
  * lives here: without a CUDA device every compute entry point fails with RS_ERR_CUDA.
  */
 #include "../../include/rs_sched.h"
+/* the device code twice: rs:: = 128 threads per cell, eight cells per SM (the headline shape);
+ * rsw:: = 512 threads per cell, two per SM, for cells with hundreds of UEs */
+#define RS_NS rs
+#define RS_THREADS 128
+#define RS_MIN_BLOCKS 8
 #include "rs_device.cuh"
+#undef RS_NS
+#undef RS_THREADS
+#undef RS_MIN_BLOCKS
+#define RS_NS rsw
+#define RS_THREADS 512
+#define RS_MIN_BLOCKS 2
+#define RS_CORE_ONLY
+#include "rs_device.cuh"
+#undef RS_NS
+#undef RS_THREADS
+#undef RS_MIN_BLOCKS
+#undef RS_CORE_ONLY
 
 #include <algorithm>
 #include <cmath>
@@ -142,6 +159,9 @@ void build_eq_table(int nmax, std::vector<unsigned short>* tab) {
   }
 }
 constexpr int kEqMax = 2048;
+#ifndef RS_WIDE_MIN_UES
+#define RS_WIDE_MIN_UES 480   /* cells with at least this many UEs run 512 threads wide (tools/sweep_bench.py) */
+#endif
 #ifndef RS_STAGE_MAX_SMEM
 #define RS_STAGE_MAX_SMEM (27 * 1024)   /* staging must leave room for eight cells per SM */
 #endif
@@ -190,7 +210,8 @@ struct rs_handle {
   DevBuf<uint8_t> trace_tab;
   DevBuf<int> ue_trace_off, trow_dev;
   int n_traces = 0, trace_rows = 0;
-  bool stage_ok = false;             /* the layout has room for a TTI of CQI (cp.async staging) */
+  bool stage_ok = false;
+  bool wide = false;                 /* 512 threads per cell (rsw::) instead of 128 */             /* the layout has room for a TTI of CQI (cp.async staging) */
   int* trow_pinned = nullptr;
   size_t trow_pinned_n = 0;
   DevBuf<unsigned long long> stats;
@@ -207,6 +228,18 @@ struct rs_handle {
 
 namespace {
 
+static_assert(sizeof(rs::DevCfg) == sizeof(rsw::DevCfg) && sizeof(rs::RunArgs) == sizeof(rsw::RunArgs) &&
+                  sizeof(rs::ConstTables) == sizeof(rsw::ConstTables),
+              "the two instantiations of rs_device.cuh share their parameter structs");
+
+#define RS_TTI_CASE(NS, A) \
+  case A: return trace ? (const void*)NS::rs_tti_kernel<A, true> : (const void*)NS::rs_tti_kernel<A, false>;
+const void* tti_kernel_wide(int algo, bool trace) {
+  switch (algo) {
+    RS_TTI_CASE(rsw, 1) RS_TTI_CASE(rsw, 7) RS_TTI_CASE(rsw, 8) RS_TTI_CASE(rsw, 10) RS_TTI_CASE(rsw, 11)
+    default: return trace ? (const void*)rsw::rs_tti_kernel<9, true> : (const void*)rsw::rs_tti_kernel<9, false>;
+  }
+}
 typedef void (*TtiKernel)(const rs::DevCfg, const rs::RunArgs);
 TtiKernel tti_kernel(int algo, bool trace) {
   switch (algo) {
@@ -221,9 +254,13 @@ TtiKernel tti_kernel(int algo, bool trace) {
 
 /* a.trace_row != NULL selects the trace-driven instantiation */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
-  const dim3 grid(h->B), block(rs::kThreads);
+  const dim3 grid(h->B), block(h->wide ? rsw::kThreads : rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
-  tti_kernel(h->d.algo, a.trace_row != nullptr)<<<grid, block, sm, h->stream>>>(h->d, a);
+  const bool trace = a.trace_row != nullptr;
+  /* by address: the rsw:: kernels take rsw::DevCfg / rsw::RunArgs, the same bytes as the rs:: structs */
+  const void* fn = h->wide ? tti_kernel_wide(h->d.algo, trace) : (const void*)tti_kernel(h->d.algo, trace);
+  void* args[2] = {(void*)&h->d, (void*)&a};
+  CU(cudaLaunchKernel(fn, grid, block, args, sm, h->stream));
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;
@@ -231,8 +268,10 @@ int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
 
 int set_smem_attr(rs_handle* h) {
   const int sm = h->layout.total;
-  CU(cudaFuncSetAttribute(tti_kernel(h->d.algo, false), cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CU(cudaFuncSetAttribute(tti_kernel(h->d.algo, true), cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  for (int t = 0; t < 2; ++t) {
+    const void* fn = h->wide ? tti_kernel_wide(h->d.algo, t != 0) : (const void*)tti_kernel(h->d.algo, t != 0);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  }
   return RS_OK;
 }
 
@@ -470,19 +509,27 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   /* Stage a TTI's CQI in shared memory (cp.async) when the layout is one value per RBG, rows are 16-byte
    * multiples and the staged cell does not cost occupancy the batch could use: eight cells per SM for
    * big batches, fewer when there are not that many cells per SM to begin with. */
+  /* hundreds of UEs per cell: the per-UE phases (EWMA, metric table, per-slice argmax, link adaptation)
+   * dominate and few cells fit an SM anyway, so give the cell 512 threads */
+  h->wide = U >= RS_WIDE_MIN_UES;
   d.ng_ues = (algo == 11) ? max_slice : 0;
   /* rand() draws a TTI consumes per cell: transport.cpp:490,511 (ids 8/9); nvs.cpp:437-446 draws
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
   d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9 || algo == 10) ? 2 : 0);
   const int min_sort_n = (algo == 10) ? 8 * G : 0;
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
-  h->layout = rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);
+  h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n)))
+                      : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
-    const rs::Layout staged = rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
+    const rsw::Layout staged_w = rsw::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
+    const rs::Layout staged = h->wide ? reinterpret_cast<const rs::Layout&>(staged_w)
+                                      : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
     const int kSmemPerSm = 227 * 1024, kSms = 148;
     const int fit = kSmemPerSm / (staged.total + 1024);
-    const int floor_fit = 2;   /* big cells: two staged cells per SM beat more unstaged ones (tools/sweep_bench.py) */
+    /* big cells: two staged cells per SM beat more unstaged ones, and a 512-thread cell is better off
+     * alone on its SM with its CQI staged than sharing it unstaged (tools/sweep_bench.py) */
+    const int floor_fit = h->wide ? 1 : 2;
     const int wanted = std::min(floor_fit, (n_cells + kSms - 1) / kSms);
     if (staged.total <= RS_STAGE_MAX_SMEM || (fit >= 1 && fit >= wanted)) { h->layout = staged; h->stage_ok = true; }
   }
@@ -502,6 +549,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   { std::string why;
     if (!build_const_tables(&ct, &why)) BAIL(fail(RS_ERR_UNSUPPORTED, "host libm: %s", why.c_str())); }
   { cudaError_t e = cudaMemcpyToSymbol(rs::c_tab, &ct, sizeof ct);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(rsw::c_tab, &ct, sizeof ct);
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e))); }
   BAIL(set_smem_attr(h));
   { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
@@ -1090,7 +1138,7 @@ int rs_get_stats(rs_handle* h, uint64_t* stats) {
 int32_t rs_rand_draws_per_cell_tti(const rs_handle* h) { return h ? h->d.rand_stride : 0; }
 int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
 int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }
-int32_t rs_threads_per_cta(const rs_handle* h) { (void)h; return rs::kThreads; }
+int32_t rs_threads_per_cta(const rs_handle* h) { return (h && h->wide) ? rsw::kThreads : rs::kThreads; }
 int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h) {
   if (!h) return 0;
   const int64_t U = h->d.U, G = h->d.G, S = h->d.S;

@@ -149,6 +149,20 @@ def test_sweep_shapes_radiosaber(S, n):
 
 
 @pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_wide_cells_all_ids(algo, layout):
+    """Cells with >= 480 UEs run 512 threads wide (the second instantiation of the device code)."""
+    S = 12
+    w = np.array([0.2, 0.1, 0.1, 0.05, 0.05, 0.1, 0.1, 0.1, 0.05, 0.05, 0.05, 0.05])
+    p = np.tile(PF, (S, 1))
+    p[1::3] = MT
+    g = sched.Scheduler(algo, w, p, np.repeat(np.arange(S), 40).astype(np.int32), 1)
+    assert sched.lib().rs_threads_per_cta(g._h) == 512
+    g.close()
+    _mk(algo, S, [40] * S, w, p, B=4, seed=700 + algo, T=5, cqi_per_rb=layout, with_active=(layout == 1))
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
 def test_inactive_bearers_and_empty_cells(algo):
     S = 8
     w = np.full(S, 1.0 / S)
