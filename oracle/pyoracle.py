@@ -35,6 +35,7 @@ class _Io(C.Structure):
         ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
         ("alloc_n", C.c_void_p), ("alloc_ue", C.c_void_p), ("alloc_rbg", C.c_void_p),
         ("rand_stride", C.c_int32),
+        ("queue_bytes", C.c_void_p), ("hol_delay", C.c_void_p),
     ]
 
 
@@ -118,7 +119,7 @@ class OracleScheduler:
         return {k: getattr(self, k).copy() for k in
                 ("avg_rate", "tx_bytes", "slice_offset", "nvs_ewma", "cum_bytes", "cum_rbs")}
 
-    def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False):
+    def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False, queue=None, hol=None):
         """One TTI.  cqi: uint8 [B][U][G] (or [B][U][R]); rand2: int32 [B][2]."""
         B, U, S, G = self.B, self.U, self.S, self.G
         cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
@@ -127,6 +128,8 @@ class OracleScheduler:
             rand2 = np.zeros((B, 2), dtype=np.int32)
         rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, -1)   # [B][2]; id 11: [B][300 * users]
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
+        q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32).reshape(B, U)
+        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(B, U)
         out = {
             "rbg_to_ue": np.empty((B, G), dtype=np.int16),
             "tbs_bits": np.empty((B, U), dtype=np.int32),
@@ -149,7 +152,7 @@ class OracleScheduler:
                  _ptr(out["rbg_to_ue"]), _ptr(out["tbs_bits"]), _ptr(out["mcs"]), _ptr(aux.get("final_cqi")),
                  _ptr(aux.get("slice_target")), _ptr(aux.get("slice_quota")), _ptr(aux.get("nvs_slice")),
                  _ptr(aux.get("alloc_n")), _ptr(aux.get("alloc_ue")), _ptr(aux.get("alloc_rbg")),
-                 int(rand2.shape[1]))
+                 int(rand2.shape[1]), _ptr(q), _ptr(h))
         rc = lib().rso_step(C.byref(self._cfg), B, C.byref(io), self.n_threads)
         if rc != 0:
             raise RuntimeError(f"rso_step failed: {rc}")

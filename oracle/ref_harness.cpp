@@ -121,6 +121,9 @@ struct Options {
                              (id 11 draws 300 x users of them, downlink-nvs-scheduler.cpp:437-446) */
   std::string alloc_log;  /* every (user, RBG) grant of each recorded TTI in the order of the users' RB lists: int32 n,
                              int16 (ue, rbg)[n] per TTI (id 10 books an RBG to several slices, which rbg_to_ue[G] cannot hold) */
+  std::string queue_log;  /* per recorded TTI, before the scheduler runs: int32 data[U] (what SelectFlowsToSchedule will take as
+                             dataToTransmit: 0 = no packets, 100000000 = infinite buffer, else the queue size) and double
+                             hol[U] (RadioBearer::GetHeadOfLinePacketDelay) */
   std::string log_out;    /* PREFIX: the reference's own stdout / stderr text of every recorded TTI goes to
                              PREFIX.stdout / PREFIX.stderr (golden text for the log-writer parity test) */
 };
@@ -135,6 +138,7 @@ static std::stringstream g_capture;
 static std::stringstream g_cerr_capture;   /* std::cerr while --log-out is active */
 static FILE* g_rand_log_file = nullptr;
 static FILE* g_alloc_log_file = nullptr;
+static FILE* g_queue_log_file = nullptr;
 static FILE* g_log_stdout = nullptr;
 static FILE* g_log_stderr = nullptr;
 static char* g_cstderr_buf = nullptr;       /* C stderr (fprintf(stderr, "all_bytes ...")) of the current TTI */
@@ -207,6 +211,20 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
     last_update[u] = b->m_lastUpdate;
   }
   state_get(state_before);
+  if (g_queue_log_file) {
+    std::vector<int32_t> qdata(U, 0);
+    std::vector<double> qhol(U, 0.0);
+    for (RadioBearer* b : *bearers) {
+      const int u = b->GetUserID();
+      if (b->HasPackets() && b->GetDestination()->GetNodeState() == NetworkNode::STATE_ACTIVE) {   /* transport.cpp:119-128 */
+        qdata[u] = (b->GetApplication()->GetApplicationType() == Application::APPLICATION_TYPE_INFINITE_BUFFER)
+                       ? 100000000 : b->GetQueueSize();
+        qhol[u] = b->GetHeadOfLinePacketDelay();
+      }
+    }
+    fwrite(qdata.data(), 4, U, g_queue_log_file);
+    fwrite(qhol.data(), 8, U, g_queue_log_file);
+  }
   std::vector<uint8_t> cqi((size_t)U * R);
   for (int u = 0; u < U; ++u) {
     std::vector<int> v = enb->GetUserEquipmentRecord(u)->GetCQI();
@@ -482,6 +500,7 @@ int main(int argc, char** argv) {
     else if (a == "--log-out") g_opt.log_out = next();
     else if (a == "--rand-log") g_opt.rand_log = next();
     else if (a == "--alloc-log") g_opt.alloc_log = next();
+    else if (a == "--queue-log") g_opt.queue_log = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -497,6 +516,10 @@ int main(int argc, char** argv) {
   if (!g_opt.alloc_log.empty()) {
     g_alloc_log_file = fopen(g_opt.alloc_log.c_str(), "wb");
     if (!g_alloc_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.alloc_log.c_str()); return 2; }
+  }
+  if (!g_opt.queue_log.empty()) {
+    g_queue_log_file = fopen(g_opt.queue_log.c_str(), "wb");
+    if (!g_queue_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.queue_log.c_str()); return 2; }
   }
   if (!g_opt.rand_log.empty()) {
     g_rand_log_file = fopen(g_opt.rand_log.c_str(), "wb");
@@ -538,6 +561,7 @@ int main(int argc, char** argv) {
   if (g_out) fclose(g_out);
   if (g_rand_log_file) fclose(g_rand_log_file);
   if (g_alloc_log_file) fclose(g_alloc_log_file);
+  if (g_queue_log_file) fclose(g_queue_log_file);
   if (g_log_stdout) fclose(g_log_stdout);
   if (g_log_stderr) fclose(g_log_stderr);
   fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f}\n", g_recorded,

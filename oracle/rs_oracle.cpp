@@ -101,6 +101,7 @@ struct User {          /* PacketScheduler::UserToSchedule, ps.h:88-123 */
   int required_rbs = 0;
   int bits = 0;
   int data = 0;
+  double hol = 0;   /* RadioBearer::GetHeadOfLinePacketDelay of the (single) bearer */
 };
 
 struct CellView {
@@ -125,6 +126,8 @@ struct CellView {
   int32_t* alloc_n;
   int16_t* alloc_ue;
   int16_t* alloc_rbg;
+  const int32_t* queue;   /* [U] bytes queued per bearer this TTI, NULL = cfg->data_to_transmit for everyone */
+  const double* hol;      /* [U] head-of-line delay, NULL = 0 */
 };
 
 /* RadioBearer::UpdateAverageTransmissionRate, flows/radio-bearer.cpp:138-164,
@@ -152,7 +155,11 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
     User usr;
     usr.id = u;
     usr.slice = cfg->ue_to_slice[u];
-    usr.data = cfg->data_to_transmit;
+    /* transport.cpp:119-128: only bearers with packets are listed; dataToTransmit = 100000000 for an
+     * infinite buffer, else the queue size */
+    usr.data = c.queue ? c.queue[u] : cfg->data_to_transmit;
+    if (c.queue && usr.data <= 0) continue;
+    usr.hol = c.hol ? c.hol[u] : 0.0;
     usr.cqi.resize(R);
     usr.eff.resize(R);
     for (int r = 0; r < R; ++r) {
@@ -174,8 +181,10 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
   return users;
 }
 
-/* ComputeSchedulingMetric, transport.cpp:677-713 (== nvs.cpp:360-390 for alpha 0). */
-double TransportMetric(const rso_config* cfg, const User& usr, double avg, double eff) {
+/* ComputeSchedulingMetric, transport.cpp:677-713; nvs = the copy in nvs.cpp:360-390, which multiplies
+ * the head-of-line delay in whenever alpha != 0 (the transport version only when beta != 0).  One
+ * bearer per UE, so the prioritised bearer of a listed user always has data. */
+double TransportMetric(const rso_config* cfg, const User& usr, double avg, double eff, bool nvs = false) {
   double metric = 0;
   double average_rate = 1;
   average_rate += avg; /* one bearer per UE */
@@ -189,9 +198,12 @@ double TransportMetric(const rso_config* cfg, const User& usr, double avg, doubl
     if (usr.data == 0) {
       metric = 0;
     } else {
-      /* beta != 0 needs head-of-line delay (queue state): not modelled */
-      (void)beta;
-      metric = pow(eff, epsilon) / pow(average_rate, psi);
+      if (beta || nvs) {
+        double HoL = usr.hol;
+        metric = HoL * pow(eff, epsilon) / pow(average_rate, psi);
+      } else {
+        metric = pow(eff, epsilon) / pow(average_rate, psi);
+      }
     }
   }
   return metric;
@@ -498,7 +510,7 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   std::vector<bool> with_queue(S, false);
   for (int u = 0; u < cfg->n_ues; ++u) {
     if (c.active && !c.active[u]) continue;
-    if (cfg->data_to_transmit > 0) with_queue[cfg->ue_to_slice[u]] = true;
+    if ((c.queue ? c.queue[u] : cfg->data_to_transmit) > 0) with_queue[cfg->ue_to_slice[u]] = true;
   }
   for (int i = 0; i < S; ++i) {
     if (!with_queue[i]) continue;
@@ -539,7 +551,7 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   std::vector<std::vector<double>> metrics(G, std::vector<double>(n));
   for (int i = 0; i < G; ++i)
     for (size_t j = 0; j < n; ++j)
-      metrics[i][j] = TransportMetric(cfg, users[j], c.avg[users[j].id], users[j].eff[i * rbg_size]);
+      metrics[i][j] = TransportMetric(cfg, users[j], c.avg[users[j].id], users[j].eff[i * rbg_size], true);
   for (int i = 0; i < G; ++i) {
     double target_metric = std::numeric_limits<double>::lowest();
     int pick = -1;
@@ -637,6 +649,8 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   c.alloc_n = io->alloc_n ? io->alloc_n + b : nullptr;
   c.alloc_ue = (io->alloc_ue && io->alloc_rbg) ? io->alloc_ue + (size_t)b * 2 * G : nullptr;
   c.alloc_rbg = (io->alloc_ue && io->alloc_rbg) ? io->alloc_rbg + (size_t)b * 2 * G : nullptr;
+  c.queue = io->queue_bytes ? io->queue_bytes + (size_t)b * U : nullptr;
+  c.hol = io->hol_delay ? io->hol_delay + (size_t)b * U : nullptr;
   ClearOutputs(c);
   switch (cfg->algo) {
     case 1: StepPf(c, row_m1); break;

@@ -65,6 +65,11 @@ typedef struct rso_io {
   int16_t* alloc_rbg;    /* [B][2G] id 10: RBG of grant e */
   int32_t rand_stride;   /* int32 values per cell in rand2: 0 or 2 for ids 8/9; id 11: >= 300 x the users of a
                             slice, the rand() draws of nvs.cpp:437-446 in call order */
+  /* queue state of the (single) bearer of each UE this TTI; both optional */
+  const int32_t* queue_bytes; /* [B][U] what SelectFlowsToSchedule takes as dataToTransmit (transport.cpp:119-128):
+                                 0 = no packets (the bearer is not listed), 100000000 = infinite buffer, else the queue
+                                 size; NULL = cfg.data_to_transmit for every UE */
+  const double* hol_delay;    /* [B][U] RadioBearer::GetHeadOfLinePacketDelay; NULL = 0 */
 } rso_io;
 
 /* One TTI for n_cells cells, n_threads host threads (cells are independent). */

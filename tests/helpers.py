@@ -39,7 +39,10 @@ def replay_golden(sched, rec, check_final_cqi=True):
     for t in range(T):
         # id 11: every rand() value of the 300-sample search (downlink-nvs-scheduler.cpp:437-446)
         draws = rec["rand_ng"][t][None] if algo == 11 else rec["rand2"][t][None]
-        out = sched.step(rec["cqi"][t][None], draws, dt=float(rec["dt"][t]), want_aux=True)
+        kw = {}
+        if "queue" in rec:   # queue-aware records: every bearer's dataToTransmit and head-of-line delay
+            kw = {"queue": rec["queue"][t][None], "hol": rec["hol"][t][None]}
+        out = sched.step(rec["cqi"][t][None], draws, dt=float(rec["dt"][t]), want_aux=True, **kw)
         st = sched.get_state()
 
         def chk(field, a, b):

@@ -44,6 +44,22 @@ SMALL_CFG = {
     "ues_per_slice": [2, 1, 3, 1, 2],
 }
 
+QMIX_CFG = {
+    # queue-aware enterprise schedulers: backlogged PF | internet flows, alpha 1 | H.264 video, alpha 1 and
+    # beta 1 (head-of-line delay in the metric) | backlogged MT; one bearer per UE
+    "slices": [
+        {"n_slices": 1, "weight": 0.25, "video_app": 0, "video_bitrate": [], "internet_flow": 0, "if_bitrate": [],
+         "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 2, "weight": 0.2, "video_app": 0, "video_bitrate": [], "internet_flow": 1, "if_bitrate": [12],
+         "backlog_flow": 0, "algo_alpha": 1, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 2, "weight": 0.1, "video_app": 1, "video_bitrate": [1280], "internet_flow": 0, "if_bitrate": [],
+         "backlog_flow": 0, "algo_alpha": 1, "algo_beta": 1, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 1, "weight": 0.15, "video_app": 0, "video_bitrate": [], "internet_flow": 0, "if_bitrate": [],
+         "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 0},
+    ],
+    "ues_per_slice": [3, 4, 2, 5, 3, 2],
+}
+
 FIX20X5 = f"{REF_EXP}/exp-fix20slices/5ues/config-pf.json"
 DIFFW = f"{REF_EXP}/exp-customization/exp-backlogged-20slicesdiffw/config.json"
 MIX20 = f"{REF_EXP}/exp-customization/exp-backlogged-20slices/config.json"
@@ -80,13 +96,25 @@ CASES = [
     ("a10_diffw_synth", 10, DIFFW, 24, "synth", 16),
     ("a10_small_synth", 10, "SMALL", 80, "synth", 17),
     ("a10_fix20x5_trace", 10, FIX20X5, 30, "trace", 1),
+    # finite queues and head-of-line delays: the records also hold every bearer's dataToTransmit and HoL delay per TTI
+    # (ref_harness --queue-log)
+    ("a9_qmix_synth", 9, "QMIX", 160, "synth", 21),
+    ("a8_qmix_synth", 8, "QMIX", 160, "synth", 22),
+    ("a7_qmix_synth", 7, "QMIX", 240, "synth", 23),
+    ("a1_qmix_synth", 1, "QMIX", 160, "synth", 24),
+    ("a10_qmix_synth", 10, "QMIX", 120, "synth", 25),
+    ("a11_qmix_synth", 11, "QMIX", 60, "synth", 26),
 ]
 
 
 def run_case(name, algo, config, n_ttis, source, seed, tmp):
+    queue_aware = config == "QMIX"
     if config == "SMALL":
         config = os.path.join(tmp, "small.json")
         json.dump(SMALL_CFG, open(config, "w"))
+    if config == "QMIX":
+        config = os.path.join(tmp, "qmix.json")
+        json.dump(QMIX_CFG, open(config, "w"))
     cfg = json.load(open(config))
     n_ues = int(sum(cfg["ues_per_slice"]))
     n_slices = len(cfg["ues_per_slice"])
@@ -105,6 +133,9 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
     rlog_path = os.path.join(tmp, name + ".rlog")
     if algo == 11:
         cmd += ["--rand-log", rlog_path]
+    qlog_path = os.path.join(tmp, name + ".qlog")
+    if queue_aware:
+        cmd += ["--queue-log", qlog_path]
     alog_path = os.path.join(tmp, name + ".alog")
     if algo == 10:
         cmd += ["--alloc-log", alog_path]
@@ -122,6 +153,10 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
         width = max(len(d) for d in draws)
         rec["rand_ng_n"] = np.array([len(d) for d in draws], dtype=np.int32)
         rec["rand_ng"] = np.stack([np.pad(d, (0, width - len(d))) for d in draws]).astype(np.int32)
+    if queue_aware:
+        raw = np.fromfile(qlog_path, dtype=np.uint8).reshape(n_ttis, n_ues * 12)
+        rec["queue"] = raw[:, :n_ues * 4].copy().view("<i4").reshape(n_ttis, n_ues)
+        rec["hol"] = raw[:, n_ues * 4:].copy().view("<f8").reshape(n_ttis, n_ues)
     if algo == 10:
         raw = np.fromfile(alog_path, dtype="<i2")
         G = int(rec["G"])
