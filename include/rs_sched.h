@@ -122,6 +122,20 @@ int rs_reset_state(rs_handle* h);
 int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
             const rs_outputs* out);
 
+/* Queue state for the NEXT rs_step / rs_run_* call on this handle (consumed by it): what the reference reads from
+ * its bearers each TTI (one bearer per UE).
+ *   queue_bytes [T][B][U] int32   dataToTransmit of each UE's bearer (downlink-transport-scheduler.cpp:119-128):
+ *                                 0 = no packets, the bearer is not listed this TTI; 100000000 = infinite buffer;
+ *                                 else the queue size.  Replaces cfg.data_to_transmit: bytes sent are capped by it
+ *                                 (:183-186), id 7 stops granting a user RBGs at m_requiredRBs
+ *                                 (packet-scheduler.cpp:321-334, downlink-nvs-scheduler.cpp:299-300), id 1 drops a
+ *                                 flow once its TBS covers the queue (downlink-packet-scheduler.cpp:264-269)
+ *   hol_delay   [T][B][U] double  RadioBearer::GetHeadOfLinePacketDelay(); multiplied into the metric of slices with
+ *                                 alpha and beta set (ids 8/9/10, :702-706) or alpha set (id 7,
+ *                                 downlink-nvs-scheduler.cpp:384-386); NULL = 0
+ * HOST pointers for rs_step / rs_run_host / rs_run_traces_host, DEVICE pointers for the *_device calls. */
+int rs_set_queues(rs_handle* h, const int32_t* queue_bytes, const double* hol_delay);
+
 /* n_ttis consecutive TTIs with every input and output already in DEVICE memory.
  *   d_cqi   [ceil(T/cqi_refresh)][B][U][row]: TTI t reads slab t / cqi_refresh (the reference refreshes
  *           CQI every 40 TTIs, enb-mac-entity.cc:38; the headline workload every TTI);

@@ -62,7 +62,7 @@ __constant__ ConstTables c_tab;
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
   int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, ng_hc, ng_list, ng_mcs, ng_red, total;
+      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, ng_hc, ng_list, ng_mcs, ng_red, done, total;
 };
 
 struct DevCfg {
@@ -93,6 +93,9 @@ struct DevCfg {
   int trace_rows;
   int rand_stride;         /* int32 rand() draws per cell-TTI in RunArgs::rand2: 2 (ids 8/9), 300 x max UEs per slice (id 11) */
   int ng_ues;              /* id 11: largest slice */
+  const unsigned char* holmul; /* [S] 1: the slice's metric carries the head-of-line delay (transport.cpp:702-706
+                                  when alpha and beta are set; nvs.cpp:384-386 whenever alpha is set) */
+  const int* tbs1;             /* [16] GetTBSizeFromMCS(mcs(cqi)) for one RB: m_requiredRBs, packet-scheduler.cpp:334 */
   int sort_depth_g;        /* id 10: 2*floor(log2(G)), the depth limit of a per-slice sort of G entries */
   /* state, [B][U] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
@@ -103,6 +106,9 @@ struct RunArgs {
   const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
   int t0, cqi_refresh;
   int stage;               /* 1: every TTI's CQI is copied to shared memory with cp.async first */
+  const int* queue;        /* [T][B][U] bytes queued on each UE's bearer (its dataToTransmit; 0 = not listed), or null:
+                              DevCfg::data for everybody */
+  const double* hol;       /* [T][B][U] head-of-line delay of the bearer, or null (0) */
   const int* trace_row;    /* device [T], trace mode: row of every UE's trace in force at TTI t */
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
@@ -161,7 +167,8 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   L.ng_red = rs_align(o, 8); o = L.ng_red + (ng_ues ? 16 * (RS_THREADS / 32) : 0);
   L.ng_list = o; o += 2 * ng_ues;
   L.ng_hc = o;   o += ng_ues;
-  L.ng_mcs = o;  o += ng_ues * RS_THREADS;
+  L.ng_mcs = rs_align(o, 4); o = L.ng_mcs + ng_ues * RS_THREADS;
+  L.done = o;    o += U;
   L.total = rs_align(o, 16);
   return L;
 }
@@ -464,7 +471,7 @@ struct Cell {
   unsigned long long* cumb; unsigned long long* cumr;   /* this cell's rows of the HBM counters */
   double* tval; int* tx; int* utr; int* sptr; unsigned short* sues; uint8_t* cq; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
-  unsigned short* ng_list; unsigned char* ng_hc; unsigned char* ng_mcs; unsigned char* ng_red;
+  unsigned short* ng_list; unsigned char* ng_hc; unsigned char* ng_mcs; unsigned char* ng_red; unsigned char* done;
   SortBufs sb;
 };
 
@@ -486,6 +493,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.ng_hc = smem + L.ng_hc;
   c.ng_mcs = smem + L.ng_mcs;
   c.ng_red = smem + L.ng_red;
+  c.done = smem + L.done;
   c.mask = (unsigned*)(smem + L.mask);
   c.target = (int*)(smem + L.target);
   c.quota = (int*)(smem + L.quota);
@@ -663,7 +671,7 @@ __device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned sho
  * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
 __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* row, int u,
                                             unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc,
-                                            const double* presum = nullptr) {
+                                            int data_u, const double* presum = nullptr) {
   int bits = 0, mcs = 0xff, fc = 0;
   const int nrbg = __popc(m_lo) + __popc(m_hi);
   if (nrbg > 0) {
@@ -695,8 +703,8 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
         c.tx[u] += avail;
         c.cumb[u] += (unsigned long long)avail;
         c.cumr[u] += (unsigned long long)nrb;
-      } else if (d.data > 0) {
-        const int sent = min(avail, d.data);
+      } else if (data_u > 0) {
+        const int sent = min(avail, data_u);
         c.tx[u] += sent;
         c.cumb[u] += (unsigned long long)sent;
         c.cumr[u] += (unsigned long long)nrb;
@@ -711,7 +719,7 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
-template <int ALGO, bool TRACE>
+template <int ALGO, bool TRACE, bool QUEUE>
 __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
   Cell c = carve(smem, d.lay);
@@ -782,6 +790,11 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
     const int rot = (b + t) % kWarps;   /* which warp plays the single-warp roles this TTI */
+    /* queue state of the TTI: a bearer is listed when it has packets (transport.cpp:119) */
+    const int* qd = QUEUE ? r.queue + tb * U : nullptr;   /* QUEUE = false: the backlogged instantiation, no queue code */
+    const double* hl = (QUEUE && r.hol) ? r.hol + tb * U : nullptr;
+    auto listed = [&](int u) { return (!act || act[u]) && (qd ? qd[u] > 0 : d.data > 0); };
+    auto data_of = [&](int u) { return qd ? qd[u] : d.data; };
     auto row_of = [&](int u) -> const uint8_t* { return stage ? c.cq + u * d.cqi_row : ue_cqi<TRACE>(d, c, cqi, u); };
     short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
     int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
@@ -795,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     if (NVS) {
       /* slices with at least one queued bearer */
       for (int u = tid; u < U; u += kThreads)
-        if ((!act || act[u]) && d.data > 0) c.wd[d.ue_to_slice[u]] = 1;
+        if (listed(u)) c.wd[d.ue_to_slice[u]] = 1;
       __syncthreads();
       if (tid == 0) {
         int slice_id = 0;
@@ -834,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         const int s = d.ue_to_slice[u];
         /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
         c.den[u] = d.psi[s] ? __ddiv_rn(__dadd_rn(1.0, a), 1000.0) : 1.0;
-        if ((ALGO == 8 || ALGO == 9 || ALGO == 10) && (!act || act[u])) c.wd[s] = 1;
+        if ((ALGO == 8 || ALGO == 9 || ALGO == 10) && listed(u)) c.wd[s] = 1;
       }
     }
     if (stage) cp_async_wait_all();   /* own copies done; the barrier publishes everybody's */
@@ -851,7 +864,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
           const int u = c.sues[j];
-          c.mtab[q] = cq ? __ddiv_rn(d.epow[d.ue_to_slice[u] * 16 + cq], c.den[u]) : 0.0;
+          const int su = d.ue_to_slice[u];
+          double e = d.epow[su * 16 + cq];
+          if (d.holmul[su]) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* HoL * pow(se, eps) / pow(avg, psi), :702-706 */
+          c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
         }
         __syncthreads();
         /* four RBGs per item (one 32-bit CQI load per UE) while that still gives every thread an item;
@@ -868,7 +884,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             int bc[4] = {0, 0, 0, 0};
             for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
               const int u = c.sues[j];
-              if (act && !act[u]) continue;
+              if (!listed(u)) continue;
               unsigned w;
               const uint8_t* row_u = row_of(u);
               if (nib) {   /* four nibbles -> one per byte, then the same extraction as the u8 layout */
@@ -900,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             int bu = kNoUe, bc = 0;
             for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
               const int u = c.sues[j];
-              if (act && !act[u]) continue;
+              if (!listed(u)) continue;
               const int cq = cqi_first_rb(d, row_of(u), g);
               const double m = c.mtab[(j - j0) * kMStride + cq];
               if (m > best) { best = m; bu = u; bc = cq; }
@@ -1034,7 +1050,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         for (int jb = j0; jb < j1; jb += 32) {
           const int j = jb + lane;
           const int u = j < j1 ? c.sues[j] : 0;
-          const bool in = j < j1 && (!act || act[u]) && d.data > 0;
+          const bool in = j < j1 && listed(u);
           const unsigned bal = __ballot_sync(kFull, in);
           if (in) c.ng_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)u;
           cnt += __popc(bal);
@@ -1112,16 +1128,74 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
         const int j = j0 + (q >> 4), cq = q & 15;
         const int u = c.sues[j];
-        c.mtab[q] = cq ? __ddiv_rn(d.epow[served * 16 + cq], c.den[u]) : 0.0;
+        double e = d.epow[served * 16 + cq];
+        if (d.holmul[served]) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* nvs.cpp:384-386 */
+        c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
       }
+      if (qd) {
+        /* finite queues: a user stops taking RBGs once it holds m_requiredRBs = dataToTransmit * 8 /
+         * TBS(1 RB at its wideband CQI) RBs (packet-scheduler.cpp:321-334, nvs.cpp:299-300), so the RBGs go
+         * one after the other (one warp, lanes over the slice's users) */
+        int* req = (int*)c.ng_mcs;
+        int* alc = req + d.ng_ues;
+        for (int j = j0 + tid; j < j1; j += kThreads) {
+          const int u = c.sues[j];
+          int need = 0;
+          if (listed(u)) {
+            const uint8_t* row = row_of(u);
+            double sum = 0;   /* EESM over every RB of the band, RB order */
+            for (int g = 0; g < G; ++g) {
+              if (d.cqi_per_rb == 1) {
+                const uint8_t* p = row + (size_t)g * d.rbg;
+                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+              } else {
+                const double tv = c.tval[cqi_first_rb(d, row, g)];
+                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+              }
+            }
+            const int wide = cqi_from_mean(__ddiv_rn(sum, (double)(G * d.rbg)));
+            need = qd[u] * 8 / d.tbs1[wide];
+          }
+          req[j - j0] = need;
+          alc[j - j0] = 0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+          for (int g = 0; g < G; ++g) {
+            double best = -1.0;
+            int bj = 0x7fffffff;
+            for (int j = j0 + lane; j < j1; j += 32) {
+              const int u = c.sues[j];
+              if (!listed(u) || alc[j - j0] >= req[j - j0]) continue;
+              const double m = c.mtab[(j - j0) * kMStride + cqi_first_rb(d, row_of(u), g)];
+              if (m > best) { best = m; bj = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double om = __shfl_xor_sync(kFull, best, o);
+              const int oj = __shfl_xor_sync(kFull, bj, o);
+              if (om > best || (om == best && oj < bj)) { best = om; bj = oj; }
+            }
+            if (lane == 0) {
+              int bu = -1;
+              if (bj != 0x7fffffff) {
+                bu = c.sues[bj];
+                alc[bj - j0] += d.rbg;
+                c.mask[2 * bu + (g >> 5)] |= 1u << (g & 31);
+              }
+              if (o_rbg) o_rbg[g] = (short)bu;
+            }
+            __syncwarp();
+          }
+        }
+      } else {
       __syncthreads();
       for (int g = tid; g < G; g += kThreads) {
         double best = -1.0;   /* metrics are >= 0, so this behaves like numeric_limits::lowest() */
         int bu = -1;
         for (int j = j0; j < j1; ++j) {
           const int u = c.sues[j];
-          if (act && !act[u]) continue;
-          if (d.data <= 0) continue;
+          if (!listed(u)) continue;
           const int cq = cqi_first_rb(d, row_of(u), g);
           const double m = c.mtab[(j - j0) * kMStride + cq];
           if (m > best) { best = m; bu = u; }
@@ -1129,13 +1203,68 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         if (bu >= 0) atomicOr(&c.mask[2 * bu + (g >> 5)], 1u << (g & 31));
         if (o_rbg) o_rbg[g] = (short)bu;
       }
+      }
+    } else if (qd) {
+      /* ---- No-slicing PF with finite queues (dlps.cpp:227-271): a flow leaves the candidates once the TBS of
+       * what it holds covers its queue, so the RBGs go one after the other (one warp, lanes over the flows) */
+      double* fsum = c.mtab;   /* running EESM sum of every flow, RB order */
+      for (int u = tid; u < U; u += kThreads) { fsum[u] = 0.0; c.done[u] = 0; }
+      __syncthreads();
+      if (warp == 0) {
+        int n_flows = 0;
+        for (int u = lane; u < U; u += 32) n_flows += listed(u) ? 1 : 0;
+        n_flows = __reduce_add_sync(kFull, n_flows);
+        int n_done = 0;
+        for (int g = 0; g < G; ++g) {
+          int bu = 0x7fffffff;
+          if (n_done < n_flows) {
+            double best = 0.0;
+            for (int u = lane; u < U; u += 32) {
+              if (!listed(u) || c.done[u]) continue;
+              const double m = __ddiv_rn(d.epow[cqi_first_rb(d, row_of(u), g)], c.den[u]);
+              if (m > best) { best = m; bu = u; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double om = __shfl_xor_sync(kFull, best, o);
+              const int ou = __shfl_xor_sync(kFull, bu, o);
+              if (om > best || (om == best && ou < bu)) { best = om; bu = ou; }
+            }
+          }
+          int finished = 0;
+          if (lane == 0) {
+            if (bu != 0x7fffffff) {
+              c.mask[2 * bu + (g >> 5)] |= 1u << (g & 31);
+              const uint8_t* row = row_of(bu);
+              double sum = fsum[bu];
+              if (d.cqi_per_rb == 1) {
+                const uint8_t* p = row + (size_t)g * d.rbg;
+                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+              } else {
+                const double tv = c.tval[cqi_first_rb(d, row, g)];
+                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+              }
+              fsum[bu] = sum;
+              const int nrbg = __popc(c.mask[2 * bu]) + __popc(c.mask[2 * bu + 1]);
+              const int fc = cqi_from_mean(__ddiv_rn(sum, (double)(nrbg * d.rbg)));
+              if (d.tbs_n[nrbg * 16 + fc] >= qd[bu] * 8) {   /* dlps.cpp:264-269 */
+                c.done[bu] = 1;
+                finished = 1;
+              }
+            }
+            if (o_rbg) o_rbg[g] = (short)(bu == 0x7fffffff ? -1 : bu);
+          }
+          n_done += __shfl_sync(kFull, finished, 0);
+          __syncwarp();
+        }
+      }
     } else {
       /* ---- No-slicing PF: per RBG, first flow with the strictly largest metric (dlps.cpp:227-246) */
       for (int g = warp; g < G; g += kWarps) {
         double best = 0.0;
         int bu = 0x7fffffff;
         for (int u = lane; u < U; u += 32) {
-          if (act && !act[u]) continue;
+          if (!listed(u)) continue;
           const int cq = cqi_first_rb(d, row_of(u), g);
           const double m = __ddiv_rn(d.epow[cq], c.den[u]);
           if (m > best) { best = m; bu = u; }
@@ -1159,7 +1288,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, ALGO == 10 ? c.den : nullptr);
+      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, data_of(u), ALGO == 10 ? c.den : nullptr);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;
     }

@@ -211,7 +211,12 @@ struct rs_handle {
   DevBuf<int> ue_trace_off, trow_dev;
   int n_traces = 0, trace_rows = 0;
   bool stage_ok = false;
-  bool wide = false;                 /* 512 threads per cell (rsw::) instead of 128 */             /* the layout has room for a TTI of CQI (cp.async staging) */
+  bool wide = false;
+  /* queue state for the next run call (rs_set_queues), consumed by it */
+  const int32_t* q_next = nullptr;
+  const double* hol_next = nullptr;
+  DevBuf<unsigned char> holmul;
+  DevBuf<int> tbs1;                 /* 512 threads per cell (rsw::) instead of 128 */             /* the layout has room for a TTI of CQI (cp.async staging) */
   int* trow_pinned = nullptr;
   size_t trow_pinned_n = 0;
   DevBuf<unsigned long long> stats;
@@ -220,7 +225,8 @@ struct rs_handle {
     DevBuf<uint8_t> cqi, active, mcs, final_cqi;
     DevBuf<int> rand2, tbs_bits, slice_target, slice_quota, nvs_slice;
     DevBuf<short> rbg_to_ue, alloc_ue, alloc_rbg;
-    DevBuf<int> alloc_n;
+    DevBuf<int> alloc_n, queue;
+    DevBuf<double> hol;
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
     int slab0 = -1;   /* first CQI slab resident in this slot (rs_run_host with a refresh > 1) */
   } slot[2];
@@ -232,33 +238,27 @@ static_assert(sizeof(rs::DevCfg) == sizeof(rsw::DevCfg) && sizeof(rs::RunArgs) =
                   sizeof(rs::ConstTables) == sizeof(rsw::ConstTables),
               "the two instantiations of rs_device.cuh share their parameter structs");
 
-#define RS_TTI_CASE(NS, A) \
-  case A: return trace ? (const void*)NS::rs_tti_kernel<A, true> : (const void*)NS::rs_tti_kernel<A, false>;
-const void* tti_kernel_wide(int algo, bool trace) {
+/* one kernel per (scheduler id, CQI source, backlogged / queue-aware, CTA width) */
+#define RS_TTI_PICK(NS, A)                                                                           \
+  (queue ? (trace ? (const void*)NS::rs_tti_kernel<A, true, true> : (const void*)NS::rs_tti_kernel<A, false, true>) \
+         : (trace ? (const void*)NS::rs_tti_kernel<A, true, false> : (const void*)NS::rs_tti_kernel<A, false, false>))
+const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
   switch (algo) {
-    RS_TTI_CASE(rsw, 1) RS_TTI_CASE(rsw, 7) RS_TTI_CASE(rsw, 8) RS_TTI_CASE(rsw, 10) RS_TTI_CASE(rsw, 11)
-    default: return trace ? (const void*)rsw::rs_tti_kernel<9, true> : (const void*)rsw::rs_tti_kernel<9, false>;
+    case 1: return wide ? RS_TTI_PICK(rsw, 1) : RS_TTI_PICK(rs, 1);
+    case 7: return wide ? RS_TTI_PICK(rsw, 7) : RS_TTI_PICK(rs, 7);
+    case 8: return wide ? RS_TTI_PICK(rsw, 8) : RS_TTI_PICK(rs, 8);
+    case 10: return wide ? RS_TTI_PICK(rsw, 10) : RS_TTI_PICK(rs, 10);
+    case 11: return wide ? RS_TTI_PICK(rsw, 11) : RS_TTI_PICK(rs, 11);
+    default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
   }
 }
-typedef void (*TtiKernel)(const rs::DevCfg, const rs::RunArgs);
-TtiKernel tti_kernel(int algo, bool trace) {
-  switch (algo) {
-    case 1: return trace ? rs::rs_tti_kernel<1, true> : rs::rs_tti_kernel<1, false>;
-    case 7: return trace ? rs::rs_tti_kernel<7, true> : rs::rs_tti_kernel<7, false>;
-    case 10: return trace ? rs::rs_tti_kernel<10, true> : rs::rs_tti_kernel<10, false>;
-    case 11: return trace ? rs::rs_tti_kernel<11, true> : rs::rs_tti_kernel<11, false>;
-    case 8: return trace ? rs::rs_tti_kernel<8, true> : rs::rs_tti_kernel<8, false>;
-    default: return trace ? rs::rs_tti_kernel<9, true> : rs::rs_tti_kernel<9, false>;
-  }
-}
-
 /* a.trace_row != NULL selects the trace-driven instantiation */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
   const dim3 grid(h->B), block(h->wide ? rsw::kThreads : rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
   const bool trace = a.trace_row != nullptr;
   /* by address: the rsw:: kernels take rsw::DevCfg / rsw::RunArgs, the same bytes as the rs:: structs */
-  const void* fn = h->wide ? tti_kernel_wide(h->d.algo, trace) : (const void*)tti_kernel(h->d.algo, trace);
+  const void* fn = tti_kernel_any(h->d.algo, trace, a.queue != nullptr, h->wide);
   void* args[2] = {(void*)&h->d, (void*)&a};
   CU(cudaLaunchKernel(fn, grid, block, args, sm, h->stream));
   CU(cudaGetLastError());
@@ -268,10 +268,9 @@ int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
 
 int set_smem_attr(rs_handle* h) {
   const int sm = h->layout.total;
-  for (int t = 0; t < 2; ++t) {
-    const void* fn = h->wide ? tti_kernel_wide(h->d.algo, t != 0) : (const void*)tti_kernel(h->d.algo, t != 0);
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  }
+  for (int t = 0; t < 4; ++t)
+    CU(cudaFuncSetAttribute(tti_kernel_any(h->d.algo, (t & 1) != 0, (t & 2) != 0, h->wide),
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   return RS_OK;
 }
 
@@ -323,6 +322,8 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
   if (want_cqi) CU(s.cqi.alloc((size_t)T * B * U * C));
   CU(s.rand2.alloc((size_t)T * B * std::max(h->d.rand_stride, 1)));
   if (want_active) CU(s.active.alloc((size_t)T * B * U));
+  if (h->q_next) CU(s.queue.alloc((size_t)T * B * U));
+  if (h->hol_next) CU(s.hol.alloc((size_t)T * B * U));
   if (out) {
     if (out->rbg_to_ue) CU(s.rbg_to_ue.alloc((size_t)T * B * G));
     if (out->tbs_bits) CU(s.tbs_bits.alloc((size_t)T * B * U));
@@ -370,6 +371,7 @@ void rs_destroy(rs_handle* h) {
     s.cqi.release(); s.active.release(); s.mcs.release(); s.final_cqi.release(); s.rand2.release();
     s.tbs_bits.release(); s.slice_target.release(); s.slice_quota.release(); s.nvs_slice.release();
     s.rbg_to_ue.release(); s.alloc_ue.release(); s.alloc_rbg.release(); s.alloc_n.release();
+    s.queue.release(); s.hol.release();
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.k_done) cudaEventDestroy(s.k_done);
     if (s.out_done) cudaEventDestroy(s.out_done);
@@ -377,6 +379,7 @@ void rs_destroy(rs_handle* h) {
   if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
   if (h->trow_pinned) cudaFreeHost(h->trow_pinned);
   h->trace_tab.release(); h->ue_trace_off.release(); h->trow_dev.release();
+  h->holmul.release(); h->tbs1.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -474,6 +477,16 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
         BAIL(fail(RS_ERR_UNSUPPORTED, "id 7 with data_to_transmit=%d: the required-RBs guard can bind; not covered", d.data));
     }
   }
+  /* head-of-line delay in the metric: transport.cpp:702-706 (alpha and beta set), nvs.cpp:384-386 (alpha set) */
+  std::vector<unsigned char> holmul(S, 0);
+  if (algo != 1 && algo != 11)
+    for (int s = 0; s < S; ++s) {
+      const int32_t* p = cfg->params + 4 * s;
+      holmul[s] = (p[0] != 0 && (algo == 7 || p[1] != 0)) ? 1 : 0;
+    }
+  std::vector<int> tbs1(16, 1);
+  for (int c = 1; c <= 15; ++c) tbs1[c] = tbs_n(mcs_from_cqi(c), 1, h->row_m1);
+  tbs1[0] = tbs1[1];
   /* CSR of UEs by slice (ascending UE id inside a slice == the reference's user order) */
   const int SL = (algo == 1) ? 1 : S;
   std::vector<int> ptr(SL + 1, 0), ues(U), u2s(cfg->ue_to_slice, cfg->ue_to_slice + U);
@@ -501,7 +514,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     m_cap = max_slice;
     chunks = {0, S};
   } else {
-    m_cap = 0;
+    m_cap = (U + 15) / 16;   /* id 1 keeps one running EESM sum per flow there when queues are finite */
     chunks = {0, 1};
   }
   d.n_chunks = (int)chunks.size() - 1;
@@ -512,7 +525,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   /* hundreds of UEs per cell: the per-UE phases (EWMA, metric table, per-slice argmax, link adaptation)
    * dominate and few cells fit an SM anyway, so give the cell 512 threads */
   h->wide = U >= RS_WIDE_MIN_UES;
-  d.ng_ues = (algo == 11) ? max_slice : 0;
+  d.ng_ues = (algo == 11 || algo == 7) ? max_slice : 0;   /* id 7: required / held RBs per user of the served slice */
   /* rand() draws a TTI consumes per cell: transport.cpp:490,511 (ids 8/9); nvs.cpp:437-446 draws
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
   d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9 || algo == 10) ? 2 : 0);
@@ -565,6 +578,10 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   BAIL(upload(h->weight, weight));
   BAIL(upload(h->epow, epow));
   BAIL(upload(h->psi, psi));
+  BAIL(upload(h->holmul, holmul));
+  BAIL(upload(h->tbs1, tbs1));
+  d.holmul = h->holmul.p;
+  d.tbs1 = h->tbs1.p;
   if ((algo == 9 && d.sort_n > 16) || (algo == 10 && G > 16)) {
     std::vector<unsigned short> eq;
     d.eq_max = std::min(algo == 10 ? G : d.sort_n, kEqMax);
@@ -670,6 +687,10 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   if (ttis_per_launch <= 0) ttis_per_launch = 16;
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
+  const int32_t* d_queue = h->q_next;
+  const double* d_hol = h->hol_next;
+  h->q_next = nullptr;
+  h->hol_next = nullptr;
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
     a.T = std::min(ttis_per_launch, n_ttis - t0);
@@ -682,6 +703,8 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.active_tti_stride = active_tti_stride;
     a.dt = h->dt_dev.p + t0;
     a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    a.queue = d_queue ? d_queue + (size_t)t0 * B * U : nullptr;
+    a.hol = d_hol ? d_hol + (size_t)t0 * B * U : nullptr;
     a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
     if (d_out) {
       a.rbg_to_ue = d_out->rbg_to_ue ? d_out->rbg_to_ue + (size_t)t0 * B * G : nullptr;
@@ -721,6 +744,10 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   if (rc != RS_OK) return rc;
   if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   for (auto& s : h->slot) { rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr); if (rc != RS_OK) return rc; }
+  const int32_t* queue = h->q_next;
+  const double* hol = h->hol_next;
+  h->q_next = nullptr;
+  h->hol_next = nullptr;
   cudaEvent_t dt_ready;
   CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
   CU(cudaEventRecord(dt_ready, h->stream));
@@ -741,6 +768,8 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     const size_t RS = (size_t)h->d.rand_stride;
     if (rand2 && RS) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * RS, (size_t)T * B * RS * 4, cudaMemcpyHostToDevice, h->copy_in));
     if (active) CU(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
+    if (queue) CU(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U, (size_t)T * B * U * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (hol) CU(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U, (size_t)T * B * U * 8, cudaMemcpyHostToDevice, h->copy_in));
     CU(cudaEventRecord(s.in_done, h->copy_in));
     /* kernel: inputs in, and the slot's previous outputs drained */
     CU(cudaStreamWaitEvent(h->stream, s.in_done, 0));
@@ -753,6 +782,8 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
     a.dt = h->dt_dev.p + t0;
     a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    a.queue = queue ? s.queue.p : nullptr;
+    a.hol = hol ? s.hol.p : nullptr;
     a.stage = h->stage_ok ? 1 : 0;   /* slot buffers come from cudaMalloc; B*U*C is a multiple of 16 when stage_ok */
     if (out) {
       a.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
@@ -1054,6 +1085,14 @@ int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs) {
   if (!lg) return fail(RS_ERR_ARG, "null log");
   if (cum_bytes) memcpy(cum_bytes, lg->cum_bytes.data(), sizeof(uint64_t) * lg->U);
   if (cum_rbs) memcpy(cum_rbs, lg->cum_rbs.data(), sizeof(uint64_t) * lg->U);
+  return RS_OK;
+}
+
+int rs_set_queues(rs_handle* h, const int32_t* queue_bytes, const double* hol_delay) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  if (hol_delay && !queue_bytes) return fail(RS_ERR_ARG, "rs_set_queues: head-of-line delays without queue sizes");
+  h->q_next = queue_bytes;
+  h->hol_next = hol_delay;
   return RS_OK;
 }
 

@@ -66,8 +66,8 @@ class RsGpuScheduler : public PacketScheduler {
 
   /* scheduler_id: 1 No-Slicing PF, 7 NVS, 8 Sequential, 9 RadioSaber (single-cell-with-interference.h:95-110).
    * Id 1 replaces DL_PF_PacketScheduler(config_fname) (ENodeB.cpp:309-313); that class schedules flows
-   * (FlowToSchedule, one per bearer), which for the one-bearer-per-UE backlogged configurations is the same
-   * list as the users kept here. */
+   * (FlowToSchedule, one per bearer), which with one bearer per UE is the same list as the users kept here.
+   * Bearers may be backlogged or have finite queues (internet flows, video); two bearers on one UE throw. */
   RsGpuScheduler(std::string config_fname, int scheduler_id) : id_(scheduler_id) {
     if (id_ != 1 && id_ != 7 && id_ != 8 && id_ != 9)
       throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8 or 9");
@@ -118,7 +118,9 @@ class RsGpuScheduler : public PacketScheduler {
       for (int i = MAX_BEARERS - 1; i >= 0 && available > 0; i--) {
         if (user->m_dataToTransmit[i] <= 0) continue;
         RadioBearer* bearer = user->m_bearers[i];
-        const int sent = available < user->m_dataToTransmit[i] ? available : user->m_dataToTransmit[i];
+        /* DL_PF_PacketScheduler::DoStopSchedule hands the RLC all allocated bytes (dl-pf-packet-scheduler.cpp:80-82);
+         * the user-level schedulers cap them by the queue (downlink-transport-scheduler.cpp:183-186) */
+        const int sent = (id_ == 1 || available < user->m_dataToTransmit[i]) ? available : user->m_dataToTransmit[i];
         available -= sent;
         bearer->UpdateTransmittedBytes(sent);
         bearer->UpdateCumulateRBs(user->GetListOfAllocatedRBs()->size());
@@ -144,7 +146,8 @@ class RsGpuScheduler : public PacketScheduler {
   int n_rbs_ = 0, rbg_size_ = 0, n_rbgs_ = 0;
   int n_users_total_ = 0;
   std::vector<uint8_t> cqi_, active_, mcs_, final_cqi_;
-  std::vector<double> avg_;
+  std::vector<double> avg_, hol_;   /* hol_: head-of-line delay of each listed bearer */
+  std::vector<int32_t> queue_;      /* dataToTransmit of each listed bearer, 0 = not listed */
   std::vector<int16_t> rbg_to_ue_;
   std::vector<int32_t> bits_, target_, quota_;
 
@@ -190,6 +193,8 @@ class RsGpuScheduler : public PacketScheduler {
     Check(rs_create(&cfg, 1, dev ? atoi(dev) : 0, &h_), "rs_create");
     cqi_.assign((size_t)U * n_rbs_, 10); /* UserEquipmentRecord's initial CQI, ENodeB.cpp:207-217 */
     active_.assign(U, 0);
+    queue_.assign(U, 0);
+    hol_.assign(U, 0.0);
     avg_.assign(U, 100000.0);
     mcs_.assign(U, 0xff);
     final_cqi_.assign(U, 0);
@@ -209,20 +214,22 @@ class RsGpuScheduler : public PacketScheduler {
     if (bearers->empty()) return;
     EnsureHandle();
     std::fill(active_.begin(), active_.end(), (uint8_t)0);
+    std::fill(queue_.begin(), queue_.end(), 0);
+    std::fill(hol_.begin(), hol_.end(), 0.0);
     ENodeB* enb = (ENodeB*)GetMacEntity()->GetDevice();
     UsersToSchedule* users = GetUsersToSchedule();
     for (auto it = bearers->begin(); it != bearers->end(); ++it) {
       RadioBearer* bearer = *it;
       if (!(bearer->HasPackets() && bearer->GetDestination()->GetNodeState() == NetworkNode::STATE_ACTIVE)) continue;
-      if (bearer->GetApplication()->GetApplicationType() != Application::APPLICATION_TYPE_INFINITE_BUFFER)
-        throw std::runtime_error("RsGpuScheduler: only backlogged (infinite-buffer) bearers are covered");
+      /* dataToTransmit as downlink-transport-scheduler.cpp:121-128 */
+      const int data = (bearer->GetApplication()->GetApplicationType() == Application::APPLICATION_TYPE_INFINITE_BUFFER)
+                           ? 100000000 : bearer->GetQueueSize();
       const int uid = bearer->GetUserID();
       if (uid < 0 || uid >= (int)user_to_slice_.size()) throw std::runtime_error("RsGpuScheduler: user id outside the slice config");
       UserToSchedule* user = nullptr;
       for (auto u = users->begin(); u != users->end(); ++u)
         if ((*u)->GetUserID() == uid) user = *u;
-      if (user && id_ == 1)
-        throw std::runtime_error("RsGpuScheduler: id 1 schedules flows; two bearers on one UE are not covered");
+      if (user) throw std::runtime_error("RsGpuScheduler: two bearers on one UE are not covered");
       if (!user) {
         user = new UserToSchedule(uid, bearer->GetDestination());
         std::vector<int> cqi = enb->GetUserEquipmentRecord(bearer->GetDestination()->GetIDNetworkNode())->GetCQI();
@@ -232,7 +239,9 @@ class RsGpuScheduler : public PacketScheduler {
         users->push_back(user);
       }
       user->m_bearers[bearer->GetPriority()] = bearer;
-      user->m_dataToTransmit[bearer->GetPriority()] = 100000000;
+      user->m_dataToTransmit[bearer->GetPriority()] = data;
+      queue_[uid] = data;
+      hol_[uid] = bearer->GetHeadOfLinePacketDelay();
       avg_[uid] += bearer->GetAverageTransmissionRate();
       active_[uid] = 1;
       n_users_total_++;
@@ -259,6 +268,9 @@ class RsGpuScheduler : public PacketScheduler {
     out.slice_target = target_.data();
     out.slice_quota = quota_.data();
     out.nvs_slice = &nvs_slice;
+    /* queue state of this TTI: finite queues cap the bytes, bind id 7's required-RBs guard and id 1's
+     * flow-satisfied cut-off, and the head-of-line delay enters the metric of alpha/beta slices */
+    Check(rs_set_queues(h_, queue_.data(), hol_.data()), "rs_set_queues");
     /* dt = 0: the EWMA was applied by the bearers themselves a few lines up */
     Check(rs_step(h_, cqi_.data(), rand2, active_.data(), 0.0, &out), "rs_step");
     Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, (id_ == 8 || id_ == 9) ? slice_state_.data() : nullptr,

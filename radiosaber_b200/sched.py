@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "rs_set_state", "rs_get_state", "rs_reset_state", "rs_step", "rs_run_device", "rs_run_host",
     "rs_synth_cqi", "rs_synth_rand2", "rs_stats_device", "rs_get_stats", "rs_launch_count",
     "rs_smem_bytes", "rs_threads_per_cta", "rs_algorithmic_bytes_per_cell_tti", "rs_test_sort",
-    "rs_test_sort_timed", "rs_rand_draws_per_cell_tti",
+    "rs_test_sort_timed", "rs_rand_draws_per_cell_tti", "rs_set_queues",
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti",
@@ -87,6 +87,7 @@ def lib():
         L.rs_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.rs_rand_draws_per_cell_tti.argtypes = [C.c_void_p]
         L.rs_rand_draws_per_cell_tti.restype = C.c_int32
+        L.rs_set_queues.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_launch_count.argtypes = [C.c_void_p]
         L.rs_launch_count.restype = C.c_int64
         L.rs_smem_bytes.argtypes = [C.c_void_p]
@@ -261,9 +262,20 @@ class Scheduler:
             r = np.concatenate([r, np.zeros(lead + (n - r.shape[-1],), dtype=np.int32)], axis=-1)
         return np.ascontiguousarray(r[..., :n])
 
-    def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False):
-        """One TTI for every cell. cqi: uint8 [B][U][G] (or [B][U][R]); rand2: int32 [B][2]."""
+    def _queues(self, queue, hol, lead):
+        """Hand the next run call its queue state (rs_set_queues); returns the arrays to keep alive."""
+        if queue is None:
+            return None
+        q = np.ascontiguousarray(queue, dtype=np.int32).reshape(lead + (self.U,))
+        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(lead + (self.U,))
+        _check(lib().rs_set_queues(self._h, _ptr(q), _ptr(h)))
+        return q, h
+
+    def step(self, cqi, rand2=None, dt=0.001, active=None, want_aux=False, queue=None, hol=None):
+        """One TTI for every cell. cqi: uint8 [B][U][G] (or [B][U][R]); rand2: int32 [B][2]; queue / hol: the
+        bearers' dataToTransmit (int32 [B][U]) and head-of-line delays (float64 [B][U]), see rs_set_queues."""
         B, U = self.B, self.U
+        keep = self._queues(queue, hol, (B,))
         cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
         assert cqi.size == B * U * self.cqi_cols, cqi.shape
         rand2 = self._draws(rand2, (B,))
@@ -272,7 +284,8 @@ class Scheduler:
         _check(lib().rs_step(self._h, _ptr(cqi), _ptr(rand2), _ptr(act), float(dt), C.byref(o)))
         return out
 
-    def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0, cqi_refresh=1):
+    def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0, cqi_refresh=1, queue=None,
+                 hol=None):
         """T TTIs with host arrays [T][B][...] (cqi: one slab per cqi_refresh TTIs); copies overlap
         the kernels."""
         B, U = self.B, self.U
@@ -283,6 +296,7 @@ class Scheduler:
         rand2 = None if rand2 is None else self._draws(rand2, (T, B))
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(T, B, U)
         out, o = self._host_outputs(T, want_aux)
+        keep = self._queues(queue, hol, (T, B))
         _check(lib().rs_run_host(self._h, T, _ptr(cqi), int(cqi_refresh), _ptr(rand2), _ptr(act), _ptr(dt),
                                  C.byref(o), int(ttis_per_launch)))
         return out

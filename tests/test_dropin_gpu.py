@@ -17,7 +17,9 @@ pytestmark = pytest.mark.gpu
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")
 
 CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_diffw_trace", "a9_small_synth", "a8_fix20x5_synth", "a8_small_synth",
-         "a7_fix20x5_synth", "a7_mix20_synth", "a7_small_synth", "a1_fix20x5_synth", "a1_small_synth"]
+         "a7_fix20x5_synth", "a7_mix20_synth", "a7_small_synth", "a1_fix20x5_synth", "a1_small_synth",
+         # finite queues and head-of-line delays (internet flows): the plug-in reads them from the bearers
+         "a9_qif_synth", "a8_qif_synth", "a7_qif_synth", "a1_qif_synth"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -32,6 +34,8 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
         cfg["slices"].append({"n_slices": 1, "weight": float(rec["weight"][s]), "video_app": 0, "video_bitrate": 0,
                               "internet_flow": 0, "if_bitrate": 0, "backlog_flow": 1, "algo_alpha": a,
                               "algo_beta": b, "algo_epsilon": e, "algo_psi": p})
+    if "queue" in rec:   # the traffic mix is part of the scenario: the recorded run's own config
+        cfg = json.loads(str(rec["config_json"]))
     (tmp_path / "cfg.json").write_text(json.dumps(cfg))
     assert int(rec["cqi_per_rb"]) == 0
     np.ascontiguousarray(rec["cqi"], dtype=np.uint8).tofile(tmp_path / "cqi.bin")
@@ -39,7 +43,7 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
     out = tmp_path / "rec.bin"
     r = subprocess.run([HARNESS, "--gpu", "--algo", str(int(rec["algo"])), "--config", str(tmp_path / "cfg.json"),
                         "--ttis", str(T), "--cqi", str(tmp_path / "cqi.bin"), "--rand", str(tmp_path / "rand.bin"),
-                        "--out", str(out)], capture_output=True, text=True, timeout=600)
+                        "--out", str(out), "--seed", str(int(rec["seed"]))], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
     got = golden_io.compact(golden_io.parse_record_stream(str(out)))
     assert int(got["T"]) == T

@@ -87,7 +87,8 @@ def test_cuda_matches_reference_record(name):
 
 
 # ---- batches against the oracle -----------------------------------------------------------------
-def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_active=False, refresh=1):
+def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_active=False, refresh=1,
+        with_queue=False):
     rng = np.random.default_rng(seed)
     u2s = np.repeat(np.arange(S), ues_per_slice).astype(np.int32)
     U = len(u2s)
@@ -107,8 +108,14 @@ def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_
             act = (rng.random((B, U)) < 0.7).astype(np.uint8)
             act[0] = 0                     # a cell with nobody to schedule
             act[1, u2s != 1] = 0           # a cell where only slice 1 has data
-        a = o.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True)
-        b = g.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True)
+        kw = {}
+        if with_queue:   # finite queues small enough for the id 7 guard and the id 1 cut-off to bind, idle bearers,
+            kind = rng.random((B, U))   # infinite buffers; head-of-line delays with exact zeros
+            queue = np.where(kind < 0.2, 0, np.where(kind < 0.6, rng.integers(40, 4000, (B, U)), 100000000))
+            hol = np.where(rng.random((B, U)) < 0.1, 0.0, rng.random((B, U)) * 0.05)
+            kw = {"queue": queue.astype(np.int32), "hol": hol}
+        a = o.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True, **kw)
+        b = g.step(cqi, rand2, dt=float(dts[t]), active=act, want_aux=True, **kw)
         for k in b:
             assert np.array_equal(a[k], b[k]), (t, k, np.argwhere(a[k] != b[k])[:5])
         sa, sb = o.get_state(), g.get_state()
@@ -160,6 +167,27 @@ def test_wide_cells_all_ids(algo, layout):
     assert sched.lib().rs_threads_per_cta(g._h) == 512
     g.close()
     _mk(algo, S, [40] * S, w, p, B=4, seed=700 + algo, T=5, cqi_per_rb=layout, with_active=(layout == 1))
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_queue_aware_enterprise_schedulers(algo, layout):
+    """per-TTI queue sizes and head-of-line delays; slices with alpha/beta set (HoL-weighted
+    metrics), finite queues (bytes capped, id 7's required-RBs guard, id 1's flow-satisfied cut-off)."""
+    S = 6
+    w = np.array([0.3, 0.1, 0.2, 0.1, 0.2, 0.1])
+    p = np.array([[0, 0, 1, 1], [1, 0, 1, 1], [1, 1, 1, 1], [1, 1, 1, 0], [0, 0, 1, 0], [1, 1, 2, 1]], dtype=np.int32)
+    _mk(algo, S, [4, 3, 5, 2, 4, 3], w, p, B=24, seed=900 + algo, T=14, cqi_per_rb=layout, with_queue=True,
+        with_active=(layout == 1))
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 1])
+def test_queue_aware_wide_cells(algo):
+    S = 12
+    w = np.full(S, 1.0 / S)
+    p = np.tile(np.array([1, 1, 1, 1], dtype=np.int32), (S, 1))
+    p[::2] = [0, 0, 1, 1]
+    _mk(algo, S, [40] * S, w, p, B=3, seed=950 + algo, T=4, with_queue=True)
 
 
 @pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])

@@ -60,6 +60,22 @@ QMIX_CFG = {
     "ues_per_slice": [3, 4, 2, 5, 3, 2],
 }
 
+QIF_CFG = {
+    # like QMIX_CFG without the video application (its trace files do not travel to the GPU box): internet flows under
+    # alpha 1 and under alpha 1 + beta 1, for the in-simulator drop-in test
+    "slices": [
+        {"n_slices": 1, "weight": 0.25, "video_app": 0, "video_bitrate": [], "internet_flow": 0, "if_bitrate": [],
+         "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 2, "weight": 0.2, "video_app": 0, "video_bitrate": [], "internet_flow": 1, "if_bitrate": [12],
+         "backlog_flow": 0, "algo_alpha": 1, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 2, "weight": 0.1, "video_app": 0, "video_bitrate": [], "internet_flow": 1, "if_bitrate": [9],
+         "backlog_flow": 0, "algo_alpha": 1, "algo_beta": 1, "algo_epsilon": 1, "algo_psi": 1},
+        {"n_slices": 1, "weight": 0.15, "video_app": 0, "video_bitrate": [], "internet_flow": 0, "if_bitrate": [],
+         "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1, "algo_psi": 0},
+    ],
+    "ues_per_slice": [3, 4, 2, 5, 3, 2],
+}
+
 FIX20X5 = f"{REF_EXP}/exp-fix20slices/5ues/config-pf.json"
 DIFFW = f"{REF_EXP}/exp-customization/exp-backlogged-20slicesdiffw/config.json"
 MIX20 = f"{REF_EXP}/exp-customization/exp-backlogged-20slices/config.json"
@@ -104,11 +120,18 @@ CASES = [
     ("a1_qmix_synth", 1, "QMIX", 160, "synth", 24),
     ("a10_qmix_synth", 10, "QMIX", 120, "synth", 25),
     ("a11_qmix_synth", 11, "QMIX", 60, "synth", 26),
+    ("a9_qif_synth", 9, "QIF", 160, "synth", 31),
+    ("a8_qif_synth", 8, "QIF", 120, "synth", 32),
+    ("a7_qif_synth", 7, "QIF", 200, "synth", 33),
+    ("a1_qif_synth", 1, "QIF", 120, "synth", 34),
 ]
 
 
 def run_case(name, algo, config, n_ttis, source, seed, tmp):
-    queue_aware = config == "QMIX"
+    queue_aware = config in ("QMIX", "QIF")
+    if config == "QIF":
+        config = os.path.join(tmp, "qif.json")
+        json.dump(QIF_CFG, open(config, "w"))
     if config == "SMALL":
         config = os.path.join(tmp, "small.json")
         json.dump(SMALL_CFG, open(config, "w"))
