@@ -231,6 +231,9 @@ int rs_log_create(const rs_config* cfg, rs_log** out);
 void rs_log_destroy(rs_log* lg);
 int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes /*[U]*/, const uint64_t* cum_rbs /*[U]*/);
 int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs);
+/* Queue state of the cell for the NEXT rs_log_tti (same meaning as rs_set_queues, [U] each, either may be NULL):
+ * bytes credited are capped by the queue and the hol_delay field prints the bearer's delay. */
+int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_delay);
 /* Appends one TTI of one cell.  cqi [U][row] in cfg's CQI layout; rbg_to_ue [G]; tbs_bits [U];
  * final_cqi [U] (ids 7/8/9); slice_target / slice_quota [S] (ids 8/9). */
 int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,

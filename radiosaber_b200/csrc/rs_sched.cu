@@ -958,6 +958,8 @@ struct rs_log {
   int algo = 9, S = 0, U = 0, G = 0, R = 0, rbg = 0, layout = 0, row = 0, data = 0;
   std::vector<int> u2s;
   std::vector<uint64_t> cum_bytes, cum_rbs;
+  std::vector<int32_t> queue;   /* per-UE dataToTransmit for the next rs_log_tti (rs_log_set_queues), empty = cfg's */
+  std::vector<double> hol;
   double eff[16];
   std::string out, err;
 };
@@ -989,6 +991,13 @@ int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes, const uint64_t* c
   if (!lg) return fail(RS_ERR_ARG, "null log");
   if (cum_bytes) lg->cum_bytes.assign(cum_bytes, cum_bytes + lg->U);
   if (cum_rbs) lg->cum_rbs.assign(cum_rbs, cum_rbs + lg->U);
+  return RS_OK;
+}
+
+int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_delay) {
+  if (!lg) return fail(RS_ERR_ARG, "null log");
+  if (queue_bytes) lg->queue.assign(queue_bytes, queue_bytes + lg->U); else lg->queue.clear();
+  if (hol_delay) lg->hol.assign(hol_delay, hol_delay + lg->U); else lg->hol.clear();
   return RS_OK;
 }
 
@@ -1048,23 +1057,26 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
     }
   }
   /* stderr, DoStopSchedule: transport.cpp:177-199, nvs.cpp:226-251, dl-pf-packet-scheduler.cpp:80-96.
-   * Application id == user id and the head-of-line delay of an infinite buffer is 0 in the backlogged
-   * configurations this library covers. */
+   * Application id == user id (one bearer per UE); the head-of-line delay (0 for an infinite buffer) is printed
+   * the way operator<< prints a double, i.e. %g. */
   for (int u = 0; u < U; ++u) {
     const int avail = tbs_bits[u] / 8;
     if (avail <= 0) continue;
     int sent = avail;
     if (algo != 1) {
-      if (lg->data <= 0) continue;
-      sent = std::min(avail, lg->data);
+      const int data = lg->queue.empty() ? lg->data : lg->queue[u];
+      if (data <= 0) continue;
+      sent = std::min(avail, data);
     }
     lg->cum_bytes[u] += (uint64_t)sent;
     lg->cum_rbs[u] += (uint64_t)n_rbg[u] * lg->rbg;
-    snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: 0 user: %d slice: %d\n",
+    snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: %g user: %d slice: %d\n",
              (unsigned long long)timestamp, u, (unsigned long long)lg->cum_bytes[u],
-             (unsigned long long)lg->cum_rbs[u], u, lg->u2s[u]);
+             (unsigned long long)lg->cum_rbs[u], lg->hol.empty() ? 0.0 : lg->hol[u], u, lg->u2s[u]);
     lg->err += buf;
   }
+  lg->queue.clear();
+  lg->hol.clear();
   return RS_OK;
 }
 

@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti",
-    "rs_log_stdout", "rs_log_stderr", "rs_log_clear",
+    "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues",
 )
 
 
@@ -113,6 +113,7 @@ def lib():
         L.rs_log_destroy.restype = None
         L.rs_log_set_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rs_log_set_queues.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_tti.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
         L.rs_log_stdout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.rs_log_stdout.restype = C.c_char_p
@@ -395,7 +396,12 @@ class LogWriter:
         self._h = C.c_void_p()
         _check(lib().rs_log_create(C.byref(cfg), C.byref(self._h)))
 
-    def tti(self, timestamp, cqi, rbg_to_ue, tbs_bits, final_cqi=None, slice_target=None, slice_quota=None):
+    def tti(self, timestamp, cqi, rbg_to_ue, tbs_bits, final_cqi=None, slice_target=None, slice_quota=None,
+            queue=None, hol=None):
+        if queue is not None or hol is not None:
+            q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32)
+            h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64)
+            _check(lib().rs_log_set_queues(self._h, _ptr(q), _ptr(h)))
         a = [np.ascontiguousarray(cqi, dtype=np.uint8), np.ascontiguousarray(rbg_to_ue, dtype=np.int16),
              np.ascontiguousarray(tbs_bits, dtype=np.int32),
              None if final_cqi is None else np.ascontiguousarray(final_cqi, dtype=np.uint8),

@@ -23,7 +23,8 @@ from tools import make_golden as mg  # noqa: E402
 
 TTIS = 6
 CASES = ["a9_fix20x5_synth", "a8_fix20x5_synth", "a7_fix20x5_synth", "a1_fix20x5_synth", "a9_small_synth",
-         "a9_fix20x5_trace"]
+         "a9_fix20x5_trace", "a9_qmix_synth", "a7_qmix_synth", "a1_qmix_synth"]
+TTIS_OF = {"a9_qmix_synth": 40, "a7_qmix_synth": 60, "a1_qmix_synth": 40}   # long enough for the finite flows to show up
 OUT = os.path.join(ROOT, "tests", "golden", "logs")
 
 
@@ -36,16 +37,20 @@ def main():
             if config == "SMALL":
                 config = os.path.join(tmp, "small.json")
                 json.dump(mg.SMALL_CFG, open(config, "w"))
+            if config == "QMIX":
+                config = os.path.join(tmp, "qmix.json")
+                json.dump(mg.QMIX_CFG, open(config, "w"))
+            ttis = TTIS_OF.get(name, TTIS)
             cfg = json.load(open(config))
             n_ues, n_slices = int(sum(cfg["ues_per_slice"])), len(cfg["ues_per_slice"])
-            cmd = [mg.HARNESS, "--algo", str(algo), "--config", config, "--ttis", str(TTIS), "--seed", str(seed),
+            cmd = [mg.HARNESS, "--algo", str(algo), "--config", config, "--ttis", str(ttis), "--seed", str(seed),
                    "--log-out", os.path.join(OUT, name)]
             rand_path = os.path.join(tmp, name + ".rand")
-            workload.synth_rand2(seed, 0, 1, 0, TTIS, n_slices)[:, 0, :].astype("<i4").tofile(rand_path)
+            workload.synth_rand2(seed, 0, 1, 0, ttis, n_slices)[:, 0, :].astype("<i4").tofile(rand_path)
             cmd += ["--rand", rand_path]
             if source == "synth":
                 cqi_path = os.path.join(tmp, name + ".cqi")
-                workload.synth_cqi(seed, 0, 1, 0, TTIS, n_ues, 64)[:, 0].tofile(cqi_path)
+                workload.synth_cqi(seed, 0, 1, 0, ttis, n_ues, 64)[:, 0].tofile(cqi_path)
                 cmd += ["--cqi", cqi_path]
             subprocess.run(cmd, check=True, capture_output=True, text=True)
             for ext in ("stdout", "stderr"):
