@@ -308,7 +308,7 @@ def run_cuda_arm(args, n_gpus):
         h_cqi.copy_(d_tmp)
         del d_tmp
         h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
-        h_r2.copy_(d_r2[:TE])
+        h_r2.copy_(torch.from_numpy(workload.synth_rand2(SEED, cell0, B, 0, TE, S)))
         h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
         h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
         h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
@@ -347,7 +347,7 @@ def run_cuda_arm(args, n_gpus):
         now, _ = workload.tti_clock(TE)
         rows = sched.trace_rows_for_run(now, 0)
         h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
-        h_r2.copy_(d_r2[:TE])
+        h_r2.copy_(torch.from_numpy(workload.synth_rand2(SEED, cell0, B, 0, TE, S)))
         h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
         h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
         h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
@@ -356,7 +356,7 @@ def run_cuda_arm(args, n_gpus):
         def one():
             sched._check(sched.lib().rs_run_traces_host(ge._h, TE, rows.ctypes.data_as(C.c_void_p),
                                                         C.c_void_p(h_r2.data_ptr()), None,
-                                                        dte.ctypes.data_as(C.c_void_p), C.byref(o), 8))
+                                                        dte.ctypes.data_as(C.c_void_p), C.byref(o), args.e2e_trace_ttis_per_launch))
 
         for _ in range(2):
             one()
@@ -437,8 +437,9 @@ def main():
     ap.add_argument("--algo", type=int, default=9)
     ap.add_argument("--ttis-per-step", type=int, default=48)
     ap.add_argument("--ttis-per-launch", type=int, default=16)
-    ap.add_argument("--e2e-ttis", type=int, default=40)
-    ap.add_argument("--e2e-ttis-per-launch", type=int, default=4)
+    ap.add_argument("--e2e-ttis", type=int, default=80)
+    ap.add_argument("--e2e-ttis-per-launch", type=int, default=3)
+    ap.add_argument("--e2e-trace-ttis-per-launch", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)
