@@ -1,0 +1,93 @@
+#!/usr/bin/env python3
+"""Randomised differential run: CUDA path against the CPU oracle on random slice configurations, shapes,
+CQI layouts, idle bearers, finite queues and head-of-line delays, several hundred TTIs each so that the
+state (EWMA rates, offsets, credits) drifts far from its initial values.  Development / soak tool; the unit
+tests under tests/ are the contract.  Usage: python tools/fuzz_parity.py [--seconds 120] [--seed 1]"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.pyoracle import OracleScheduler  # noqa: E402
+from radiosaber_b200 import sched, workload  # noqa: E402
+
+
+def one_case(rng, case):
+    algo = int(rng.choice([9, 9, 9, 8, 7, 1, 10, 11]))
+    S = int(rng.integers(1, 33))
+    ues = rng.integers(1, 9 if algo == 11 else 13, S)
+    if rng.random() < 0.15:
+        ues[int(rng.integers(0, S))] = int(rng.integers(20, 60))
+    u2s = np.repeat(np.arange(S), ues).astype(np.int32)
+    U, G = len(u2s), 64
+    w = rng.dirichlet(np.ones(S) * rng.choice([0.3, 1.0, 5.0]))
+    p = np.zeros((S, 4), dtype=np.int32)
+    p[:, 0] = rng.integers(0, 2, S)
+    p[:, 1] = rng.integers(0, 2, S)
+    p[:, 2] = rng.choice([0, 1, 1, 1, 2], S)
+    p[:, 3] = rng.integers(0, 2, S)
+    layout = int(rng.choice([0, 0, 1, 2]))
+    B = int(rng.integers(1, 24))
+    T = int(rng.integers(40, 260))
+    queue_aware = rng.random() < 0.4
+    with_active = rng.random() < 0.3
+    g = sched.Scheduler(algo, w, p, u2s, B, cqi_per_rb=layout)
+    o = OracleScheduler(algo, w, p, u2s, B, cqi_per_rb=1 if layout == 1 else 0, n_threads=8)
+    _, dts = workload.tti_clock(T)
+    seed = int(rng.integers(1, 1 << 30))
+    refresh = int(rng.choice([1, 1, 7, 40]))
+    for t in range(T):
+        cqi = workload.synth_cqi(seed, 0, B, t, 1, U, G, refresh)[0]
+        dev_cqi = cqi
+        if layout == 1:
+            cqi = np.clip(np.repeat(cqi, 8, axis=-1).astype(np.int64) + rng.integers(-1, 2, (B, U, 512)), 1, 15).astype(np.uint8)
+            dev_cqi = cqi
+        elif layout == 2:
+            dev_cqi = sched.pack_cqi(cqi)
+        draws = workload.synth_rand_draws(seed, 0, B, t, 1, S, max(g.rand_stride, 2))[0]
+        kw = {}
+        if with_active:
+            kw["active"] = (rng.random((B, U)) < 0.8).astype(np.uint8)
+        if queue_aware:
+            kind = rng.random((B, U))
+            kw["queue"] = np.where(kind < 0.15, 0, np.where(kind < 0.6, rng.integers(20, 20000, (B, U)), 100000000)).astype(np.int32)
+            kw["hol"] = np.where(rng.random((B, U)) < 0.1, 0.0, rng.random((B, U)) * 0.08)
+        a = o.step(cqi, draws, dt=float(dts[t]), want_aux=True, **kw)
+        b = g.step(dev_cqi, draws, dt=float(dts[t]), want_aux=True, **kw)
+        for k in b:
+            if not np.array_equal(a[k], b[k]):
+                return f"case {case}: id {algo} S {S} U {U} layout {layout} queue {queue_aware} tti {t}: {k} differs"
+    sa, sb = o.get_state(), g.get_state()
+    for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs", "slice_offset", "nvs_ewma"):
+        if k == "slice_offset" and algo not in (8, 9, 10):
+            continue
+        if k == "nvs_ewma" and algo not in (7, 11):
+            continue
+        if not np.array_equal(sa[k], sb[k]):
+            return f"case {case}: id {algo} S {S} U {U}: state {k} differs after {T} TTIs"
+    g.close()
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    t0, n, ttis = time.time(), 0, 0
+    while time.time() - t0 < args.seconds:
+        err = one_case(rng, n)
+        if err:
+            print("MISMATCH", err)
+            return 1
+        n += 1
+    print(f"fuzz ok: {n} random configurations, no mismatch ({time.time() - t0:.0f} s, seed {args.seed})")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
