@@ -12,6 +12,10 @@
  *     9  DownlinkTransportScheduler(cfg,2) MaximizeCell  downlink-transport-scheduler.cpp:351-376
  *    10  DownlinkTransportScheduler(cfg,4) UpperBound    downlink-transport-scheduler.cpp:223-246
  *    11  DownlinkNVSScheduler(cfg,true)   downlink-nvs-scheduler.cpp:405-528 (300-sample non-greedy PF)
+ *   101  DownlinkTransportScheduler(cfg,1) SubOpt            downlink-transport-scheduler.cpp:274-349
+ *   103  DownlinkTransportScheduler(cfg,3) VogelApproximate  downlink-transport-scheduler.cpp:378-451
+ *        (ENodeB::DLScheduler_SUBOPT / DLScheduler_VOGEL, ENodeB.cpp:363-379, have no id in the scenario:
+ *        100 + the constructor's second argument)
  * This library is what a host-side subclass of PacketScheduler binds to (see
  * INTEGRATION.md and radiosaber_b200/host/rs_gpu_scheduler.h): every entry
  * point below takes plain pointers and sizes, returns an int status and never
@@ -43,7 +47,7 @@ extern "C" {
  * config (downlink-transport-scheduler.cpp:55-97, downlink-nvs-scheduler.cpp:46-87,
  * dl-pf-packet-scheduler.cpp:39-57). */
 typedef struct rs_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy, 101 SubOpt, 103 Vogel */
   int32_t n_slices;         /* S  <= RS_MAX_SLICES */
   int32_t n_ues;            /* U; user j == UE id j (flows/application/Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (core/spectrum/bandwidth-manager.cpp:98-102) */

@@ -452,7 +452,9 @@ struct Installer {
       case 7: s = new ObservedNvs(g_opt.config); break;
       case 11: s = new ObservedNvs(g_opt.config, true); break;   /* DLScheduler_NVS_NONGREEDY, ENodeB.cpp:351-355 */
       case 8: s = new ObservedTransport(g_opt.config, 0); break;
-      case 10: s = new ObservedTransport(g_opt.config, 4); break;   /* DLScheduler_UpperBound, ENodeB.cpp:381-385 */
+      case 10: s = new ObservedTransport(g_opt.config, 4); break;
+      case 101: s = new ObservedTransport(g_opt.config, 1); break;  /* DLScheduler_SUBOPT, ENodeB.cpp:363-367 */
+      case 103: s = new ObservedTransport(g_opt.config, 3); break;  /* DLScheduler_VOGEL, ENodeB.cpp:375-379 */   /* DLScheduler_UpperBound, ENodeB.cpp:381-385 */
       default: s = new ObservedTransport(g_opt.config, 2); break;
     }
     s->SetMacEntity(mac);
@@ -552,7 +554,7 @@ int main(int argc, char** argv) {
   Installer inst;
   sim->Schedule(0.0, &Installer::Install, &inst);
   double duration = g_opt.n_ttis * 0.001 + 0.0035;
-  int sched_type = g_opt.algo;
+  int sched_type = g_opt.algo > 100 ? 9 : g_opt.algo;   /* SubOpt / Vogel have no scenario id: any transport id will do, the scheduler is swapped at t = 0 */
   SingleCellWithInterference(1.0, sched_type, 1, 30, g_opt.seed, duration, g_opt.config);
 
   stderr = saved_stderr;

@@ -20,6 +20,7 @@
 #include <limits>
 #include <thread>
 #include <utility>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -231,6 +232,104 @@ std::vector<int> GreedyByRow(const std::vector<std::vector<double>>& se, const s
   return out;
 }
 
+/* SubOpt, transport.cpp:274-349 (DLScheduler_SUBOPT, constructor argument 1): every RBG first goes to the
+ * slice with the best efficiency, then RBGs move one at a time from slices above their quota to slices below
+ * it, always the move that loses the least efficiency.  Ties are broken by the iteration order of the
+ * reference's two std::unordered_map<int,int> (the same containers, filled in the same order, here). */
+std::vector<int> SubOpt(const std::vector<std::vector<double>>& se, std::vector<int> quota, int G, int S) {
+  std::vector<int> held(S, 0), out(G, -1);
+  for (int& q : quota)
+    if (q < 0) q = 0;
+  for (int i = 0; i < G; ++i) {
+    double best = -1;
+    int pick = -1;
+    for (int j = 0; j < S; ++j)
+      if (se[i][j] > best) {
+        best = se[i][j];
+        pick = j;
+      }
+    out[i] = pick;
+    held[pick] += 1;
+  }
+  std::unordered_map<int, int> over, under;
+  for (int i = 0; i < S; ++i) {
+    if (held[i] > quota[i]) over[i] = held[i] - quota[i];
+    else if (held[i] < quota[i]) under[i] = quota[i] - held[i];
+  }
+  while (over.size() > 0 && under.size() > 0) {
+    int from = -1, to = -1, rbg = -1;
+    double least = std::numeric_limits<double>::max();
+    for (int i = 0; i < G; ++i) {
+      if (over.find(out[i]) == over.end()) continue;
+      for (auto it = under.begin(); it != under.end(); ++it) {
+        const double loss = se[i][out[i]] - se[i][it->first];
+        if (loss < least) {
+          least = loss;
+          from = out[i];
+          to = it->first;
+          rbg = i;
+        }
+      }
+    }
+    if (from < 0) break; /* assert in the reference */
+    held[from] -= 1;
+    held[to] += 1;
+    out[rbg] = to;
+    over.at(from) -= 1;
+    under.at(to) -= 1;
+    if (over.at(from) <= 0 || held[from] <= 0) over.erase(from);
+    if (under.at(to) <= 0) under.erase(to);
+  }
+  return out;
+}
+
+/* VogelApproximate, transport.cpp:378-451 (DLScheduler_VOGEL, constructor argument 3): G rounds; each round
+ * looks at every free RBG (best and "second" efficiency among the slices with quota left) and at every such
+ * slice (best and "second" among the free RBGs) and grants the best cell of the row / column with the
+ * largest gap.  Reproduced with its quirks: the running largest gap is an int (the gap is truncated when it
+ * is stored), and "second" is the best of the candidates seen AFTER the current best, not the runner-up. */
+std::vector<int> VogelApproximate(const std::vector<std::vector<double>>& se, const std::vector<int>& quota, int G, int S) {
+  std::vector<int> held(S, 0), out(G, -1);
+  for (int round = 0; round < G; ++round) {
+    int max_diff = -1;
+    int grant_rbg = -1, grant_slice = -1;
+    for (int j = 0; j < G; ++j) {
+      if (out[j] != -1) continue;
+      double e1 = -1, e2 = -1;
+      int s1 = -1;
+      for (int k = 0; k < S; ++k) {
+        if (held[k] >= quota[k]) continue;
+        if (e1 == -1 || se[j][k] > e1) { s1 = k; e1 = se[j][k]; continue; }
+        if (e2 == -1 || se[j][k] > e2) { e2 = se[j][k]; continue; }
+      }
+      if (e1 - e2 > max_diff) {
+        max_diff = e1 - e2;
+        grant_rbg = j;
+        grant_slice = s1;
+      }
+    }
+    for (int k = 0; k < S; ++k) {
+      if (held[k] >= quota[k]) continue;
+      double e1 = -1, e2 = -1;
+      int r1 = -1;
+      for (int j = 0; j < G; ++j) {
+        if (out[j] != -1) continue;
+        if (e1 == -1 || se[j][k] > e1) { r1 = j; e1 = se[j][k]; continue; }
+        if (e2 == -1 || se[j][k] > e2) { e2 = se[j][k]; continue; }
+      }
+      if (e1 - e2 > max_diff) {
+        max_diff = e1 - e2;
+        grant_rbg = r1;
+        grant_slice = k;
+      }
+    }
+    if (grant_rbg < 0 || grant_slice < 0) break; /* the reference would index with an uninitialised pair */
+    out[grant_rbg] = grant_slice;
+    held[grant_slice] += 1;
+  }
+  return out;
+}
+
 /* MaximizeCell, transport.cpp:351-376 */
 std::vector<int> MaximizeCell(const std::vector<std::vector<double>>& se, const std::vector<int>& quota,
                               int G, int S) {
@@ -412,7 +511,10 @@ void StepTransport(const CellView& c, const int32_t* row_m1) {
   }
 
   std::vector<int> rbg_to_slice =           /* :569-586 */
-      (cfg->algo == 8) ? GreedyByRow(se, quota, G, S) : MaximizeCell(se, quota, G, S);
+      (cfg->algo == 8) ? GreedyByRow(se, quota, G, S)
+      : (cfg->algo == 101) ? SubOpt(se, quota, G, S)
+      : (cfg->algo == 103) ? VogelApproximate(se, quota, G, S)
+                           : MaximizeCell(se, quota, G, S);
 
   for (int i = 0; i < G; ++i) {             /* :589-601 */
     if (rbg_to_slice[i] < 0) continue;      /* assert in the reference */
@@ -746,8 +848,9 @@ extern "C" {
 
 int rso_step(const rso_config* cfg, int32_t n_cells, rso_io* io, int32_t n_threads) {
   if (!cfg || !io || n_cells < 0) return 1;
-  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 8 && cfg->algo != 9 && cfg->algo != 10 && cfg->algo != 11) return 2;
-  if ((cfg->algo == 8 || cfg->algo == 9 || cfg->algo == 10) && (!io->rand2 || !io->slice_offset)) return 3;
+  const bool transport = cfg->algo == 8 || cfg->algo == 9 || cfg->algo == 10 || cfg->algo == 101 || cfg->algo == 103;
+  if (cfg->algo != 1 && cfg->algo != 7 && cfg->algo != 11 && !transport) return 2;
+  if (transport && (!io->rand2 || !io->slice_offset)) return 3;
   if ((cfg->algo == 7 || cfg->algo == 11) && !io->nvs_ewma) return 3;
   if (cfg->algo == 11 && (!io->rand2 || io->rand_stride < 300)) return 3;
   int32_t row_m1[27];

@@ -21,7 +21,8 @@ extern "C" {
 #endif
 
 typedef struct rso_config {
-  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy (single-cell-with-interference.h:94-118) */
+  int32_t algo;             /* 1 PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound, 11 NVS non-greedy; 101 SubOpt and 103 VogelApproximate = 100 + the
+                               constructor argument of DownlinkTransportScheduler (no scenario id, ENodeB.cpp:363-379) (single-cell-with-interference.h:94-118) */
   int32_t n_slices;         /* S */
   int32_t n_ues;            /* U; user j == UE id j (Application.cpp:72-123) */
   int32_t n_rbs;            /* 512 for 100 MHz (bandwidth-manager.cpp:98-102) */

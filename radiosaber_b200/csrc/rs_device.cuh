@@ -54,6 +54,8 @@ constexpr unsigned short kNoUe = 0xffff;
 /* ---- tables that are the same for every handle (set once per device) ------------------------- */
 struct ConstTables {
   double tval[16];   /* exp(-10^(SINR[cqi]/10)), the EESM summand of a CQI (eesm-effective-sinr.h:39-41) */
+  double eff[16];    /* AMCModule::GetEfficiencyFromCQI per CQI (AMCModule.cpp:319-327), eff[0] = 0: the
+                        flow_spectraleff of a (rbg, slice) pair (ids 101/103 work on differences of it) */
   double cut[16];    /* cut[k], k=1..14: largest mean with 10*log10(-log(mean)) >= SINRForCQIIndex[k]
                         (AMCModule.cpp:252-261 expressed on the EESM mean) */
 };
@@ -716,6 +718,206 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
   if (o_fc) o_fc[u] = (uint8_t)fc;
 }
 
+/* Scratch of ids 101 / 103 in the (dead) slot arrays of the sort: at least 64 * max(G, S) bytes
+ * (make_layout's min_sort_n). */
+struct InterScratch {
+  double* val;             /* [G + S] candidate gap / loss */
+  int* pick;               /* [G + S] */
+  int* over;               /* [S] RBGs above quota, 0 = not in the map */
+  int* under;              /* [S] RBGs below quota */
+  unsigned char* order;    /* [S] the slices below quota in std::unordered_map iteration order */
+  unsigned char* nxt;      /* [S + 1] singly linked list of the emulated hashtable, S = before-begin */
+  unsigned char* bkt;      /* [128] node before the first node of each bucket, 0xff = empty bucket */
+};
+__device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Cell& c) {
+  InterScratch x;
+  unsigned char* p = (unsigned char*)c.sb.posl;
+  const int n = d.G + d.S;
+  x.val = (double*)p;
+  x.pick = (int*)(p + 8 * n);
+  x.over = x.pick + n;
+  x.under = x.over + d.S;
+  x.order = (unsigned char*)(x.under + d.S);
+  x.nxt = x.order + d.S;
+  x.bkt = x.nxt + d.S + 1;
+  return x;
+}
+/* efficiency of the (rbg, slice) pair: the slice winner's, 0 for a slice without a listed user */
+__device__ __forceinline__ double pair_eff(const Cell& c, int S, int g, int s) { return c_tab.eff[c.sb.a[g * S + s] >> 12]; }
+
+/* VogelApproximate, transport.cpp:378-451: G rounds; in each, every free RBG (thread g) and every slice with
+ * quota left (thread G + s) reports the gap between its best and its "second" efficiency, then one thread walks
+ * the candidates in the reference's order with the reference's int-truncated running maximum.  Result in
+ * c.outsl. */
+__device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
+  const int tid = threadIdx.x, G = d.G, S = d.S;
+  const InterScratch x = inter_scratch(d, c);
+  int* held = c.wd;   /* free once the quotas exist; cleared again at the end of the TTI */
+  for (int s = tid; s < S; s += kThreads) held[s] = 0;
+  __syncthreads();
+  for (int round = 0; round < G; ++round) {
+    for (int q = tid; q < G + S; q += kThreads) {
+      double e1 = -1, e2 = -1;
+      int first = -1;
+      if (q < G) {
+        if (c.outsl[q] == 0xff)
+          for (int k = 0; k < S; ++k) {
+            if (held[k] >= c.quota[k]) continue;
+            const double e = pair_eff(c, S, q, k);
+            if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
+            if (e2 == -1 || e > e2) e2 = e;
+          }
+      } else if (held[q - G] < c.quota[q - G]) {
+        for (int j = 0; j < G; ++j) {
+          if (c.outsl[j] != 0xff) continue;
+          const double e = pair_eff(c, S, j, q - G);
+          if (e1 == -1 || e > e1) { first = j; e1 = e; continue; }
+          if (e2 == -1 || e > e2) e2 = e;
+        }
+      }
+      x.val[q] = __dsub_rn(e1, e2);
+      x.pick[q] = first;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int max_diff = -1, gr = -1, gs = -1;
+      for (int q = 0; q < G + S; ++q) {
+        if (x.pick[q] < 0) continue;   /* an allocated RBG / a slice at its quota is skipped by the reference too */
+        if (x.val[q] > (double)max_diff) {
+          max_diff = (int)x.val[q];
+          if (q < G) { gr = q; gs = x.pick[q]; } else { gr = x.pick[q]; gs = q - G; }
+        }
+      }
+      if (gr >= 0) {
+        c.outsl[gr] = (unsigned char)gs;
+        held[gs] += 1;
+      }
+      c.misc[12] = (gr >= 0) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!c.misc[12]) break;
+  }
+}
+
+/* SubOpt, transport.cpp:274-349: every RBG to its best slice, then single-RBG moves from slices above their
+ * quota to slices below it, each time the move that loses the least efficiency (first in RBG order, then in
+ * the iteration order of the reference's std::unordered_map of the slices below quota, which is emulated:
+ * libstdc++'s hashtable with its prime bucket counts 13 / 29 / 59 / 127, nodes of an empty bucket go to the
+ * front of the list, a rehash re-links the nodes in list order).  Result in c.outsl. */
+__device__ void sub_opt(const DevCfg& d, const Cell& c) {
+  const int tid = threadIdx.x, G = d.G, S = d.S;
+  const InterScratch x = inter_scratch(d, c);
+  int* held = c.wd;
+  for (int s = tid; s < S; s += kThreads) held[s] = 0;
+  __syncthreads();
+  for (int g = tid; g < G; g += kThreads) {
+    double best = -1;
+    int pick = 0;
+    for (int k = 0; k < S; ++k) {
+      const double e = pair_eff(c, S, g, k);
+      if (e > best) { best = e; pick = k; }
+    }
+    c.outsl[g] = (unsigned char)pick;
+    atomicAdd(&held[pick], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n_over = 0, n_under = 0, n_bkt = 1, n_elt = 0;
+    x.nxt[S] = 0xff;
+    x.bkt[0] = 0xff;
+    for (int i = 0; i < S; ++i) {
+      const int q = max(c.quota[i], 0);
+      x.over[i] = 0;
+      x.under[i] = 0;
+      if (held[i] > q) { x.over[i] = held[i] - q; n_over++; }
+      else if (held[i] < q) {
+        x.under[i] = q - held[i];
+        n_under++;
+        /* under[i] = ...: _M_insert_unique_node with the prime rehash policy (max load factor 1) */
+        if (n_elt + 1 > (n_bkt == 1 ? 0 : n_bkt)) {
+          const int nb = (n_bkt == 1) ? 13 : (n_bkt == 13 ? 29 : (n_bkt == 29 ? 59 : 127));
+          for (int b = 0; b < nb; ++b) x.bkt[b] = 0xff;
+          int p = x.nxt[S], bbegin = 0;
+          x.nxt[S] = 0xff;
+          while (p != 0xff) {   /* _M_rehash_aux, unique keys */
+            const int nx = x.nxt[p], b = p % nb;
+            if (x.bkt[b] == 0xff) {
+              x.nxt[p] = x.nxt[S];
+              x.nxt[S] = (unsigned char)p;
+              x.bkt[b] = (unsigned char)S;
+              if (x.nxt[p] != 0xff) x.bkt[bbegin] = (unsigned char)p;
+              bbegin = b;
+            } else {
+              x.nxt[p] = x.nxt[x.bkt[b]];
+              x.nxt[x.bkt[b]] = (unsigned char)p;
+            }
+            p = nx;
+          }
+          n_bkt = nb;
+        }
+        const int b = i % n_bkt;   /* _M_insert_bucket_begin */
+        if (x.bkt[b] != 0xff) {
+          x.nxt[i] = x.nxt[x.bkt[b]];
+          x.nxt[x.bkt[b]] = (unsigned char)i;
+        } else {
+          x.nxt[i] = x.nxt[S];
+          x.nxt[S] = (unsigned char)i;
+          if (x.nxt[i] != 0xff) x.bkt[x.nxt[i] % n_bkt] = (unsigned char)i;
+          x.bkt[b] = (unsigned char)S;
+        }
+        n_elt++;
+      }
+    }
+    int k = 0;
+    for (int p = x.nxt[S]; p != 0xff; p = x.nxt[p]) x.order[k++] = (unsigned char)p;
+    c.misc[11] = (unsigned)n_over;
+    c.misc[12] = (unsigned)n_under;
+  }
+  __syncthreads();
+  while (c.misc[11] > 0 && c.misc[12] > 0) {
+    const int n_under = (int)c.misc[12];
+    for (int g = tid; g < G; g += kThreads) {   /* the cheapest move of RBG g, first in map order */
+      double least = 1.7976931348623157e308;
+      int to = -1;
+      const int from = c.outsl[g];
+      if (x.over[from] > 0) {
+        const double mine = pair_eff(c, S, g, from);
+        for (int q = 0; q < n_under; ++q) {
+          const double loss = __dsub_rn(mine, pair_eff(c, S, g, x.order[q]));
+          if (loss < least) { least = loss; to = x.order[q]; }
+        }
+      }
+      x.val[g] = least;
+      x.pick[g] = to;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double least = 1.7976931348623157e308;
+      int rbg = -1;
+      for (int g = 0; g < G; ++g)
+        if (x.pick[g] >= 0 && x.val[g] < least) { least = x.val[g]; rbg = g; }
+      if (rbg < 0) {
+        c.misc[11] = 0;   /* the reference asserts a move exists */
+      } else {
+        const int from = c.outsl[rbg], to = x.pick[rbg];
+        held[from] -= 1;
+        held[to] += 1;
+        c.outsl[rbg] = (unsigned char)to;
+        x.over[from] -= 1;
+        x.under[to] -= 1;
+        if (x.over[from] <= 0 || held[from] <= 0) { x.over[from] = 0; c.misc[11] -= 1; }
+        if (x.under[to] <= 0) {   /* erase keeps the order of the others */
+          int w = 0;
+          for (int q = 0; q < n_under; ++q)
+            if (x.order[q] != to) x.order[w++] = x.order[q];
+          c.misc[12] -= 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
@@ -729,6 +931,9 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   const int S = d.S, U = d.U, G = d.G;
   const int b = blockIdx.x;
   constexpr bool NVS = ALGO == 7 || ALGO == 11;   /* DownlinkNVSScheduler, greedy and non-greedy */
+  /* DownlinkTransportScheduler with one of its inter-slice algorithms: GreedyByRow (8), MaximizeCell (9),
+   * UpperBound (10), SubOpt (101), VogelApproximate (103) */
+  constexpr bool TRANSPORT = ALGO == 8 || ALGO == 9 || ALGO == 10 || ALGO == 101 || ALGO == 103;
   if (b >= d.n_cells) return;
   c.cumb = d.cum_bytes + (size_t)b * U;
   c.cumr = d.cum_rbs + (size_t)b * U;
@@ -847,14 +1052,14 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         const int s = d.ue_to_slice[u];
         /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
         c.den[u] = d.psi[s] ? __ddiv_rn(__dadd_rn(1.0, a), 1000.0) : 1.0;
-        if ((ALGO == 8 || ALGO == 9 || ALGO == 10) && listed(u)) c.wd[s] = 1;
+        if (TRANSPORT && listed(u)) c.wd[s] = 1;
       }
     }
     if (stage) cp_async_wait_all();   /* own copies done; the barrier publishes everybody's */
     __syncthreads();
 
     RS_TICK(0);
-    if (ALGO == 8 || ALGO == 9 || ALGO == 10) {
+    if (TRANSPORT) {
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < d.n_chunks; ++ch) {
         const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
@@ -1002,6 +1207,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             if (g_rbg[e] == g && g_ue[e] != kNoUe) ue = max(ue, (int)g_ue[e]);
           if (o_rbg) o_rbg[g] = (short)ue;
         }
+      } else if (ALGO == 103) {
+        vogel_approximate(d, c);
+      } else if (ALGO == 101) {
+        sub_opt(d, c);
       } else if (ALGO == 9) {
 #ifndef RS_SKIP_SORT
         sort_desc(c.sb, d.sort_n, d.sort_depth, kWarps - rot);
@@ -1314,7 +1523,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     d.avg[i] = c.avg[u];
     d.tx[i] = c.tx[u];
   }
-  if (NVS || ALGO == 8 || ALGO == 9 || ALGO == 10) {
+  if (NVS || TRANSPORT) {
     double* dst = NVS ? d.ewma : d.offset;
     for (int s = tid; s < S; s += kThreads) dst[(size_t)b * S + s] = c.off[s];
   }

@@ -96,6 +96,7 @@ bool build_const_tables(rs::ConstTables* t, std::string* why) {
     volatile double s = pow(10, kSinrForCqi[c - 1] / 10);
     volatile double beta = 1;
     t->tval[c] = exp(-s / beta);
+    t->eff[c] = eff_from_cqi(c);
   }
   t->tval[0] = t->tval[1];
   for (int k = 1; k <= 14; ++k) {
@@ -248,6 +249,8 @@ const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
     case 7: return wide ? RS_TTI_PICK(rsw, 7) : RS_TTI_PICK(rs, 7);
     case 8: return wide ? RS_TTI_PICK(rsw, 8) : RS_TTI_PICK(rs, 8);
     case 10: return wide ? RS_TTI_PICK(rsw, 10) : RS_TTI_PICK(rs, 10);
+    case 101: return wide ? RS_TTI_PICK(rsw, 101) : RS_TTI_PICK(rs, 101);
+    case 103: return wide ? RS_TTI_PICK(rsw, 103) : RS_TTI_PICK(rs, 103);
     case 11: return wide ? RS_TTI_PICK(rsw, 11) : RS_TTI_PICK(rs, 11);
     default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
   }
@@ -346,9 +349,14 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
   return RS_OK;
 }
 
+/* DownlinkTransportScheduler with one of its inter-slice algorithms (the constructor's second argument):
+ * 8 GreedyByRow (0), 9 MaximizeCell (2), 10 UpperBound (4); SubOpt (1) and VogelApproximate (3) have no id in the
+ * SingleCellWithI scenario (ENodeB.cpp:363-379) and go by 100 + that argument */
+bool is_transport(int a) { return a == 8 || a == 9 || a == 10 || a == 101 || a == 103; }
+
 bool wants(const rs_handle* h, int which) { /* outputs that exist for this scheduler id */
   const int a = h->d.algo;
-  if (which == 0) return a == 8 || a == 9 || a == 10;   /* slice_target / slice_quota */
+  if (which == 0) return is_transport(a);   /* slice_target / slice_quota */
   return a == 7 || a == 11;                  /* nvs_slice */
 }
 
@@ -390,8 +398,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   if (!cfg || !out || n_cells <= 0) return fail(RS_ERR_ARG, "rs_create: bad argument");
   *out = nullptr;
   const int algo = cfg->algo, S = cfg->n_slices, U = cfg->n_ues;
-  if (algo != 1 && algo != 7 && algo != 8 && algo != 9 && algo != 10 && algo != 11)
-    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 10 (UpperBound), 11 (NVS non-greedy)", algo);
+  if (algo != 1 && algo != 7 && algo != 11 && !is_transport(algo))
+    return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 10 (UpperBound), "
+                "11 (NVS non-greedy), 101 (SubOpt), 103 (VogelApproximate)", algo);
   if (S < 1 || S > RS_MAX_SLICES) return fail(RS_ERR_UNSUPPORTED, "n_slices %d outside 1..%d", S, RS_MAX_SLICES);
   if (U < 1 || U > 65000) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..65000", U);
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0)
@@ -499,7 +508,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   /* metric-table chunks: consecutive slices whose UEs fit the table */
   std::vector<int> chunks;
   int m_cap = 0;
-  if (algo == 8 || algo == 9 || algo == 10) {
+  if (is_transport(algo)) {
     const int cap = std::max(max_slice, std::min(U, 32));   /* small table: more cells resident per SM */
     chunks.push_back(0);
     int cur = 0;
@@ -528,8 +537,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   d.ng_ues = (algo == 11 || algo == 7) ? max_slice : 0;   /* id 7: required / held RBs per user of the served slice */
   /* rand() draws a TTI consumes per cell: transport.cpp:490,511 (ids 8/9); nvs.cpp:437-446 draws
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
-  d.rand_stride = (algo == 11) ? 300 * max_slice : ((algo == 8 || algo == 9 || algo == 10) ? 2 : 0);
-  const int min_sort_n = (algo == 10) ? 8 * G : 0;
+  d.rand_stride = (algo == 11) ? 300 * max_slice : (is_transport(algo) ? 2 : 0);
+  /* id 10 sorts G entries at a time next to the parked grants; ids 101/103 keep their scratch in the slot arrays */
+  const int min_sort_n = (algo == 10) ? 8 * G : ((algo == 101 || algo == 103) ? 16 * std::max(G, S) : 0);
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
   h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n)))
                       : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);
@@ -1005,7 +1015,8 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
                const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota) {
   if (!lg || !cqi || !rbg_to_ue || !tbs_bits) return fail(RS_ERR_ARG, "rs_log_tti: bad argument");
   const int U = lg->U, G = lg->G, S = lg->S, algo = lg->algo;
-  if ((algo == 8 || algo == 9) && (!slice_target || !slice_quota)) return fail(RS_ERR_ARG, "rs_log_tti: ids 8/9 need targets and quotas");
+  const bool tr = algo == 8 || algo == 9 || algo == 101 || algo == 103;   /* RBsAllocation's log lines */
+  if (tr && (!slice_target || !slice_quota)) return fail(RS_ERR_ARG, "rs_log_tti: ids 8/9/101/103 need targets and quotas");
   if (algo != 1 && !final_cqi) return fail(RS_ERR_ARG, "rs_log_tti: final_cqi missing");
   char buf[256];
   auto cqi_at = [&](int u, int g) -> int {   /* CQI on the first RB of RBG g, what :641 prints */
@@ -1023,10 +1034,10 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
   /* RBsAllocation only runs (and prints) when at least one user is schedulable (transport.cpp:152-168);
    * with every bearer idle nothing is allocated and nothing is printed */
   bool ran = scheduled > 0;
-  if (!ran && (algo == 8 || algo == 9))
+  if (!ran && tr)
     for (int s = 0; s < S; ++s) ran = ran || slice_target[s] != 0 || slice_quota[s] != 0;
   if (ran && algo != 1) {
-    if (algo == 8 || algo == 9) {
+    if (tr) {
       /* stdout, downlink-transport-scheduler.cpp:523-527 */
       lg->out += "slice_id, target_rbs, quota_rbgs: ";
       for (int s = 0; s < S; ++s) {

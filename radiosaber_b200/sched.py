@@ -242,7 +242,7 @@ class Scheduler:
                 out["alloc_n"] = np.empty(lead, np.int32)
                 out["alloc_ue"] = np.empty(lead + (2 * G,), np.int16)
                 out["alloc_rbg"] = np.empty(lead + (2 * G,), np.int16)
-            if self.algo in (8, 9, 10):
+            if self.algo in (8, 9, 10, 101, 103):
                 out["slice_target"] = np.empty(lead + (S,), np.int32)
                 out["slice_quota"] = np.empty(lead + (S,), np.int32)
             if self.algo in (7, 11):

@@ -34,7 +34,7 @@ def replay_golden(sched, rec, check_final_cqi=True):
     algo, T = int(rec["algo"]), int(rec["T"])
     bad = []
     sched.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
-                    slice_offset=rec["state_before"][0][None] if algo in (8, 9, 10) else None,
+                    slice_offset=rec["state_before"][0][None] if algo in (8, 9, 10, 101, 103) else None,
                     nvs_ewma=rec["state_before"][0][None] if algo in (7, 11) else None)
     for t in range(T):
         # id 11: every rand() value of the 300-sample search (downlink-nvs-scheduler.cpp:437-446)
@@ -63,7 +63,7 @@ def replay_golden(sched, rec, check_final_cqi=True):
         chk("tx_bytes", st["tx_bytes"][0], rec["tx_after"][t])
         chk("cum_bytes", st["cum_bytes"][0], rec["cum_bytes"][t])
         chk("cum_rbs", st["cum_rbs"][0], rec["cum_rbs"][t])
-        if algo in (8, 9, 10):
+        if algo in (8, 9, 10, 101, 103):
             if "slice_target" in out:
                 chk("slice_target", out["slice_target"][0], rec["target"][t])
                 chk("slice_quota", out["slice_quota"][0], rec["quota"][t])

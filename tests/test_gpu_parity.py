@@ -121,7 +121,7 @@ def _mk(algo, S, ues_per_slice, weights, params, B, seed, T, cqi_per_rb=0, with_
         sa, sb = o.get_state(), g.get_state()
         for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs"):
             assert np.array_equal(sa[k], sb[k]), (t, k)
-        if algo in (8, 9, 10):
+        if algo in (8, 9, 10, 101, 103):
             assert np.array_equal(sa["slice_offset"], sb["slice_offset"]), t
         if algo in (7, 11):
             assert np.array_equal(sa["nvs_ewma"], sb["nvs_ewma"]), t
@@ -132,13 +132,13 @@ PF = [0, 0, 1, 1]
 MT = [0, 0, 1, 0]
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10, 101, 103])
 def test_headline_shape_20x5(algo):
     S = 20
     _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 10])
+@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103])
 def test_mixed_enterprise_schedulers_diff_weights(algo):
     S = 20
     w = np.array([0.025] * 10 + [0.075] * 10)
@@ -169,7 +169,7 @@ def test_wide_cells_all_ids(algo, layout):
     _mk(algo, S, [40] * S, w, p, B=4, seed=700 + algo, T=5, cqi_per_rb=layout, with_active=(layout == 1))
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10, 101, 103])
 @pytest.mark.parametrize("layout", [0, 1])
 def test_queue_aware_enterprise_schedulers(algo, layout):
     """per-TTI queue sizes and head-of-line delays; slices with alpha/beta set (HoL-weighted
@@ -181,6 +181,14 @@ def test_queue_aware_enterprise_schedulers(algo, layout):
         with_active=(layout == 1))
 
 
+@pytest.mark.parametrize("S,n", [(14, 3), (20, 2), (31, 2), (40, 2), (61, 1), (64, 2)])
+def test_subopt_many_slices_hashtable_order(S, n):
+    """SubOpt's tie-break is std::unordered_map iteration order: cross the 13 / 29 / 59 bucket counts."""
+    rng = np.random.default_rng(S)
+    w = rng.dirichlet(np.ones(S) * 0.4)
+    _mk(101, S, [n] * S, w, np.tile(PF, (S, 1)), B=12, seed=1200 + S, T=10, with_active=True)
+
+
 @pytest.mark.parametrize("algo", [9, 8, 7, 1])
 def test_queue_aware_wide_cells(algo):
     S = 12
@@ -190,14 +198,14 @@ def test_queue_aware_wide_cells(algo):
     _mk(algo, S, [40] * S, w, p, B=3, seed=950 + algo, T=4, with_queue=True)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10, 101, 103])
 def test_inactive_bearers_and_empty_cells(algo):
     S = 8
     w = np.full(S, 1.0 / S)
     _mk(algo, S, [4] * S, w, np.tile(PF, (S, 1)), B=10, seed=300 + algo, T=12, with_active=True)
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10])
+@pytest.mark.parametrize("algo", [9, 8, 7, 1, 11, 10, 101, 103])
 def test_per_rb_cqi_layout(algo):
     S = 6
     w = np.full(S, 1.0 / S)

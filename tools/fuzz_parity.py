@@ -16,7 +16,7 @@ from radiosaber_b200 import sched, workload  # noqa: E402
 
 
 def one_case(rng, case):
-    algo = int(rng.choice([9, 9, 9, 8, 7, 1, 10, 11]))
+    algo = int(rng.choice([9, 9, 9, 8, 7, 1, 10, 11, 101, 103]))
     S = int(rng.integers(1, 33))
     ues = rng.integers(1, 9 if algo == 11 else 13, S)
     if rng.random() < 0.15:
@@ -62,7 +62,7 @@ def one_case(rng, case):
                 return f"case {case}: id {algo} S {S} U {U} layout {layout} queue {queue_aware} tti {t}: {k} differs"
     sa, sb = o.get_state(), g.get_state()
     for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs", "slice_offset", "nvs_ewma"):
-        if k == "slice_offset" and algo not in (8, 9, 10):
+        if k == "slice_offset" and algo not in (8, 9, 10, 101, 103):
             continue
         if k == "nvs_ewma" and algo not in (7, 11):
             continue

@@ -120,6 +120,13 @@ CASES = [
     ("a1_qmix_synth", 1, "QMIX", 160, "synth", 24),
     ("a10_qmix_synth", 10, "QMIX", 120, "synth", 25),
     ("a11_qmix_synth", 11, "QMIX", 60, "synth", 26),
+    # SubOpt (101) and VogelApproximate (103): DownlinkTransportScheduler(config, 1 / 3), no scenario id
+    ("a101_fix20x5_synth", 101, FIX20X5, 50, "synth", 41),
+    ("a101_diffw_synth", 101, DIFFW, 24, "synth", 42),
+    ("a101_small_synth", 101, "SMALL", 100, "synth", 43),
+    ("a103_fix20x5_synth", 103, FIX20X5, 50, "synth", 44),
+    ("a103_diffw_synth", 103, DIFFW, 24, "synth", 45),
+    ("a103_small_synth", 103, "SMALL", 100, "synth", 46),
     ("a9_qif_synth", 9, "QIF", 160, "synth", 31),
     ("a8_qif_synth", 8, "QIF", 120, "synth", 32),
     ("a7_qif_synth", 7, "QIF", 200, "synth", 33),
@@ -196,7 +203,7 @@ def run_case(name, algo, config, n_ttis, source, seed, tmp):
             ue[t, :k], rb[t, :k] = pairs[:, 0], pairs[:, 1]
         assert pos == len(raw) and cnt.max() <= 2 * G
         rec["alloc_n"], rec["alloc_ue"], rec["alloc_rbg"] = cnt, ue, rb
-    if algo in (8, 9, 10):
+    if algo in (8, 9, 10, 101, 103):
         assert (rec["rand2"] == rand2).all(), "scripted rand() values were not the ones consumed"
     rec["config_json"] = json.dumps(cfg)
     rec["source"] = source

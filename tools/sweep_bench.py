@@ -88,9 +88,9 @@ def main():
         pf = np.tile(np.array([0, 0, 1, 1], dtype=np.int32), (S, 1))
         mix = pf.copy()
         mix[1::2, 3] = 0      # every other slice MT (max-CI): eps 1, psi 0
-        for algo in (9, 8, 7, 1, 11, 10):
+        for algo in (9, 8, 7, 1, 11, 10, 101, 103):
             emit(measure(algo, w, pf, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF"))
-            if algo not in (1, 11, 10):
+            if algo not in (1, 11, 10, 101, 103):
                 emit(measure(algo, w, mix, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF/MT mix"))
     if args.only in (None, "sweep"):
         for S in (5, 10, 15, 20, 30, 40, 50):
