@@ -224,6 +224,15 @@ def run_cuda_arm(args, n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's "NCCL version ..." banner at
+    # communicator creation, for one) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -375,8 +384,8 @@ def run_cuda_arm(args, n_gpus):
 
     if args.kernel_only:   # development aid: the device-resident number alone (not a valid bench line)
         if rank == 0:
-            print(json.dumps({"kernel_only": True, "value": value, "ms_per_step": ms_max / K,
-                              "smem_bytes_per_cta": g.smem_bytes, "clocks": sampler.result()}))
+            emit({"kernel_only": True, "value": value, "ms_per_step": ms_max / K,
+                  "smem_bytes_per_cta": g.smem_bytes, "clocks": sampler.result()})
         g.close()
         if world > 1:
             dist.destroy_process_group()
@@ -421,7 +430,7 @@ def run_cuda_arm(args, n_gpus):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(args)
-        print(json.dumps(line))
+        emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()
