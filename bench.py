@@ -240,6 +240,18 @@ def run_cuda_arm(args, n_gpus):
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local_rank if world > 1 else 0)
+    if world > 1:
+        # one process per GPU: run on (and, by first touch, take pinned host memory from) the cores next to it,
+        # otherwise the end-to-end legs of all ranks pull their CQI through one socket
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev.index), (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            if cpus:
+                os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        except Exception:
+            pass
     B, TT, K, W = args.cells, args.ttis_per_step, args.steps, args.warmup
     w, p, u2s = slice_setup()
     g = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index)
