@@ -10,7 +10,11 @@
  *   RadioSaber MaximizeCell        transport.cpp:351-376 (std::sort order)
  *   Sequential GreedyByRow         transport.cpp:249-272
  *   NVS slice selection / argmax   nvs.cpp:94-142, 275-311
- *   No-slicing PF argmax           dlps.cpp:179-271
+ *   No-slicing PF argmax           dlps.cpp:179-271 (flow-satisfied cut-off :264-269 with finite queues)
+ *   UpperBound / SubOpt / Vogel    transport.cpp:223-246, 274-349, 378-451
+ *   NVS non-greedy PF search       nvs.cpp:405-528
+ *   queue-aware metrics            transport.cpp:694-711, nvs.cpp:384-386, packet-scheduler.cpp:321-334
+ *   trace-driven CQI               protocolStack/mac/enb-mac-entity.cc:160-193
  *   EESM -> CQI -> MCS -> TBS      transport.cpp:632-660, utility/eesm-effective-sinr.h:33-46,
  *                                  protocolStack/mac/AMCModule.cpp:252-317
  *   byte / RB accounting           transport.cpp:170-199, dl-pf-packet-scheduler.cpp:64-96,
