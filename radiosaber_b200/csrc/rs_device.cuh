@@ -722,9 +722,12 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
   if (o_fc) o_fc[u] = (uint8_t)fc;
 }
 
-/* Scratch of ids 101 / 103 in the (dead) slot arrays of the sort: at least 64 * max(G, S) bytes
+/* Scratch of ids 101 / 103 in the (dead) slot arrays of the sort; inter_scratch_bytes() of it
  * (make_layout's min_sort_n). */
+__host__ __device__ inline int inter_scratch_bytes(int G, int S) { return 128 + 12 * (G + S) + 8 * S + S + (S + 1) + 128 + 16; }
 struct InterScratch {
+  double* eff;             /* [16] AMC efficiency per CQI: lanes index it with different CQIs, which the constant
+                              cache would serialise */
   double* val;             /* [G + S] candidate gap / loss */
   int* pick;               /* [G + S] */
   int* over;               /* [S] RBGs above quota, 0 = not in the map */
@@ -737,6 +740,8 @@ __device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Cel
   InterScratch x;
   unsigned char* p = (unsigned char*)c.sb.posl;
   const int n = d.G + d.S;
+  x.eff = (double*)p;
+  p += 128;
   x.val = (double*)p;
   x.pick = (int*)(p + 8 * n);
   x.over = x.pick + n;
@@ -747,7 +752,9 @@ __device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Cel
   return x;
 }
 /* efficiency of the (rbg, slice) pair: the slice winner's, 0 for a slice without a listed user */
-__device__ __forceinline__ double pair_eff(const Cell& c, int S, int g, int s) { return c_tab.eff[c.sb.a[g * S + s] >> 12]; }
+__device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x, int S, int g, int s) {
+  return x.eff[c.sb.a[g * S + s] >> 12];
+}
 
 /* VogelApproximate, transport.cpp:378-451: G rounds; in each, every free RBG (thread g) and every slice with
  * quota left (thread G + s) reports the gap between its best and its "second" efficiency, then one thread walks
@@ -758,6 +765,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
   const InterScratch x = inter_scratch(d, c);
   int* held = c.wd;   /* free once the quotas exist; cleared again at the end of the TTI */
   for (int s = tid; s < S; s += kThreads) held[s] = 0;
+  if (tid < 16) x.eff[tid] = c_tab.eff[tid];
   __syncthreads();
   for (int round = 0; round < G; ++round) {
     for (int q = tid; q < G + S; q += kThreads) {
@@ -767,14 +775,14 @@ __device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
         if (c.outsl[q] == 0xff)
           for (int k = 0; k < S; ++k) {
             if (held[k] >= c.quota[k]) continue;
-            const double e = pair_eff(c, S, q, k);
+            const double e = pair_eff(c, x, S, q, k);
             if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
             if (e2 == -1 || e > e2) e2 = e;
           }
       } else if (held[q - G] < c.quota[q - G]) {
         for (int j = 0; j < G; ++j) {
           if (c.outsl[j] != 0xff) continue;
-          const double e = pair_eff(c, S, j, q - G);
+          const double e = pair_eff(c, x, S, j, q - G);
           if (e1 == -1 || e > e1) { first = j; e1 = e; continue; }
           if (e2 == -1 || e > e2) e2 = e;
         }
@@ -783,20 +791,39 @@ __device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
       x.pick[q] = first;
     }
     __syncthreads();
-    if (tid == 0) {
-      int max_diff = -1, gr = -1, gs = -1;
-      for (int q = 0; q < G + S; ++q) {
-        if (x.pick[q] < 0) continue;   /* an allocated RBG / a slice at its quota is skipped by the reference too */
-        if (x.val[q] > (double)max_diff) {
-          max_diff = (int)x.val[q];
-          if (q < G) { gr = q; gs = x.pick[q]; } else { gr = x.pick[q]; gs = q - G; }
+    if (tid < 32) {
+      /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int
+       * that is set to the (truncated) gap whenever a candidate is taken.  max_diff is therefore always the
+       * truncated largest gap seen so far (-1 before the first), so q is taken iff gap_q > trunc(max of the gaps
+       * before q) and the grant is the LAST candidate taken: a prefix maximum per 32 candidates. */
+      double run = -1.0;   /* largest gap so far; -1 = none (gaps are >= 0) */
+      int win = -1;
+      for (int q0 = 0; q0 < G + S; q0 += 32) {
+        const int q = q0 + tid;
+        const bool valid = q < G + S && x.pick[q] >= 0;   /* allocated RBGs / slices at their quota are skipped */
+        const double v = valid ? x.val[q] : -1.0;
+        double incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(kFull, incl, o);
+          if (tid >= o && up > incl) incl = up;
         }
+        double before = __shfl_up_sync(kFull, incl, 1);
+        if (tid == 0 || before < run) before = run;
+        const bool taken = valid && v > (double)(int)before;
+        const unsigned bal = __ballot_sync(kFull, taken);
+        if (bal) win = q0 + 31 - __clz(bal);
+        const double last = __shfl_sync(kFull, incl, 31);
+        if (last > run) run = last;
       }
-      if (gr >= 0) {
-        c.outsl[gr] = (unsigned char)gs;
-        held[gs] += 1;
+      if (tid == 0) {
+        if (win >= 0) {
+          const int gr = win < G ? win : x.pick[win], gs = win < G ? x.pick[win] : win - G;
+          c.outsl[gr] = (unsigned char)gs;
+          held[gs] += 1;
+        }
+        c.misc[12] = (win >= 0) ? 1u : 0u;
       }
-      c.misc[12] = (gr >= 0) ? 1u : 0u;
     }
     __syncthreads();
     if (!c.misc[12]) break;
@@ -813,12 +840,13 @@ __device__ void sub_opt(const DevCfg& d, const Cell& c) {
   const InterScratch x = inter_scratch(d, c);
   int* held = c.wd;
   for (int s = tid; s < S; s += kThreads) held[s] = 0;
+  if (tid < 16) x.eff[tid] = c_tab.eff[tid];
   __syncthreads();
   for (int g = tid; g < G; g += kThreads) {
     double best = -1;
     int pick = 0;
     for (int k = 0; k < S; ++k) {
-      const double e = pair_eff(c, S, g, k);
+      const double e = pair_eff(c, x, S, g, k);
       if (e > best) { best = e; pick = k; }
     }
     c.outsl[g] = (unsigned char)pick;
@@ -885,9 +913,9 @@ __device__ void sub_opt(const DevCfg& d, const Cell& c) {
       int to = -1;
       const int from = c.outsl[g];
       if (x.over[from] > 0) {
-        const double mine = pair_eff(c, S, g, from);
+        const double mine = pair_eff(c, x, S, g, from);
         for (int q = 0; q < n_under; ++q) {
-          const double loss = __dsub_rn(mine, pair_eff(c, S, g, x.order[q]));
+          const double loss = __dsub_rn(mine, pair_eff(c, x, S, g, x.order[q]));
           if (loss < least) { least = loss; to = x.order[q]; }
         }
       }

@@ -539,7 +539,8 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
   d.rand_stride = (algo == 11) ? 300 * max_slice : (is_transport(algo) ? 2 : 0);
   /* id 10 sorts G entries at a time next to the parked grants; ids 101/103 keep their scratch in the slot arrays */
-  const int min_sort_n = (algo == 10) ? 8 * G : ((algo == 101 || algo == 103) ? 16 * std::max(G, S) : 0);
+  const int min_sort_n = (algo == 10) ? 8 * G
+                         : ((algo == 101 || algo == 103) ? (rs::inter_scratch_bytes(G, S) + 3) / 4 : 0);   /* posl + posr = 4 n bytes */
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
   h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n)))
                       : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);

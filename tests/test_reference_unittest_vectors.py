@@ -47,6 +47,14 @@ def test_cuda_maximize_cell_on_the_reference_unittest_matrix():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("algo", [8, 10, 101, 103])
+def test_cuda_other_inter_slice_algorithms_on_the_unittest_matrix(algo):
+    """The same tiny cell (5 RBGs, 3 slices: far below the 64 x 20 the scratch buffers are sized for in the other
+    tests) under the other inter-slice algorithms: CUDA == oracle."""
+    assert _cell(sched.Scheduler, algo) == _cell(OracleScheduler, algo)
+
+
+@pytest.mark.gpu
 def test_cuda_link_adaptation_on_the_reference_unittest_vector():
     """Seven RBs whose CQI maps to >= 20 dB and one at the CQI of 8 dB cannot be fed as dB values (the path takes
     CQI); instead the same vector through CQI: the device EESM/TBS of one UE holding 8 one-RB RBGs equals the oracle's."""
