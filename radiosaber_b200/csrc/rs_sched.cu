@@ -320,13 +320,14 @@ int ensure_dt(rs_handle* h, const double* dt, int n) {
   return RS_OK;
 }
 
-int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active, bool want_cqi) {
+int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, bool want_active, bool want_cqi,
+               bool want_queue, bool want_hol) {
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   if (want_cqi) CU(s.cqi.alloc((size_t)T * B * U * C));
   CU(s.rand2.alloc((size_t)T * B * std::max(h->d.rand_stride, 1)));
   if (want_active) CU(s.active.alloc((size_t)T * B * U));
-  if (h->q_next) CU(s.queue.alloc((size_t)T * B * U));
-  if (h->hol_next) CU(s.hol.alloc((size_t)T * B * U));
+  if (want_queue) CU(s.queue.alloc((size_t)T * B * U));
+  if (want_hol) CU(s.hol.alloc((size_t)T * B * U));
   if (out) {
     if (out->rbg_to_ue) CU(s.rbg_to_ue.alloc((size_t)T * B * G));
     if (out->tbs_bits) CU(s.tbs_bits.alloc((size_t)T * B * U));
@@ -687,7 +688,13 @@ namespace {
 int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                     const int32_t* trace_row, const int32_t* d_rand2, const uint8_t* d_active,
                     int64_t active_tti_stride, const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch) {
-  if (!h || (!d_cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  /* rs_set_queues: consumed by this call whether it succeeds or not */
+  const int32_t* d_queue = h->q_next;
+  const double* d_hol = h->hol_next;
+  h->q_next = nullptr;
+  h->hol_next = nullptr;
+  if ((!d_cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_device: bad argument");
   if (h->d.rand_stride > 0 && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (!trace_row && (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3))) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
@@ -698,10 +705,6 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   if (ttis_per_launch <= 0) ttis_per_launch = 16;
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
-  const int32_t* d_queue = h->q_next;
-  const double* d_hol = h->hol_next;
-  h->q_next = nullptr;
-  h->hol_next = nullptr;
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
     a.T = std::min(ttis_per_launch, n_ttis - t0);
@@ -743,7 +746,13 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
 int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* trace_row,
                   const int32_t* rand2, const uint8_t* active, const double* dt, const rs_outputs* out,
                   int32_t ttis_per_launch) {
-  if (!h || (!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  /* rs_set_queues: consumed by this call whether it succeeds or not */
+  const int32_t* queue = h->q_next;
+  const double* hol = h->hol_next;
+  h->q_next = nullptr;
+  h->hol_next = nullptr;
+  if ((!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
   if (h->d.rand_stride > 0 && !rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
@@ -754,11 +763,10 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   int rc = ensure_dt(h, dt, n_ttis);
   if (rc != RS_OK) return rc;
   if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
-  for (auto& s : h->slot) { rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr); if (rc != RS_OK) return rc; }
-  const int32_t* queue = h->q_next;
-  const double* hol = h->hol_next;
-  h->q_next = nullptr;
-  h->hol_next = nullptr;
+  for (auto& s : h->slot) {
+    rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr, queue != nullptr, hol != nullptr);
+    if (rc != RS_OK) return rc;
+  }
   cudaEvent_t dt_ready;
   CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
   CU(cudaEventRecord(dt_ready, h->stream));
