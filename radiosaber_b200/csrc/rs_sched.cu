@@ -15,9 +15,13 @@
 #undef RS_NS
 #undef RS_THREADS
 #undef RS_MIN_BLOCKS
+#ifndef RS_WIDE_THREADS
+#define RS_WIDE_THREADS 512
+#define RS_WIDE_MIN_BLOCKS 2
+#endif
 #define RS_NS rsw
-#define RS_THREADS 512
-#define RS_MIN_BLOCKS 2
+#define RS_THREADS RS_WIDE_THREADS
+#define RS_MIN_BLOCKS RS_WIDE_MIN_BLOCKS
 #define RS_CORE_ONLY
 #include "rs_device.cuh"
 #undef RS_NS
