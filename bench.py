@@ -316,7 +316,9 @@ def run_cuda_arm(args, n_gpus):
     import ctypes as C
     TE = args.e2e_ttis
     KE = max(2, min(K, args.e2e_steps))
-    _, dte = workload.tti_clock(TE)
+    # one continuing TTI clock over all calls (warm-up included), like the device-resident leg: restarting it would
+    # hand every call a first TTI with dt = 7e-17 s and a non-zero byte count, i.e. a burst in the EWMA rates
+    now_e, dte_all = workload.tti_clock((2 + KE) * TE)
 
     def e2e_run(layout, refresh):
         ge = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index, cqi_per_rb=layout)
@@ -335,19 +337,20 @@ def run_cuda_arm(args, n_gpus):
         h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
         o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
 
-        def one():
+        def one(k):
+            dte = dte_all[k * TE:(k + 1) * TE]
             sched._check(sched.lib().rs_run_host(ge._h, TE, C.c_void_p(h_cqi.data_ptr()), refresh,
                                                  C.c_void_p(h_r2.data_ptr()), None, dte.ctypes.data_as(C.c_void_p),
                                                  C.byref(o), args.e2e_ttis_per_launch))
 
-        for _ in range(2):
-            one()
+        for k in range(2):
+            one(k)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(KE):
-            one()          # synchronous: returns when the results are in host memory
+        for k in range(2, 2 + KE):
+            one(k)          # synchronous: returns when the results are in host memory
         torch.cuda.synchronize(dev)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -365,8 +368,7 @@ def run_cuda_arm(args, n_gpus):
         rng = np.random.default_rng(SEED + rank)
         traces = np.repeat(workload.histogram_cqi(rng, (158, 475, G)), 8, axis=2)
         ge.set_traces(traces, rng.integers(0, 158, (B, U)).astype(np.int32))
-        now, _ = workload.tti_clock(TE)
-        rows = sched.trace_rows_for_run(now, 0)
+        rows_all = sched.trace_rows_for_run(now_e, 0)
         h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
         h_r2.copy_(torch.from_numpy(workload.synth_rand2(SEED, cell0, B, 0, TE, S)))
         h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
@@ -374,19 +376,20 @@ def run_cuda_arm(args, n_gpus):
         h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
         o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
 
-        def one():
+        def one(k):
+            rows, dte = rows_all[k * TE:(k + 1) * TE], dte_all[k * TE:(k + 1) * TE]
             sched._check(sched.lib().rs_run_traces_host(ge._h, TE, rows.ctypes.data_as(C.c_void_p),
                                                         C.c_void_p(h_r2.data_ptr()), None,
                                                         dte.ctypes.data_as(C.c_void_p), C.byref(o), args.e2e_trace_ttis_per_launch))
 
-        for _ in range(2):
-            one()
+        for k in range(2):
+            one(k)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(KE):
-            one()
+        for k in range(2, 2 + KE):
+            one(k)
         torch.cuda.synchronize(dev)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
