@@ -771,9 +771,6 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr, queue != nullptr, hol != nullptr);
     if (rc != RS_OK) return rc;
   }
-  cudaEvent_t dt_ready;
-  CU(cudaEventCreateWithFlags(&dt_ready, cudaEventDisableTiming));
-  CU(cudaEventRecord(dt_ready, h->stream));
   int k = 0;
   h->slot[0].slab0 = h->slot[1].slab0 = -1;
   for (int t0 = 0, T = 0; t0 < n_ttis; t0 += T, ++k) {
@@ -846,7 +843,6 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   CU(cudaStreamSynchronize(h->copy_out));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaStreamSynchronize(h->copy_in));
-  cudaEventDestroy(dt_ready);
   return RS_OK;
 }
 }  // namespace
