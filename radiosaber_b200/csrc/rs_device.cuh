@@ -627,33 +627,26 @@ __device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int
  * ran out.  c.quota is consumed (the host-visible quotas were written by slice_quotas). */
 __device__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
   const int n = d.sort_n;
-  const unsigned lt = (1u << lane) - 1u;
   int nfree = d.G;
   for (int base = 0; base < n && nfree > 0; base += 32) {
     const int i = base + lane;
     const unsigned e = (i < n) ? sorted[i] : 0u;
     const int g = (e >> 6) & 63, s = e & 63;
     int rem = c.quota[s];
-    bool cand = (i < n) && c.outsl[g] == 0xff && rem > 0;
-    /* Batches instead of one entry per round: as long as every candidate's rank among the candidates of its own
-     * slice stays below that slice's remaining quota, the quota cannot bind, and the first fit takes exactly the
-     * first candidate of every RBG.  The batch ends before the first lane where the quota might bind; that lane
-     * is looked at again with the exact state in the next round. */
-    while (__any_sync(kFull, cand)) {
-      const unsigned ms = __match_any_sync(kFull, cand ? s : 64 + lane);
-      const int rank = __popc(ms & lt);
-      const unsigned vb = __ballot_sync(kFull, cand && rank >= rem);
-      const unsigned batch = vb ? ((1u << (__ffs(vb) - 1)) - 1u) : kFull;
-      const bool inb = cand && ((batch >> lane) & 1u);
-      const unsigned mg = __match_any_sync(kFull, inb ? g : 64 + lane);
-      const bool acc = inb && (mg & lt) == 0;
-      const unsigned ab = __ballot_sync(kFull, acc);
-      if (acc) c.outsl[g] = (unsigned char)s;
-      rem -= __popc(ms & ab);
-      if (cand && rank == 0) c.quota[s] = rem;
-      nfree -= __popc(ab);
-      __syncwarp();
-      cand = cand && !inb && rem > 0 && c.outsl[g] == 0xff;
+    bool feas = (i < n) && c.outsl[g] == 0xff && rem > 0;
+    unsigned v = feas ? (((unsigned)lane << 12) | (e & 0xfffu)) : 0xffffffffu;
+    unsigned w = __reduce_min_sync(kFull, v);
+    while (w != 0xffffffffu) {
+      const int pg = (w >> 6) & 63, ps = w & 63, ld = (int)(w >> 12);
+      if (s == ps) rem--;
+      if (lane == ld) {
+        c.outsl[pg] = (unsigned char)ps;
+        c.quota[ps] = rem;
+      }
+      nfree--;
+      feas = feas && lane != ld && g != pg && rem > 0;
+      if (!feas) v = 0xffffffffu;
+      w = __reduce_min_sync(kFull, v);
     }
     __syncwarp();
   }
