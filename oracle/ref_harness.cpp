@@ -437,8 +437,9 @@ struct Installer {
     PacketScheduler* s = nullptr;
 #ifdef RS_WITH_GPU_ADAPTOR
     if (g_opt.gpu) {
-      if (g_opt.algo != 1 && g_opt.algo != 7 && g_opt.algo != 8 && g_opt.algo != 9) {
-        fprintf(stderr, "the host plug-in covers ids 1, 7, 8, 9\n");
+      if (g_opt.algo != 1 && g_opt.algo != 7 && g_opt.algo != 8 && g_opt.algo != 9 && g_opt.algo != 10 &&
+          g_opt.algo != 101 && g_opt.algo != 103) {
+        fprintf(stderr, "the host plug-in covers ids 1, 7, 8, 9, 10, 101, 103\n");
         exit(2);
       }
       s = new ObservedGpu(g_opt.config, g_opt.algo);

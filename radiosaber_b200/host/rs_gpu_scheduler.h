@@ -8,6 +8,7 @@
  *       scheduler = new RsGpuScheduler(config_fname, 1);   // was DL_PF_PacketScheduler(config_fname)
  *     case ENodeB::DLScheduler_MAXCELL:      // id 9
  *       scheduler = new RsGpuScheduler(config_fname, 9);   // was DownlinkTransportScheduler(config_fname, 2)
+ *   (likewise 7 NVS, 8 Sequential, 10 UpperBound, 101 SubOpt, 103 VogelApproximate; id 11 is batch-only)
  *
  * What stays on the host, done by the reference's own objects exactly as before:
  *   - RadioBearer::UpdateAverageTransmissionRate / UpdateTransmittedBytes / UpdateCumulateRBs
@@ -64,13 +65,14 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<SchedulerAlgoParam> slice_algo_params_;
   std::vector<double> slice_state_; /* slice_rbs_offset_ (ids 8/9) or slice_ewma_time_ (id 7) */
 
-  /* scheduler_id: 1 No-Slicing PF, 7 NVS, 8 Sequential, 9 RadioSaber (single-cell-with-interference.h:95-110).
+  /* scheduler_id: 1 No-Slicing PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound (single-cell-with-interference.h:95-110),
+   * and 101 SubOpt / 103 VogelApproximate, the two inter-slice algorithms ENodeB.cpp:363-379 can install.
    * Id 1 replaces DL_PF_PacketScheduler(config_fname) (ENodeB.cpp:309-313); that class schedules flows
    * (FlowToSchedule, one per bearer), which with one bearer per UE is the same list as the users kept here.
    * Bearers may be backlogged or have finite queues (internet flows, video); two bearers on one UE throw. */
   RsGpuScheduler(std::string config_fname, int scheduler_id) : id_(scheduler_id) {
-    if (id_ != 1 && id_ != 7 && id_ != 8 && id_ != 9)
-      throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8 or 9");
+    if (id_ != 1 && id_ != 7 && !Transport())
+      throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8, 9, 10, 101 or 103");
     std::ifstream ifs(config_fname);
     if (!ifs.is_open()) throw std::runtime_error("Fail to open configuration file.");
     Json::Reader reader;
@@ -148,8 +150,12 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<uint8_t> cqi_, active_, mcs_, final_cqi_;
   std::vector<double> avg_, hol_;   /* hol_: head-of-line delay of each listed bearer */
   std::vector<int32_t> queue_;      /* dataToTransmit of each listed bearer, 0 = not listed */
-  std::vector<int16_t> rbg_to_ue_;
+  std::vector<int16_t> rbg_to_ue_, grant_ue_, grant_rbg_;
   std::vector<int32_t> bits_, target_, quota_;
+
+  /* DownlinkTransportScheduler with one of its inter-slice algorithms (ENodeB.cpp:357-385): 8 Sequential,
+   * 9 MaximizeCell (RadioSaber), 10 UpperBound, 101 SubOpt, 103 VogelApproximate */
+  bool Transport() const { return id_ == 8 || id_ == 9 || id_ == 10 || id_ == 101 || id_ == 103; }
 
   static void Check(int rc, const char* what) {
     if (rc != RS_OK) throw std::runtime_error(std::string("RsGpuScheduler: ") + what + ": " + rs_last_error());
@@ -252,12 +258,12 @@ class RsGpuScheduler : public PacketScheduler {
   void RBsAllocation() {
     const int U = (int)user_to_slice_.size(), S = num_slices_;
     int32_t rand2[2] = {0, 0};
-    if (id_ == 8 || id_ == 9) { /* the two draws of :490 and :511, in the reference's order */
+    if (Transport()) { /* the two draws of :490 and :511, in the reference's order */
       rand2[0] = rand();
       rand2[1] = rand();
     }
     std::vector<double> state(slice_state_);
-    Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, (id_ == 8 || id_ == 9) ? state.data() : nullptr,
+    Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, Transport() ? state.data() : nullptr,
                        id_ == 7 ? state.data() : nullptr), "rs_set_state");
     rs_outputs out = {};
     int32_t nvs_slice = -1;
@@ -268,12 +274,20 @@ class RsGpuScheduler : public PacketScheduler {
     out.slice_target = target_.data();
     out.slice_quota = quota_.data();
     out.nvs_slice = &nvs_slice;
+    int32_t n_grants = 0;
+    if (id_ == 10) { /* UpperBound books an RBG to several slices: the grants come back as a list */
+      grant_ue_.assign(2 * (size_t)n_rbgs_, -1);
+      grant_rbg_.assign(2 * (size_t)n_rbgs_, -1);
+      out.alloc_n = &n_grants;
+      out.alloc_ue = grant_ue_.data();
+      out.alloc_rbg = grant_rbg_.data();
+    }
     /* queue state of this TTI: finite queues cap the bytes, bind id 7's required-RBs guard and id 1's
      * flow-satisfied cut-off, and the head-of-line delay enters the metric of alpha/beta slices */
     Check(rs_set_queues(h_, queue_.data(), hol_.data()), "rs_set_queues");
     /* dt = 0: the EWMA was applied by the bearers themselves a few lines up */
     Check(rs_step(h_, cqi_.data(), rand2, active_.data(), 0.0, &out), "rs_step");
-    Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, (id_ == 8 || id_ == 9) ? slice_state_.data() : nullptr,
+    Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, Transport() ? slice_state_.data() : nullptr,
                        id_ == 7 ? slice_state_.data() : nullptr), "rs_get_state");
 
     UsersToSchedule* users = GetUsersToSchedule();
@@ -288,10 +302,19 @@ class RsGpuScheduler : public PacketScheduler {
     }
     std::vector<UserToSchedule*> by_id(U, nullptr);
     for (auto it = users->begin(); it != users->end(); ++it) by_id[(*it)->GetUserID()] = *it;
-    for (int g = 0; g < n_rbgs_; ++g) {
-      const int ue = rbg_to_ue_[g];
-      if (ue < 0 || !by_id[ue]) continue;
-      for (int r = g * rbg_size_; r < (g + 1) * rbg_size_; ++r) by_id[ue]->GetListOfAllocatedRBs()->push_back(r);
+    if (id_ == 10) {
+      if (n_grants > 2 * n_rbgs_) throw std::runtime_error("RsGpuScheduler: more grants than the list holds");
+      for (int k = 0; k < n_grants; ++k) {   /* per user in grant order, like the reference fills the RB lists */
+        const int ue = grant_ue_[k], g = grant_rbg_[k];
+        if (ue < 0 || ue >= U || !by_id[ue]) continue;
+        for (int r = g * rbg_size_; r < (g + 1) * rbg_size_; ++r) by_id[ue]->GetListOfAllocatedRBs()->push_back(r);
+      }
+    } else {
+      for (int g = 0; g < n_rbgs_; ++g) {
+        const int ue = rbg_to_ue_[g];
+        if (ue < 0 || !by_id[ue]) continue;
+        for (int r = g * rbg_size_; r < (g + 1) * rbg_size_; ++r) by_id[ue]->GetListOfAllocatedRBs()->push_back(r);
+      }
     }
     PdcchMapIdealControlMessage* pdcch = new PdcchMapIdealControlMessage();
     if (id_ != 1) std::cout << GetTimeStamp() << std::endl;   /* DownlinkPacketScheduler::RBsAllocation prints nothing */

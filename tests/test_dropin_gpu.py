@@ -1,7 +1,7 @@
 """GPU: the drop-in itself.  oracle/_ref/ref_harness_gpu is the reference's own LTE-Sim
 (SingleCellWithI scenario, unmodified sources) with the product's host plug-in
 (radiosaber_b200/host/rs_gpu_scheduler.h -> C ABI -> CUDA) installed in the eNB instead of the
-reference scheduler class.  It must reproduce, record for record, what the reference classes
+reference scheduler class (ids 1, 7, 8, 9, 10, 101, 103).  It must reproduce, record for record, what the reference classes
 produced on the same CQI / rand() inputs (tests/golden)."""
 import json
 import os
@@ -19,7 +19,11 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")
 CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_diffw_trace", "a9_small_synth", "a8_fix20x5_synth", "a8_small_synth",
          "a7_fix20x5_synth", "a7_mix20_synth", "a7_small_synth", "a1_fix20x5_synth", "a1_small_synth",
          # finite queues and head-of-line delays (internet flows): the plug-in reads them from the bearers
-         "a9_qif_synth", "a8_qif_synth", "a7_qif_synth", "a1_qif_synth"]
+         "a9_qif_synth", "a8_qif_synth", "a7_qif_synth", "a1_qif_synth",
+         # the other inter-slice algorithms of DownlinkTransportScheduler: UpperBound (grants as a list), SubOpt, Vogel
+         "a10_fix20x5_synth", "a10_diffw_synth", "a10_small_synth", "a10_qif_synth",
+         "a101_fix20x5_synth", "a101_diffw_synth", "a101_small_synth", "a101_qif_synth",
+         "a103_fix20x5_synth", "a103_diffw_synth", "a103_small_synth", "a103_qif_synth"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -41,17 +45,29 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
     np.ascontiguousarray(rec["cqi"], dtype=np.uint8).tofile(tmp_path / "cqi.bin")
     np.ascontiguousarray(rec["rand2"], dtype=np.int32).tofile(tmp_path / "rand.bin")
     out = tmp_path / "rec.bin"
-    r = subprocess.run([HARNESS, "--gpu", "--algo", str(int(rec["algo"])), "--config", str(tmp_path / "cfg.json"),
+    algo = int(rec["algo"])
+    extra = ["--alloc-log", str(tmp_path / "alloc.bin")] if algo == 10 else []
+    r = subprocess.run([HARNESS, "--gpu", "--algo", str(algo), "--config", str(tmp_path / "cfg.json"),
                         "--ttis", str(T), "--cqi", str(tmp_path / "cqi.bin"), "--rand", str(tmp_path / "rand.bin"),
-                        "--out", str(out), "--seed", str(int(rec["seed"]))], capture_output=True, text=True, timeout=600)
+                        "--out", str(out), "--seed", str(int(rec["seed"]))] + extra, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
     got = golden_io.compact(golden_io.parse_record_stream(str(out)))
     assert int(got["T"]) == T
     fields = ["rbg_to_ue", "bits", "final_cqi", "avg_before", "avg_after", "tx_after", "cum_bytes", "cum_rbs",
               "state_before", "state_after", "dt"]
-    if int(rec["algo"]) in (8, 9):
+    if algo in (8, 9, 10, 101, 103):
         fields += ["target", "quota", "rand2"]
     if int(rec["algo"]) == 7:
         fields += ["nvs_slice"]
     for f in fields:
         assert np.array_equal(np.asarray(got[f]), np.asarray(rec[f])), (name, f)
+    if algo == 10:   # every (user, RBG) grant of every TTI, in the order of the users' RB lists
+        raw = np.fromfile(tmp_path / "alloc.bin", dtype="<i2")
+        pos = 0
+        for t in range(T):
+            k = int(raw[pos]) | (int(raw[pos + 1]) << 16)
+            pairs = raw[pos + 2:pos + 2 + 2 * k].reshape(k, 2)
+            pos += 2 + 2 * k
+            assert k == int(rec["alloc_n"][t]), (name, t)
+            assert np.array_equal(pairs[:, 0], rec["alloc_ue"][t, :k]) and np.array_equal(pairs[:, 1], rec["alloc_rbg"][t, :k]), (name, t)
+        assert pos == len(raw)

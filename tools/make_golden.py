@@ -131,6 +131,9 @@ CASES = [
     ("a8_qif_synth", 8, "QIF", 120, "synth", 32),
     ("a7_qif_synth", 7, "QIF", 200, "synth", 33),
     ("a1_qif_synth", 1, "QIF", 120, "synth", 34),
+    ("a10_qif_synth", 10, "QIF", 120, "synth", 35),
+    ("a101_qif_synth", 101, "QIF", 120, "synth", 36),
+    ("a103_qif_synth", 103, "QIF", 120, "synth", 37),
 ]
 
 
