@@ -417,7 +417,7 @@ class ObservedGpu : public RsGpuScheduler {
         [this](std::vector<double>& st) { for (int s = 0; s < num_slices_; ++s) st[s] = slice_state_[s]; },
         [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t& nvs, int rbg) {
           CollectUsers(GetUsersToSchedule(), active, r2u, bits, rbg);
-          if (id_ == 7) {
+          if (id_ == 7 || id_ == 11) {
             std::fill(active.begin(), active.end(), (uint8_t)1);
             if (!GetUsersToSchedule()->empty())
               nvs = user_to_slice_[GetUsersToSchedule()->at(0)->GetUserID()];
@@ -438,8 +438,8 @@ struct Installer {
 #ifdef RS_WITH_GPU_ADAPTOR
     if (g_opt.gpu) {
       if (g_opt.algo != 1 && g_opt.algo != 7 && g_opt.algo != 8 && g_opt.algo != 9 && g_opt.algo != 10 &&
-          g_opt.algo != 101 && g_opt.algo != 103) {
-        fprintf(stderr, "the host plug-in covers ids 1, 7, 8, 9, 10, 101, 103\n");
+          g_opt.algo != 11 && g_opt.algo != 101 && g_opt.algo != 103) {
+        fprintf(stderr, "the host plug-in covers ids 1, 7, 8, 9, 10, 11, 101, 103\n");
         exit(2);
       }
       s = new ObservedGpu(g_opt.config, g_opt.algo);

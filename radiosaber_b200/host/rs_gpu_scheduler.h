@@ -8,7 +8,7 @@
  *       scheduler = new RsGpuScheduler(config_fname, 1);   // was DL_PF_PacketScheduler(config_fname)
  *     case ENodeB::DLScheduler_MAXCELL:      // id 9
  *       scheduler = new RsGpuScheduler(config_fname, 9);   // was DownlinkTransportScheduler(config_fname, 2)
- *   (likewise 7 NVS, 8 Sequential, 10 UpperBound, 101 SubOpt, 103 VogelApproximate; id 11 is batch-only)
+ *   (likewise 7 NVS, 8 Sequential, 10 UpperBound, 11 NVS non-greedy, 101 SubOpt, 103 VogelApproximate)
  *
  * What stays on the host, done by the reference's own objects exactly as before:
  *   - RadioBearer::UpdateAverageTransmissionRate / UpdateTransmittedBytes / UpdateCumulateRBs
@@ -71,8 +71,8 @@ class RsGpuScheduler : public PacketScheduler {
    * (FlowToSchedule, one per bearer), which with one bearer per UE is the same list as the users kept here.
    * Bearers may be backlogged or have finite queues (internet flows, video); two bearers on one UE throw. */
   RsGpuScheduler(std::string config_fname, int scheduler_id) : id_(scheduler_id) {
-    if (id_ != 1 && id_ != 7 && !Transport())
-      throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8, 9, 10, 101 or 103");
+    if (id_ != 1 && !Nvs() && !Transport())
+      throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8, 9, 10, 11, 101 or 103");
     std::ifstream ifs(config_fname);
     if (!ifs.is_open()) throw std::runtime_error("Fail to open configuration file.");
     Json::Reader reader;
@@ -151,10 +151,11 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<double> avg_, hol_;   /* hol_: head-of-line delay of each listed bearer */
   std::vector<int32_t> queue_;      /* dataToTransmit of each listed bearer, 0 = not listed */
   std::vector<int16_t> rbg_to_ue_, grant_ue_, grant_rbg_;
-  std::vector<int32_t> bits_, target_, quota_;
+  std::vector<int32_t> bits_, target_, quota_, draws_;
 
   /* DownlinkTransportScheduler with one of its inter-slice algorithms (ENodeB.cpp:357-385): 8 Sequential,
    * 9 MaximizeCell (RadioSaber), 10 UpperBound, 101 SubOpt, 103 VogelApproximate */
+  bool Nvs() const { return id_ == 7 || id_ == 11; }   /* DownlinkNVSScheduler(config, non_greedy), ENodeB.cpp:345-355 */
   bool Transport() const { return id_ == 8 || id_ == 9 || id_ == 10 || id_ == 101 || id_ == 103; }
 
   static void Check(int rc, const char* what) {
@@ -258,13 +259,39 @@ class RsGpuScheduler : public PacketScheduler {
   void RBsAllocation() {
     const int U = (int)user_to_slice_.size(), S = num_slices_;
     int32_t rand2[2] = {0, 0};
+    const int32_t* draws = rand2;
+    int host_slice = -1;
     if (Transport()) { /* the two draws of :490 and :511, in the reference's order */
       rand2[0] = rand();
       rand2[1] = rand();
+    } else if (id_ == 11) {
+      /* The non-greedy search draws 300 x (listed users of the served slice) libc rand() values
+       * (downlink-nvs-scheduler.cpp:437-446).  To take exactly that many from the process's stream the host must
+       * know the slice first: the choice of SelectSliceToServe (:94-127) from the credits it already holds.  The
+       * device makes the same choice from the same numbers; a disagreement throws below. */
+      std::vector<char> with_queue(S, 0);
+      for (int u = 0; u < U; ++u)
+        if (active_[u] && queue_[u] > 0) with_queue[user_to_slice_[u]] = 1;
+      double max_score = 0;
+      host_slice = 0;
+      for (int i = 0; i < S; ++i) {
+        if (!with_queue[i]) continue;
+        if (slice_state_[i] == 0) { host_slice = i; break; }
+        const double score = slice_weights_[i] / slice_state_[i];
+        if (score >= max_score) { max_score = score; host_slice = i; }
+      }
+      int listed = 0;
+      for (int u = 0; u < U; ++u)
+        if (active_[u] && queue_[u] > 0 && user_to_slice_[u] == host_slice) listed++;
+      const int stride = rs_rand_draws_per_cell_tti(h_);
+      if (300 * listed > stride) throw std::runtime_error("RsGpuScheduler: more rand() draws than the ABI takes");
+      draws_.assign((size_t)(stride > 2 ? stride : 2), 0);
+      for (int k = 0; k < 300 * listed; ++k) draws_[k] = rand();
+      draws = draws_.data();
     }
     std::vector<double> state(slice_state_);
     Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, Transport() ? state.data() : nullptr,
-                       id_ == 7 ? state.data() : nullptr), "rs_set_state");
+                       Nvs() ? state.data() : nullptr), "rs_set_state");
     rs_outputs out = {};
     int32_t nvs_slice = -1;
     out.rbg_to_ue = rbg_to_ue_.data();
@@ -286,12 +313,13 @@ class RsGpuScheduler : public PacketScheduler {
      * flow-satisfied cut-off, and the head-of-line delay enters the metric of alpha/beta slices */
     Check(rs_set_queues(h_, queue_.data(), hol_.data()), "rs_set_queues");
     /* dt = 0: the EWMA was applied by the bearers themselves a few lines up */
-    Check(rs_step(h_, cqi_.data(), rand2, active_.data(), 0.0, &out), "rs_step");
+    Check(rs_step(h_, cqi_.data(), draws, active_.data(), 0.0, &out), "rs_step");
+    if (id_ == 11 && nvs_slice != host_slice) throw std::runtime_error("RsGpuScheduler: host and device disagree on the NVS slice");
     Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, Transport() ? slice_state_.data() : nullptr,
-                       id_ == 7 ? slice_state_.data() : nullptr), "rs_get_state");
+                       Nvs() ? slice_state_.data() : nullptr), "rs_get_state");
 
     UsersToSchedule* users = GetUsersToSchedule();
-    if (id_ == 7) { /* only the served slice's users are "users to schedule" (downlink-nvs-scheduler.cpp:161-162) */
+    if (Nvs()) { /* only the served slice's users are "users to schedule" (downlink-nvs-scheduler.cpp:161-162) */
       for (auto it = users->begin(); it != users->end();) {
         if (user_to_slice_[(*it)->GetUserID()] != nvs_slice) { delete *it; it = users->erase(it); } else ++it;
       }

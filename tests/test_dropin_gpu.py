@@ -1,7 +1,7 @@
 """GPU: the drop-in itself.  oracle/_ref/ref_harness_gpu is the reference's own LTE-Sim
 (SingleCellWithI scenario, unmodified sources) with the product's host plug-in
 (radiosaber_b200/host/rs_gpu_scheduler.h -> C ABI -> CUDA) installed in the eNB instead of the
-reference scheduler class (ids 1, 7, 8, 9, 10, 101, 103).  It must reproduce, record for record, what the reference classes
+reference scheduler class (ids 1, 7, 8, 9, 10, 11, 101, 103).  It must reproduce, record for record, what the reference classes
 produced on the same CQI / rand() inputs (tests/golden)."""
 import json
 import os
@@ -23,7 +23,9 @@ CASES = ["a9_fix20x5_synth", "a9_diffw_synth", "a9_diffw_trace", "a9_small_synth
          # the other inter-slice algorithms of DownlinkTransportScheduler: UpperBound (grants as a list), SubOpt, Vogel
          "a10_fix20x5_synth", "a10_diffw_synth", "a10_small_synth", "a10_qif_synth",
          "a101_fix20x5_synth", "a101_diffw_synth", "a101_small_synth", "a101_qif_synth",
-         "a103_fix20x5_synth", "a103_diffw_synth", "a103_small_synth", "a103_qif_synth"]
+         "a103_fix20x5_synth", "a103_diffw_synth", "a103_small_synth", "a103_qif_synth",
+         # NVS non-greedy: the plug-in takes 300 x (listed users of the served slice) rand() values per TTI from the process
+         "a11_fix20x5_synth", "a11_small_synth", "a11_qif_synth"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -47,6 +49,8 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
     out = tmp_path / "rec.bin"
     algo = int(rec["algo"])
     extra = ["--alloc-log", str(tmp_path / "alloc.bin")] if algo == 10 else []
+    if algo == 11:
+        extra = ["--rand-log", str(tmp_path / "draws.bin")]
     r = subprocess.run([HARNESS, "--gpu", "--algo", str(algo), "--config", str(tmp_path / "cfg.json"),
                         "--ttis", str(T), "--cqi", str(tmp_path / "cqi.bin"), "--rand", str(tmp_path / "rand.bin"),
                         "--out", str(out), "--seed", str(int(rec["seed"]))] + extra, capture_output=True, text=True, timeout=600)
@@ -57,10 +61,19 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
               "state_before", "state_after", "dt"]
     if algo in (8, 9, 10, 101, 103):
         fields += ["target", "quota", "rand2"]
-    if int(rec["algo"]) == 7:
+    if algo in (7, 11):
         fields += ["nvs_slice"]
     for f in fields:
         assert np.array_equal(np.asarray(got[f]), np.asarray(rec[f])), (name, f)
+    if algo == 11:   # every rand() value drawn inside DoSchedule: the same count and the same values as the reference's
+        raw = np.fromfile(tmp_path / "draws.bin", dtype="<i4")
+        pos = 0
+        for t in range(T):
+            k = int(raw[pos])
+            assert k == int(rec["rand_ng_n"][t]), (name, t)
+            assert np.array_equal(raw[pos + 1:pos + 1 + k], rec["rand_ng"][t, :k]), (name, t)
+            pos += 1 + k
+        assert pos == len(raw)
     if algo == 10:   # every (user, RBG) grant of every TTI, in the order of the users' RB lists
         raw = np.fromfile(tmp_path / "alloc.bin", dtype="<i2")
         pos = 0

@@ -134,6 +134,7 @@ CASES = [
     ("a10_qif_synth", 10, "QIF", 120, "synth", 35),
     ("a101_qif_synth", 101, "QIF", 120, "synth", 36),
     ("a103_qif_synth", 103, "QIF", 120, "synth", 37),
+    ("a11_qif_synth", 11, "QIF", 60, "synth", 38),
 ]
 
 
