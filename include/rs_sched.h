@@ -239,9 +239,16 @@ int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs);
  * bytes credited are capped by the queue and the hol_delay field prints the bearer's delay. */
 int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_delay);
 /* Appends one TTI of one cell.  cqi [U][row] in cfg's CQI layout; rbg_to_ue [G]; tbs_bits [U];
- * final_cqi [U] (ids 7/8/9); slice_target / slice_quota [S] (ids 8/9). */
+ * final_cqi [U] (every id but 1); slice_target / slice_quota [S] (ids 8/9/101/103).  Not for id 10 (next call). */
 int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,
                const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota);
+/* Id 10 (UpperBound, :223-246) books an RBG to several slices: its TTI is logged from the grant list the device
+ * returns (rs_outputs.alloc_n / alloc_ue / alloc_rbg of that cell: slice by slice in the order the grants were made,
+ * user -1 = a slice without a listed user on that RBG), which is the order of the users' RB lists and of the
+ * efficiency sum behind "all_bytes". */
+int rs_log_tti_grants(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, int32_t n_grants, const int16_t* grant_ue,
+                      const int16_t* grant_rbg, const int32_t* tbs_bits, const uint8_t* final_cqi,
+                      const int32_t* slice_target, const int32_t* slice_quota);
 /* The text accumulated so far (NUL-terminated, owned by the log) and a reset. */
 const char* rs_log_stdout(rs_log* lg, int64_t* len);
 const char* rs_log_stderr(rs_log* lg, int64_t* len);

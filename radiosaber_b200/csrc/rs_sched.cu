@@ -985,8 +985,6 @@ struct rs_log {
 
 int rs_log_create(const rs_config* cfg, rs_log** out) {
   if (!cfg || !out || !cfg->ue_to_slice) return fail(RS_ERR_ARG, "rs_log_create: bad argument");
-  if (cfg->algo == 10)
-    return fail(RS_ERR_UNSUPPORTED, "rs_log: id 10 prints each user's RBGs in grant order, which the single-valued rbg_to_ue cannot carry");
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0 || cfg->n_ues < 1 ||
       cfg->n_slices < 1 || cfg->cqi_per_rb < 0 || cfg->cqi_per_rb > 2)
     return fail(RS_ERR_ARG, "rs_log_create: bad configuration");
@@ -1020,26 +1018,21 @@ int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_
   return RS_OK;
 }
 
-int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,
-               const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota) {
-  if (!lg || !cqi || !rbg_to_ue || !tbs_bits) return fail(RS_ERR_ARG, "rs_log_tti: bad argument");
-  const int U = lg->U, G = lg->G, S = lg->S, algo = lg->algo;
-  const bool tr = algo == 8 || algo == 9 || algo == 101 || algo == 103;   /* RBsAllocation's log lines */
-  if (tr && (!slice_target || !slice_quota)) return fail(RS_ERR_ARG, "rs_log_tti: ids 8/9/101/103 need targets and quotas");
-  if (algo != 1 && !final_cqi) return fail(RS_ERR_ARG, "rs_log_tti: final_cqi missing");
+/* Shared by rs_log_tti and rs_log_tti_grants: rbgs[u] = the RBGs of user u in the order of its RB list,
+ * sum_bits = the efficiency sum of the inter-slice algorithm's all_bytes line (in the reference's order). */
+static int log_tti_core(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const std::vector<std::vector<int>>& rbgs,
+                        double sum_bits, const int32_t* tbs_bits, const uint8_t* final_cqi, const int32_t* slice_target,
+                        const int32_t* slice_quota) {
+  const int U = lg->U, S = lg->S, algo = lg->algo;
+  const bool tr = algo == 8 || algo == 9 || algo == 10 || algo == 101 || algo == 103;   /* RBsAllocation's log lines */
   char buf[256];
   auto cqi_at = [&](int u, int g) -> int {   /* CQI on the first RB of RBG g, what :641 prints */
     const uint8_t* p = cqi + (size_t)u * lg->row;
     if (lg->layout == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
     return lg->layout == 1 ? p[(size_t)g * lg->rbg] : p[g];
   };
-  std::vector<int> n_rbg(U, 0);
   int scheduled = 0;
-  for (int g = 0; g < G; ++g) {
-    const int u = rbg_to_ue[g];
-    if (u < -1 || u >= U) return fail(RS_ERR_ARG, "rs_log_tti: rbg_to_ue[%d] = %d", g, u);
-    if (u >= 0) { n_rbg[u]++; scheduled++; }
-  }
+  for (int u = 0; u < U; ++u) scheduled += (int)rbgs[u].size();
   /* RBsAllocation only runs (and prints) when at least one user is schedulable (transport.cpp:152-168);
    * with every bearer idle nothing is allocated and nothing is printed */
   bool ran = scheduled > 0;
@@ -1054,9 +1047,7 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
         lg->out += buf;
       }
       lg->out += "\n";
-      /* stderr, :366-374 / :265-270: sum over RBGs of the winner's efficiency, in RBG order */
-      double sum_bits = 0;
-      for (int g = 0; g < G; ++g) sum_bits += rbg_to_ue[g] >= 0 ? lg->eff[cqi_at(rbg_to_ue[g], g)] : 0.0;
+      /* stderr, :244 / :270 / :347 / :374 / :449 */
       snprintf(buf, sizeof buf, "all_bytes: %.0f\n", sum_bits * 180 / 8 * 4);
       lg->err += buf;
     }
@@ -1064,14 +1055,13 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
     snprintf(buf, sizeof buf, "%llu\n", (unsigned long long)timestamp);
     lg->out += buf;
     for (int u = 0; u < U; ++u) {
-      if (!n_rbg[u]) continue;
+      if (rbgs[u].empty()) continue;
       snprintf(buf, sizeof buf, "User(%d) allocated RBGS:", u);
       lg->out += buf;
-      for (int g = 0; g < G; ++g)
-        if (rbg_to_ue[g] == u) {
-          snprintf(buf, sizeof buf, " %d(%d)", g, cqi_at(u, g));
-          lg->out += buf;
-        }
+      for (int g : rbgs[u]) {
+        snprintf(buf, sizeof buf, " %d(%d)", g, cqi_at(u, g));
+        lg->out += buf;
+      }
       snprintf(buf, sizeof buf, " final_cqi: %d\n", (int)final_cqi[u]);
       lg->out += buf;
     }
@@ -1089,7 +1079,7 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
       sent = std::min(avail, data);
     }
     lg->cum_bytes[u] += (uint64_t)sent;
-    lg->cum_rbs[u] += (uint64_t)n_rbg[u] * lg->rbg;
+    lg->cum_rbs[u] += (uint64_t)rbgs[u].size() * lg->rbg;
     snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: %g user: %d slice: %d\n",
              (unsigned long long)timestamp, u, (unsigned long long)lg->cum_bytes[u],
              (unsigned long long)lg->cum_rbs[u], lg->hol.empty() ? 0.0 : lg->hol[u], u, lg->u2s[u]);
@@ -1098,6 +1088,51 @@ int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t
   lg->queue.clear();
   lg->hol.clear();
   return RS_OK;
+}
+
+static int log_cqi_at(const rs_log* lg, const uint8_t* cqi, int u, int g) {
+  const uint8_t* p = cqi + (size_t)u * lg->row;
+  if (lg->layout == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
+  return lg->layout == 1 ? p[(size_t)g * lg->rbg] : p[g];
+}
+
+int rs_log_tti(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, const int16_t* rbg_to_ue, const int32_t* tbs_bits,
+               const uint8_t* final_cqi, const int32_t* slice_target, const int32_t* slice_quota) {
+  if (!lg || !cqi || !rbg_to_ue || !tbs_bits) return fail(RS_ERR_ARG, "rs_log_tti: bad argument");
+  const int U = lg->U, G = lg->G, algo = lg->algo;
+  if (algo == 10) return fail(RS_ERR_ARG, "rs_log_tti: id 10 books an RBG to several users, use rs_log_tti_grants");
+  const bool tr = algo == 8 || algo == 9 || algo == 101 || algo == 103;
+  if (tr && (!slice_target || !slice_quota)) return fail(RS_ERR_ARG, "rs_log_tti: ids 8/9/101/103 need targets and quotas");
+  if (algo != 1 && !final_cqi) return fail(RS_ERR_ARG, "rs_log_tti: final_cqi missing");
+  std::vector<std::vector<int>> rbgs(U);
+  double sum_bits = 0;   /* :366-374 / :265-270: sum over RBGs of the winner's efficiency, in RBG order */
+  for (int g = 0; g < G; ++g) {
+    const int u = rbg_to_ue[g];
+    if (u < -1 || u >= U) return fail(RS_ERR_ARG, "rs_log_tti: rbg_to_ue[%d] = %d", g, u);
+    if (u >= 0) rbgs[u].push_back(g);
+    sum_bits += u >= 0 ? lg->eff[log_cqi_at(lg, cqi, u, g)] : 0.0;
+  }
+  return log_tti_core(lg, timestamp, cqi, rbgs, sum_bits, tbs_bits, final_cqi, slice_target, slice_quota);
+}
+
+int rs_log_tti_grants(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, int32_t n_grants, const int16_t* grant_ue,
+                      const int16_t* grant_rbg, const int32_t* tbs_bits, const uint8_t* final_cqi,
+                      const int32_t* slice_target, const int32_t* slice_quota) {
+  if (!lg || !cqi || n_grants < 0 || (n_grants > 0 && (!grant_ue || !grant_rbg)) || !tbs_bits || !final_cqi || !slice_target ||
+      !slice_quota)
+    return fail(RS_ERR_ARG, "rs_log_tti_grants: bad argument");
+  if (lg->algo != 10) return fail(RS_ERR_ARG, "rs_log_tti_grants: the grant list is id 10's output");
+  const int U = lg->U, G = lg->G;
+  std::vector<std::vector<int>> rbgs(U);
+  double sum_bits = 0;   /* :240-244: sum over the grants in the order they were made (slice by slice) */
+  for (int e = 0; e < n_grants && e < 2 * G; ++e) {
+    const int u = grant_ue[e], g = grant_rbg[e];
+    if (u < 0) continue;   /* a slice without a listed user on that RBG: efficiency 0, nobody's RB list grows */
+    if (u >= U || g < 0 || g >= G) return fail(RS_ERR_ARG, "rs_log_tti_grants: grant %d = (%d, %d)", e, u, g);
+    rbgs[u].push_back(g);
+    sum_bits += lg->eff[log_cqi_at(lg, cqi, u, g)];
+  }
+  return log_tti_core(lg, timestamp, cqi, rbgs, sum_bits, tbs_bits, final_cqi, slice_target, slice_quota);
 }
 
 const char* rs_log_stdout(rs_log* lg, int64_t* len) {

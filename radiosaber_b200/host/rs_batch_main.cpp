@@ -11,8 +11,7 @@
  *   rs_batch --algo 9 --config cfg.json --cells 4096 --ttis 1000 [--seed 1]
  *            [--traces DIR --mapping FILE]      replay DIR/ue<id>.log; cell b, UE u replays map[(u + 7 b) % n]
  *            [--trace-rows N]                   lines per trace file (475 in cqi-traces-noise0)
- *            [--log-cell B --log-prefix P]      P.stdout / P.stderr as the reference prints them (ids 1/7/8/9/101/103,
- *                                               synthetic CQI only)
+ *            [--log-cell B --log-prefix P]      P.stdout / P.stderr as the reference prints them (synthetic CQI only)
  *
  * Host logic only; every scheduling decision is made by the CUDA kernels behind the ABI (no CPU fallback).
  */
@@ -217,7 +216,8 @@ int main(int argc, char** argv) {
     const int TB = 16;
     uint8_t* d_cqi = nullptr;
     int32_t* d_draws = nullptr;
-    int16_t* d_rbg = nullptr;
+    int16_t *d_rbg = nullptr, *d_gue = nullptr, *d_grbg = nullptr;   /* d_g*: id 10's grant list */
+    int32_t* d_gn = nullptr;
     int32_t *d_bits = nullptr, *d_tgt = nullptr, *d_quo = nullptr;
     uint8_t* d_fc = nullptr;
     const size_t row = G / 2;
@@ -225,7 +225,7 @@ int main(int argc, char** argv) {
     if (n_draws > 0) cu(cudaMalloc(&d_draws, sizeof(int32_t) * (size_t)TB * B * n_draws), "cudaMalloc");
     const bool want_log = a.log_cell >= 0 && a.log_cell < B && !a.log_prefix.empty();
     rs_log* lg = nullptr;
-    std::vector<int16_t> h_rbg;
+    std::vector<int16_t> h_rbg, h_gue, h_grbg;
     std::vector<int32_t> h_bits, h_tgt, h_quo;
     std::vector<uint8_t> h_fc, h_cqi;
     rs_outputs out;
@@ -238,6 +238,13 @@ int main(int argc, char** argv) {
       cu(cudaMalloc(&d_tgt, sizeof(int32_t) * (size_t)TB * B * S), "cudaMalloc");
       cu(cudaMalloc(&d_quo, sizeof(int32_t) * (size_t)TB * B * S), "cudaMalloc");
       out.rbg_to_ue = d_rbg; out.tbs_bits = d_bits; out.final_cqi = d_fc; out.slice_target = d_tgt; out.slice_quota = d_quo;
+      if (a.algo == 10) {
+        cu(cudaMalloc(&d_gn, sizeof(int32_t) * (size_t)TB * B), "cudaMalloc");
+        cu(cudaMalloc(&d_gue, sizeof(int16_t) * (size_t)TB * B * 2 * G), "cudaMalloc");
+        cu(cudaMalloc(&d_grbg, sizeof(int16_t) * (size_t)TB * B * 2 * G), "cudaMalloc");
+        out.alloc_n = d_gn; out.alloc_ue = d_gue; out.alloc_rbg = d_grbg;
+        h_gue.resize(2 * (size_t)G); h_grbg.resize(2 * (size_t)G);
+      }
       h_rbg.resize(G); h_bits.resize(U); h_fc.resize(U); h_tgt.resize(S); h_quo.resize(S); h_cqi.resize((size_t)U * row);
     }
     std::vector<int32_t> trow(TB);
@@ -268,7 +275,17 @@ int main(int argc, char** argv) {
           cu(cudaMemcpy(h_tgt.data(), d_tgt + tb * S, sizeof(int32_t) * S, cudaMemcpyDeviceToHost), "copy");
           cu(cudaMemcpy(h_quo.data(), d_quo + tb * S, sizeof(int32_t) * S, cudaMemcpyDeviceToHost), "copy");
           /* PacketScheduler::m_ts counts TTIs since the eNB was created: 100 at the first TTI with bearers */
-          check(rs_log_tti(lg, 100 + (uint64_t)(t0 + k), h_cqi.data(), h_rbg.data(), h_bits.data(), h_fc.data(), h_tgt.data(), h_quo.data()), "rs_log_tti");
+          const uint64_t ts = 100 + (uint64_t)(t0 + k);
+          if (a.algo == 10) {
+            int32_t n_grants = 0;
+            cu(cudaMemcpy(&n_grants, d_gn + tb, sizeof n_grants, cudaMemcpyDeviceToHost), "copy");
+            cu(cudaMemcpy(h_gue.data(), d_gue + tb * 2 * G, sizeof(int16_t) * 2 * G, cudaMemcpyDeviceToHost), "copy");
+            cu(cudaMemcpy(h_grbg.data(), d_grbg + tb * 2 * G, sizeof(int16_t) * 2 * G, cudaMemcpyDeviceToHost), "copy");
+            check(rs_log_tti_grants(lg, ts, h_cqi.data(), n_grants, h_gue.data(), h_grbg.data(), h_bits.data(), h_fc.data(),
+                                    h_tgt.data(), h_quo.data()), "rs_log_tti_grants");
+          } else {
+            check(rs_log_tti(lg, ts, h_cqi.data(), h_rbg.data(), h_bits.data(), h_fc.data(), h_tgt.data(), h_quo.data()), "rs_log_tti");
+          }
         }
       }
     }
@@ -293,7 +310,7 @@ int main(int argc, char** argv) {
     }
     if (lg) rs_log_destroy(lg);
     rs_destroy(h);
-    cudaFree(d_cqi); cudaFree(d_draws); cudaFree(d_rbg); cudaFree(d_bits); cudaFree(d_fc); cudaFree(d_tgt); cudaFree(d_quo);
+    cudaFree(d_cqi); cudaFree(d_draws); cudaFree(d_rbg); cudaFree(d_bits); cudaFree(d_fc); cudaFree(d_tgt); cudaFree(d_quo); cudaFree(d_gn); cudaFree(d_gue); cudaFree(d_grbg);
     return 0;
   } catch (const std::exception& e) {
     fprintf(stderr, "rs_batch: %s\n", e.what());

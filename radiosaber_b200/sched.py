@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "rs_test_sort_timed", "rs_rand_draws_per_cell_tti", "rs_set_queues",
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
-    "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti",
+    "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti", "rs_log_tti_grants",
     "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues",
 )
 
@@ -115,6 +115,7 @@ def lib():
         L.rs_log_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_set_queues.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_tti.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.rs_log_tti_grants.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         L.rs_log_stdout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.rs_log_stdout.restype = C.c_char_p
         L.rs_log_stderr.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -408,6 +409,20 @@ class LogWriter:
              None if slice_target is None else np.ascontiguousarray(slice_target, dtype=np.int32),
              None if slice_quota is None else np.ascontiguousarray(slice_quota, dtype=np.int32)]
         _check(lib().rs_log_tti(self._h, int(timestamp), *[_ptr(x) for x in a]))
+
+    def tti_grants(self, timestamp, cqi, n_grants, grant_ue, grant_rbg, tbs_bits, final_cqi, slice_target, slice_quota,
+                   queue=None, hol=None):
+        """Id 10: one TTI from the grant list (rs_outputs.alloc_*) instead of the single-valued RBG->UE map."""
+        if queue is not None or hol is not None:
+            q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32)
+            h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64)
+            _check(lib().rs_log_set_queues(self._h, _ptr(q), _ptr(h)))
+        a = [np.ascontiguousarray(grant_ue, dtype=np.int16), np.ascontiguousarray(grant_rbg, dtype=np.int16),
+             np.ascontiguousarray(tbs_bits, dtype=np.int32), np.ascontiguousarray(final_cqi, dtype=np.uint8),
+             np.ascontiguousarray(slice_target, dtype=np.int32), np.ascontiguousarray(slice_quota, dtype=np.int32)]
+        c = np.ascontiguousarray(cqi, dtype=np.uint8)
+        assert a[0].size >= min(int(n_grants), 2 * self.G) and a[1].size >= min(int(n_grants), 2 * self.G)
+        _check(lib().rs_log_tti_grants(self._h, int(timestamp), _ptr(c), int(n_grants), *[_ptr(x) for x in a]))
 
     def set_counters(self, cum_bytes=None, cum_rbs=None):
         cb = None if cum_bytes is None else np.ascontiguousarray(cum_bytes, dtype=np.uint64)

@@ -39,10 +39,15 @@ def test_writer_reproduces_reference_text_from_reference_results(name):
     T = _n_ttis(name, rec)
     assert T >= 4
     lw = sched.LogWriter(algo, rec["ue_to_slice"], int(rec["S"]), cqi_per_rb=int(rec["cqi_per_rb"]))
+    tq = algo in (8, 9, 101, 103)
     for t in range(T):
         kw = {"queue": rec["queue"][t], "hol": rec["hol"][t]} if "queue" in rec else {}
+        if algo == 10:   # the grant list; the record holds it user by user, the order of the RB lists
+            lw.tti_grants(FIRST_TS + t, rec["cqi"][t], int(rec["alloc_n"][t]), rec["alloc_ue"][t], rec["alloc_rbg"][t],
+                          rec["bits"][t], rec["final_cqi"][t], rec["target"][t], rec["quota"][t], **kw)
+            continue
         lw.tti(FIRST_TS + t, rec["cqi"][t], rec["rbg_to_ue"][t], rec["bits"][t], rec["final_cqi"][t],
-               rec["target"][t] if algo in (8, 9) else None, rec["quota"][t] if algo in (8, 9) else None, **kw)
+               rec["target"][t] if tq else None, rec["quota"][t] if tq else None, **kw)
     out, err = _ref_text(name)
     assert lw.stdout == out
     assert lw.stderr == err
@@ -88,17 +93,23 @@ def test_cuda_results_reproduce_reference_text(name):
     algo = int(rec["algo"])
     T = _n_ttis(name, rec)
     g = sched.Scheduler(algo, rec["weight"], rec["params"], rec["ue_to_slice"], 1, cqi_per_rb=int(rec["cqi_per_rb"]))
+    tq = algo in (8, 9, 10, 101, 103)
     g.set_state(avg_rate=rec["avg_before"][0][None], tx_bytes=rec["tx_before"][0][None],
-                slice_offset=rec["state_before"][0][None] if algo in (8, 9) else None,
-                nvs_ewma=rec["state_before"][0][None] if algo == 7 else None)
+                slice_offset=rec["state_before"][0][None] if tq else None,
+                nvs_ewma=rec["state_before"][0][None] if algo in (7, 11) else None)
     qkw = {"queue": rec["queue"][:T, None], "hol": rec["hol"][:T, None]} if "queue" in rec else {}
-    res = g.run_host(rec["cqi"][:T, None], rec["rand2"][:T, None, :], rec["dt"][:T], want_aux=True, **qkw)
+    draws = rec["rand_ng"] if algo == 11 else rec["rand2"]
+    res = g.run_host(rec["cqi"][:T, None], draws[:T, None, :], rec["dt"][:T], want_aux=True, **qkw)
     lw = sched.LogWriter(algo, rec["ue_to_slice"], int(rec["S"]), cqi_per_rb=int(rec["cqi_per_rb"]))
     for t in range(T):
         kw = {"queue": rec["queue"][t], "hol": rec["hol"][t]} if "queue" in rec else {}
+        if algo == 10:
+            lw.tti_grants(FIRST_TS + t, rec["cqi"][t], int(res["alloc_n"][t, 0]), res["alloc_ue"][t, 0], res["alloc_rbg"][t, 0],
+                          res["tbs_bits"][t, 0], res["final_cqi"][t, 0], res["slice_target"][t, 0], res["slice_quota"][t, 0], **kw)
+            continue
         lw.tti(FIRST_TS + t, rec["cqi"][t], res["rbg_to_ue"][t, 0], res["tbs_bits"][t, 0], res["final_cqi"][t, 0],
-               res["slice_target"][t, 0] if algo in (8, 9) else None,
-               res["slice_quota"][t, 0] if algo in (8, 9) else None, **kw)
+               res["slice_target"][t, 0] if tq else None,
+               res["slice_quota"][t, 0] if tq else None, **kw)
     out, err = _ref_text(name)
     assert lw.stdout == out and lw.stderr == err
     st = g.get_state()

@@ -35,8 +35,7 @@ def _run(*args):
 def test_synthetic_batch_equals_python_mirror(algo, tmp_path):
     B, T, seed = 37, 35, 4
     path = _config(tmp_path, [(3, 0.2, (0, 0, 1, 1)), (2, 0.2, (0, 0, 1, 0))], [4, 2, 6, 1, 3])
-    logs = algo in (9, 8, 7, 1, 101, 103)
-    extra = ["--log-cell", 11, "--log-prefix", tmp_path / "cell11"] if logs else []
+    extra = ["--log-cell", 11, "--log-prefix", tmp_path / "cell11"]
     got = _run("--algo", algo, "--config", path, "--cells", B, "--ttis", T, "--seed", seed, *extra)
     w, p, u2s = sched.load_slice_config(path)
     S, U, G = len(w), len(u2s), 64
@@ -53,16 +52,20 @@ def test_synthetic_batch_equals_python_mirror(algo, tmp_path):
     assert got["slice_rbs"] == [int(x) for x in st[1]]
     assert got["cells"] == B and got["ttis"] == T and got["slices"] == S and got["ues"] == U
     assert int(st[1].sum()) > 0
-    if logs:
-        lw = sched.LogWriter(algo, u2s, S, cqi_per_rb=2)
-        for t in range(T):
-            lw.tti(100 + t, sched.pack_cqi(cqi[t, 11]), res["rbg_to_ue"][t, 11], res["tbs_bits"][t, 11],
-                   res["final_cqi"][t, 11] if algo != 1 else None,
-                   res["slice_target"][t, 11] if algo in (8, 9, 101, 103) else None,
-                   res["slice_quota"][t, 11] if algo in (8, 9, 101, 103) else None)
-        assert (tmp_path / "cell11.stdout").read_text() == lw.stdout
-        assert (tmp_path / "cell11.stderr").read_text() == lw.stderr
-        assert lw.stderr.count("\n") > T
+    lw = sched.LogWriter(algo, u2s, S, cqi_per_rb=2)
+    for t in range(T):
+        if algo == 10:
+            lw.tti_grants(100 + t, sched.pack_cqi(cqi[t, 11]), int(res["alloc_n"][t, 11]), res["alloc_ue"][t, 11],
+                          res["alloc_rbg"][t, 11], res["tbs_bits"][t, 11], res["final_cqi"][t, 11],
+                          res["slice_target"][t, 11], res["slice_quota"][t, 11])
+            continue
+        lw.tti(100 + t, sched.pack_cqi(cqi[t, 11]), res["rbg_to_ue"][t, 11], res["tbs_bits"][t, 11],
+               res["final_cqi"][t, 11] if algo != 1 else None,
+               res["slice_target"][t, 11] if algo in (8, 9, 101, 103) else None,
+               res["slice_quota"][t, 11] if algo in (8, 9, 101, 103) else None)
+    assert (tmp_path / "cell11.stdout").read_text() == lw.stdout
+    assert (tmp_path / "cell11.stderr").read_text() == lw.stderr
+    assert lw.stderr.count("\n") > T
     g.close()
 
 

@@ -23,8 +23,9 @@ from tools import make_golden as mg  # noqa: E402
 
 TTIS = 6
 CASES = ["a9_fix20x5_synth", "a8_fix20x5_synth", "a7_fix20x5_synth", "a1_fix20x5_synth", "a9_small_synth",
-         "a9_fix20x5_trace", "a9_qmix_synth", "a7_qmix_synth", "a1_qmix_synth"]
-TTIS_OF = {"a9_qmix_synth": 40, "a7_qmix_synth": 60, "a1_qmix_synth": 40}   # long enough for the finite flows to show up
+         "a9_fix20x5_trace", "a9_qmix_synth", "a7_qmix_synth", "a1_qmix_synth",
+         "a10_fix20x5_synth", "a10_qmix_synth", "a11_fix20x5_synth", "a101_fix20x5_synth", "a103_fix20x5_synth"]
+TTIS_OF = {"a9_qmix_synth": 40, "a7_qmix_synth": 60, "a1_qmix_synth": 40, "a10_qmix_synth": 40}   # long enough for the finite flows to show up
 OUT = os.path.join(ROOT, "tests", "golden", "logs")
 
 
