@@ -136,7 +136,10 @@ int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_
  *                                 flow once its TBS covers the queue (downlink-packet-scheduler.cpp:264-269)
  *   hol_delay   [T][B][U] double  RadioBearer::GetHeadOfLinePacketDelay(); multiplied into the metric of slices with
  *                                 alpha and beta set (ids 8/9/10, :702-706) or alpha set (id 7,
- *                                 downlink-nvs-scheduler.cpp:384-386); NULL = 0
+ *                                 downlink-nvs-scheduler.cpp:384-386); NULL = 0.  A caller that folds two bearers
+ *                                 of a UE into one entry (the LTE-Sim plug-in) marks "the bearer of the slice's
+ *                                 priority is empty", which zeroes the metric (:696-698), with a delay of 0 where the
+ *                                 delay is in the metric and with a NEGATIVE delay in alpha-without-beta slices
  * HOST pointers for rs_step / rs_run_host / rs_run_traces_host, DEVICE pointers for the *_device calls. */
 int rs_set_queues(rs_handle* h, const int32_t* queue_bytes, const double* hol_delay);
 

@@ -124,6 +124,9 @@ struct Options {
   std::string queue_log;  /* per recorded TTI, before the scheduler runs: int32 data[U] (what SelectFlowsToSchedule will take as
                              dataToTransmit: 0 = no packets, 100000000 = infinite buffer, else the queue size) and double
                              hol[U] (RadioBearer::GetHeadOfLinePacketDelay) */
+  int n_bearers = 0;      /* bearers the eNB has once every application has started (0 = one per UE); recording starts
+                             then.  With more than one bearer per UE only --log-out is meaningful: the record's
+                             per-UE bearer fields hold the last bearer of each UE */
   std::string log_out;    /* PREFIX: the reference's own stdout / stderr text of every recorded TTI goes to
                              PREFIX.stdout / PREFIX.stderr (golden text for the log-writer parity test) */
 };
@@ -169,7 +172,7 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
                              StateGet state_get, Collect collect) {
   std::vector<RadioBearer*>* bearers = Bearers(self);
   const int U = (int)user_to_slice.size();
-  if ((int)bearers->size() != U || g_recorded >= g_opt.n_ttis) {
+  if ((int)bearers->size() != (g_opt.n_bearers > 0 ? g_opt.n_bearers : U) || g_recorded >= g_opt.n_ttis) {
     base_call();
     return;
   }
@@ -503,6 +506,7 @@ int main(int argc, char** argv) {
     else if (a == "--log-out") g_opt.log_out = next();
     else if (a == "--rand-log") g_opt.rand_log = next();
     else if (a == "--alloc-log") g_opt.alloc_log = next();
+    else if (a == "--bearers") g_opt.n_bearers = atoi(next().c_str());
     else if (a == "--queue-log") g_opt.queue_log = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }

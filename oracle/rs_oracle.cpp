@@ -183,8 +183,7 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
 }
 
 /* ComputeSchedulingMetric, transport.cpp:677-713; nvs = the copy in nvs.cpp:360-390, which multiplies
- * the head-of-line delay in whenever alpha != 0 (the transport version only when beta != 0).  One
- * bearer per UE, so the prioritised bearer of a listed user always has data. */
+ * the head-of-line delay in whenever alpha != 0 (the transport version only when beta != 0). */
 double TransportMetric(const rso_config* cfg, const User& usr, double avg, double eff, bool nvs = false) {
   double metric = 0;
   double average_rate = 1;
@@ -196,7 +195,9 @@ double TransportMetric(const rso_config* cfg, const User& usr, double avg, doubl
   if (alpha == 0) {
     metric = pow(eff, epsilon) / pow(average_rate, psi);
   } else {
-    if (usr.data == 0) {
+    /* two bearers per UE: the caller marks "the bearer of the slice's priority is empty" (:696-698) with a head-of-line
+     * delay of 0 where the delay multiplies the metric anyway, and with a negative one where it does not */
+    if (usr.data == 0 || (!(beta || nvs) && usr.hol < 0)) {
       metric = 0;
     } else {
       if (beta || nvs) {

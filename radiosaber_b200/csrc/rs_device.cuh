@@ -1103,7 +1103,9 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           const int u = c.sues[j];
           const int su = d.ue_to_slice[u];
           double e = d.epow[su * 16 + cq];
-          if (d.holmul[su]) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* HoL * pow(se, eps) / pow(avg, psi), :702-706 */
+          const int hm = d.holmul[su];
+          if (hm == 1) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* HoL * pow(se, eps) / pow(avg, psi), :702-706 */
+          else if (hm == 2 && hl && hl[u] < 0.0) e = 0.0;     /* the bearer of the slice's priority is empty, :696-698 */
           c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
         }
         __syncthreads();

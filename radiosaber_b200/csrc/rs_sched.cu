@@ -497,6 +497,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     for (int s = 0; s < S; ++s) {
       const int32_t* p = cfg->params + 4 * s;
       holmul[s] = (p[0] != 0 && (algo == 7 || p[1] != 0)) ? 1 : 0;
+      /* alpha without beta (transport ids): the delay is not in the metric, but a NEGATIVE hol_delay of rs_set_queues
+       * marks a user whose prioritised bearer is empty (two bearers per UE, transport.cpp:696-698): metric 0 */
+      if (p[0] != 0 && algo != 7 && p[1] == 0) holmul[s] = 2;
     }
   std::vector<int> tbs1(16, 1);
   for (int c = 1; c <= 15; ++c) tbs1[c] = tbs_n(mcs_from_cqi(c), 1, h->row_m1);

@@ -69,7 +69,8 @@ class RsGpuScheduler : public PacketScheduler {
    * and 101 SubOpt / 103 VogelApproximate, the two inter-slice algorithms ENodeB.cpp:363-379 can install.
    * Id 1 replaces DL_PF_PacketScheduler(config_fname) (ENodeB.cpp:309-313); that class schedules flows
    * (FlowToSchedule, one per bearer), which with one bearer per UE is the same list as the users kept here.
-   * Bearers may be backlogged or have finite queues (internet flows, video); two bearers on one UE throw. */
+   * Bearers may be backlogged or have finite queues (internet flows, video); two bearers on one UE are folded into one
+   * user like InsertFlowToUser does (ids 1 and 11 throw). */
   RsGpuScheduler(std::string config_fname, int scheduler_id) : id_(scheduler_id) {
     if (id_ != 1 && !Nvs() && !Transport())
       throw std::runtime_error("RsGpuScheduler: scheduler id must be 1, 7, 8, 9, 10, 11, 101 or 103");
@@ -151,6 +152,7 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<double> avg_, hol_;   /* hol_: head-of-line delay of each listed bearer */
   std::vector<int32_t> queue_;      /* dataToTransmit of each listed bearer, 0 = not listed */
   std::vector<int16_t> rbg_to_ue_, grant_ue_, grant_rbg_;
+  std::vector<int> slice_priority_;   /* highest priority among the listed bearers of each slice */
   std::vector<int32_t> bits_, target_, quota_, draws_;
 
   /* DownlinkTransportScheduler with one of its inter-slice algorithms (ENodeB.cpp:357-385): 8 Sequential,
@@ -223,6 +225,7 @@ class RsGpuScheduler : public PacketScheduler {
     std::fill(active_.begin(), active_.end(), (uint8_t)0);
     std::fill(queue_.begin(), queue_.end(), 0);
     std::fill(hol_.begin(), hol_.end(), 0.0);
+    slice_priority_.assign(num_slices_, 0);   /* :115 */
     ENodeB* enb = (ENodeB*)GetMacEntity()->GetDevice();
     UsersToSchedule* users = GetUsersToSchedule();
     for (auto it = bearers->begin(); it != bearers->end(); ++it) {
@@ -236,7 +239,13 @@ class RsGpuScheduler : public PacketScheduler {
       UserToSchedule* user = nullptr;
       for (auto u = users->begin(); u != users->end(); ++u)
         if ((*u)->GetUserID() == uid) user = *u;
-      if (user) throw std::runtime_error("RsGpuScheduler: two bearers on one UE are not covered");
+      /* A second bearer of a UE joins the same UserToSchedule (InsertFlowToUser, packet-scheduler.cpp:304-318).  Id 1
+       * schedules flows, and id 11's 300-sample search has no gate for an empty prioritised bearer: not covered. */
+      if (user && (id_ == 1 || id_ == 11)) throw std::runtime_error("RsGpuScheduler: two bearers on one UE are not covered for ids 1 and 11");
+      const int prio = bearer->GetPriority();
+      if (prio < 0 || prio >= MAX_BEARERS) throw std::runtime_error("RsGpuScheduler: bearer priority outside MAX_BEARERS");
+      const int slice = user_to_slice_[uid];
+      if (prio > slice_priority_[slice]) slice_priority_[slice] = prio;   /* :144-146 */
       if (!user) {
         user = new UserToSchedule(uid, bearer->GetDestination());
         std::vector<int> cqi = enb->GetUserEquipmentRecord(bearer->GetDestination()->GetIDNetworkNode())->GetCQI();
@@ -244,14 +253,23 @@ class RsGpuScheduler : public PacketScheduler {
         for (int r = 0; r < n_rbs_ && r < (int)cqi.size(); ++r) cqi_[(size_t)uid * n_rbs_ + r] = (uint8_t)cqi[r];
         avg_[uid] = 0.0;
         users->push_back(user);
+        queue_[uid] = data;   /* m_requiredRBs counts the bearer that created the user (packet-scheduler.cpp:333) */
       }
-      user->m_bearers[bearer->GetPriority()] = bearer;
-      user->m_dataToTransmit[bearer->GetPriority()] = data;
-      queue_[uid] = data;
-      hol_[uid] = bearer->GetHeadOfLinePacketDelay();
-      avg_[uid] += bearer->GetAverageTransmissionRate();
+      user->m_bearers[prio] = bearer;
+      user->m_dataToTransmit[prio] = data;
+      avg_[uid] += bearer->GetAverageTransmissionRate();   /* :683-687: the sum over the listed bearers */
       active_[uid] = 1;
       n_users_total_++;
+    }
+    /* the head-of-line delay in the metric is the one of the bearer with the slice's priority; a user whose bearer of
+     * that priority is empty has metric 0 (:696-706, nvs :379-386) -- see rs_set_queues for how that is passed */
+    for (auto u = users->begin(); u != users->end(); ++u) {
+      const int uid = (*u)->GetUserID(), slice = user_to_slice_[uid], pr = slice_priority_[slice];
+      if (id_ == 1 || slice_algo_params_[slice].alpha == 0) { hol_[uid] = 0.0; continue; }
+      if ((*u)->m_dataToTransmit[pr] == 0)
+        hol_[uid] = (Nvs() || slice_algo_params_[slice].beta) ? 0.0 : -1.0;
+      else
+        hol_[uid] = (*u)->m_bearers[pr]->GetHeadOfLinePacketDelay();
     }
   }
 

@@ -84,3 +84,35 @@ def test_plugin_inside_lte_sim_matches_reference(name, tmp_path):
             assert k == int(rec["alloc_n"][t]), (name, t)
             assert np.array_equal(pairs[:, 0], rec["alloc_ue"][t, :k]) and np.array_equal(pairs[:, 1], rec["alloc_rbg"][t, :k]), (name, t)
         assert pos == len(raw)
+
+
+# ---- two bearers per UE (internet_flow: 2) ---------------------------------------------------------------------
+# The record format is per UE, so here the golden is the reference's own log text (tools/make_golden_logs_two_bearers.py):
+# the plug-in inside LTE-Sim must print the same allocation dump (stdout) and the same per-bearer cumu_bytes / cumu_rbs
+# lines (stderr) -- which only happens if every TTI's allocation, every bearer's share of the bytes and, through the
+# bearers' own EWMA, every later TTI are identical.
+TWO_BEARER_LOGS = os.path.join(ROOT, "tests", "golden", "logs_two_bearers")
+
+
+def _scheduler_lines(text):
+    """Drop what is not scheduler output: the RLC's "ipflow end ..." lines and the inter-slice function's all_bytes."""
+    return [l for l in text.splitlines() if not l.startswith("ipflow ") and not l.startswith("all_bytes")]
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103])
+def test_two_bearers_per_ue_inside_lte_sim(algo, tmp_path):
+    from tools import make_golden_logs_two_bearers as mb
+    if not os.path.exists(HARNESS):
+        pytest.fail("oracle/_ref/ref_harness_gpu missing: run __graft_entry__.build() where /root/reference is mounted")
+    cfg = json.load(open(mb.CFG))
+    cqi, rnd = mb.write_inputs(str(tmp_path), cfg)
+    cmd = mb.command(HARNESS, algo, cqi, rnd, str(tmp_path / "got"), cfg)
+    r = subprocess.run(cmd[:1] + ["--gpu"] + cmd[1:], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
+    for ext in ("stdout", "stderr"):
+        want = _scheduler_lines(open(os.path.join(TWO_BEARER_LOGS, f"a{algo}.{ext}")).read())
+        got = _scheduler_lines((tmp_path / f"got.{ext}").read_text())
+        assert len(want) > mb.TTIS
+        for k, (a, b) in enumerate(zip(want, got)):
+            assert a == b, (algo, ext, k, a, b)
+        assert len(got) == len(want), (algo, ext)
