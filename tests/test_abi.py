@@ -77,3 +77,22 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "rs_oracle" not in txt and "librs_oracle" not in txt, f
+
+
+def test_batch_runner_fails_loudly_without_a_gpu(tmp_path):
+    """radiosaber_b200/rs_batch (C++ over the C ABI): config errors read like the reference's, and without a CUDA
+    device it exits non-zero with the library's message instead of computing anything on the host."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "radiosaber_b200", "rs_batch")
+    assert os.path.exists(exe), "build with make -C radiosaber_b200/csrc"
+    r = subprocess.run([exe, "--algo", "9", "--config", str(tmp_path / "missing.json"), "--cells", "4", "--ttis", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Fail to open configuration file." in r.stderr   # downlink-transport-scheduler.cpp:58-60
+    r = subprocess.run([exe, "--cells", "4"], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([exe, "--algo", "9", "--config", os.path.join(ROOT, "tests", "data", "cfg20x5.json"), "--cells", "4",
+                        "--ttis", "2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "rs_create" in r.stderr and r.stdout == ""
