@@ -116,3 +116,22 @@ def test_cuda_results_reproduce_reference_text(name):
     cb, cr = lw.counters()
     assert np.array_equal(cb, st["cum_bytes"][0]) and np.array_equal(cr, st["cum_rbs"][0])
     g.close()
+
+
+def test_grant_list_call_belongs_to_id_10():
+    """rs_log_tti wants the single-valued RBG->UE map (every id but 10), rs_log_tti_grants the grant list (id 10 only)."""
+    rec = load_golden("a10_fix20x5_synth")
+    U, S, G = int(rec["U"]), int(rec["S"]), int(rec["G"])
+    lw10 = sched.LogWriter(10, rec["ue_to_slice"], S)
+    with pytest.raises(sched.RsError, match="rs_log_tti_grants"):
+        lw10.tti(100, rec["cqi"][0], rec["rbg_to_ue"][0], rec["bits"][0], rec["final_cqi"][0], rec["target"][0], rec["quota"][0])
+    lw9 = sched.LogWriter(9, rec["ue_to_slice"], S)
+    with pytest.raises(sched.RsError, match="id 10"):
+        lw9.tti_grants(100, rec["cqi"][0], int(rec["alloc_n"][0]), rec["alloc_ue"][0], rec["alloc_rbg"][0], rec["bits"][0],
+                       rec["final_cqi"][0], rec["target"][0], rec["quota"][0])
+    bad = rec["alloc_ue"][0].copy()
+    bad[0] = U   # a user outside the cell
+    with pytest.raises(sched.RsError, match="grant 0"):
+        lw10.tti_grants(100, rec["cqi"][0], int(rec["alloc_n"][0]), bad, rec["alloc_rbg"][0], rec["bits"][0],
+                        rec["final_cqi"][0], rec["target"][0], rec["quota"][0])
+    assert lw10.stdout == "" and lw10.stderr == ""
