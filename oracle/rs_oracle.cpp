@@ -15,6 +15,7 @@
 #include "rs_oracle.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -331,6 +332,11 @@ std::vector<int> VogelApproximate(const std::vector<std::vector<double>>& se, co
   return out;
 }
 
+/* Diagnostic (rso_diag_*): histogram of the position of the last entry MaximizeCell's scan accepts, in 64ths of
+ * the list length.  Off by default; results never depend on it. */
+static std::atomic<int> g_diag_on{0};
+static std::atomic<uint64_t> g_diag_stop[66];
+
 /* MaximizeCell, transport.cpp:351-376 */
 std::vector<int> MaximizeCell(const std::vector<std::vector<double>>& se, const std::vector<int>& quota,
                               int G, int S) {
@@ -340,12 +346,18 @@ std::vector<int> MaximizeCell(const std::vector<std::vector<double>>& se, const 
     for (int j = 0; j < S; ++j) sorted.emplace_back(coord_t(i, j), se[i][j]);
   std::sort(sorted.begin(), sorted.end(),
             [](coord_cqi_t a, coord_cqi_t b) { return a.second > b.second; });
+  size_t last_take = 0;
   for (auto it = sorted.begin(); it != sorted.end(); ++it) {
     int rbg = it->first.first, sl = it->first.second;
     if (used[sl] < quota[sl] && out[rbg] == -1) {
       out[rbg] = sl;
       used[sl] += 1;
+      last_take = (size_t)(it - sorted.begin()) + 1;
     }
+  }
+  if (g_diag_on.load(std::memory_order_relaxed)) {   /* diagnostic: how far into the sorted list the scan has to look */
+    const size_t n = sorted.size();
+    g_diag_stop[n ? (last_take * 64 + n - 1) / n : 0].fetch_add(1, std::memory_order_relaxed);
   }
   return out;
 }
@@ -922,3 +934,11 @@ void rso_introsort_emul_desc(const double* keys, int32_t n, int32_t depth_limit,
 }
 
 }  /* extern "C" */
+
+extern "C" void rso_diag_enable(int on) {
+  g_diag_on.store(on);
+  if (on) for (auto& x : g_diag_stop) x.store(0);
+}
+extern "C" void rso_diag_stop_hist(uint64_t* out66) {
+  for (int i = 0; i < 66; ++i) out66[i] = g_diag_stop[i].load();
+}
