@@ -28,6 +28,7 @@
 #ifndef RS_SCHED_H_
 #define RS_SCHED_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -100,7 +101,16 @@ void rs_destroy(rs_handle* h);
 
 /* Use an existing CUDA stream (a cudaStream_t passed as void*); NULL = the handle's own. */
 int rs_set_stream(rs_handle* h, void* cuda_stream);
+/* The cudaStream_t (as void*) the handle launches its kernels on. */
+void* rs_get_stream(rs_handle* h);
+/* Waits for everything the handle has enqueued (kernels and the copies of the *_host calls). */
 int rs_sync(rs_handle* h);
+
+/* Page-locked host memory for the buffers of the *_host calls (cudaHostAlloc, portable; write_combined != 0 for
+ * buffers the CPU only writes, such as the CQI and rand() inputs).  A process that pins itself to the cores next
+ * to its GPU before calling this gets the pages from that NUMA node (first touch). */
+int rs_host_alloc(size_t bytes, int32_t write_combined, void** out);
+void rs_host_free(void* p);
 
 /* Per-bearer / per-slice state the reference keeps between TTIs (flows/radio-bearer.h:81-85,
  * downlink-transport-scheduler.h:38, downlink-nvs-scheduler.h:38).  Host arrays, [B][U] / [B][S];
@@ -126,11 +136,34 @@ int rs_reset_state(rs_handle* h);
 int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_t* active, double dt,
             const rs_outputs* out);
 
+/* rs_step for the in-simulator drop-in (n_cells = 1, but any batch works): the per-bearer and per-slice state the
+ * reference keeps in ITS objects goes up with the TTI's inputs and comes back with the results, in one
+ * host-to-device copy, one launch, one device-to-host copy and one synchronisation (rs_set_state + rs_set_queues +
+ * rs_step + rs_get_state cost four round trips).  Replaces DownlinkTransportScheduler::RBsAllocation
+ * (downlink-transport-scheduler.cpp:453-675) / DownlinkNVSScheduler::RBsAllocation (downlink-nvs-scheduler.cpp:
+ * 275-358) / DownlinkPacketScheduler::RBsAllocation (downlink-packet-scheduler.cpp:179-331) as called once per TTI
+ * from PacketScheduler::Schedule (packet-scheduler.cpp:72-90).  HOST pointers, synchronous. */
+typedef struct rs_cell_io {
+  double* avg_rate;           /* [B][U] in/out: m_averageTransmissionRate of each user's bearer(s), radio-bearer.cpp:138-164;
+                                 NULL = the handle's own state */
+  double* slice_state;        /* [B][S] in/out: slice_rbs_offset_ (ids 8/9/10/101/103, :618-620) or slice_ewma_time_
+                                 (ids 7/11, downlink-nvs-scheduler.cpp:128-140); NULL = the handle's own */
+  const uint8_t* cqi;         /* as rs_step */
+  const int32_t* rand2;       /* as rs_step */
+  const uint8_t* active;      /* as rs_step, may be NULL */
+  const int32_t* queue_bytes; /* [B][U] as rs_set_queues (one TTI), may be NULL */
+  const double* hol_delay;    /* [B][U] as rs_set_queues (one TTI), may be NULL */
+  double dt;                  /* as rs_step */
+  rs_outputs out;             /* as rs_step */
+} rs_cell_io;
+int rs_step_cell(rs_handle* h, const rs_cell_io* io);
+
 /* Queue state for the NEXT rs_step / rs_run_* call on this handle (consumed by it): what the reference reads from
  * its bearers each TTI (one bearer per UE).
  *   queue_bytes [T][B][U] int32   dataToTransmit of each UE's bearer (downlink-transport-scheduler.cpp:119-128):
  *                                 0 = no packets, the bearer is not listed this TTI; 100000000 = infinite buffer;
- *                                 else the queue size.  Replaces cfg.data_to_transmit: bytes sent are capped by it
+ *                                 else the queue size (values above 2^28-1 count as 2^28-1 where the reference
+ *                                 multiplies by 8 in an int; negative = not listed).  Replaces cfg.data_to_transmit: bytes sent are capped by it
  *                                 (:183-186), id 7 stops granting a user RBGs at m_requiredRBs
  *                                 (packet-scheduler.cpp:321-334, downlink-nvs-scheduler.cpp:299-300), id 1 drops a
  *                                 flow once its TBS covers the queue (downlink-packet-scheduler.cpp:264-269)
@@ -152,16 +185,27 @@ int rs_set_queues(rs_handle* h, const int32_t* queue_bytes, const double* hol_de
  *   dt      HOST array [T]
  *   d_out   device pointers, arrays [T][B][...]; NULL members are skipped
  *   ttis_per_launch  TTIs handled by one kernel launch with the cell state held on chip
- *                    (<= 0: library default)
+ *                    (<= 0: library default 16; at most 32: the TTIs' dt / trace rows ride in the kernel parameters)
  * Asynchronous on the handle's stream; rs_sync() waits. */
 int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                   const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
                   const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch);
 
-/* Same, HOST buffers in and out ([T][B][...]): the library stages them through pinned memory in
- * chunks and overlaps the copies with the kernels.  Synchronous. */
+/* Same, HOST buffers in and out ([T][B][...]): the library moves them in chunks of ttis_per_launch TTIs (at most
+ * 32; <= 0: library default) through a ring of device slots and overlaps the copies with the kernels on three
+ * streams.  Page-locked buffers (rs_host_alloc) make the copies asynchronous.  Synchronous: returns when the
+ * results are in `out`. */
 int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
                 const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
+/* The same call without the wait: everything is enqueued and *ticket names the call.  The slot ring stays in
+ * flight from one call to the next, so the first copies of call n+1 overlap the last kernels of call n.  The
+ * caller keeps every buffer of the call untouched until rs_wait(ticket) (or rs_sync) has returned; rs_wait
+ * returns once the call's results are in its `out` buffers.  A run loop alternates two sets of buffers:
+ *     rs_run_host_async(h, ..., bufs[k & 1], &t[k]);  if (k) { rs_wait(h, t[k-1]); consume(bufs[(k-1) & 1]); } */
+int rs_run_host_async(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
+                      const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch,
+                      int64_t* ticket);
+int rs_wait(rs_handle* h, int64_t ticket);
 
 /* ---- trace-driven CQI ingest ---------------------------------------------------------------------
  * Replaces EnbMacEntity's USE_REAL_TRACE path (src/protocolStack/mac/enb-mac-entity.cc:42-56 and
@@ -204,6 +248,9 @@ int rs_run_traces_device(rs_handle* h, int32_t n_ttis, const int32_t* trace_row,
                          const rs_outputs* d_out, int32_t ttis_per_launch);
 int rs_run_traces_host(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
                        const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch);
+int rs_run_traces_host_async(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
+                             const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch,
+                             int64_t* ticket);
 
 /* Synthetic workload of SURVEY.md section 8(d), generated on the device (bit-identical twin of
  * radiosaber_b200/workload.py): CQI i.i.d. from the cqi-traces-noise0 histogram, counter-based so
@@ -258,6 +305,8 @@ const char* rs_log_stderr(rs_log* lg, int64_t* len);
 void rs_log_clear(rs_log* lg);
 
 /* Introspection for benchmarks and tests. */
+/* Shape of the batch behind a handle; any pointer may be NULL. */
+int rs_dims(const rs_handle* h, int32_t* n_cells, int32_t* n_slices, int32_t* n_ues, int32_t* n_rbgs, int32_t* device);
 int32_t rs_rand_draws_per_cell_tti(const rs_handle* h);   /* int32 values per cell in rand2 (0, 2 or 300 x largest slice) */
 int64_t rs_launch_count(const rs_handle* h);      /* kernels launched by this handle so far */
 int32_t rs_smem_bytes(const rs_handle* h);        /* dynamic shared memory per CTA of the TTI kernel */

@@ -54,6 +54,8 @@ constexpr int kSortThreshold = 16;     /* libstdc++ _S_threshold, bits/stl_algo.
 constexpr int kMStride = 16;           /* metric table row: entries for CQI 0..15 */
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned short kNoUe = 0xffff;
+constexpr int kMaxQueueBytes = 268435455;  /* queue sizes saturate here: data * 8 is an int in the reference (2^31 overflows there) */
+constexpr int kMaxTtisPerLaunch = 32;  /* TTIs one launch can take (their dt / trace row ride in the kernel parameters) */
 
 /* ---- tables that are the same for every handle (set once per device) ------------------------- */
 struct ConstTables {
@@ -115,10 +117,11 @@ struct RunArgs {
   const int* queue;        /* [T][B][U] bytes queued on each UE's bearer (its dataToTransmit; 0 = not listed), or null:
                               DevCfg::data for everybody */
   const double* hol;       /* [T][B][U] head-of-line delay of the bearer, or null (0) */
-  const int* trace_row;    /* device [T], trace mode: row of every UE's trace in force at TTI t */
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
-  const double* dt;        /* device [T] */
+  /* per-TTI scalars travel in the kernel parameters (no copy, no staging buffer): at most kMaxTtisPerLaunch TTIs */
+  double dt[kMaxTtisPerLaunch];       /* Now - lastUpdate of the EWMA at TTI t (flows/radio-bearer.cpp:150) */
+  int trace_row[kMaxTtisPerLaunch];   /* trace mode: row of every UE's trace in force at TTI t */
   int T;
   short* rbg_to_ue; int* tbs_bits; uint8_t* mcs; uint8_t* final_cqi;
   int* slice_target; int* slice_quota; int* nvs_slice;
@@ -1397,7 +1400,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               }
             }
             const int wide = cqi_from_mean(__ddiv_rn(sum, (double)(G * d.rbg)));
-            need = qd[u] * 8 / d.tbs1[wide];
+            need = min(qd[u], kMaxQueueBytes) * 8 / d.tbs1[wide];
           }
           req[j - j0] = need;
           alc[j - j0] = 0;
@@ -1490,7 +1493,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               fsum[bu] = sum;
               const int nrbg = __popc(c.mask[2 * bu]) + __popc(c.mask[2 * bu + 1]);
               const int fc = cqi_from_mean(__ddiv_rn(sum, (double)(nrbg * d.rbg)));
-              if (d.tbs_n[nrbg * 16 + fc] >= qd[bu] * 8) {   /* dlps.cpp:264-269 */
+              if (d.tbs_n[nrbg * 16 + fc] >= min(qd[bu], kMaxQueueBytes) * 8) {   /* dlps.cpp:264-269 */
                 c.done[bu] = 1;
                 finished = 1;
               }

@@ -207,25 +207,23 @@ struct rs_handle {
   DevBuf<double> avg, offset, ewma;
   DevBuf<int> tx;
   DevBuf<unsigned long long> cum_bytes, cum_rbs;
-  /* per-call scratch */
-  DevBuf<double> dt_dev;
-  double* dt_pinned = nullptr;
-  size_t dt_pinned_n = 0;
   /* trace-driven CQI (rs_set_traces) */
   DevBuf<uint8_t> trace_tab;
-  DevBuf<int> ue_trace_off, trow_dev;
+  DevBuf<int> ue_trace_off;
   int n_traces = 0, trace_rows = 0;
-  bool stage_ok = false;
-  bool wide = false;
+  bool stage_ok = false;   /* the layout has room for a TTI of CQI (staged in shared memory) */
+  bool wide = false;       /* 512 threads per cell (rsw::) instead of 128 */
   /* queue state for the next run call (rs_set_queues), consumed by it */
   const int32_t* q_next = nullptr;
   const double* hol_next = nullptr;
   DevBuf<unsigned char> holmul;
-  DevBuf<int> tbs1;                 /* 512 threads per cell (rsw::) instead of 128 */             /* the layout has room for a TTI of CQI (cp.async staging) */
-  int* trow_pinned = nullptr;
-  size_t trow_pinned_n = 0;
+  DevBuf<int> tbs1;
   DevBuf<unsigned long long> stats;
-  /* staging for rs_step / rs_run_host: two slots */
+  /* staging for rs_step / rs_run_host*: a ring of slots that stays in flight across calls.  Chunk n of the
+   * handle's lifetime uses slot n % kSlots; a slot is refilled once the kernel that read it is done (k_done) and
+   * its kernel starts once the previous results have left it (out_done) -- all stream-side waits, the host never
+   * blocks while enqueueing. */
+  static constexpr int kSlots = 3;
   struct Slot {
     DevBuf<uint8_t> cqi, active, mcs, final_cqi;
     DevBuf<int> rand2, tbs_bits, slice_target, slice_quota, nvs_slice;
@@ -233,8 +231,25 @@ struct rs_handle {
     DevBuf<int> alloc_n, queue;
     DevBuf<double> hol;
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
-    int slab0 = -1;   /* first CQI slab resident in this slot (rs_run_host with a refresh > 1) */
-  } slot[2];
+    bool k_rec = false, out_rec = false;   /* the events have been recorded at least once */
+  } slot[kSlots];
+  uint64_t chunk_seq = 0;
+  /* CQI slabs shared by consecutive chunks (rs_run_host with a refresh > 1): two buffers, the kernels of the slab
+   * before last must be done before it is overwritten */
+  struct Slab {
+    DevBuf<uint8_t> cqi;
+    cudaEvent_t used = nullptr;   /* recorded after the last kernel that read the slab */
+    bool used_rec = false;
+    int index = -1;               /* slab of the CURRENT call resident here */
+  } slab[2];
+  /* completion of whole rs_run_host* calls: ticket n -> call_done[n % kTickets] (recorded on copy_out) */
+  static constexpr int kTickets = 16;
+  cudaEvent_t call_done[kTickets] = {};
+  int64_t calls = 0;
+  /* rs_step_cell: one pinned and one device mailbox (inputs | state | outputs) */
+  unsigned char* mb_host = nullptr;
+  DevBuf<unsigned char> mb_dev;
+  size_t mb_bytes = 0;
 };
 
 namespace {
@@ -259,45 +274,42 @@ const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
     default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
   }
 }
-/* a.trace_row != NULL selects the trace-driven instantiation */
-int launch_ttis(rs_handle* h, const rs::RunArgs& a) {
+int launch_ttis(rs_handle* h, const rs::RunArgs& a, bool trace, const rs::DevCfg* cfg = nullptr) {
   const dim3 grid(h->B), block(h->wide ? rsw::kThreads : rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
-  const bool trace = a.trace_row != nullptr;
   /* by address: the rsw:: kernels take rsw::DevCfg / rsw::RunArgs, the same bytes as the rs:: structs */
   const void* fn = tti_kernel_any(h->d.algo, trace, a.queue != nullptr, h->wide);
-  void* args[2] = {(void*)&h->d, (void*)&a};
+  void* args[2] = {(void*)(cfg ? cfg : &h->d), (void*)&a};
   CU(cudaLaunchKernel(fn, grid, block, args, sm, h->stream));
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;
 }
 
+/* cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel function (per device), not to a handle:
+ * every instantiation is opened up to the device's opt-in maximum once, so handles of different cell sizes
+ * can be alive together and launch in any order. */
 int set_smem_attr(rs_handle* h) {
-  const int sm = h->layout.total;
+  int max_optin = 0;
+  CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   for (int t = 0; t < 4; ++t)
     CU(cudaFuncSetAttribute(tti_kernel_any(h->d.algo, (t & 1) != 0, (t & 2) != 0, h->wide),
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
   return RS_OK;
 }
 
-/* the row of every UE's trace in force at each TTI -> device (same staging as dt) */
-int ensure_trow(rs_handle* h, const int32_t* trace_row, int n) {
+/* dt and trace rows of one launch ride in the kernel parameters.  trace_row -1 = no report received yet: the
+ * extra all-10 row behind every trace (ENodeB.cpp:207-217). */
+void fill_scalars(const rs_handle* h, rs::RunArgs* a, const double* dt, const int32_t* trace_row, int T) {
+  for (int t = 0; t < T; ++t) {
+    a->dt[t] = dt[t];
+    a->trace_row[t] = trace_row ? (trace_row[t] < 0 ? h->trace_rows : trace_row[t]) : 0;
+  }
+}
+int check_trace_rows(const rs_handle* h, const int32_t* trace_row, int n) {
   for (int t = 0; t < n; ++t)
     if (trace_row[t] < -1 || trace_row[t] >= h->trace_rows)
       return fail(RS_ERR_ARG, "trace_row[%d] = %d outside -1..%d", t, trace_row[t], h->trace_rows - 1);
-  CU(h->trow_dev.alloc((size_t)n));
-  if (h->trow_pinned_n < (size_t)n) {
-    if (h->trow_pinned) cudaFreeHost(h->trow_pinned);
-    h->trow_pinned = nullptr;
-    h->trow_pinned_n = 0;
-    CU(cudaMallocHost((void**)&h->trow_pinned, sizeof(int) * (size_t)n));
-    h->trow_pinned_n = (size_t)n;
-  }
-  CU(cudaStreamSynchronize(h->stream));
-  /* -1 = no report received yet: the extra all-10 row behind every trace (ENodeB.cpp:207-217) */
-  for (int t = 0; t < n; ++t) h->trow_pinned[t] = trace_row[t] < 0 ? h->trace_rows : trace_row[t];
-  CU(cudaMemcpyAsync(h->trow_dev.p, h->trow_pinned, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   return RS_OK;
 }
 
@@ -305,22 +317,6 @@ template <typename T>
 int upload(DevBuf<T>& b, const std::vector<T>& v) {
   CU(b.alloc(v.size()));
   if (!v.empty()) CU(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return RS_OK;
-}
-
-int ensure_dt(rs_handle* h, const double* dt, int n) {
-  CU(h->dt_dev.alloc((size_t)n));
-  if (h->dt_pinned_n < (size_t)n) {
-    if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
-    h->dt_pinned = nullptr;
-    h->dt_pinned_n = 0;
-    CU(cudaMallocHost((void**)&h->dt_pinned, sizeof(double) * (size_t)n));
-    h->dt_pinned_n = (size_t)n;
-  }
-  /* the previous async copy out of dt_pinned must be over before it is overwritten */
-  CU(cudaStreamSynchronize(h->stream));
-  memcpy(h->dt_pinned, dt, sizeof(double) * (size_t)n);
-  CU(cudaMemcpyAsync(h->dt_dev.p, h->dt_pinned, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   return RS_OK;
 }
 
@@ -370,16 +366,18 @@ bool wants(const rs_handle* h, int which) { /* outputs that exist for this sched
 extern "C" {
 
 const char* rs_last_error(void) { return g_err.c_str(); }
-int32_t rs_abi_version(void) { return 2; }
+int32_t rs_abi_version(void) { return 3; }
 
 void rs_destroy(rs_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_in) cudaStreamSynchronize(h->copy_in);
+  if (h->copy_out) cudaStreamSynchronize(h->copy_out);
   h->ue_to_slice.release(); h->slice_ptr.release(); h->slice_ues.release(); h->chunk_slice.release();
   h->tbs_n.release(); h->weight.release(); h->epow.release(); h->psi.release(); h->eq_tab.release();
   h->avg.release(); h->offset.release(); h->ewma.release(); h->tx.release();
-  h->cum_bytes.release(); h->cum_rbs.release(); h->dt_dev.release(); h->stats.release();
+  h->cum_bytes.release(); h->cum_rbs.release(); h->stats.release();
   for (auto& s : h->slot) {
     s.cqi.release(); s.active.release(); s.mcs.release(); s.final_cqi.release(); s.rand2.release();
     s.tbs_bits.release(); s.slice_target.release(); s.slice_quota.release(); s.nvs_slice.release();
@@ -389,9 +387,11 @@ void rs_destroy(rs_handle* h) {
     if (s.k_done) cudaEventDestroy(s.k_done);
     if (s.out_done) cudaEventDestroy(s.out_done);
   }
-  if (h->dt_pinned) cudaFreeHost(h->dt_pinned);
-  if (h->trow_pinned) cudaFreeHost(h->trow_pinned);
-  h->trace_tab.release(); h->ue_trace_off.release(); h->trow_dev.release();
+  for (auto& sl : h->slab) { sl.cqi.release(); if (sl.used) cudaEventDestroy(sl.used); }
+  for (auto& e : h->call_done) if (e) cudaEventDestroy(e);
+  if (h->mb_host) cudaFreeHost(h->mb_host);
+  h->mb_dev.release();
+  h->trace_tab.release(); h->ue_trace_off.release();
   h->holmul.release(); h->tbs1.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
@@ -407,7 +407,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     return fail(RS_ERR_UNSUPPORTED, "scheduler id %d: only 1 (PF), 7 (NVS), 8 (Sequential), 9 (RadioSaber), 10 (UpperBound), "
                 "11 (NVS non-greedy), 101 (SubOpt), 103 (VogelApproximate)", algo);
   if (S < 1 || S > RS_MAX_SLICES) return fail(RS_ERR_UNSUPPORTED, "n_slices %d outside 1..%d", S, RS_MAX_SLICES);
-  if (U < 1 || U > 65000) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..65000", U);
+  if (U < 1 || U > 32767) return fail(RS_ERR_UNSUPPORTED, "n_ues %d outside 1..32767 (rbg_to_ue / alloc_ue are int16)", U);
   if (cfg->rbg_size < 1 || cfg->n_rbs < cfg->rbg_size || cfg->n_rbs % cfg->rbg_size != 0)
     return fail(RS_ERR_UNSUPPORTED, "n_rbs %d must be a positive multiple of rbg_size %d", cfg->n_rbs, cfg->rbg_size);
   const int G = cfg->n_rbs / cfg->rbg_size;
@@ -639,9 +639,21 @@ int rs_set_stream(rs_handle* h, void* cuda_stream) {
 int rs_sync(rs_handle* h) {
   if (!h) return fail(RS_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->copy_in));
   CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->copy_out));
   return RS_OK;
 }
+
+void* rs_get_stream(rs_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int rs_host_alloc(size_t bytes, int32_t write_combined, void** out) {
+  if (!out || bytes == 0) return fail(RS_ERR_ARG, "rs_host_alloc: bad argument");
+  *out = nullptr;
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return RS_OK;
+}
+void rs_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int rs_reset_state(rs_handle* h) {
   if (!h) return fail(RS_ERR_ARG, "null handle");
@@ -691,6 +703,41 @@ int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cu
 }  /* extern "C" */
 
 namespace {
+/* Every stream of the handle idle.  Error exits of the pipelined calls go through here so that no copy is still
+ * reading or writing the caller's buffers when a "failed" call returns. */
+void drain(rs_handle* h) {
+  cudaStreamSynchronize(h->copy_in);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_out);
+}
+#define CU_DRAIN(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      drain(h);                                                                                    \
+      return fail(RS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                           \
+    }                                                                                              \
+  } while (0)
+
+void point_outputs(const rs_handle* h, rs::RunArgs* a, const rs_outputs* o, size_t t0) {
+  if (!o) return;
+  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
+  a->rbg_to_ue = o->rbg_to_ue ? o->rbg_to_ue + t0 * B * G : nullptr;
+  a->tbs_bits = o->tbs_bits ? o->tbs_bits + t0 * B * U : nullptr;
+  a->mcs = o->mcs ? o->mcs + t0 * B * U : nullptr;
+  a->final_cqi = o->final_cqi ? o->final_cqi + t0 * B * U : nullptr;
+  if (wants(h, 0)) {
+    a->slice_target = o->slice_target ? o->slice_target + t0 * B * S : nullptr;
+    a->slice_quota = o->slice_quota ? o->slice_quota + t0 * B * S : nullptr;
+  }
+  if (wants(h, 1)) a->nvs_slice = o->nvs_slice ? o->nvs_slice + t0 * B : nullptr;
+  if (h->d.algo == 10) {
+    a->alloc_n = o->alloc_n ? o->alloc_n + t0 * B : nullptr;
+    a->alloc_ue = o->alloc_ue ? o->alloc_ue + t0 * B * 2 * G : nullptr;
+    a->alloc_rbg = o->alloc_rbg ? o->alloc_rbg + t0 * B * 2 * G : nullptr;
+  }
+}
+
 /* trace_row == NULL: CQI slabs in device memory; else trace-driven (d_cqi unused) */
 int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                     const int32_t* trace_row, const int32_t* d_rand2, const uint8_t* d_active,
@@ -707,11 +754,10 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
-  int rc = ensure_dt(h, dt, n_ttis);
-  if (rc != RS_OK) return rc;
-  if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
+  if (trace_row) { const int rc = check_trace_rows(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   if (ttis_per_launch <= 0) ttis_per_launch = 16;
-  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G;
+  ttis_per_launch = std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch);
+  const size_t B = h->B, U = h->d.U;
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
     a.T = std::min(ttis_per_launch, n_ttis - t0);
@@ -722,130 +768,138 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.rand2 = (d_rand2 && h->d.rand_stride) ? d_rand2 + (size_t)t0 * B * h->d.rand_stride : nullptr;
     a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
     a.active_tti_stride = active_tti_stride;
-    a.dt = h->dt_dev.p + t0;
-    a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    fill_scalars(h, &a, dt + t0, trace_row ? trace_row + t0 : nullptr, a.T);
     a.queue = d_queue ? d_queue + (size_t)t0 * B * U : nullptr;
     a.hol = d_hol ? d_hol + (size_t)t0 * B * U : nullptr;
     a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
-    if (d_out) {
-      a.rbg_to_ue = d_out->rbg_to_ue ? d_out->rbg_to_ue + (size_t)t0 * B * G : nullptr;
-      a.tbs_bits = d_out->tbs_bits ? d_out->tbs_bits + (size_t)t0 * B * U : nullptr;
-      a.mcs = d_out->mcs ? d_out->mcs + (size_t)t0 * B * U : nullptr;
-      a.final_cqi = d_out->final_cqi ? d_out->final_cqi + (size_t)t0 * B * U : nullptr;
-      if (wants(h, 0)) {
-        a.slice_target = d_out->slice_target ? d_out->slice_target + (size_t)t0 * B * S : nullptr;
-        a.slice_quota = d_out->slice_quota ? d_out->slice_quota + (size_t)t0 * B * S : nullptr;
-      }
-      if (wants(h, 1)) a.nvs_slice = d_out->nvs_slice ? d_out->nvs_slice + (size_t)t0 * B : nullptr;
-      if (h->d.algo == 10) {
-        a.alloc_n = d_out->alloc_n ? d_out->alloc_n + (size_t)t0 * B : nullptr;
-        a.alloc_ue = d_out->alloc_ue ? d_out->alloc_ue + (size_t)t0 * B * 2 * G : nullptr;
-        a.alloc_rbg = d_out->alloc_rbg ? d_out->alloc_rbg + (size_t)t0 * B * 2 * G : nullptr;
-      }
-    }
-    rc = launch_ttis(h, a);
+    point_outputs(h, &a, d_out, (size_t)t0);
+    const int rc = launch_ttis(h, a, trace_row != nullptr);
     if (rc != RS_OK) return rc;
   }
   return RS_OK;
 }
 
-/* trace_row == NULL: CQI slabs from the host; else trace-driven (cqi unused, nothing but rand2/active goes up) */
+/* trace_row == NULL: CQI slabs from the host; else trace-driven (cqi unused, nothing but rand2/active goes up).
+ * Enqueues the whole call on the handle's three streams and returns a ticket; `wait` blocks until the call's
+ * results are in the caller's buffers.  The slot ring is NOT drained at the end of a call: the first chunks of
+ * the next call overlap the last kernels and copies of this one. */
 int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* trace_row,
                   const int32_t* rand2, const uint8_t* active, const double* dt, const rs_outputs* out,
-                  int32_t ttis_per_launch) {
+                  int32_t ttis_per_launch, bool wait, int64_t* ticket) {
   if (!h) return fail(RS_ERR_ARG, "null handle");
   /* rs_set_queues: consumed by this call whether it succeeds or not */
   const int32_t* queue = h->q_next;
   const double* hol = h->hol_next;
   h->q_next = nullptr;
   h->hol_next = nullptr;
+  if (ticket) *ticket = -1;
   if ((!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
   if (h->d.rand_stride > 0 && !rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
-  if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
-  if (ttis_per_launch <= 0) ttis_per_launch = trace_row ? 16 : 4;
-  const int TC = std::min(ttis_per_launch, n_ttis);
+  if (trace_row) { const int rc = check_trace_rows(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
+  if (ttis_per_launch <= 0) ttis_per_launch = trace_row ? 16 : 8;
+  const int TC = std::max(1, std::min(std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch), n_ttis));
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
-  int rc = ensure_dt(h, dt, n_ttis);
-  if (rc != RS_OK) return rc;
-  if (trace_row) { rc = ensure_trow(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
+  const bool slabs = !trace_row && cqi_refresh > 1;   /* consecutive chunks share a CQI slab */
   for (auto& s : h->slot) {
-    rc = alloc_slot(h, s, TC, out, active != nullptr, trace_row == nullptr, queue != nullptr, hol != nullptr);
-    if (rc != RS_OK) return rc;
+    const int rc = alloc_slot(h, s, TC, out, active != nullptr, !trace_row && !slabs, queue != nullptr, hol != nullptr);
+    if (rc != RS_OK) { drain(h); return rc; }
   }
-  int k = 0;
-  h->slot[0].slab0 = h->slot[1].slab0 = -1;
-  for (int t0 = 0, T = 0; t0 < n_ttis; t0 += T, ++k) {
-    rs_handle::Slot& s = h->slot[k & 1];
+  if (slabs)
+    for (auto& sl : h->slab) {
+      CU_DRAIN(sl.cqi.alloc(B * U * C));
+      if (!sl.used) CU_DRAIN(cudaEventCreateWithFlags(&sl.used, cudaEventDisableTiming));
+      sl.index = -1;   /* slab numbers are relative to this call's cqi pointer */
+    }
+  for (auto& e : h->call_done)
+    if (!e) CU_DRAIN(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  int next_slab_buf = 0;
+  for (int t0 = 0, T = 0; t0 < n_ttis; t0 += T) {
+    rs_handle::Slot& s = h->slot[h->chunk_seq % rs_handle::kSlots];
     T = std::min(TC, n_ttis - t0);
-    /* a chunk never straddles more CQI slabs than the slot holds: with a refresh > 1 it ends at the
-     * next refresh boundary and needs exactly one slab */
-    if (cqi_refresh > 1 && !trace_row) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
-    const int slab0 = t0 / cqi_refresh, n_slabs = (t0 + T - 1) / cqi_refresh - slab0 + 1;
+    /* with a refresh > 1 a chunk ends at the next refresh boundary: it reads exactly one slab */
+    if (slabs) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
+    const int slab0 = t0 / cqi_refresh;
     /* inputs: the slot's previous kernel must be done with them */
-    if (k >= 2) CU(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
-    if (!trace_row && !(cqi_refresh > 1 && s.slab0 == slab0))   /* the slab may still be resident from the chunk before last */
-      CU(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)slab0 * B * U * C, (size_t)n_slabs * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
-    s.slab0 = slab0;
+    if (s.k_rec) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
+    const uint8_t* d_cqi = nullptr;
+    rs_handle::Slab* sl = nullptr;
+    if (slabs) {
+      for (auto& c : h->slab) if (c.index == slab0) sl = &c;
+      if (!sl) {
+        sl = &h->slab[next_slab_buf];
+        next_slab_buf ^= 1;
+        if (sl->used_rec) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used, 0));
+        CU_DRAIN(cudaMemcpyAsync(sl->cqi.p, cqi + (size_t)slab0 * B * U * C, B * U * C, cudaMemcpyHostToDevice, h->copy_in));
+        sl->index = slab0;
+      }
+      d_cqi = sl->cqi.p;
+    } else if (!trace_row) {
+      CU_DRAIN(cudaMemcpyAsync(s.cqi.p, cqi + (size_t)t0 * B * U * C, (size_t)T * B * U * C, cudaMemcpyHostToDevice, h->copy_in));
+      d_cqi = s.cqi.p;
+    }
     const size_t RS = (size_t)h->d.rand_stride;
-    if (rand2 && RS) CU(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * RS, (size_t)T * B * RS * 4, cudaMemcpyHostToDevice, h->copy_in));
-    if (active) CU(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
-    if (queue) CU(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U, (size_t)T * B * U * 4, cudaMemcpyHostToDevice, h->copy_in));
-    if (hol) CU(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U, (size_t)T * B * U * 8, cudaMemcpyHostToDevice, h->copy_in));
-    CU(cudaEventRecord(s.in_done, h->copy_in));
+    if (rand2 && RS) CU_DRAIN(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * RS, (size_t)T * B * RS * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (active) CU_DRAIN(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
+    if (queue) CU_DRAIN(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U, (size_t)T * B * U * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (hol) CU_DRAIN(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U, (size_t)T * B * U * 8, cudaMemcpyHostToDevice, h->copy_in));
+    CU_DRAIN(cudaEventRecord(s.in_done, h->copy_in));
     /* kernel: inputs in, and the slot's previous outputs drained */
-    CU(cudaStreamWaitEvent(h->stream, s.in_done, 0));
-    if (k >= 2) CU(cudaStreamWaitEvent(h->stream, s.out_done, 0));
+    CU_DRAIN(cudaStreamWaitEvent(h->stream, s.in_done, 0));
+    if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->stream, s.out_done, 0));
     rs::RunArgs a{};
     a.T = T;
-    a.cqi = s.cqi.p; a.cqi_tti_stride = (long long)(B * U * C);
-    a.t0 = t0 - slab0 * cqi_refresh; a.cqi_refresh = cqi_refresh;
+    a.cqi = d_cqi; a.cqi_tti_stride = (long long)(B * U * C);
+    a.t0 = 0; a.cqi_refresh = slabs ? cqi_refresh : 1;   /* one resident slab, or one slab per TTI of the chunk */
     a.rand2 = (rand2 && RS) ? s.rand2.p : nullptr;
     a.active = active ? s.active.p : nullptr; a.active_tti_stride = (long long)(B * U);
-    a.dt = h->dt_dev.p + t0;
-    a.trace_row = trace_row ? h->trow_dev.p + t0 : nullptr;
+    fill_scalars(h, &a, dt + t0, trace_row ? trace_row + t0 : nullptr, T);
     a.queue = queue ? s.queue.p : nullptr;
     a.hol = hol ? s.hol.p : nullptr;
     a.stage = h->stage_ok ? 1 : 0;   /* slot buffers come from cudaMalloc; B*U*C is a multiple of 16 when stage_ok */
+    rs_outputs so{};
     if (out) {
-      a.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
-      a.tbs_bits = out->tbs_bits ? s.tbs_bits.p : nullptr;
-      a.mcs = out->mcs ? s.mcs.p : nullptr;
-      a.final_cqi = out->final_cqi ? s.final_cqi.p : nullptr;
-      if (wants(h, 0)) {
-        a.slice_target = out->slice_target ? s.slice_target.p : nullptr;
-        a.slice_quota = out->slice_quota ? s.slice_quota.p : nullptr;
-      }
-      if (wants(h, 1)) a.nvs_slice = out->nvs_slice ? s.nvs_slice.p : nullptr;
-      if (h->d.algo == 10) {
-        a.alloc_n = out->alloc_n ? s.alloc_n.p : nullptr;
-        a.alloc_ue = out->alloc_ue ? s.alloc_ue.p : nullptr;
-        a.alloc_rbg = out->alloc_rbg ? s.alloc_rbg.p : nullptr;
-      }
+      so.rbg_to_ue = out->rbg_to_ue ? s.rbg_to_ue.p : nullptr;
+      so.tbs_bits = out->tbs_bits ? s.tbs_bits.p : nullptr;
+      so.mcs = out->mcs ? s.mcs.p : nullptr;
+      so.final_cqi = out->final_cqi ? s.final_cqi.p : nullptr;
+      so.slice_target = out->slice_target ? s.slice_target.p : nullptr;
+      so.slice_quota = out->slice_quota ? s.slice_quota.p : nullptr;
+      so.nvs_slice = out->nvs_slice ? s.nvs_slice.p : nullptr;
+      so.alloc_n = out->alloc_n ? s.alloc_n.p : nullptr;
+      so.alloc_ue = out->alloc_ue ? s.alloc_ue.p : nullptr;
+      so.alloc_rbg = out->alloc_rbg ? s.alloc_rbg.p : nullptr;
+      point_outputs(h, &a, &so, 0);
     }
-    rc = launch_ttis(h, a);
-    if (rc != RS_OK) return rc;
-    CU(cudaEventRecord(s.k_done, h->stream));
+    const int rc = launch_ttis(h, a, trace_row != nullptr);
+    if (rc != RS_OK) { drain(h); return rc; }
+    CU_DRAIN(cudaEventRecord(s.k_done, h->stream));
+    s.k_rec = true;
+    if (sl) { CU_DRAIN(cudaEventRecord(sl->used, h->stream)); sl->used_rec = true; }
     /* outputs */
-    CU(cudaStreamWaitEvent(h->copy_out, s.k_done, 0));
+    CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done, 0));
     if (out) {
-      if (a.rbg_to_ue) CU(cudaMemcpyAsync(out->rbg_to_ue + (size_t)t0 * B * G, s.rbg_to_ue.p, (size_t)T * B * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.tbs_bits) CU(cudaMemcpyAsync(out->tbs_bits + (size_t)t0 * B * U, s.tbs_bits.p, (size_t)T * B * U * 4, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.mcs) CU(cudaMemcpyAsync(out->mcs + (size_t)t0 * B * U, s.mcs.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.final_cqi) CU(cudaMemcpyAsync(out->final_cqi + (size_t)t0 * B * U, s.final_cqi.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.slice_target) CU(cudaMemcpyAsync(out->slice_target + (size_t)t0 * B * S, s.slice_target.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.slice_quota) CU(cudaMemcpyAsync(out->slice_quota + (size_t)t0 * B * S, s.slice_quota.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.nvs_slice) CU(cudaMemcpyAsync(out->nvs_slice + (size_t)t0 * B, s.nvs_slice.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.alloc_n) CU(cudaMemcpyAsync(out->alloc_n + (size_t)t0 * B, s.alloc_n.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.alloc_ue) CU(cudaMemcpyAsync(out->alloc_ue + (size_t)t0 * B * 2 * G, s.alloc_ue.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
-      if (a.alloc_rbg) CU(cudaMemcpyAsync(out->alloc_rbg + (size_t)t0 * B * 2 * G, s.alloc_rbg.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.rbg_to_ue) CU_DRAIN(cudaMemcpyAsync(out->rbg_to_ue + (size_t)t0 * B * G, s.rbg_to_ue.p, (size_t)T * B * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.tbs_bits) CU_DRAIN(cudaMemcpyAsync(out->tbs_bits + (size_t)t0 * B * U, s.tbs_bits.p, (size_t)T * B * U * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.mcs) CU_DRAIN(cudaMemcpyAsync(out->mcs + (size_t)t0 * B * U, s.mcs.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.final_cqi) CU_DRAIN(cudaMemcpyAsync(out->final_cqi + (size_t)t0 * B * U, s.final_cqi.p, (size_t)T * B * U, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.slice_target) CU_DRAIN(cudaMemcpyAsync(out->slice_target + (size_t)t0 * B * S, s.slice_target.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.slice_quota) CU_DRAIN(cudaMemcpyAsync(out->slice_quota + (size_t)t0 * B * S, s.slice_quota.p, (size_t)T * B * S * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.nvs_slice) CU_DRAIN(cudaMemcpyAsync(out->nvs_slice + (size_t)t0 * B, s.nvs_slice.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_n) CU_DRAIN(cudaMemcpyAsync(out->alloc_n + (size_t)t0 * B, s.alloc_n.p, (size_t)T * B * 4, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_ue) CU_DRAIN(cudaMemcpyAsync(out->alloc_ue + (size_t)t0 * B * 2 * G, s.alloc_ue.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
+      if (a.alloc_rbg) CU_DRAIN(cudaMemcpyAsync(out->alloc_rbg + (size_t)t0 * B * 2 * G, s.alloc_rbg.p, (size_t)T * B * 2 * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
     }
-    CU(cudaEventRecord(s.out_done, h->copy_out));
+    CU_DRAIN(cudaEventRecord(s.out_done, h->copy_out));
+    s.out_rec = true;
+    h->chunk_seq++;
   }
-  CU(cudaStreamSynchronize(h->copy_out));
-  CU(cudaStreamSynchronize(h->stream));
-  CU(cudaStreamSynchronize(h->copy_in));
+  /* copy_out is behind every kernel of the call (it waited on each k_done), and every kernel is behind its inputs */
+  const int64_t tk = h->calls++;
+  CU_DRAIN(cudaEventRecord(h->call_done[tk % rs_handle::kTickets], h->copy_out));
+  if (ticket) *ticket = tk;
+  if (wait) CU_DRAIN(cudaEventSynchronize(h->call_done[tk % rs_handle::kTickets]));
   return RS_OK;
 }
 }  // namespace
@@ -863,7 +917,14 @@ int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cq
 int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
                 const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
   if (!cqi) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
-  return run_host_impl(h, n_ttis, cqi, cqi_refresh, nullptr, rand2, active, dt, out, ttis_per_launch);
+  return run_host_impl(h, n_ttis, cqi, cqi_refresh, nullptr, rand2, active, dt, out, ttis_per_launch, true, nullptr);
+}
+
+int rs_run_host_async(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,
+                      const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch,
+                      int64_t* ticket) {
+  if (!cqi || !ticket) return fail(RS_ERR_ARG, "rs_run_host_async: bad argument");
+  return run_host_impl(h, n_ttis, cqi, cqi_refresh, nullptr, rand2, active, dt, out, ttis_per_launch, false, ticket);
 }
 
 int rs_run_traces_device(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* d_rand2,
@@ -877,7 +938,23 @@ int rs_run_traces_device(rs_handle* h, int32_t n_ttis, const int32_t* trace_row,
 int rs_run_traces_host(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
                        const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch) {
   if (!trace_row) return fail(RS_ERR_ARG, "rs_run_traces_host: bad argument");
-  return run_host_impl(h, n_ttis, nullptr, 1, trace_row, rand2, active, dt, out, ttis_per_launch);
+  return run_host_impl(h, n_ttis, nullptr, 1, trace_row, rand2, active, dt, out, ttis_per_launch, true, nullptr);
+}
+
+int rs_run_traces_host_async(rs_handle* h, int32_t n_ttis, const int32_t* trace_row, const int32_t* rand2,
+                             const uint8_t* active, const double* dt, const rs_outputs* out, int32_t ttis_per_launch,
+                             int64_t* ticket) {
+  if (!trace_row || !ticket) return fail(RS_ERR_ARG, "rs_run_traces_host_async: bad argument");
+  return run_host_impl(h, n_ttis, nullptr, 1, trace_row, rand2, active, dt, out, ttis_per_launch, false, ticket);
+}
+
+int rs_wait(rs_handle* h, int64_t ticket) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  if (ticket < 0 || ticket >= h->calls) return fail(RS_ERR_ARG, "rs_wait: ticket %lld was never issued", (long long)ticket);
+  CU(cudaSetDevice(h->device));
+  /* an event that has been re-used by a later call completes after the earlier call did */
+  CU(cudaEventSynchronize(h->call_done[ticket % rs_handle::kTickets]));
+  return RS_OK;
 }
 
 /* EnbMacEntity::ReceiveCqiIdealControlMessage under USE_REAL_TRACE, enb-mac-entity.cc:189-191:
@@ -1171,6 +1248,98 @@ int rs_step(rs_handle* h, const uint8_t* cqi, const int32_t* rand2, const uint8_
   return rs_run_host(h, 1, cqi, 1, rand2, active, &dt, out, 1);
 }
 
+/* One TTI with everything the in-simulator plug-in moves per TTI in ONE host-to-device copy, one launch, one
+ * device-to-host copy and one synchronisation: the mailbox is [inputs | state | outputs], the state part goes up
+ * and comes back. */
+int rs_step_cell(rs_handle* h, const rs_cell_io* io) {
+  if (!h || !io || !io->cqi) return fail(RS_ERR_ARG, "rs_step_cell: bad argument");
+  h->q_next = nullptr;
+  h->hol_next = nullptr;
+  if (io->hol_delay && !io->queue_bytes) return fail(RS_ERR_ARG, "rs_step_cell: head-of-line delays without queue sizes");
+  if (h->d.rand_stride > 0 && !io->rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
+  CU(cudaSetDevice(h->device));
+  const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols, RS = (size_t)h->d.rand_stride;
+  const rs_outputs& o = io->out;
+  const bool nvs = h->d.algo == 7 || h->d.algo == 11, tr = is_transport(h->d.algo);
+  size_t off = 0;
+  auto take = [&](bool want, size_t bytes) { const size_t at = off; if (want) off += (bytes + 15) & ~(size_t)15; return at; };
+  const size_t o_cqi = take(true, B * U * C), o_rand = take(io->rand2 && RS, B * RS * 4), o_act = take(io->active, B * U),
+               o_q = take(io->queue_bytes, B * U * 4), o_hol = take(io->hol_delay, B * U * 8);
+  const size_t state0 = off;
+  const bool st = io->slice_state && (nvs || tr);
+  const size_t o_avg = take(io->avg_rate, B * U * 8), o_st = take(st, B * S * 8);
+  const size_t out0 = off;
+  const size_t o_rbg = take(o.rbg_to_ue, B * G * 2), o_bits = take(o.tbs_bits, B * U * 4), o_mcs = take(o.mcs, B * U),
+               o_fc = take(o.final_cqi, B * U), o_tgt = take(o.slice_target && tr, B * S * 4),
+               o_quo = take(o.slice_quota && tr, B * S * 4), o_nvs = take(o.nvs_slice && nvs, B * 4),
+               o_an = take(o.alloc_n && h->d.algo == 10, B * 4), o_au = take(o.alloc_ue && h->d.algo == 10, B * 2 * G * 2),
+               o_ar = take(o.alloc_rbg && h->d.algo == 10, B * 2 * G * 2);
+  const size_t total = off;
+  if (h->mb_bytes < total) {
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->mb_host) cudaFreeHost(h->mb_host);
+    h->mb_host = nullptr;
+    h->mb_bytes = 0;
+    CU(cudaMallocHost((void**)&h->mb_host, total));
+    CU(h->mb_dev.alloc(total));
+    h->mb_bytes = total;
+  }
+  unsigned char* m = h->mb_host;
+  unsigned char* dm = h->mb_dev.p;
+  memcpy(m + o_cqi, io->cqi, B * U * C);
+  if (io->rand2 && RS) memcpy(m + o_rand, io->rand2, B * RS * 4);
+  if (io->active) memcpy(m + o_act, io->active, B * U);
+  if (io->queue_bytes) memcpy(m + o_q, io->queue_bytes, B * U * 4);
+  if (io->hol_delay) memcpy(m + o_hol, io->hol_delay, B * U * 8);
+  if (io->avg_rate) memcpy(m + o_avg, io->avg_rate, B * U * 8);
+  if (st) memcpy(m + o_st, io->slice_state, B * S * 8);
+  CU(cudaMemcpyAsync(dm, m, out0, cudaMemcpyHostToDevice, h->stream));
+  rs::DevCfg d = h->d;
+  if (io->avg_rate) d.avg = (double*)(dm + o_avg);
+  if (st) { if (nvs) d.ewma = (double*)(dm + o_st); else d.offset = (double*)(dm + o_st); }
+  rs::RunArgs a{};
+  a.T = 1;
+  a.cqi = dm + o_cqi; a.cqi_tti_stride = (long long)(B * U * C);
+  a.t0 = 0; a.cqi_refresh = 1;
+  a.rand2 = (io->rand2 && RS) ? (const int*)(dm + o_rand) : nullptr;
+  a.active = io->active ? dm + o_act : nullptr; a.active_tti_stride = (long long)(B * U);
+  a.dt[0] = io->dt;
+  a.queue = io->queue_bytes ? (const int*)(dm + o_q) : nullptr;
+  a.hol = io->hol_delay ? (const double*)(dm + o_hol) : nullptr;
+  a.stage = h->stage_ok ? 1 : 0;
+  rs_outputs so{};
+  so.rbg_to_ue = o.rbg_to_ue ? (int16_t*)(dm + o_rbg) : nullptr;
+  so.tbs_bits = o.tbs_bits ? (int32_t*)(dm + o_bits) : nullptr;
+  so.mcs = o.mcs ? dm + o_mcs : nullptr;
+  so.final_cqi = o.final_cqi ? dm + o_fc : nullptr;
+  so.slice_target = (o.slice_target && tr) ? (int32_t*)(dm + o_tgt) : nullptr;
+  so.slice_quota = (o.slice_quota && tr) ? (int32_t*)(dm + o_quo) : nullptr;
+  so.nvs_slice = (o.nvs_slice && nvs) ? (int32_t*)(dm + o_nvs) : nullptr;
+  if (h->d.algo == 10) {
+    so.alloc_n = o.alloc_n ? (int32_t*)(dm + o_an) : nullptr;
+    so.alloc_ue = o.alloc_ue ? (int16_t*)(dm + o_au) : nullptr;
+    so.alloc_rbg = o.alloc_rbg ? (int16_t*)(dm + o_ar) : nullptr;
+  }
+  point_outputs(h, &a, &so, 0);
+  const int rc = launch_ttis(h, a, false, &d);
+  if (rc != RS_OK) { cudaStreamSynchronize(h->stream); return rc; }
+  if (total > state0) CU(cudaMemcpyAsync(m + state0, dm + state0, total - state0, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (io->avg_rate) memcpy(io->avg_rate, m + o_avg, B * U * 8);
+  if (st) memcpy(io->slice_state, m + o_st, B * S * 8);
+  if (so.rbg_to_ue) memcpy(o.rbg_to_ue, m + o_rbg, B * G * 2);
+  if (so.tbs_bits) memcpy(o.tbs_bits, m + o_bits, B * U * 4);
+  if (so.mcs) memcpy(o.mcs, m + o_mcs, B * U);
+  if (so.final_cqi) memcpy(o.final_cqi, m + o_fc, B * U);
+  if (so.slice_target) memcpy(o.slice_target, m + o_tgt, B * S * 4);
+  if (so.slice_quota) memcpy(o.slice_quota, m + o_quo, B * S * 4);
+  if (so.nvs_slice) memcpy(o.nvs_slice, m + o_nvs, B * 4);
+  if (so.alloc_n) memcpy(o.alloc_n, m + o_an, B * 4);
+  if (so.alloc_ue) memcpy(o.alloc_ue, m + o_au, B * 2 * G * 2);
+  if (so.alloc_rbg) memcpy(o.alloc_rbg, m + o_ar, B * 2 * G * 2);
+  return RS_OK;
+}
+
 int rs_synth_cqi(rs_handle* h, uint64_t seed, int64_t cell0, int64_t epoch0, int32_t n_slabs, uint8_t* d_out) {
   if (!h || !d_out || n_slabs < 0) return fail(RS_ERR_ARG, "rs_synth_cqi: bad argument");
   if (h->d.cqi_per_rb == 1) return fail(RS_ERR_UNSUPPORTED, "synthetic CQI is one value per RBG");
@@ -1244,6 +1413,15 @@ int rs_get_stats(rs_handle* h, uint64_t* stats) {
   return RS_OK;
 }
 
+int rs_dims(const rs_handle* h, int32_t* n_cells, int32_t* n_slices, int32_t* n_ues, int32_t* n_rbgs, int32_t* device) {
+  if (!h) return fail(RS_ERR_ARG, "null handle");
+  if (n_cells) *n_cells = h->B;
+  if (n_slices) *n_slices = h->d.S;
+  if (n_ues) *n_ues = h->d.U;
+  if (n_rbgs) *n_rbgs = h->d.G;
+  if (device) *device = h->device;
+  return RS_OK;
+}
 int32_t rs_rand_draws_per_cell_tti(const rs_handle* h) { return h ? h->d.rand_stride : 0; }
 int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
 int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }

@@ -168,6 +168,10 @@ class RsGpuScheduler : public PacketScheduler {
     if (h_) return;
     n_rbs_ = (int)GetMacEntity()->GetDevice()->GetPhy()->GetBandwidthManager()->GetDlSubChannels().size();
     rbg_size_ = get_rbg_size(n_rbs_);
+    /* nb_rbs = nb_rbs - (nb_rbs % rbg_size), downlink-transport-scheduler.cpp:460 / downlink-nvs-scheduler.cpp:281;
+     * DownlinkPacketScheduler rounds up instead (a short last RBG, downlink-packet-scheduler.cpp:190): id 1 keeps
+     * the full count and rs_create refuses a band that is not whole RBGs */
+    if (id_ != 1) n_rbs_ -= n_rbs_ % rbg_size_;
     n_rbgs_ = n_rbs_ / rbg_size_;
     const int U = (int)user_to_slice_.size(), S = num_slices_;
     std::vector<int32_t> params(4 * S), u2s(user_to_slice_.begin(), user_to_slice_.end());

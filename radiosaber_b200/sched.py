@@ -33,6 +33,8 @@ ABI_SYMBOLS = (
     "rs_run_traces_device", "rs_run_traces_host",
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti", "rs_log_tti_grants",
     "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues",
+    "rs_get_stream", "rs_host_alloc", "rs_host_free", "rs_step_cell", "rs_run_host_async", "rs_run_traces_host_async",
+    "rs_wait", "rs_dims",
 )
 
 
@@ -54,6 +56,14 @@ class _Out(C.Structure):
         ("rbg_to_ue", C.c_void_p), ("tbs_bits", C.c_void_p), ("mcs", C.c_void_p), ("final_cqi", C.c_void_p),
         ("slice_target", C.c_void_p), ("slice_quota", C.c_void_p), ("nvs_slice", C.c_void_p),
         ("alloc_n", C.c_void_p), ("alloc_ue", C.c_void_p), ("alloc_rbg", C.c_void_p),
+    ]
+
+
+class _CellIo(C.Structure):
+    _fields_ = [
+        ("avg_rate", C.c_void_p), ("slice_state", C.c_void_p), ("cqi", C.c_void_p), ("rand2", C.c_void_p),
+        ("active", C.c_void_p), ("queue_bytes", C.c_void_p), ("hol_delay", C.c_void_p), ("dt", C.c_double),
+        ("out", _Out),
     ]
 
 
@@ -122,6 +132,15 @@ def lib():
         L.rs_log_stderr.restype = C.c_char_p
         L.rs_log_clear.argtypes = [C.c_void_p]
         L.rs_log_clear.restype = None
+        L.rs_get_stream.argtypes = [C.c_void_p]
+        L.rs_get_stream.restype = C.c_void_p
+        L.rs_host_alloc.argtypes = [C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
+        L.rs_host_free.argtypes = [C.c_void_p]
+        L.rs_host_free.restype = None
+        L.rs_step_cell.argtypes = [C.c_void_p, C.POINTER(_CellIo)]
+        L.rs_run_host_async.argtypes = L.rs_run_host.argtypes + [C.POINTER(C.c_int64)]
+        L.rs_run_traces_host_async.argtypes = L.rs_run_traces_host.argtypes + [C.POINTER(C.c_int64)]
+        L.rs_wait.argtypes = [C.c_void_p, C.c_int64]
         _lib = L
     return _lib
 
@@ -285,6 +304,36 @@ class Scheduler:
         out, o = self._host_outputs(None, want_aux)
         _check(lib().rs_step(self._h, _ptr(cqi), _ptr(rand2), _ptr(act), float(dt), C.byref(o)))
         return out
+
+    def step_cell(self, cqi, rand2=None, dt=0.001, active=None, queue=None, hol=None, avg_rate=None,
+                  slice_state=None):
+        """rs_step_cell: one TTI with the caller's state (avg_rate [B][U], slice_state [B][S], both updated in
+        place when given) travelling with the inputs -- one copy up, one launch, one copy down."""
+        B, U = self.B, self.U
+        cqi = np.ascontiguousarray(cqi, dtype=np.uint8)
+        assert cqi.size == B * U * self.cqi_cols, cqi.shape
+        rand2 = self._draws(rand2, (B,))
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
+        q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32).reshape(B, U)
+        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(B, U)
+        for st, shape in ((avg_rate, (B, U)), (slice_state, (B, self.S))):
+            assert st is None or (st.dtype == np.float64 and st.flags.c_contiguous and st.shape == shape)
+        out, o = self._host_outputs(None, True)
+        io = _CellIo(_ptr(avg_rate), _ptr(slice_state), _ptr(cqi), _ptr(rand2), _ptr(act), _ptr(q), _ptr(h), float(dt), o)
+        _check(lib().rs_step_cell(self._h, C.byref(io)))
+        return out
+
+    def run_host_async(self, cqi, rand2, dt, out, o, ttis_per_launch=0, cqi_refresh=1):
+        """rs_run_host_async on caller-owned arrays (kept alive and untouched until wait(ticket)); out / o come from
+        _host_outputs().  Returns the ticket."""
+        T = int(dt.shape[0])
+        ticket = C.c_int64(-1)
+        _check(lib().rs_run_host_async(self._h, T, _ptr(cqi), int(cqi_refresh), _ptr(rand2), None, _ptr(dt),
+                                       C.byref(o), int(ttis_per_launch), C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait(self, ticket):
+        _check(lib().rs_wait(self._h, int(ticket)))
 
     def run_host(self, cqi, rand2, dt, active=None, want_aux=False, ttis_per_launch=0, cqi_refresh=1, queue=None,
                  hol=None):

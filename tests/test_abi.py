@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(sched.LIB_PATH)
     for name in _declared_symbols():
         assert hasattr(L, name), name
-    assert sched.lib().rs_abi_version() == 2
+    assert sched.lib().rs_abi_version() == 3
 
 
 def test_create_rejects_bad_configs_without_touching_the_gpu():
