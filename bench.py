@@ -10,10 +10,16 @@ with PF enterprise schedulers.  A "step" is `--ttis-per-step` consecutive TTIs o
   python bench.py --impl reference [...]                          # the reference's own CPU scheduler
 
 One JSON line on stdout (rank 0).  `value` = cell-TTIs/s with inputs resident in HBM, timed with
-CUDA events on the launching stream; `e2e` = the same metric through the host-buffer C-ABI call
-(rs_run_host) with the host<->device copies inside the timed region; `roofline` = algorithmic
-bytes of the TTI kernel / its launch time against the measured HBM peak; `cpu_baseline` = the CPU
-oracle port on this box's host cores (a reported baseline, not the target).
+CUDA events on the launching stream; `e2e` = the same metric through the host-buffer C-ABI calls
+(rs_run_host_async / rs_wait, pinned host buffers) with the host<->device copies inside the timed
+region, CQI reported every 40 TTIs like the reference's CQI_INTERVAL (enb-mac-entity.cc:38), and the
+every-TTI CQI stream as the stated worst case next to a measured host-to-device ceiling; `roofline` =
+algorithmic bytes of the TTI kernel / its launch time against the measured HBM peak; `parity_spot` =
+three cells of the TIMED run replayed through the CPU oracle over every TTI of the run; `cpu_baseline`
+= the CPU oracle port on this box's host cores (a reported baseline, not the target).
+
+  --cells-total N   BASELINE configs[4]: N cells in total, block-partitioned over the ranks (strong
+                    sharding: 65536 cells -> 8192 per GPU at 8 GPUs) instead of --cells per GPU.
 """
 from __future__ import annotations
 
@@ -49,17 +55,21 @@ def slice_setup():
 
 
 def workload_config(args, n_gpus):
+    total = args.cells_total if args.cells_total > 0 else args.cells * n_gpus
+    per = f"{total} cells in total sharded over {n_gpus} GPU(s) (BASELINE configs[4])" if args.cells_total > 0 \
+        else f"{args.cells} cells/GPU (BASELINE configs[1])"
     return {
-        "workload": f"{args.cells} cells/GPU x {S} slices x {UES_PER_SLICE} backlogged UEs, 100 MHz "
+        "workload": f"{per} x {S} slices x {UES_PER_SLICE} backlogged UEs, 100 MHz "
                     f"({R} RBs, {G} RBGs), RadioSaber id {args.algo}, PF enterprise schedulers, synthetic CQI "
-                    f"from the cqi-traces-noise0 histogram refreshed every TTI (BASELINE configs[1])",
-        "cells_per_gpu": args.cells, "cells_total": args.cells * n_gpus, "slices": S, "ues": U, "rbgs": G,
+                    f"from the cqi-traces-noise0 histogram refreshed every TTI",
+        "cells_per_gpu": (total + n_gpus - 1) // n_gpus if args.cells_total > 0 else args.cells,
+        "cells_total": total, "slices": S, "ues": U, "rbgs": G,
         "scheduler_id": args.algo, "ttis_per_step": args.ttis_per_step, "ttis_per_launch": args.ttis_per_launch,
         "cqi_refresh_ttis": 1, "seed": SEED,
         "l2": f"each step streams {args.cells * U * G * args.ttis_per_step / 1e6:.0f} MB of CQI per GPU "
               "(> 126 MB L2), so no input is L2-resident between timed iterations",
         "parallelism": f"cells sharded over {n_gpus} GPU(s), no data-path collective; one NCCL reduce of "
-                       "per-slice stats after the timed region",
+                       "per-slice stats after the timed region (rs_reduce_stats, C ABI)",
     }
 
 
@@ -106,18 +116,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+TRAFFIC_CAPTURES = ("r02_tti_kernel_ncu_full.csv", "r01_tti_kernel_ncu_full.csv")
+
+
 def ncu_traffic_bytes():
-    """DRAM bytes of one TTI-kernel launch from the committed ncu --set full capture
-    (profiles/r01_tti_kernel_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum)."""
-    try:
-        tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "r01_tti_kernel_ncu_full.csv")):
-            name, unit, val = line.strip().split(",")[:3]
-            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-        return tot or None
-    except Exception:
-        return None
+    """(DRAM bytes of one TTI-kernel launch, file) from the newest committed ncu --set full capture
+    (dram__bytes_read.sum + dram__bytes_write.sum of a 4096-cell x 16-TTI launch).  A citation of a capture, not
+    a property of this run: the file is named in the line so that a stale one is visible."""
+    for fn in TRAFFIC_CAPTURES:
+        try:
+            tot = 0.0
+            for line in open(os.path.join(ROOT, "profiles", fn)):
+                name, unit, val = line.strip().split(",")[:3]
+                if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+            if tot:
+                return tot, "profiles/" + fn
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak_gbs():
@@ -216,7 +233,44 @@ def run_reference_arm(args, n_gpus):
 
 
 # ---------------------------------------------------------------------------------------------
+def pinned(nbytes, write_combined=False):
+    """uint8 numpy view of page-locked host memory from the library (rs_host_alloc)."""
+    import ctypes as C
+    from radiosaber_b200 import sched
+    ptr = C.c_void_p()
+    sched._check(sched.lib().rs_host_alloc(int(nbytes), 1 if write_combined else 0, C.byref(ptr)))
+    buf = (C.c_uint8 * int(nbytes)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    return arr, ptr
+
+
+def oracle_spot_check(args, g, cells, cell0, n_ttis, period, dts, last_out, last_t0):
+    """Replays `cells` of the timed device-resident run through the CPU oracle for all n_ttis TTIs (TTI n read CQI /
+    rand() slab n % period) and compares the final state of those cells and the outputs of the run's last step."""
+    from oracle.pyoracle import OracleScheduler
+    w, p, u2s = slice_setup()
+    st = g.get_state()
+    o = OracleScheduler(args.algo, w, p, u2s, len(cells))
+    cqi = np.stack([workload.synth_cqi(SEED, cell0 + c, 1, 0, period, U, G)[:, 0] for c in cells], axis=1)   # [period][n][U][G]
+    r2 = np.stack([workload.synth_rand2(SEED, cell0 + c, 1, 0, period, S)[:, 0] for c in cells], axis=1)
+    bad = 0
+    for n in range(n_ttis):
+        out = o.step(cqi[n % period], r2[n % period], dt=float(dts[n]))
+        if n >= last_t0:
+            for k in ("rbg_to_ue", "tbs_bits", "mcs"):
+                bad += int(not np.array_equal(out[k], last_out[k][n - last_t0][cells]))
+    so = o.get_state()
+    fields = ["avg_rate", "tx_bytes", "cum_bytes", "cum_rbs"] + (["slice_offset"] if args.algo in (8, 9, 10, 101, 103) else []) \
+        + (["nvs_ewma"] if args.algo in (7, 11) else [])
+    for k in fields:
+        bad += int(not np.array_equal(so[k], st[k][cells]))
+    return {"cells": len(cells), "ttis": int(n_ttis), "mismatches": int(bad),
+            "compared": f"final {'/'.join(fields)} of cells {list(map(int, cells))} after every TTI of the run (warm-up + timed) "
+                        f"and rbg_to_ue/tbs_bits/mcs of the last {n_ttis - last_t0} TTIs, against oracle/rs_oracle.cpp"}
+
+
 def run_cuda_arm(args, n_gpus):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from radiosaber_b200 import sched, shard
@@ -252,12 +306,18 @@ def run_cuda_arm(args, n_gpus):
                 os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
         except Exception:
             pass
-    B, TT, K, W = args.cells, args.ttis_per_step, args.steps, args.warmup
+    TT, K, W = args.ttis_per_step, args.steps, args.warmup
+    if args.cells_total > 0:     # BASELINE configs[4]: a fixed batch, block-partitioned over the ranks
+        cell0, B = shard.shard_cells(args.cells_total, world, rank)
+        total_cells = args.cells_total
+    else:                         # configs[1]: --cells per GPU, every rank its own Monte-Carlo cells
+        B = args.cells
+        cell0, _ = shard.shard_cells(B * world, world, rank)
+        total_cells = B * world
     w, p, u2s = slice_setup()
     g = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index)
     stream = torch.cuda.current_stream(dev)
     g.set_stream(stream.cuda_stream)
-    cell0, _ = shard.shard_cells(B * world, world, rank)   # every rank schedules its own Monte-Carlo cells
 
     # inputs resident in HBM before the timed region: CQI and rand() streams of one step's TTIs
     d_cqi = torch.empty((TT, B, U, G), dtype=torch.uint8, device=dev)
@@ -301,114 +361,190 @@ def run_cuda_arm(args, n_gpus):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
     ms_max = float(tms.item())
-    value = world * B * TT * K / (ms_max * 1e-3)
+    value = total_cells * TT * K / (ms_max * 1e-3)
 
-    # end-of-run per-slice totals: the single NCCL reduce of the north star
-    d_stats = torch.zeros((4, S), dtype=torch.int64, device=dev)
-    g.stats_device(d_stats.data_ptr())
-    torch.cuda.synchronize(dev)
-    shard.reduce_stats(d_stats, dst=0)      # NCCL sum-reduce over NVLink (no-op at N=1)
-    stats = d_stats.cpu().numpy().view(np.uint64)
+    # ---- the run that was just timed, checked: three of its cells through the CPU oracle, every TTI ----------
+    parity_spot = None
+    if rank == 0 and not args.no_parity_spot:
+        last = {"rbg_to_ue": d_rbg.cpu().numpy(), "tbs_bits": d_bits.cpu().numpy(), "mcs": d_mcs.cpu().numpy()}
+        cells = sorted({0, B // 2, B - 1})
+        parity_spot = oracle_spot_check(args, g, np.array(cells), cell0, (W + K) * TT, TT, dts, last, (W + K - 1) * TT)
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed) --------
-    # Headline e2e: CQI in the 4-bit wire layout (cqi_per_rb = 2), refreshed every TTI.  Variants:
-    # the u8 layout, and CQI refreshed every 40 TTIs like the reference's CQI_INTERVAL.
-    import ctypes as C
+    # ---- end-of-run per-slice totals: the single NCCL reduce of the north star, from C (rs_reduce_stats) -------
+    stats_how = "rs_get_stats (one GPU: nothing to reduce)"
+    stats = g.get_stats()
+    if world > 1:
+        try:
+            Ln = C.CDLL(os.path.join(ROOT, "radiosaber_b200", "librs_nccl.so"))
+            Ln.rs_nccl_last_error.restype = C.c_char_p
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                raw = (C.c_uint8 * 128)()
+                assert Ln.rs_comm_unique_id(raw) == 0, Ln.rs_nccl_last_error()
+                uid = torch.tensor(list(raw), dtype=torch.uint8)
+            uid = uid.to(dev)
+            dist.broadcast(uid, src=0)      # the id travels through the launcher's process group
+            raw = (C.c_uint8 * 128)(*uid.cpu().tolist())
+            comm = C.c_void_p()
+            assert Ln.rs_comm_init_rank(world, rank, raw, dev.index, C.byref(comm)) == 0, Ln.rs_nccl_last_error()
+            red = np.zeros((4, S), dtype=np.uint64)
+            Ln.rs_reduce_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+            assert Ln.rs_reduce_stats(g._h, comm, 0, red.ctypes.data_as(C.c_void_p)) == 0, Ln.rs_nccl_last_error()
+            Ln.rs_comm_destroy.argtypes = [C.c_void_p]
+            Ln.rs_comm_destroy(comm)
+            stats = red
+            stats_how = "rs_reduce_stats (include/rs_sched_nccl.h): ncclReduce(sum, root 0) of uint64 [4][S] on the handle's stream"
+        except Exception as exc:   # the statistic is not the measurement: fall back to the launcher's collective, and say so
+            d_stats = torch.from_numpy(stats.view(np.int64).copy()).to(dev)
+            shard.reduce_stats(d_stats, dst=0)
+            stats = d_stats.cpu().numpy().view(np.uint64)
+            stats_how = f"torch.distributed.reduce (rs_reduce_stats unavailable: {exc})"
+
+    # ---- end to end through the host-buffer C-ABI calls (pinned host memory, copies timed) ---------------
+    # A step = TE TTIs through rs_run_host_async; the loop alternates two sets of result buffers and reads step k-1's
+    # results on the host (rs_wait) while step k is in flight, so the slot ring never drains between calls.
+    # Headline: CQI in the 4-bit wire layout reported every 40 TTIs (the reference's CQI_INTERVAL).  Variants: fresh
+    # CQI every TTI (worst case: PCIe- / host-memory-bound, shown against a measured copy ceiling), the u8 layout, and
+    # trace replay.
     TE = args.e2e_ttis
     KE = max(2, min(K, args.e2e_steps))
     # one continuing TTI clock over all calls (warm-up included), like the device-resident leg: restarting it would
     # hand every call a first TTI with dt = 7e-17 s and a non-zero byte count, i.e. a burst in the EWMA rates
     now_e, dte_all = workload.tti_clock((2 + KE) * TE)
+    lib = sched.lib()
 
-    def e2e_run(layout, refresh):
+    def host_results():
+        rbg, p1 = pinned(TE * B * G * 2)
+        bits, p2 = pinned(TE * B * U * 4)
+        mcs, p3 = pinned(TE * B * U)
+        o = sched._Out(p1, p2, p3, None, None, None, None, None, None, None)
+        return {"rbg": rbg.view(np.int16), "bits": bits.view(np.int32), "mcs": mcs, "o": o, "ptrs": (p1, p2, p3)}
+
+    def timed_async_loop(call):
+        """call(k, results) -> ticket.  Two warm-up steps, then KE timed steps; returns (seconds, checksum)."""
+        res = [host_results(), host_results()]
+        tickets = {}
+        for k in range(2):
+            tickets[k] = call(k, res[k & 1])
+        sched._check(lib.rs_sync(ge_box[0]._h))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        acc = 0
+        t0 = time.perf_counter()
+        for k in range(2, 2 + KE):
+            tickets[k] = call(k, res[k & 1])
+            if k > 2:
+                sched._check(lib.rs_wait(ge_box[0]._h, tickets[k - 1]))
+                acc += int(res[(k - 1) & 1]["bits"][-1])          # the step's results are read on the host
+        sched._check(lib.rs_wait(ge_box[0]._h, tickets[1 + KE]))
+        acc += int(res[(1 + KE) & 1]["bits"][-1])
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        sched._check(lib.rs_sync(ge_box[0]._h))
+        for r in res:
+            for ptr in r["ptrs"]:
+                lib.rs_host_free(ptr)
+        return float(te.item()), acc
+
+    ge_box = [None]
+
+    def e2e_run(layout, refresh, tpl):
         ge = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index, cqi_per_rb=layout)
+        ge_box[0] = ge
         n_slabs = -(-TE // refresh)
         row = G // 2 if layout == 2 else G
         d_tmp = torch.empty((n_slabs, B, U, row), dtype=torch.uint8, device=dev)
         ge.synth_cqi(SEED, cell0, 0, n_slabs, d_tmp.data_ptr())
         ge.sync()
-        h_cqi = torch.empty((n_slabs, B, U, row), dtype=torch.uint8).pin_memory()
-        h_cqi.copy_(d_tmp)
+        h_cqi, p_cqi = pinned(n_slabs * B * U * row, write_combined=args.e2e_write_combined)
+        torch.from_numpy(h_cqi).copy_(d_tmp.reshape(-1))
         del d_tmp
-        h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
-        h_r2.copy_(torch.from_numpy(workload.synth_rand2(SEED, cell0, B, 0, TE, S)))
-        h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
-        h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
-        h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
-        o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
+        h_r2, p_r2 = pinned(TE * B * 2 * 4, write_combined=args.e2e_write_combined)
+        h_r2.view(np.int32)[:] = workload.synth_rand2(SEED, cell0, B, 0, TE, S).reshape(-1)
 
-        def one(k):
+        def call(k, r):
             dte = dte_all[k * TE:(k + 1) * TE]
-            sched._check(sched.lib().rs_run_host(ge._h, TE, C.c_void_p(h_cqi.data_ptr()), refresh,
-                                                 C.c_void_p(h_r2.data_ptr()), None, dte.ctypes.data_as(C.c_void_p),
-                                                 C.byref(o), args.e2e_ttis_per_launch))
+            tk = C.c_int64(-1)
+            sched._check(lib.rs_run_host_async(ge._h, TE, p_cqi, refresh, p_r2, None, dte.ctypes.data_as(C.c_void_p),
+                                               C.byref(r["o"]), tpl, C.byref(tk)))
+            return int(tk.value)
 
-        for k in range(2):
-            one(k)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for k in range(2, 2 + KE):
-            one(k)          # synchronous: returns when the results are in host memory
-        torch.cuda.synchronize(dev)
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el, _ = timed_async_loop(call)
         ge.close()
-        h2d = n_slabs * B * U * row + TE * (B * 2 * 4) + TE * 8
+        lib.rs_host_free(p_cqi)
+        lib.rs_host_free(p_r2)
+        h2d = n_slabs * B * U * row + TE * (B * 2 * 4)
         d2h = TE * (B * G * 2 + B * U * 4 + B * U)
-        return world * B * TE * KE / float(te.item()), h2d, d2h
+        return total_cells * TE * KE / el, h2d, d2h
 
     def e2e_trace_run():
         """Trace-driven variant: 158 synthetic traces x 475 lines of the same CQI histogram
         resident in HBM (4-bit, 2.4 MB), every (cell, UE) replays a random one, a report every 40 TTIs as in
         the reference; only rand2 goes up, the same results come down."""
         ge = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index, cqi_per_rb=2)
+        ge_box[0] = ge
         rng = np.random.default_rng(SEED + rank)
         traces = np.repeat(workload.histogram_cqi(rng, (158, 475, G)), 8, axis=2)
         ge.set_traces(traces, rng.integers(0, 158, (B, U)).astype(np.int32))
         rows_all = sched.trace_rows_for_run(now_e, 0)
-        h_r2 = torch.empty((TE, B, 2), dtype=torch.int32).pin_memory()
-        h_r2.copy_(torch.from_numpy(workload.synth_rand2(SEED, cell0, B, 0, TE, S)))
-        h_rbg = torch.empty((TE, B, G), dtype=torch.int16).pin_memory()
-        h_bits = torch.empty((TE, B, U), dtype=torch.int32).pin_memory()
-        h_mcs = torch.empty((TE, B, U), dtype=torch.uint8).pin_memory()
-        o = sched._Out(h_rbg.data_ptr(), h_bits.data_ptr(), h_mcs.data_ptr(), None, None, None, None)
+        h_r2, p_r2 = pinned(TE * B * 2 * 4)
+        h_r2.view(np.int32)[:] = workload.synth_rand2(SEED, cell0, B, 0, TE, S).reshape(-1)
 
-        def one(k):
+        def call(k, r):
             rows, dte = rows_all[k * TE:(k + 1) * TE], dte_all[k * TE:(k + 1) * TE]
-            sched._check(sched.lib().rs_run_traces_host(ge._h, TE, rows.ctypes.data_as(C.c_void_p),
-                                                        C.c_void_p(h_r2.data_ptr()), None,
-                                                        dte.ctypes.data_as(C.c_void_p), C.byref(o), args.e2e_trace_ttis_per_launch))
+            tk = C.c_int64(-1)
+            sched._check(lib.rs_run_traces_host_async(ge._h, TE, rows.ctypes.data_as(C.c_void_p), p_r2, None,
+                                                      dte.ctypes.data_as(C.c_void_p), C.byref(r["o"]),
+                                                      args.e2e_trace_ttis_per_launch, C.byref(tk)))
+            return int(tk.value)
 
-        for k in range(2):
-            one(k)
-        torch.cuda.synchronize(dev)
+        el, _ = timed_async_loop(call)
+        ge.close()
+        lib.rs_host_free(p_r2)
+        return total_cells * TE * KE / el, TE * (B * 2 * 4)
+
+    def h2d_ceiling(nbytes_per_copy, copies):
+        """What this host gives this rank when every rank copies at once and nothing else runs: `copies` pinned
+        host-to-device copies of the streaming leg's chunk size, GB/s per rank (max time over ranks)."""
+        src, p_src = pinned(nbytes_per_copy, write_combined=args.e2e_write_combined)
+        src[:] = 7
+        dst = torch.empty(nbytes_per_copy, dtype=torch.uint8, device=dev)
+        hsrc = torch.from_numpy(src)
+        cs = torch.cuda.Stream(dev)
+        with torch.cuda.stream(cs):
+            dst.copy_(hsrc, non_blocking=True)
+        cs.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for k in range(2, 2 + KE):
-            one(k)
-        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(cs):
+            for _ in range(copies):
+                dst.copy_(hsrc, non_blocking=True)
+        cs.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ge.close()
-        return world * B * TE * KE / float(te.item()), TE * (B * 2 * 4) + TE * 12
+        lib.rs_host_free(p_src)
+        return nbytes_per_copy * copies / float(te.item()) / 1e9
 
     if args.kernel_only:   # development aid: the device-resident number alone (not a valid bench line)
         if rank == 0:
             emit({"kernel_only": True, "value": value, "ms_per_step": ms_max / K,
-                  "smem_bytes_per_cta": g.smem_bytes, "clocks": sampler.result()})
+                  "smem_bytes_per_cta": g.smem_bytes, "clocks": sampler.result(), "parity_spot": parity_spot})
         g.close()
         if world > 1:
             dist.destroy_process_group()
         return
-    e2e_value, h2d, d2h = e2e_run(2, 1)
-    e2e_u8, h2d_u8, _ = e2e_run(0, 1)
-    e2e_r40, h2d_r40, _ = e2e_run(2, 40)
+    e2e_value, h2d, d2h = e2e_run(2, 40, args.e2e_refresh_ttis_per_launch)
+    e2e_r1, h2d_r1, _ = e2e_run(2, 1, args.e2e_ttis_per_launch)
+    e2e_u8, h2d_u8, _ = e2e_run(0, 1, args.e2e_ttis_per_launch)
     e2e_tr, h2d_tr = e2e_trace_run()
+    chunk_bytes = args.e2e_ttis_per_launch * B * U * (G // 2)
+    ceil_gbs = h2d_ceiling(chunk_bytes, max(4, (TE * KE) // args.e2e_ttis_per_launch))
+    r1_gbs = e2e_r1 / world * (h2d_r1 / (B * TE)) / 1e9           # bytes/s this rank's every-TTI leg pulled up
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -417,31 +553,45 @@ def run_cuda_arm(args, n_gpus):
         launch_ms = ms_max / launches_rank0
         ttis_launch = min(TT, args.ttis_per_launch)
         achieved = alg * B * ttis_launch / (launch_ms * 1e-3) / 1e9
+        traffic, traffic_file = ncu_traffic_bytes()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "strong" if args.cells_total > 0 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "gpu_launches": int(tl.item()),
+            "parity_spot": parity_spot,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ttis_per_step": TE, "steps": KE,
-                    "api": "rs_run_host (C ABI, pinned host buffers, copies overlapped with kernels); CQI in the "
-                           "4-bit layout (cqi_per_rb=2), fresh CQI every TTI",
-                    "variants": {"u8_cqi_refresh1": {"value": e2e_u8, "h2d_bytes_per_step": h2d_u8},
-                                 "packed_cqi_refresh40": {"value": e2e_r40, "h2d_bytes_per_step": h2d_r40},
+                    "api": "rs_run_host_async + rs_wait (C ABI, page-locked host buffers from rs_host_alloc, copies "
+                           "overlapped with kernels, two alternating result sets read on the host every step); CQI in "
+                           "the 4-bit layout (cqi_per_rb=2) reported every 40 TTIs = the reference's CQI_INTERVAL "
+                           "(enb-mac-entity.cc:38)",
+                    "variants": {"packed_cqi_every_tti": {
+                                     "value": e2e_r1, "h2d_bytes_per_step": h2d_r1,
+                                     "note": "worst case: 3200 B of fresh CQI per cell-TTI; bound by the host-to-device "
+                                             "path, not by the kernel",
+                                     "h2d_gbs_per_gpu": r1_gbs, "h2d_ceiling_gbs_per_gpu": ceil_gbs,
+                                     "frac_of_h2d_ceiling": r1_gbs / ceil_gbs if ceil_gbs else None,
+                                     "ceiling": f"{world} rank(s) copying {chunk_bytes} B chunks from pinned memory at once, "
+                                                "no kernels, max time over ranks"},
+                                 "u8_cqi_every_tti": {"value": e2e_u8, "h2d_bytes_per_step": h2d_u8},
                                  "trace_replay_refresh40": {"value": e2e_tr, "h2d_bytes_per_step": h2d_tr,
-                                                            "api": "rs_run_traces_host: CQI replayed from 158 traces resident in HBM"}}},
+                                                            "api": "rs_run_traces_host_async: CQI replayed from 158 traces resident in HBM"}}},
             "roofline": {"bound": "hbm", "kernel": f"rs_tti_kernel<{args.algo}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes() if (args.cells, ttis_launch) == (4096, 16) else None,
-                         "traffic_note": "DRAM bytes of one launch (65536 cell-TTIs), ncu --set full, profiles/r01_tti_kernel_ncu_full.csv",
+                         "traffic": traffic if (B, ttis_launch) == (4096, 16) else None,
+                         "traffic_note": f"DRAM bytes of one launch (65536 cell-TTIs), ncu --set full, {traffic_file} "
+                                         "(a committed capture, not measured by this run)",
                          "algorithmic_bytes_per_launch": alg * B * ttis_launch, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_tti": alg, "cell_ttis_per_launch": B * ttis_launch,
                          "launch_ms": launch_ms,
                          "note": "path is bound by shared-memory sort/scan and FP64 issue, not HBM (DESIGN.md)"},
             "clocks": sampler.result(),
             "smem_bytes_per_cta": g.smem_bytes,
+            "stats_reduce": stats_how,
             "slice_bytes_total": [int(x) for x in stats[0]],
-            "jain_fairness_per_slice_mean": float(np.mean(sched.jain_index(stats, np.full(S, UES_PER_SLICE * B * world)))),
+            "jain_fairness_per_slice_mean": float(np.mean(sched.jain_index(stats, np.full(S, UES_PER_SLICE * total_cells)))),
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(args)
@@ -462,8 +612,12 @@ def main():
     ap.add_argument("--ttis-per-step", type=int, default=48)
     ap.add_argument("--ttis-per-launch", type=int, default=16)
     ap.add_argument("--e2e-ttis", type=int, default=80)
-    ap.add_argument("--e2e-ttis-per-launch", type=int, default=3)
+    ap.add_argument("--e2e-ttis-per-launch", type=int, default=8)
+    ap.add_argument("--e2e-write-combined", action="store_true", help="write-combined pinned input buffers")
+    ap.add_argument("--cells-total", type=int, default=0, help="BASELINE configs[4]: total cells, sharded over the ranks")
+    ap.add_argument("--no-parity-spot", action="store_true")
     ap.add_argument("--e2e-trace-ttis-per-launch", type=int, default=16)
+    ap.add_argument("--e2e-refresh-ttis-per-launch", type=int, default=20, help="headline e2e leg (a CQI slab every 40 TTIs)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)

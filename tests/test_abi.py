@@ -96,3 +96,17 @@ def test_batch_runner_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "--algo", "9", "--config", os.path.join(ROOT, "tests", "data", "cfg20x5.json"), "--cells", "4",
                         "--ttis", "2"], capture_output=True, text=True)
     assert r.returncode == 1 and "rs_create" in r.stderr and r.stdout == ""
+
+
+def test_nccl_library_exports_every_declared_symbol():
+    """include/rs_sched_nccl.h -> radiosaber_b200/librs_nccl.so (loads without a GPU; no calls made)."""
+    src = open(os.path.join(ROOT, "include", "rs_sched_nccl.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", src)))
+    assert names == ["rs_comm_destroy", "rs_comm_init_all", "rs_comm_init_rank", "rs_comm_unique_id",
+                     "rs_nccl_last_error", "rs_reduce_stats"]
+    path = os.path.join(ROOT, "radiosaber_b200", "librs_nccl.so")
+    assert os.path.exists(path), "build with make -C radiosaber_b200/csrc"
+    L = ctypes.CDLL(path)
+    for name in names:
+        assert hasattr(L, name), name
