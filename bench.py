@@ -180,7 +180,7 @@ def run_reference_arm(args, n_gpus):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    harness = os.path.join(ROOT, "oracle", "_ref", "O2" if args.ref_opt == "O2" else "", "ref_harness")
     cfg = workload_config(args, n_gpus)
     K, W = args.steps, args.warmup
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
@@ -204,12 +204,16 @@ def run_reference_arm(args, n_gpus):
                      "--ttis", str(T), "--cqi", os.path.join(tmp, f"cqi{pi}.bin"),
                      "--rand", os.path.join(tmp, f"rand{pi}.bin"), "--time-every", str(ttis_step)],
                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=tmp))
-            cum = []
+            cum, cum_stop = [], []
             for pr in running:
                 out, _ = pr.communicate()
                 marks = [json.loads(l) for l in out.splitlines() if l.startswith('{"sched_calls"')]
                 cum.append([m["sched_seconds"] for m in marks][: K + W])
-        cum = np.array([c for c in cum if len(c) == K + W])
+                cum_stop.append([m.get("stop_seconds", 0.0) for m in marks][: K + W])
+        keep = [i for i, c in enumerate(cum) if len(c) == K + W]
+        cum_all = np.array([cum[i] for i in keep])
+        cum_alloc = cum_all - np.array([cum_stop[i] for i in keep]) if keep else cum_all
+        cum = cum_alloc if args.ref_region == "alloc" else cum_all
         if cum.size == 0:
             print(json.dumps({"impl": "reference", "unavailable": "ref_harness produced no timing"}))
             return
@@ -218,11 +222,24 @@ def run_reference_arm(args, n_gpus):
         step_s = steps.max(axis=0)
         total = float(step_s.sum())
         value = cum.shape[0] * ttis_step * K / total
+        region = ("EWMA + SelectFlowsToSchedule + RBsAllocation (DoSchedule minus DoStopSchedule: no RLC, packets or cerr lines)"
+                  if args.ref_region == "alloc" else
+                  "the reference's DoSchedule (EWMA + SelectFlows + RBsAllocation + DoStopSchedule)")
         kind, sample = "reference", (f"{cum.shape[0]} single-threaded LTE-Sim processes (one per core) x {ttis_step} TTIs "
-                                     f"per step, 1 cell each; timed region = the reference's DoSchedule "
-                                     f"(EWMA + SelectFlows + RBsAllocation + DoStopSchedule), -O0 as shipped")
+                                     f"per step, 1 cell each; timed region = {region}, "
+                                     f"-{args.ref_opt}{' as shipped' if args.ref_opt == 'O0' else ' (second build, oracle/_ref/O2)'}")
         ms = 1e3 * total / K
         ncores = int(cum.shape[0])
+
+        def rate(c):   # cell-TTIs/s summed over the processes, timed steps only
+            st = np.diff(np.concatenate([np.zeros((c.shape[0], 1)), c], axis=1), axis=1)[:, W:]
+            return float(c.shape[0] * ttis_step * K / st.max(axis=0).sum())
+        line["reference_regions"] = {
+            "build": "-" + args.ref_opt, "cores": ncores,
+            "do_schedule": {"summed": rate(cum_all), "per_core": rate(cum_all) / ncores},
+            "ewma_select_alloc": {"summed": rate(cum_alloc), "per_core": rate(cum_alloc) / ncores},
+            "note": "SURVEY 8(d): the allocation region excludes DoStopSchedule (byte accounting interleaved with RLC / "
+                    "packet objects / cerr); BASELINE.md section 3"}
     else:
         base = cpu_baseline_port(args, budget_s=20.0)
         value, kind, sample, ms, ncores = base["value"], "port", base["sample"], None, base["cores"]
@@ -316,7 +333,13 @@ def run_cuda_arm(args, n_gpus):
         total_cells = B * world
     w, p, u2s = slice_setup()
     g = sched.Scheduler(args.algo, w, p, u2s, B, device=dev.index)
-    stream = torch.cuda.current_stream(dev)
+    # a stream of our own, made current: the kernels, the generators and the timing events all go to it.  (The legacy
+    # default stream has handle 0, which rs_set_stream reads as "the handle's own stream": events recorded on the
+    # default stream would then not be ordered after the kernels.  Round 1 timed that way and hid it behind a host
+    # synchronisation per step -- the last step's kernels were outside its events.)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     g.set_stream(stream.cuda_stream)
 
     # inputs resident in HBM before the timed region: CQI and rand() streams of one step's TTIs
@@ -344,16 +367,22 @@ def run_cuda_arm(args, n_gpus):
     launches0 = g.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
     e0.record(stream)
     for k in range(W, W + K):
         step(k)
     e1.record(stream)
     torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - wall0) * 1e3
     if world > 1:
         dist.barrier()
     sampler.stop_flag = True
     sampler.join()
     ms = e0.elapsed_time(e1)
+    # the device clock and the host clock around the same synchronised region must tell the same story
+    if not (0.8 * wall_ms <= ms <= 1.02 * wall_ms + 0.5):
+        raise RuntimeError(f"timing events ({ms:.3f} ms) disagree with the host clock ({wall_ms:.3f} ms): the kernels are "
+                           "not on the stream the events were recorded on")
     launches = g.launch_count - launches0
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     tl = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -556,7 +585,7 @@ def run_cuda_arm(args, n_gpus):
         traffic, traffic_file = ncu_traffic_bytes()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True,
+            "ms_per_step": ms_max / K, "wall_ms_per_step_rank0": wall_ms / K, "higher_is_better": True,
             "scaling": "strong" if args.cells_total > 0 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "gpu_launches": int(tl.item()),
@@ -621,6 +650,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-opt", default="O0", choices=["O0", "O2"], help="reference build: -O0 as shipped, or oracle/_ref/O2")
+    ap.add_argument("--ref-region", default="all", choices=["all", "alloc"],
+                    help="timed region of the reference arm: all of DoSchedule, or without DoStopSchedule")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
     args = ap.parse_args()

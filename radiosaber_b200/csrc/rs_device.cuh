@@ -70,7 +70,7 @@ __constant__ ConstTables c_tab;
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
   int avg, den, mtab, tx, mask, seg0, seg1, cnt, a, win, posl, posr,
-      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, ng_hc, ng_list, ng_mcs, ng_red, done, total;
+      target, quota, frb, wd, outsl, off, tval, misc, utr, sptr, sues, cq, mbar, ng_hc, ng_list, ng_mcs, ng_red, done, total;
 };
 
 struct DevCfg {
@@ -173,6 +173,7 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   L.sptr = rs_align(o, 4); o = L.sptr + 4 * (S + 1);
   L.sues = o; o += 2 * U;
   L.cq = rs_align(o, 16); o = L.cq + cq_bytes;
+  L.mbar = rs_align(o, 8); o = L.mbar + 8;   /* mbarrier of the bulk copy that stages the CQI */
   L.ng_red = rs_align(o, 8); o = L.ng_red + (ng_ues ? 16 * (RS_THREADS / 32) : 0);
   L.ng_list = o; o += 2 * ng_ues;
   L.ng_hc = o;   o += ng_ues;
@@ -481,6 +482,7 @@ struct Cell {
   double* tval; int* tx; int* utr; int* sptr; unsigned short* sues; uint8_t* cq; unsigned* mask; int* target; int* quota; int* frb; int* wd;
   unsigned short* win; unsigned char* outsl; unsigned* misc;
   unsigned short* ng_list; unsigned char* ng_hc; unsigned char* ng_mcs; unsigned char* ng_red; unsigned char* done;
+  unsigned long long* mbar;
   SortBufs sb;
 };
 
@@ -498,6 +500,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   c.sptr = (int*)(smem + L.sptr);
   c.sues = (unsigned short*)(smem + L.sues);
   c.cq = smem + L.cq;
+  c.mbar = (unsigned long long*)(smem + L.mbar);
   c.ng_list = (unsigned short*)(smem + L.ng_list);
   c.ng_hc = smem + L.ng_hc;
   c.ng_mcs = smem + L.ng_mcs;
@@ -524,6 +527,7 @@ __device__ __forceinline__ Cell carve(unsigned char* smem, const Layout& L) {
   return c;
 }
 
+#ifdef RS_NO_BULK
 /* Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS); both addresses 16-byte aligned */
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -531,6 +535,38 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+/* Bulk asynchronous copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP): one instruction moves
+ * a whole contiguous block (the cell's CQI slab, 3.2-6.4 KB at the headline shape) and reports the bytes landed to
+ * an mbarrier in shared memory; the consumers sleep on the barrier's phase instead of a wait_group + CTA barrier.
+ * Addresses and size are multiples of 16. */
+__device__ __forceinline__ void mbar_init(void* mbar, unsigned count) {
+  const unsigned ma = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ma), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, unsigned bytes) {
+  const unsigned ma = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ma), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, void* mbar) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst), ma = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sa), "l"(gsrc), "r"(bytes), "r"(ma) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, unsigned parity) {
+  const unsigned ma = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RS_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RS_MBAR_DONE;\n"
+      "bra RS_MBAR_WAIT;\n"
+      "RS_MBAR_DONE:\n"
+      "}\n" ::"r"(ma), "r"(parity) : "memory");
+}
+#endif
 
 /* Where UE u's CQI vector of this TTI starts: row u of the [U][cqi_row] slab, or (trace mode) the
  * current row of the trace the UE replays (cqi then points at that row of trace 0). */
@@ -1001,6 +1037,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   const bool stage = r.stage != 0;
   int staged_key = -1;
   auto cqi_key = [&](int t) { return TRACE ? r.trace_row[t] : (r.t0 + t) / r.cqi_refresh; };
+#ifdef RS_NO_BULK
   auto stage_cqi = [&](int t) {
     if (TRACE) {
       const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row;
@@ -1016,6 +1053,37 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     }
     cp_async_commit();
   };
+  auto stage_wait = [&]() { cp_async_wait_all(); };   /* own copies done; the barrier that follows publishes everybody's */
+#else
+  /* thread 0 arms the mbarrier with the byte count; the slab is ONE bulk copy, the trace rows of the cell's UEs one
+   * bulk copy per UE (issued by the threads in parallel); every thread then waits for the phase to flip */
+  unsigned stage_parity = 0;
+  bool stage_pending = false;
+  if (stage) {
+    if (tid == 0) mbar_init(c.mbar, 1);
+    __syncthreads();
+  }
+  auto stage_cqi = [&](int t) {
+    const unsigned total = (unsigned)(U * d.cqi_row);
+    if (TRACE) {
+      if (tid == 0) mbar_expect_tx(c.mbar, total);
+      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row;
+      for (int u = tid; u < U; u += kThreads) bulk_g2s(c.cq + u * d.cqi_row, base + c.utr[u], (unsigned)d.cqi_row, c.mbar);
+    } else if (tid == 0) {
+      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * d.cqi_row;
+      mbar_expect_tx(c.mbar, total);
+      bulk_g2s(c.cq, src, total, c.mbar);
+    }
+    stage_pending = true;
+  };
+  auto stage_wait = [&]() {
+    if (stage_pending) {
+      mbar_wait(c.mbar, stage_parity);
+      stage_parity ^= 1u;
+      stage_pending = false;
+    }
+  };
+#endif
   if (stage && r.T > 0) { stage_cqi(0); staged_key = cqi_key(0); }
 
 #ifdef RS_PHASE_TIMING
@@ -1090,7 +1158,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         if (TRANSPORT && listed(u)) c.wd[s] = 1;
       }
     }
-    if (stage) cp_async_wait_all();   /* own copies done; the barrier publishes everybody's */
+    if (stage) stage_wait();
     __syncthreads();
 
     RS_TICK(0);

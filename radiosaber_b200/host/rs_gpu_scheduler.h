@@ -311,34 +311,37 @@ class RsGpuScheduler : public PacketScheduler {
       for (int k = 0; k < 300 * listed; ++k) draws_[k] = rand();
       draws = draws_.data();
     }
-    std::vector<double> state(slice_state_);
-    Check(rs_set_state(h_, avg_.data(), nullptr, nullptr, nullptr, Transport() ? state.data() : nullptr,
-                       Nvs() ? state.data() : nullptr), "rs_set_state");
-    rs_outputs out = {};
+    /* One call per TTI (rs_step_cell): the bearers' rates, the slice offsets / NVS credits and the queue state go up
+     * with the CQI in one copy, the results and the updated per-slice state come back in one copy.  Finite queues cap
+     * the bytes, bind id 7's required-RBs guard and id 1's flow-satisfied cut-off, and the head-of-line delay enters
+     * the metric of alpha/beta slices.  dt = 0: the EWMA was applied by the bearers themselves a few lines up. */
+    rs_cell_io io = {};
     int32_t nvs_slice = -1;
-    out.rbg_to_ue = rbg_to_ue_.data();
-    out.tbs_bits = bits_.data();
-    out.mcs = mcs_.data();
-    out.final_cqi = final_cqi_.data();
-    out.slice_target = target_.data();
-    out.slice_quota = quota_.data();
-    out.nvs_slice = &nvs_slice;
     int32_t n_grants = 0;
+    io.avg_rate = avg_.data();
+    io.slice_state = (Transport() || Nvs()) ? slice_state_.data() : nullptr;
+    io.cqi = cqi_.data();
+    io.rand2 = draws;
+    io.active = active_.data();
+    io.queue_bytes = queue_.data();
+    io.hol_delay = hol_.data();
+    io.dt = 0.0;
+    io.out.rbg_to_ue = rbg_to_ue_.data();
+    io.out.tbs_bits = bits_.data();
+    io.out.mcs = mcs_.data();
+    io.out.final_cqi = final_cqi_.data();
+    io.out.slice_target = target_.data();
+    io.out.slice_quota = quota_.data();
+    io.out.nvs_slice = &nvs_slice;
     if (id_ == 10) { /* UpperBound books an RBG to several slices: the grants come back as a list */
       grant_ue_.assign(2 * (size_t)n_rbgs_, -1);
       grant_rbg_.assign(2 * (size_t)n_rbgs_, -1);
-      out.alloc_n = &n_grants;
-      out.alloc_ue = grant_ue_.data();
-      out.alloc_rbg = grant_rbg_.data();
+      io.out.alloc_n = &n_grants;
+      io.out.alloc_ue = grant_ue_.data();
+      io.out.alloc_rbg = grant_rbg_.data();
     }
-    /* queue state of this TTI: finite queues cap the bytes, bind id 7's required-RBs guard and id 1's
-     * flow-satisfied cut-off, and the head-of-line delay enters the metric of alpha/beta slices */
-    Check(rs_set_queues(h_, queue_.data(), hol_.data()), "rs_set_queues");
-    /* dt = 0: the EWMA was applied by the bearers themselves a few lines up */
-    Check(rs_step(h_, cqi_.data(), draws, active_.data(), 0.0, &out), "rs_step");
+    Check(rs_step_cell(h_, &io), "rs_step_cell");
     if (id_ == 11 && nvs_slice != host_slice) throw std::runtime_error("RsGpuScheduler: host and device disagree on the NVS slice");
-    Check(rs_get_state(h_, nullptr, nullptr, nullptr, nullptr, Transport() ? slice_state_.data() : nullptr,
-                       Nvs() ? slice_state_.data() : nullptr), "rs_get_state");
 
     UsersToSchedule* users = GetUsersToSchedule();
     if (Nvs()) { /* only the served slice's users are "users to schedule" (downlink-nvs-scheduler.cpp:161-162) */
