@@ -58,7 +58,14 @@ typedef struct rs_config {
                                low and 2k+1 in the high nibble of byte k (a CQI is 4 bits on the air) */
   int32_t data_to_transmit; /* bytes queued per bearer; 100000000 = infinite buffer
                                (downlink-transport-scheduler.cpp:123-125) */
-  int32_t reserved;
+  int32_t n_bearers;        /* bearers per UE: 0 or 1 = one (every shipped backlogged config); 2 = MAX_BEARERS
+                               (packet-scheduler.h:31, `internet_flow: 2` in exp-customize-20slices/config.json): slot i
+                               of a UE holds its bearer of priority i, which is also the order of the two in the eNB's
+                               bearer container.  Per-bearer arrays (rates, byte counters, queues, delays) are then
+                               [B][U][2], every run call needs rs_set_queues, and the kernels do what
+                               SelectFlowsToSchedule / ComputeSchedulingMetric / DoStopSchedule do with two bearers
+                               (downlink-transport-scheduler.cpp:115-146, 179-191, 683-711).  Ids 7/8/9/10/101/103; id 1
+                               schedules flows, not users: give it one user per bearer instead */
   const double* weight;       /* [S] slice_weights_ */
   const int32_t* params;      /* [S][4] alpha,beta,epsilon,psi (SchedulerAlgoParam, packet-scheduler.h:31-49) */
   const int32_t* ue_to_slice; /* [U] user_to_slice_ */
@@ -113,8 +120,8 @@ int rs_host_alloc(size_t bytes, int32_t write_combined, void** out);
 void rs_host_free(void* p);
 
 /* Per-bearer / per-slice state the reference keeps between TTIs (flows/radio-bearer.h:81-85,
- * downlink-transport-scheduler.h:38, downlink-nvs-scheduler.h:38).  Host arrays, [B][U] / [B][S];
- * NULL = leave alone / not wanted.  Synchronous. */
+ * downlink-transport-scheduler.h:38, downlink-nvs-scheduler.h:38).  Host arrays, [B][U] ([B][U][2] with two
+ * bearers per UE) / [B][S]; NULL = leave alone / not wanted.  Synchronous. */
 int rs_set_state(rs_handle* h, const double* avg_rate, const int32_t* tx_bytes, const uint64_t* cum_bytes,
                  const uint64_t* cum_rbs, const double* slice_offset, const double* nvs_ewma);
 int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cum_bytes, uint64_t* cum_rbs,
@@ -160,7 +167,7 @@ int rs_step_cell(rs_handle* h, const rs_cell_io* io);
 
 /* Queue state for the NEXT rs_step / rs_run_* call on this handle (consumed by it): what the reference reads from
  * its bearers each TTI (one bearer per UE).
- *   queue_bytes [T][B][U] int32   dataToTransmit of each UE's bearer (downlink-transport-scheduler.cpp:119-128):
+ *   queue_bytes [T][B][U] int32   ([T][B][U][2] with two bearers per UE, here and below) dataToTransmit of each UE's bearer (downlink-transport-scheduler.cpp:119-128):
  *                                 0 = no packets, the bearer is not listed this TTI; 100000000 = infinite buffer;
  *                                 else the queue size (values above 2^28-1 count as 2^28-1 where the reference
  *                                 multiplies by 8 in an int; negative = not listed).  Replaces cfg.data_to_transmit: bytes sent are capped by it

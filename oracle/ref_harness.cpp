@@ -123,6 +123,9 @@ struct Options {
                              (id 11 draws 300 x users of them, downlink-nvs-scheduler.cpp:437-446) */
   std::string alloc_log;  /* every (user, RBG) grant of each recorded TTI in the order of the users' RB lists: int32 n,
                              int16 (ue, rbg)[n] per TTI (id 10 books an RBG to several slices, which rbg_to_ue[G] cannot hold) */
+  std::string bearer_log; /* per recorded TTI: int32 n, then per bearer in container order int32 user, prio, data (0 = not
+                             listed), tx_before; double hol, avg_before; and after the call double avg_after; int32 tx_after, pad;
+                             uint64 cum_bytes, cum_rbs */
   std::string queue_log;  /* per recorded TTI, before the scheduler runs: int32 data[U] (what SelectFlowsToSchedule will take as
                              dataToTransmit: 0 = no packets, 100000000 = infinite buffer, else the queue size) and double
                              hol[U] (RadioBearer::GetHeadOfLinePacketDelay) */
@@ -144,6 +147,7 @@ static std::stringstream g_cerr_capture;   /* std::cerr while --log-out is activ
 static FILE* g_rand_log_file = nullptr;
 static FILE* g_alloc_log_file = nullptr;
 static FILE* g_queue_log_file = nullptr;
+static FILE* g_bearer_log_file = nullptr;   /* --bearer-log: per-bearer inputs and state, for cells with several bearers per UE */
 static FILE* g_log_stdout = nullptr;
 static FILE* g_log_stderr = nullptr;
 static char* g_cstderr_buf = nullptr;       /* C stderr (fprintf(stderr, "all_bytes ...")) of the current TTI */
@@ -229,6 +233,21 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
     }
     fwrite(qdata.data(), 4, U, g_queue_log_file);
     fwrite(qhol.data(), 8, U, g_queue_log_file);
+  }
+  if (g_bearer_log_file) {
+    const int32_t n = (int32_t)bearers->size();
+    fwrite(&n, 4, 1, g_bearer_log_file);
+    for (RadioBearer* b : *bearers) {
+      int32_t rec[4] = {b->GetUserID(), b->GetPriority(), 0, b->m_transmittedBytes};
+      double dv[2] = {0.0, b->m_averageTransmissionRate};
+      if (b->HasPackets() && b->GetDestination()->GetNodeState() == NetworkNode::STATE_ACTIVE) {
+        rec[2] = (b->GetApplication()->GetApplicationType() == Application::APPLICATION_TYPE_INFINITE_BUFFER)
+                     ? 100000000 : b->GetQueueSize();
+        dv[0] = b->GetHeadOfLinePacketDelay();
+      }
+      fwrite(rec, 4, 4, g_bearer_log_file);
+      fwrite(dv, 8, 2, g_bearer_log_file);
+    }
   }
   std::vector<uint8_t> cqi((size_t)U * R);
   for (int u = 0; u < U; ++u) {
@@ -324,6 +343,15 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
     cum_rbs[u] = b->m_cumulativeRBs;
   }
   state_get(state_after);
+  if (g_bearer_log_file)
+    for (RadioBearer* b : *bearers) {
+      const double av = b->m_averageTransmissionRate;
+      const int32_t tx[2] = {b->m_transmittedBytes, 0};
+      const uint64_t cu[2] = {(uint64_t)b->m_cumulativeBytes, (uint64_t)b->m_cumulativeRBs};
+      fwrite(&av, 8, 1, g_bearer_log_file);
+      fwrite(tx, 4, 2, g_bearer_log_file);
+      fwrite(cu, 8, 2, g_bearer_log_file);
+    }
 
   Put1<int32_t>(0x54544921); Put1<int32_t>(g_recorded); Put1<double>(now);
   Put(avg_before.data(), U); Put(tx_before.data(), U); Put(last_update.data(), U);
@@ -529,6 +557,7 @@ int main(int argc, char** argv) {
     else if (a == "--alloc-log") g_opt.alloc_log = next();
     else if (a == "--bearers") g_opt.n_bearers = atoi(next().c_str());
     else if (a == "--queue-log") g_opt.queue_log = next();
+    else if (a == "--bearer-log") g_opt.bearer_log = next();
     else if (a == "--gpu") g_opt.gpu = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -544,6 +573,10 @@ int main(int argc, char** argv) {
   if (!g_opt.alloc_log.empty()) {
     g_alloc_log_file = fopen(g_opt.alloc_log.c_str(), "wb");
     if (!g_alloc_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.alloc_log.c_str()); return 2; }
+  }
+  if (!g_opt.bearer_log.empty()) {
+    g_bearer_log_file = fopen(g_opt.bearer_log.c_str(), "wb");
+    if (!g_bearer_log_file) { fprintf(stderr, "cannot write %s\n", g_opt.bearer_log.c_str()); return 2; }
   }
   if (!g_opt.queue_log.empty()) {
     g_queue_log_file = fopen(g_opt.queue_log.c_str(), "wb");
@@ -590,6 +623,7 @@ int main(int argc, char** argv) {
   if (g_rand_log_file) fclose(g_rand_log_file);
   if (g_alloc_log_file) fclose(g_alloc_log_file);
   if (g_queue_log_file) fclose(g_queue_log_file);
+  if (g_bearer_log_file) fclose(g_bearer_log_file);
   if (g_log_stdout) fclose(g_log_stdout);
   if (g_log_stderr) fclose(g_log_stderr);
   fprintf(stdout, "{\"recorded_ttis\": %d, \"sched_calls\": %ld, \"sched_seconds\": %.6f, \"stop_seconds\": %.6f}\n", g_recorded,

@@ -105,7 +105,9 @@ struct DevCfg {
                                   when alpha and beta are set; nvs.cpp:384-386 whenever alpha is set) */
   const int* tbs1;             /* [16] GetTBSizeFromMCS(mcs(cqi)) for one RB: m_requiredRBs, packet-scheduler.cpp:334 */
   int sort_depth_g;        /* id 10: 2*floor(log2(G)), the depth limit of a per-slice sort of G entries */
-  /* state, [B][U] / [B][S] */
+  int nb;                  /* bearers per UE (MAX_BEARERS, packet-scheduler.h:31): 1, or 2 = slot i holds the bearer of priority i;
+                              state arrays are then [B][U][2] and the queue-aware kernels (QUEUE) are the only ones used */
+  /* state, [B][U][nb] / [B][S] */
   double* avg; int* tx; unsigned long long* cum_bytes; unsigned long long* cum_rbs;
   double* offset; double* ewma;
 };
@@ -114,9 +116,9 @@ struct RunArgs {
   const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
   int t0, cqi_refresh;
   int stage;               /* 1: every TTI's CQI is copied to shared memory with cp.async first */
-  const int* queue;        /* [T][B][U] bytes queued on each UE's bearer (its dataToTransmit; 0 = not listed), or null:
+  const int* queue;        /* [T][B][U][nb] bytes queued on each UE's bearer(s) (its dataToTransmit; 0 = not listed), or null:
                               DevCfg::data for everybody */
-  const double* hol;       /* [T][B][U] head-of-line delay of the bearer, or null (0) */
+  const double* hol;       /* [T][B][U][nb] head-of-line delay of the bearer(s), or null (0) */
   const int* rand2;
   const uint8_t* active; long long active_tti_stride;
   /* per-TTI scalars travel in the kernel parameters (no copy, no staging buffer): at most kMaxTtisPerLaunch TTIs */
@@ -139,12 +141,12 @@ __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a *
 /* min_sort_n: id 10 sorts one slice's G entries at a time and parks the grants next to them: it needs
  * the slot arrays at least 8 G entries long whatever S is. */
 __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
-                                              int min_sort_n = 0) {
+                                              int min_sort_n = 0, int nb = 1) {
   Layout L;
   const int n = (S * G > min_sort_n) ? S * G : min_sort_n;
   const int nw = (n + 31) / 32;
   int o = 0;
-  L.avg = o;  o += 8 * U;
+  L.avg = o;  o += 8 * U * nb;
   L.den = o;  o += 8 * U;
   L.off = o;  o += 8 * S;
   L.tval = o; o += 8 * 16;
@@ -156,7 +158,7 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   } else {
     L.mtab = o; o += 8 * kMStride * m_cap;
   }
-  L.tx = o;   o += 4 * U;
+  L.tx = o;   o += 4 * U * nb;
   L.utr = o;  o += 4 * U;
   L.mask = o; o += 8 * U;
   L.seg0 = o; o += 4 * (n / 16 + 2);
@@ -592,7 +594,7 @@ __device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int
     tgt[h] = 0;
     wd[h] = 0;
     if (s < S) {
-      wd[h] = c.wd[s];
+      wd[h] = c.wd[s] & 1;   /* bit 8: the slice's bearer priority of this TTI */
       if (wd[h]) tgt[h] = (int)__dadd_rn(__dmul_rn((double)nb_rbs, d.weight[s]), c.off[s]);   /* :475 */
     }
     sum += tgt[h];
@@ -716,7 +718,7 @@ __device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned sho
  * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
 __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* row, int u,
                                             unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc,
-                                            int data_u, const double* presum = nullptr) {
+                                            int data_u, const double* presum = nullptr, const int* qd2 = nullptr) {
   int bits = 0, mcs = 0xff, fc = 0;
   const int nrbg = __popc(m_lo) + __popc(m_hi);
   if (nrbg > 0) {
@@ -742,12 +744,24 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
     fc = cqi_from_mean(mean);
     mcs = 2 * (fc - 1);                        /* MapCQIToMCS, AMCModule.cpp:36-40 */
     bits = d.tbs_n[nrbg * 16 + fc];
-    const int avail = bits / 8;
+    int avail = bits / 8;
     if (avail > 0) {
       if (d.algo == 1) {
         c.tx[u] += avail;
         c.cumb[u] += (unsigned long long)avail;
         c.cumr[u] += (unsigned long long)nrb;
+      } else if (qd2) {
+        /* two bearers: the bearer of the higher priority is served first and what is left goes to the other one;
+         * every bearer that sends is booked the user's whole RB count (transport.cpp:179-191, nvs.cpp:229-243) */
+        for (int i = 1; i >= 0 && avail > 0; --i) {
+          const int data_i = qd2[2 * u + i];
+          if (data_i <= 0) continue;
+          const int sent = min(avail, data_i);
+          avail -= sent;
+          c.tx[2 * u + i] += sent;
+          c.cumb[2 * u + i] += (unsigned long long)sent;
+          c.cumr[2 * u + i] += (unsigned long long)nrb;
+        }
       } else if (data_u > 0) {
         const int sent = min(avail, data_u);
         c.tx[u] += sent;
@@ -1006,14 +1020,17 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
    * UpperBound (10), SubOpt (101), VogelApproximate (103) */
   constexpr bool TRANSPORT = ALGO == 8 || ALGO == 9 || ALGO == 10 || ALGO == 101 || ALGO == 103;
   if (b >= d.n_cells) return;
-  c.cumb = d.cum_bytes + (size_t)b * U;
-  c.cumr = d.cum_rbs + (size_t)b * U;
+  c.cumb = d.cum_bytes + (size_t)b * U * (QUEUE ? d.nb : 1);
+  c.cumr = d.cum_rbs + (size_t)b * U * (QUEUE ? d.nb : 1);
 
   /* cell state -> shared memory */
+  const int nb = QUEUE ? d.nb : 1;   /* bearers per UE: the backlogged instantiations know one */
   for (int u = tid; u < U; u += kThreads) {
     const size_t i = (size_t)b * U + u;
-    c.avg[u] = d.avg[i];
-    c.tx[u] = d.tx[i];
+    for (int k = 0; k < nb; ++k) {
+      c.avg[nb * u + k] = d.avg[nb * i + k];
+      c.tx[nb * u + k] = d.tx[nb * i + k];
+    }
     c.mask[2 * u] = 0;
     c.mask[2 * u + 1] = 0;
     if (TRACE) c.utr[u] = d.ue_trace_off[i];
@@ -1099,10 +1116,31 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     const size_t tb = (size_t)t * d.n_cells + b;
     const int rot = (b + t) % kWarps;   /* which warp plays the single-warp roles this TTI */
     /* queue state of the TTI: a bearer is listed when it has packets (transport.cpp:119) */
-    const int* qd = QUEUE ? r.queue + tb * U : nullptr;   /* QUEUE = false: the backlogged instantiation, no queue code */
-    const double* hl = (QUEUE && r.hol) ? r.hol + tb * U : nullptr;
-    auto listed = [&](int u) { return (!act || act[u]) && (qd ? qd[u] > 0 : d.data > 0); };
-    auto data_of = [&](int u) { return qd ? qd[u] : d.data; };
+    const int* qd = QUEUE ? r.queue + tb * U * nb : nullptr;   /* QUEUE = false: the backlogged instantiation, no queue code */
+    const double* hl = (QUEUE && r.hol) ? r.hol + tb * U * nb : nullptr;
+    const bool two = QUEUE && nb == 2;   /* two bearers per UE, slot i = priority i = position in the bearer container */
+    /* a user is listed when one of its bearers has packets (transport.cpp:119, packet-scheduler.cpp:304-318) */
+    auto listed = [&](int u) {
+      return (!act || act[u]) && (two ? (qd[2 * u] > 0 || qd[2 * u + 1] > 0) : (qd ? qd[u] > 0 : d.data > 0));
+    };
+    /* dataToTransmit of the bearer that created the user record (m_requiredRBs, packet-scheduler.cpp:333) / of the
+     * single bearer */
+    auto data_of = [&](int u) { return two ? (qd[2 * u] > 0 ? qd[2 * u] : qd[2 * u + 1]) : (qd ? qd[u] : d.data); };
+    /* slice_priority_ (transport.cpp:115, 143-146): the highest priority among the slice's listed bearers, kept in
+     * bit 8 of wd[s] next to the "slice has data" flag in bit 0 */
+    auto slice_flags = [&](int u) { return 1 | ((two && qd[2 * u + 1] > 0) ? 0x100 : 0); };
+    /* metric factor of user u of an alpha slice (hm = holmul): 0 when the bearer of the slice's priority has nothing
+     * queued, the bearer's head-of-line delay when the delay is in the metric, else 1 (transport.cpp:694-711) */
+    auto prio_gate = [&](int u, int su, int hm, double e) -> double {
+      if (two) {
+        const int pr = (c.wd[su] >> 8) & 1;
+        if (qd[2 * u + pr] == 0) return 0.0;
+        return hm == 1 ? __dmul_rn(hl ? hl[2 * u + pr] : 0.0, e) : e;
+      }
+      if (hm == 1) return __dmul_rn(hl ? hl[u] : 0.0, e);   /* HoL * pow(se, eps) / pow(avg, psi), :702-706 */
+      if (hm == 2 && hl && hl[u] < 0.0) return 0.0;          /* the bearer of the slice's priority is empty, :696-698 */
+      return e;
+    };
     auto row_of = [&](int u) -> const uint8_t* { return stage ? c.cq + u * d.cqi_row : ue_cqi<TRACE>(d, c, cqi, u); };
     short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
     int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
@@ -1116,7 +1154,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     if (NVS) {
       /* slices with at least one queued bearer */
       for (int u = tid; u < U; u += kThreads)
-        if (listed(u)) c.wd[d.ue_to_slice[u]] = 1;
+        if (listed(u)) atomicOr(&c.wd[d.ue_to_slice[u]], slice_flags(u));
       __syncthreads();
       if (tid == 0) {
         int slice_id = 0;
@@ -1143,19 +1181,34 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
     /* ---- P0: EWMA of every bearer; metric denominators; slices with data --------------------- */
     for (int u = tid; u < U; u += kThreads) {
-      double a = c.avg[u];
+      double a = c.avg[nb * u];
       if (dt != 0) {
-        a = ewma_update(a, c.tx[u], dt);
-        c.avg[u] = a;
-        c.tx[u] = 0;
+        a = ewma_update(a, c.tx[nb * u], dt);
+        c.avg[nb * u] = a;
+        c.tx[nb * u] = 0;
+      }
+      double sum = __dadd_rn(1.0, a);   /* averageRate = 1 + the listed bearers' rates, in slot order (transport.cpp:680-687) */
+      if (two) {
+        double a1 = c.avg[2 * u + 1];
+        if (dt != 0) {
+          a1 = ewma_update(a1, c.tx[2 * u + 1], dt);
+          c.avg[2 * u + 1] = a1;
+          c.tx[2 * u + 1] = 0;
+        }
+        sum = 1.0;
+        if (qd[2 * u] > 0) sum = __dadd_rn(sum, a);
+        if (qd[2 * u + 1] > 0) sum = __dadd_rn(sum, a1);
       }
       if (ALGO == 1) {
         c.den[u] = a;                                             /* dl-pf-packet-scheduler.cpp:128-140 */
       } else {
         const int s = d.ue_to_slice[u];
         /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
-        c.den[u] = d.psi[s] ? __ddiv_rn(__dadd_rn(1.0, a), 1000.0) : 1.0;
-        if (TRANSPORT && listed(u)) c.wd[s] = 1;
+        c.den[u] = d.psi[s] ? __ddiv_rn(sum, 1000.0) : 1.0;
+        if (TRANSPORT && listed(u)) {
+          if (two) atomicOr(&c.wd[s], slice_flags(u));
+          else c.wd[s] = 1;
+        }
       }
     }
     if (stage) stage_wait();
@@ -1175,8 +1228,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           const int su = d.ue_to_slice[u];
           double e = d.epow[su * 16 + cq];
           const int hm = d.holmul[su];
-          if (hm == 1) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* HoL * pow(se, eps) / pow(avg, psi), :702-706 */
-          else if (hm == 2 && hl && hl[u] < 0.0) e = 0.0;     /* the bearer of the slice's priority is empty, :696-698 */
+          if (QUEUE && hm) e = prio_gate(u, su, hm, e);
           c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
         }
         __syncthreads();
@@ -1443,7 +1495,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         const int j = j0 + (q >> 4), cq = q & 15;
         const int u = c.sues[j];
         double e = d.epow[served * 16 + cq];
-        if (d.holmul[served]) e = __dmul_rn(hl ? hl[u] : 0.0, e);   /* nvs.cpp:384-386 */
+        if (d.holmul[served]) e = QUEUE ? prio_gate(u, served, 1, e) : 0.0;   /* nvs.cpp:379-386; no queue state: HoL 0 */
         c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
       }
       if (qd) {
@@ -1468,7 +1520,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               }
             }
             const int wide = cqi_from_mean(__ddiv_rn(sum, (double)(G * d.rbg)));
-            need = min(qd[u], kMaxQueueBytes) * 8 / d.tbs1[wide];
+            need = min(data_of(u), kMaxQueueBytes) * 8 / d.tbs1[wide];
           }
           req[j - j0] = need;
           alc[j - j0] = 0;
@@ -1602,7 +1654,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, data_of(u), ALGO == 10 ? c.den : nullptr);
+      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, data_of(u), ALGO == 10 ? c.den : nullptr,
+                  two ? qd : nullptr);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;
     }
@@ -1623,10 +1676,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
            ph_[0] / r.T, ph_[1] / r.T, ph_[2] / r.T, ph_[3] / r.T, ph_[4] / r.T, ph_[5] / r.T, ph_[6] / r.T);
 #endif
   /* cell state -> HBM */
-  for (int u = tid; u < U; u += kThreads) {
-    const size_t i = (size_t)b * U + u;
-    d.avg[i] = c.avg[u];
-    d.tx[i] = c.tx[u];
+  for (int q = tid; q < U * nb; q += kThreads) {
+    const size_t i = (size_t)b * U * nb + q;
+    d.avg[i] = c.avg[q];
+    d.tx[i] = c.tx[q];
   }
   if (NVS || TRANSPORT) {
     double* dst = NVS ? d.ewma : d.offset;
@@ -1712,9 +1765,9 @@ __global__ void rs_stats_kernel(const DevCfg d, unsigned long long* stats) {
   const int S = d.S;
   for (int i = threadIdx.x; i < 4 * S; i += blockDim.x) s_acc[i] = 0;
   __syncthreads();
-  const size_t total = (size_t)d.n_cells * d.U;
+  const size_t total = (size_t)d.n_cells * d.U * d.nb;   /* one entry per bearer */
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int s = d.ue_to_slice[i % d.U];
+    const int s = d.ue_to_slice[(i / d.nb) % d.U];
     const unsigned long long by = d.cum_bytes[i], rb = d.cum_rbs[i], q = by >> 10;
     atomicAdd(&s_acc[0 * S + s], by);
     atomicAdd(&s_acc[1 * S + s], rb);

@@ -326,8 +326,8 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
   if (want_cqi) CU(s.cqi.alloc((size_t)T * B * U * C));
   CU(s.rand2.alloc((size_t)T * B * std::max(h->d.rand_stride, 1)));
   if (want_active) CU(s.active.alloc((size_t)T * B * U));
-  if (want_queue) CU(s.queue.alloc((size_t)T * B * U));
-  if (want_hol) CU(s.hol.alloc((size_t)T * B * U));
+  if (want_queue) CU(s.queue.alloc((size_t)T * B * U * h->d.nb));
+  if (want_hol) CU(s.hol.alloc((size_t)T * B * U * h->d.nb));
   if (out) {
     if (out->rbg_to_ue) CU(s.rbg_to_ue.alloc((size_t)T * B * G));
     if (out->tbs_bits) CU(s.tbs_bits.alloc((size_t)T * B * U));
@@ -414,6 +414,10 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   if (G > RS_MAX_RBGS) return fail(RS_ERR_UNSUPPORTED, "%d RBGs > %d", G, RS_MAX_RBGS);
   if (!cfg->ue_to_slice || (algo != 1 && (!cfg->weight || !cfg->params)))
     return fail(RS_ERR_ARG, "rs_create: weight/params/ue_to_slice missing");
+  const int nb = cfg->n_bearers == 2 ? 2 : 1;
+  if (cfg->n_bearers < 0 || cfg->n_bearers > 2) return fail(RS_ERR_ARG, "n_bearers %d outside 0..2 (MAX_BEARERS = 2)", cfg->n_bearers);
+  if (nb == 2 && (algo == 1 || algo == 11))
+    return fail(RS_ERR_UNSUPPORTED, "two bearers per UE: id 1 schedules flows (give it one user per bearer), id 11 is not covered");
   if (cfg->data_to_transmit < 0 || cfg->data_to_transmit > 268435455)
     return fail(RS_ERR_ARG, "data_to_transmit %d outside 0..2^28-1 (data*8 is an int in the reference)", cfg->data_to_transmit);
   for (int u = 0; u < U; ++u)
@@ -432,6 +436,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   if (cfg->cqi_per_rb == 2 && (G % 8) != 0) { delete h; return fail(RS_ERR_UNSUPPORTED, "4-bit CQI layout needs a multiple of 8 RBGs"); }
   d.cqi_per_rb = cfg->cqi_per_rb;
   d.data = cfg->data_to_transmit;
+  d.nb = nb;
   d.n_cells = n_cells;
   d.sort_n = G * S;
   { int lg = 0; for (int m = d.sort_n; m > 1; m >>= 1) lg++; d.sort_depth = 2 * lg; }
@@ -550,13 +555,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   const int min_sort_n = (algo == 10) ? 8 * G
                          : ((algo == 101 || algo == 103) ? (rs::inter_scratch_bytes(G, S) + 3) / 4 : 0);   /* posl + posr = 4 n bytes */
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
-  h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n)))
-                      : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n);
+  h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb)))
+                      : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb);
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
-    const rsw::Layout staged_w = rsw::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
+    const rsw::Layout staged_w = rsw::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb);
     const rs::Layout staged = h->wide ? reinterpret_cast<const rs::Layout&>(staged_w)
-                                      : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n);
+                                      : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb);
     const int kSmemPerSm = 227 * 1024, kSms = 148;
     const int fit = kSmemPerSm / (staged.total + 1024);
     /* big cells: two staged cells per SM beat more unstaged ones, and a 512-thread cell is better off
@@ -611,7 +616,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   d.ue_to_slice = h->ue_to_slice.p; d.slice_ptr = h->slice_ptr.p; d.slice_ues = h->slice_ues.p;
   d.chunk_slice = h->chunk_slice.p; d.tbs_n = h->tbs_n.p; d.weight = h->weight.p; d.epow = h->epow.p;
   d.psi = h->psi.p;
-  const size_t BU = (size_t)n_cells * U, BS = (size_t)n_cells * S;
+  const size_t BU = (size_t)n_cells * U * nb, BS = (size_t)n_cells * S;   /* per-bearer state */
   { cudaError_t e = h->avg.alloc(BU);
     if (e == cudaSuccess) e = h->tx.alloc(BU);
     if (e == cudaSuccess) e = h->cum_bytes.alloc(BU);
@@ -658,7 +663,7 @@ void rs_host_free(void* p) { if (p) cudaFreeHost(p); }
 int rs_reset_state(rs_handle* h) {
   if (!h) return fail(RS_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
-  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  const size_t BU = (size_t)h->B * h->d.U * h->d.nb, BS = (size_t)h->B * h->d.S;
   std::vector<double> avg(BU, 100000.0);   /* m_averageTransmissionRate, radio-bearer.cpp:54 */
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(h->avg.p, avg.data(), BU * 8, cudaMemcpyHostToDevice));
@@ -675,7 +680,7 @@ int rs_set_state(rs_handle* h, const double* avg_rate, const int32_t* tx_bytes, 
   if (!h) return fail(RS_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  const size_t BU = (size_t)h->B * h->d.U * h->d.nb, BS = (size_t)h->B * h->d.S;
   if (avg_rate) CU(cudaMemcpy(h->avg.p, avg_rate, BU * 8, cudaMemcpyHostToDevice));
   if (tx_bytes) CU(cudaMemcpy(h->tx.p, tx_bytes, BU * 4, cudaMemcpyHostToDevice));
   if (cum_bytes) CU(cudaMemcpy(h->cum_bytes.p, cum_bytes, BU * 8, cudaMemcpyHostToDevice));
@@ -690,7 +695,7 @@ int rs_get_state(rs_handle* h, double* avg_rate, int32_t* tx_bytes, uint64_t* cu
   if (!h) return fail(RS_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  const size_t BU = (size_t)h->B * h->d.U, BS = (size_t)h->B * h->d.S;
+  const size_t BU = (size_t)h->B * h->d.U * h->d.nb, BS = (size_t)h->B * h->d.S;
   if (avg_rate) CU(cudaMemcpy(avg_rate, h->avg.p, BU * 8, cudaMemcpyDeviceToHost));
   if (tx_bytes) CU(cudaMemcpy(tx_bytes, h->tx.p, BU * 4, cudaMemcpyDeviceToHost));
   if (cum_bytes) CU(cudaMemcpy(cum_bytes, h->cum_bytes.p, BU * 8, cudaMemcpyDeviceToHost));
@@ -752,6 +757,7 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   if (h->d.rand_stride > 0 && !d_rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (!trace_row && (((uintptr_t)d_cqi & 3) || (cqi_tti_stride & 3))) return fail(RS_ERR_ARG, "cqi must be 4-byte aligned");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
+  if (h->d.nb == 2 && !d_queue) return fail(RS_ERR_ARG, "two bearers per UE: every run call needs rs_set_queues");
   if (n_ttis == 0) return RS_OK;
   CU(cudaSetDevice(h->device));
   if (trace_row) { const int rc = check_trace_rows(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
@@ -769,8 +775,8 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.active = d_active ? d_active + (size_t)t0 * active_tti_stride : nullptr;
     a.active_tti_stride = active_tti_stride;
     fill_scalars(h, &a, dt + t0, trace_row ? trace_row + t0 : nullptr, a.T);
-    a.queue = d_queue ? d_queue + (size_t)t0 * B * U : nullptr;
-    a.hol = d_hol ? d_hol + (size_t)t0 * B * U : nullptr;
+    a.queue = d_queue ? d_queue + (size_t)t0 * B * U * h->d.nb : nullptr;
+    a.hol = d_hol ? d_hol + (size_t)t0 * B * U * h->d.nb : nullptr;
     a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
     point_outputs(h, &a, d_out, (size_t)t0);
     const int rc = launch_ttis(h, a, trace_row != nullptr);
@@ -796,9 +802,11 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   if ((!cqi && !trace_row) || !dt || n_ttis < 0 || cqi_refresh < 1) return fail(RS_ERR_ARG, "rs_run_host: bad argument");
   if (h->d.rand_stride > 0 && !rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
   if (trace_row && !h->trace_tab.p) return fail(RS_ERR_ARG, "no traces loaded: call rs_set_traces first");
+  if (h->d.nb == 2 && !queue) return fail(RS_ERR_ARG, "two bearers per UE: every run call needs rs_set_queues");
   CU(cudaSetDevice(h->device));
   if (trace_row) { const int rc = check_trace_rows(h, trace_row, n_ttis); if (rc != RS_OK) return rc; }
   if (ttis_per_launch <= 0) ttis_per_launch = trace_row ? 16 : 8;
+  const size_t NB = (size_t)h->d.nb;
   const int TC = std::max(1, std::min(std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch), n_ttis));
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   const bool slabs = !trace_row && cqi_refresh > 1;   /* consecutive chunks share a CQI slab */
@@ -842,8 +850,8 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     const size_t RS = (size_t)h->d.rand_stride;
     if (rand2 && RS) CU_DRAIN(cudaMemcpyAsync(s.rand2.p, rand2 + (size_t)t0 * B * RS, (size_t)T * B * RS * 4, cudaMemcpyHostToDevice, h->copy_in));
     if (active) CU_DRAIN(cudaMemcpyAsync(s.active.p, active + (size_t)t0 * B * U, (size_t)T * B * U, cudaMemcpyHostToDevice, h->copy_in));
-    if (queue) CU_DRAIN(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U, (size_t)T * B * U * 4, cudaMemcpyHostToDevice, h->copy_in));
-    if (hol) CU_DRAIN(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U, (size_t)T * B * U * 8, cudaMemcpyHostToDevice, h->copy_in));
+    if (queue) CU_DRAIN(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U * NB, (size_t)T * B * U * NB * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (hol) CU_DRAIN(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U * NB, (size_t)T * B * U * NB * 8, cudaMemcpyHostToDevice, h->copy_in));
     CU_DRAIN(cudaEventRecord(s.in_done, h->copy_in));
     /* kernel: inputs in, and the slot's previous outputs drained */
     CU_DRAIN(cudaStreamWaitEvent(h->stream, s.in_done, 0));
@@ -1257,17 +1265,19 @@ int rs_step_cell(rs_handle* h, const rs_cell_io* io) {
   h->hol_next = nullptr;
   if (io->hol_delay && !io->queue_bytes) return fail(RS_ERR_ARG, "rs_step_cell: head-of-line delays without queue sizes");
   if (h->d.rand_stride > 0 && !io->rand2) return fail(RS_ERR_ARG, "ids 8/9/11 need the rand() draws");
+  if (h->d.nb == 2 && !io->queue_bytes) return fail(RS_ERR_ARG, "two bearers per UE: the call needs queue_bytes");
   CU(cudaSetDevice(h->device));
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols, RS = (size_t)h->d.rand_stride;
+  const size_t NB = (size_t)h->d.nb;
   const rs_outputs& o = io->out;
   const bool nvs = h->d.algo == 7 || h->d.algo == 11, tr = is_transport(h->d.algo);
   size_t off = 0;
   auto take = [&](bool want, size_t bytes) { const size_t at = off; if (want) off += (bytes + 15) & ~(size_t)15; return at; };
   const size_t o_cqi = take(true, B * U * C), o_rand = take(io->rand2 && RS, B * RS * 4), o_act = take(io->active, B * U),
-               o_q = take(io->queue_bytes, B * U * 4), o_hol = take(io->hol_delay, B * U * 8);
+               o_q = take(io->queue_bytes, B * U * NB * 4), o_hol = take(io->hol_delay, B * U * NB * 8);
   const size_t state0 = off;
   const bool st = io->slice_state && (nvs || tr);
-  const size_t o_avg = take(io->avg_rate, B * U * 8), o_st = take(st, B * S * 8);
+  const size_t o_avg = take(io->avg_rate, B * U * NB * 8), o_st = take(st, B * S * 8);
   const size_t out0 = off;
   const size_t o_rbg = take(o.rbg_to_ue, B * G * 2), o_bits = take(o.tbs_bits, B * U * 4), o_mcs = take(o.mcs, B * U),
                o_fc = take(o.final_cqi, B * U), o_tgt = take(o.slice_target && tr, B * S * 4),
@@ -1289,9 +1299,9 @@ int rs_step_cell(rs_handle* h, const rs_cell_io* io) {
   memcpy(m + o_cqi, io->cqi, B * U * C);
   if (io->rand2 && RS) memcpy(m + o_rand, io->rand2, B * RS * 4);
   if (io->active) memcpy(m + o_act, io->active, B * U);
-  if (io->queue_bytes) memcpy(m + o_q, io->queue_bytes, B * U * 4);
-  if (io->hol_delay) memcpy(m + o_hol, io->hol_delay, B * U * 8);
-  if (io->avg_rate) memcpy(m + o_avg, io->avg_rate, B * U * 8);
+  if (io->queue_bytes) memcpy(m + o_q, io->queue_bytes, B * U * NB * 4);
+  if (io->hol_delay) memcpy(m + o_hol, io->hol_delay, B * U * NB * 8);
+  if (io->avg_rate) memcpy(m + o_avg, io->avg_rate, B * U * NB * 8);
   if (st) memcpy(m + o_st, io->slice_state, B * S * 8);
   CU(cudaMemcpyAsync(dm, m, out0, cudaMemcpyHostToDevice, h->stream));
   rs::DevCfg d = h->d;
@@ -1325,7 +1335,7 @@ int rs_step_cell(rs_handle* h, const rs_cell_io* io) {
   if (rc != RS_OK) { cudaStreamSynchronize(h->stream); return rc; }
   if (total > state0) CU(cudaMemcpyAsync(m + state0, dm + state0, total - state0, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (io->avg_rate) memcpy(io->avg_rate, m + o_avg, B * U * 8);
+  if (io->avg_rate) memcpy(io->avg_rate, m + o_avg, B * U * NB * 8);
   if (st) memcpy(io->slice_state, m + o_st, B * S * 8);
   if (so.rbg_to_ue) memcpy(o.rbg_to_ue, m + o_rbg, B * G * 2);
   if (so.tbs_bits) memcpy(o.tbs_bits, m + o_bits, B * U * 4);

@@ -197,7 +197,7 @@ class RsGpuScheduler : public PacketScheduler {
     cfg.rbg_size = rbg_size_;
     cfg.cqi_per_rb = 1; /* ENodeB::UserEquipmentRecord::GetCQI() is one value per RB */
     cfg.data_to_transmit = 100000000;
-    cfg.reserved = 0;
+    cfg.n_bearers = 1; /* two bearers of a UE are folded into one user here, like InsertFlowToUser does */
     cfg.weight = slice_weights_.data();
     cfg.params = params.data();
     cfg.ue_to_slice = u2s.data();

@@ -46,7 +46,7 @@ class _Cfg(C.Structure):
     _fields_ = [
         ("algo", C.c_int32), ("n_slices", C.c_int32), ("n_ues", C.c_int32), ("n_rbs", C.c_int32),
         ("rbg_size", C.c_int32), ("cqi_per_rb", C.c_int32), ("data_to_transmit", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_bearers", C.c_int32),
         ("weight", C.c_void_p), ("params", C.c_void_p), ("ue_to_slice", C.c_void_p), ("tbs_row_m1", C.c_void_p),
     ]
 
@@ -187,8 +187,9 @@ class Scheduler:
     """
 
     def __init__(self, algo, weight, params, ue_to_slice, n_cells, n_rbs=512, rbg_size=8, cqi_per_rb=0,
-                 data_to_transmit=100000000, tbs_row_m1=None, device=0):
+                 data_to_transmit=100000000, tbs_row_m1=None, device=0, n_bearers=1):
         self.algo = int(algo)
+        self.nb = 2 if int(n_bearers) == 2 else 1   # bearers per UE: per-bearer arrays are [B][U] or [B][U][2]
         self.ue_to_slice = np.ascontiguousarray(ue_to_slice, dtype=np.int32)
         self.U = int(self.ue_to_slice.shape[0])
         self.weight = np.ascontiguousarray(weight, dtype=np.float64)
@@ -202,8 +203,8 @@ class Scheduler:
         self.cqi_cols = {0: self.G, 1: self.R, 2: self.G // 2}[self.cqi_per_rb]
         self.device = int(device)
         self._row_m1 = None if tbs_row_m1 is None else np.ascontiguousarray(tbs_row_m1, dtype=np.int32)
-        cfg = _Cfg(self.algo, self.S, self.U, self.R, self.rbg_size, self.cqi_per_rb, int(data_to_transmit), 0,
-                   _ptr(self.weight), _ptr(self.params), _ptr(self.ue_to_slice), _ptr(self._row_m1))
+        cfg = _Cfg(self.algo, self.S, self.U, self.R, self.rbg_size, self.cqi_per_rb, int(data_to_transmit),
+                   int(n_bearers), _ptr(self.weight), _ptr(self.params), _ptr(self.ue_to_slice), _ptr(self._row_m1))
         self._h = C.c_void_p()
         _check(lib().rs_create(C.byref(cfg), self.B, self.device, C.byref(self._h)))
         # rand() draws per cell-TTI the scheduler consumes: 0 (ids 1/7), 2 (ids 8/9), 300 x largest slice (id 11)
@@ -229,19 +230,21 @@ class Scheduler:
     def set_state(self, avg_rate=None, tx_bytes=None, slice_offset=None, nvs_ewma=None, cum_bytes=None,
                   cum_rbs=None):
         B, U, S = self.B, self.U, self.S
+        BU = (B, U) if self.nb == 1 else (B, U, 2)
 
         def arr(v, dt, shape):
             return None if v is None else np.ascontiguousarray(np.asarray(v).reshape(shape), dtype=dt)
 
-        a = arr(avg_rate, np.float64, (B, U)); t = arr(tx_bytes, np.int32, (B, U))
-        cb = arr(cum_bytes, np.uint64, (B, U)); cr = arr(cum_rbs, np.uint64, (B, U))
+        a = arr(avg_rate, np.float64, BU); t = arr(tx_bytes, np.int32, BU)
+        cb = arr(cum_bytes, np.uint64, BU); cr = arr(cum_rbs, np.uint64, BU)
         so = arr(slice_offset, np.float64, (B, S)); ne = arr(nvs_ewma, np.float64, (B, S))
         _check(lib().rs_set_state(self._h, _ptr(a), _ptr(t), _ptr(cb), _ptr(cr), _ptr(so), _ptr(ne)))
 
     def get_state(self):
         B, U, S = self.B, self.U, self.S
-        st = {"avg_rate": np.empty((B, U), np.float64), "tx_bytes": np.empty((B, U), np.int32),
-              "cum_bytes": np.empty((B, U), np.uint64), "cum_rbs": np.empty((B, U), np.uint64),
+        BU = (B, U) if self.nb == 1 else (B, U, 2)
+        st = {"avg_rate": np.empty(BU, np.float64), "tx_bytes": np.empty(BU, np.int32),
+              "cum_bytes": np.empty(BU, np.uint64), "cum_rbs": np.empty(BU, np.uint64),
               "slice_offset": np.empty((B, S), np.float64), "nvs_ewma": np.empty((B, S), np.float64)}
         _check(lib().rs_get_state(self._h, _ptr(st["avg_rate"]), _ptr(st["tx_bytes"]), _ptr(st["cum_bytes"]),
                                   _ptr(st["cum_rbs"]), _ptr(st["slice_offset"]), _ptr(st["nvs_ewma"])))
@@ -287,8 +290,9 @@ class Scheduler:
         """Hand the next run call its queue state (rs_set_queues); returns the arrays to keep alive."""
         if queue is None:
             return None
-        q = np.ascontiguousarray(queue, dtype=np.int32).reshape(lead + (self.U,))
-        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(lead + (self.U,))
+        per_ue = (self.U,) if self.nb == 1 else (self.U, 2)
+        q = np.ascontiguousarray(queue, dtype=np.int32).reshape(lead + per_ue)
+        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(lead + per_ue)
         _check(lib().rs_set_queues(self._h, _ptr(q), _ptr(h)))
         return q, h
 
