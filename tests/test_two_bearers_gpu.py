@@ -50,7 +50,7 @@ def test_batch_path_reproduces_the_reference_with_two_bearers(algo, mode):
             n, m = int(out["alloc_n"][i][CELL]), int(rec["alloc_n"][t])
             assert n == m, (t, "alloc_n")
             from tests.helpers import grants_by_user
-            assert grants_by_user(out["alloc_ue"][i][CELL][:n], out["alloc_rbg"][i][CELL][:n]) == \\
+            assert grants_by_user(out["alloc_ue"][i][CELL][:n], out["alloc_rbg"][i][CELL][:n]) == \
                 grants_by_user(rec["alloc_ue"][t][:m], rec["alloc_rbg"][t][:m]), (t, "grants")
         else:
             assert np.array_equal(out["rbg_to_ue"][i][CELL], rec["rbg_to_ue"][t]), (t, "rbg_to_ue")
