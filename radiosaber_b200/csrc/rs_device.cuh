@@ -131,7 +131,7 @@ struct RunArgs {
 };
 
 /* ---- shared-memory layout (same function on host and device) --------------------------------- */
-__host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
+__host__ __device__ constexpr inline int rs_align(int x, int a) { return (x + a - 1) / a * a; }
 /* The cumulative byte / RB counters stay in HBM (touched only for the few UEs a TTI serves); the
  * metric table is dead once the sort starts, so it shares the bytes of the sort's slot arrays
  * when it fits there. */
@@ -140,9 +140,9 @@ __host__ __device__ inline int rs_align(int x, int a) { return (x + a - 1) / a *
 /* ng_ues: id 11 only, the largest number of UEs in a slice (scratch of the 300-sample search). */
 /* min_sort_n: id 10 sorts one slice's G entries at a time and parks the grants next to them: it needs
  * the slot arrays at least 8 G entries long whatever S is. */
-__host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
-                                              int min_sort_n = 0, int nb = 1) {
-  Layout L;
+__host__ __device__ constexpr inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
+                                                        int min_sort_n = 0, int nb = 1) {
+  Layout L{};
   const int n = (S * G > min_sort_n) ? S * G : min_sort_n;
   const int nw = (n + 31) / 32;
   int o = 0;
@@ -184,6 +184,33 @@ __host__ __device__ inline Layout make_layout(int S, int U, int G, int m_cap, in
   L.total = rs_align(o, 16);
   return L;
 }
+
+/* ---- shape policies of the TTI kernel ------------------------------------------------------------
+ * DynShape: every dimension, the shared-memory layout and the slice tables come from DevCfg at run time (any cell).
+ * FixedShape: a cell of S slices x UPS UEs each (UE u in slice u / UPS), G RBGs of RBG RBs, CQI layout LAY, one
+ * bearer per UE, staged CQI -- known when the kernel is compiled, so shared-memory addresses are immediates, the
+ * slice tables are arithmetic, divisions are shifts / multiplies and the short loops unroll.  The host picks a
+ * FixedShape instantiation when a handle's configuration AND its host-computed layout match it bit for bit
+ * (rs_sched.cu fixed_kernel_for), otherwise the DynShape kernel runs; results are identical either way
+ * (tests/test_gpu_parity.py::test_fixed_shape_equals_dynamic). */
+struct DynShape {
+  static constexpr bool kStatic = false;
+};
+template <int S_, int UPS_, int G_, int RBG_, int LAY_>
+struct FixedShape {
+  static constexpr bool kStatic = true;
+  static constexpr int S = S_, UPS = UPS_, U = S_ * UPS_, G = G_, RBG = RBG_, R = G_ * RBG_, LAY = LAY_;
+  static constexpr int kCqiRow = LAY_ == 1 ? R : (LAY_ == 2 ? G_ / 2 : G_);
+  /* metric-table chunks as rs_create packs them: consecutive slices while their UEs fit max(UPS, min(U, 32)) */
+  static constexpr int kCap = UPS_ > (U < 32 ? U : 32) ? UPS_ : (U < 32 ? U : 32);
+  static constexpr int kSlicesPerChunk = kCap / UPS_;
+  static constexpr int kChunks = (S_ + kSlicesPerChunk - 1) / kSlicesPerChunk;
+  static constexpr int kMCap = (S_ < kSlicesPerChunk ? S_ : kSlicesPerChunk) * UPS_;
+  static constexpr int kSortN = G_ * S_;
+  __host__ __device__ static constexpr int log2_floor(int v) { int lg = 0; while (v > 1) { v >>= 1; ++lg; } return lg; }
+  static constexpr int kSortDepth = 2 * log2_floor(kSortN);
+  __host__ __device__ static constexpr Layout layout() { return make_layout(S_, U, G_, kMCap, U * kCqiRow, 0, 0, 1); }
+};
 
 /* ================================================================================================
  * libstdc++ std::sort (introsort) order of n entries, key = bits 12..15 (descending), payload =
@@ -368,7 +395,7 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
  * ranges longer than _S_threshold to the warps, one range per warp at a time. */
 /* `rot` rotates which warp takes which range: warp w of every CTA sits on SM sub-partition w % 4, so
  * without it the single-range levels of all resident cells would pile up on one scheduler. */
-__device__ void sort_desc(const SortBufs& b, int n, int depth_limit, int rot) {
+__device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_limit, int rot) {
   const int tid = threadIdx.x, lane = tid & 31, warp = ((tid >> 5) + rot) % kWarps;
   const int nw = (n + 31) >> 5;
   if (tid == 0) {
@@ -583,7 +610,7 @@ __device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* p, i
 }
 
 /* Slice targets and RBG quotas, transport.cpp:463-521, by one warp (lane s and lane s+32). */
-__device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int lane, int* g_target, int* g_quota) {
+__device__ __forceinline__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int lane, int* g_target, int* g_quota) {
   const int S = d.S;
   const int nb_rbs = d.G * d.rbg;
   int tgt[2], wd[2];
@@ -666,7 +693,7 @@ __device__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int
  * of its own entry's slice in a register, one redux.sync(min) finds the lowest feasible lane and
  * broadcasts its (rbg,slice), and the other lanes drop out if they lost their RBG or their slice
  * ran out.  c.quota is consumed (the host-visible quotas were written by slice_quotas). */
-__device__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
+__device__ __forceinline__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
   const int n = d.sort_n;
   int nfree = d.G;
   for (int base = 0; base < n && nfree > 0; base += 32) {
@@ -694,7 +721,7 @@ __device__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned sh
 }
 
 /* GreedyByRow, transport.cpp:249-272, by one warp. a[] holds the unsorted (rbg-major) entries. */
-__device__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned short* a, int lane) {
+__device__ __forceinline__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned short* a, int lane) {
   const int S = d.S;
   int rem_a = (lane < S) ? c.quota[lane] : 0;
   int rem_b = (lane + 32 < S) ? c.quota[lane + 32] : 0;
@@ -1006,9 +1033,18 @@ __device__ void sub_opt(const DevCfg& d, const Cell& c) {
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
-template <int ALGO, bool TRACE, bool QUEUE>
-__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
+template <int ALGO, bool TRACE, bool QUEUE, class SH = DynShape>
+__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d_in, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
+  DevCfg d = d_in;
+  if constexpr (SH::kStatic) {   /* the dimensions and the layout become compile-time constants of this instantiation */
+    d.S = SH::S; d.U = SH::U; d.G = SH::G; d.R = SH::R; d.rbg = SH::RBG;
+    d.cqi_per_rb = SH::LAY; d.cqi_row = SH::kCqiRow;
+    constexpr Layout kLay = SH::layout();
+    d.lay = kLay;
+    d.n_chunks = SH::kChunks; d.m_cap = SH::kMCap; d.sort_n = SH::kSortN; d.sort_depth = SH::kSortDepth;
+    d.nb = 1;
+  }
   Cell c = carve(smem, d.lay);
   c.sb.eq_tab = d.eq_tab;
   c.sb.eq_max = d.eq_max;
@@ -1044,8 +1080,17 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   }
   if (tid < 16) c.tval[tid] = c_tab.tval[tid];
   for (int g = tid; g < G; g += kThreads) c.outsl[g] = 0xff;
-  for (int s = tid; s <= ((ALGO == 1) ? 1 : S); s += kThreads) c.sptr[s] = d.slice_ptr[s];
-  for (int u = tid; u < U; u += kThreads) c.sues[u] = (unsigned short)d.slice_ues[u];
+  if constexpr (!SH::kStatic) {
+    for (int s = tid; s <= ((ALGO == 1) ? 1 : S); s += kThreads) c.sptr[s] = d.slice_ptr[s];
+    for (int u = tid; u < U; u += kThreads) c.sues[u] = (unsigned short)d.slice_ues[u];
+  }
+  /* the slice tables: CSR of the UEs by slice in shared memory, or plain arithmetic for a FixedShape */
+  auto slice_of = [&](int u) -> int { if constexpr (SH::kStatic) return u / SH::UPS; else return d.ue_to_slice[u]; };
+  auto sptr_of = [&](int s) -> int { if constexpr (SH::kStatic) return s * SH::UPS; else return c.sptr[s]; };
+  auto sue_of = [&](int j) -> int { if constexpr (SH::kStatic) return j; else return (int)c.sues[j]; };
+  auto chunk_lo = [&](int ch) -> int {
+    if constexpr (SH::kStatic) return min(ch * SH::kSlicesPerChunk, SH::S); else return d.chunk_slice[ch];
+  };
   __syncthreads();
 
   /* One TTI of this cell's CQI lands in shared memory while P0 runs: rows [U][cqi_row], from the slab or
@@ -1154,7 +1199,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     if (NVS) {
       /* slices with at least one queued bearer */
       for (int u = tid; u < U; u += kThreads)
-        if (listed(u)) atomicOr(&c.wd[d.ue_to_slice[u]], slice_flags(u));
+        if (listed(u)) atomicOr(&c.wd[slice_of(u)], slice_flags(u));
       __syncthreads();
       if (tid == 0) {
         int slice_id = 0;
@@ -1202,7 +1247,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       if (ALGO == 1) {
         c.den[u] = a;                                             /* dl-pf-packet-scheduler.cpp:128-140 */
       } else {
-        const int s = d.ue_to_slice[u];
+        const int s = slice_of(u);
         /* average_rate = (1 + sum avg) / 1000.0; pow(x, psi) for psi in {0,1}  (transport.cpp:680-692) */
         c.den[u] = d.psi[s] ? __ddiv_rn(sum, 1000.0) : 1.0;
         if (TRANSPORT && listed(u)) {
@@ -1218,14 +1263,14 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     if (TRANSPORT) {
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < d.n_chunks; ++ch) {
-        const int s0 = d.chunk_slice[ch], s1 = d.chunk_slice[ch + 1];
-        const int j0 = c.sptr[s0], j1 = c.sptr[s1];
+        const int s0 = chunk_lo(ch), s1 = chunk_lo(ch + 1);
+        const int j0 = sptr_of(s0), j1 = sptr_of(s1);
         if (ch == 0 && warp == (rot + kWarps - 1) % kWarps)
           slice_quotas(d, c, r.rand2[tb * d.rand_stride], r.rand2[tb * d.rand_stride + 1], lane, o_tgt, o_quo);
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
-          const int u = c.sues[j];
-          const int su = d.ue_to_slice[u];
+          const int u = sue_of(j);
+          const int su = slice_of(u);
           double e = d.epow[su * 16 + cq];
           const int hm = d.holmul[su];
           if (QUEUE && hm) e = prio_gate(u, su, hm, e);
@@ -1244,8 +1289,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             double best[4] = {-1.0, -1.0, -1.0, -1.0};
             int bu[4] = {kNoUe, kNoUe, kNoUe, kNoUe};
             int bc[4] = {0, 0, 0, 0};
-            for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
-              const int u = c.sues[j];
+            for (int j = sptr_of(s); j < sptr_of(s + 1); ++j) {
+              const int u = sue_of(j);
               if (!listed(u)) continue;
               unsigned w;
               const uint8_t* row_u = row_of(u);
@@ -1276,8 +1321,8 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             const int s = s0 + q / G, g = q % G;
             double best = -1.0;
             int bu = kNoUe, bc = 0;
-            for (int j = c.sptr[s]; j < c.sptr[s + 1]; ++j) {
-              const int u = c.sues[j];
+            for (int j = sptr_of(s); j < sptr_of(s + 1); ++j) {
+              const int u = sue_of(j);
               if (!listed(u)) continue;
               const int cq = cqi_first_rb(d, row_of(u), g);
               const double m = c.mtab[(j - j0) * kMStride + cq];
@@ -1410,12 +1455,12 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       /* ---- NVS non-greedy (RBsAllocationNonGreedyPF + AssignRBsGivenMCS, nvs.cpp:405-528): 300 samples
        * of per-user CQI back-offs, one sample per thread at a time; the first sample with the largest
        * sum over RBGs of the winning PF metric is kept. */
-      const int j0 = c.sptr[served], j1 = c.sptr[served + 1];
+      const int j0 = sptr_of(served), j1 = sptr_of(served + 1);
       if (warp == 0) {   /* the users the reference lists: bearers of the served slice with packets, in order */
         int cnt = 0;
         for (int jb = j0; jb < j1; jb += 32) {
           const int j = jb + lane;
-          const int u = j < j1 ? c.sues[j] : 0;
+          const int u = j < j1 ? sue_of(j) : 0;
           const bool in = j < j1 && listed(u);
           const unsigned bal = __ballot_sync(kFull, in);
           if (in) c.ng_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)u;
@@ -1490,10 +1535,10 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       }
     } else if (ALGO == 7) {
       /* ---- NVS: enterprise argmax over the served slice's users for every RBG (nvs.cpp:275-311) */
-      const int j0 = c.sptr[served], j1 = c.sptr[served + 1];
+      const int j0 = sptr_of(served), j1 = sptr_of(served + 1);
       for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
         const int j = j0 + (q >> 4), cq = q & 15;
-        const int u = c.sues[j];
+        const int u = sue_of(j);
         double e = d.epow[served * 16 + cq];
         if (d.holmul[served]) e = QUEUE ? prio_gate(u, served, 1, e) : 0.0;   /* nvs.cpp:379-386; no queue state: HoL 0 */
         c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
@@ -1505,7 +1550,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         int* req = (int*)c.ng_mcs;
         int* alc = req + d.ng_ues;
         for (int j = j0 + tid; j < j1; j += kThreads) {
-          const int u = c.sues[j];
+          const int u = sue_of(j);
           int need = 0;
           if (listed(u)) {
             const uint8_t* row = row_of(u);
@@ -1531,7 +1576,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             double best = -1.0;
             int bj = 0x7fffffff;
             for (int j = j0 + lane; j < j1; j += 32) {
-              const int u = c.sues[j];
+              const int u = sue_of(j);
               if (!listed(u) || alc[j - j0] >= req[j - j0]) continue;
               const double m = c.mtab[(j - j0) * kMStride + cqi_first_rb(d, row_of(u), g)];
               if (m > best) { best = m; bj = j; }
@@ -1545,7 +1590,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             if (lane == 0) {
               int bu = -1;
               if (bj != 0x7fffffff) {
-                bu = c.sues[bj];
+                bu = sue_of(bj);
                 alc[bj - j0] += d.rbg;
                 c.mask[2 * bu + (g >> 5)] |= 1u << (g & 31);
               }
@@ -1560,7 +1605,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         double best = -1.0;   /* metrics are >= 0, so this behaves like numeric_limits::lowest() */
         int bu = -1;
         for (int j = j0; j < j1; ++j) {
-          const int u = c.sues[j];
+          const int u = sue_of(j);
           if (!listed(u)) continue;
           const int cq = cqi_first_rb(d, row_of(u), g);
           const double m = c.mtab[(j - j0) * kMStride + cq];

@@ -213,6 +213,7 @@ struct rs_handle {
   int n_traces = 0, trace_rows = 0;
   bool stage_ok = false;   /* the layout has room for a TTI of CQI (staged in shared memory) */
   bool wide = false;       /* 512 threads per cell (rsw::) instead of 128 */
+  int fixed = -1;          /* >= 0: the FixedShape instantiation this handle's backlogged launches use (fixed_kernel) */
   /* queue state for the next run call (rs_set_queues), consumed by it */
   const int32_t* q_next = nullptr;
   const double* hol_next = nullptr;
@@ -274,11 +275,39 @@ const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
     default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
   }
 }
+/* The headline cell -- 20 slices x 5 UEs, 64 RBGs of 8 RBs, one CQI value per RBG (u8 or 4-bit), backlogged, ids 9
+ * and 8 -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
+ * layout known at compile time.  A handle uses one only if its configuration and its host-computed layout match the
+ * instantiation exactly; RS_NO_FIXED_SHAPE=1 in the environment keeps every handle on the general kernel. */
+using FixedU8 = rs::FixedShape<20, 5, 64, 8, 0>;
+using FixedNib = rs::FixedShape<20, 5, 64, 8, 2>;
+template <class SH>
+bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
+  const rs::DevCfg& d = h->d;
+  if (h->wide || d.nb != 1 || d.S != SH::S || d.U != SH::U || d.G != SH::G || d.rbg != SH::RBG || d.cqi_per_rb != SH::LAY ||
+      d.n_chunks != SH::kChunks || d.m_cap != SH::kMCap || d.sort_n != SH::kSortN || d.sort_depth != SH::kSortDepth ||
+      !h->stage_ok)
+    return false;
+  for (int u = 0; u < d.U; ++u)
+    if (u2s[(size_t)u] != u / SH::UPS) return false;
+  const rs::Layout want = SH::layout();
+  return memcmp(&want, &h->layout, sizeof want) == 0;
+}
+const void* fixed_kernel(int algo, int which, bool trace) {
+  if (algo == 9) {
+    if (which == 0) return trace ? (const void*)rs::rs_tti_kernel<9, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<9, false, false, FixedU8>;
+    return trace ? (const void*)rs::rs_tti_kernel<9, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<9, false, false, FixedNib>;
+  }
+  if (which == 0) return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<8, false, false, FixedU8>;
+  return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<8, false, false, FixedNib>;
+}
+
 int launch_ttis(rs_handle* h, const rs::RunArgs& a, bool trace, const rs::DevCfg* cfg = nullptr) {
   const dim3 grid(h->B), block(h->wide ? rsw::kThreads : rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
   /* by address: the rsw:: kernels take rsw::DevCfg / rsw::RunArgs, the same bytes as the rs:: structs */
-  const void* fn = tti_kernel_any(h->d.algo, trace, a.queue != nullptr, h->wide);
+  const void* fn = (h->fixed >= 0 && !a.queue) ? fixed_kernel(h->d.algo, h->fixed, trace)
+                                               : tti_kernel_any(h->d.algo, trace, a.queue != nullptr, h->wide);
   void* args[2] = {(void*)(cfg ? cfg : &h->d), (void*)&a};
   CU(cudaLaunchKernel(fn, grid, block, args, sm, h->stream));
   CU(cudaGetLastError());
@@ -295,6 +324,9 @@ int set_smem_attr(rs_handle* h) {
   for (int t = 0; t < 4; ++t)
     CU(cudaFuncSetAttribute(tti_kernel_any(h->d.algo, (t & 1) != 0, (t & 2) != 0, h->wide),
                             cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  if (h->fixed >= 0)
+    for (int t = 0; t < 2; ++t)
+      CU(cudaFuncSetAttribute(fixed_kernel(h->d.algo, h->fixed, t != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
   return RS_OK;
 }
 
@@ -581,6 +613,10 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e)));
     if (h->layout.total > max_optin)
       BAIL(fail(RS_ERR_UNSUPPORTED, "cell needs %d B of shared memory, device allows %d", h->layout.total, max_optin));
+  }
+  if ((algo == 9 || algo == 8) && !getenv("RS_NO_FIXED_SHAPE")) {
+    if (shape_matches<FixedU8>(h, u2s)) h->fixed = 0;
+    else if (shape_matches<FixedNib>(h, u2s)) h->fixed = 1;
   }
   rs::ConstTables ct;
   { std::string why;
@@ -1436,6 +1472,7 @@ int32_t rs_rand_draws_per_cell_tti(const rs_handle* h) { return h ? h->d.rand_st
 int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
 int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }
 int32_t rs_threads_per_cta(const rs_handle* h) { return (h && h->wide) ? rsw::kThreads : rs::kThreads; }
+int32_t rs_fixed_shape(const rs_handle* h) { return h ? h->fixed : -1; }
 int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h) {
   if (!h) return 0;
   const int64_t U = h->d.U, G = h->d.G, S = h->d.S;

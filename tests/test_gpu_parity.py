@@ -411,3 +411,62 @@ def test_full_size_batch_invariants():
             assert np.array_equal(want["tbs_bits"], bits[t, sl]), t
         assert np.array_equal(o.get_state()["avg_rate"], st["avg_rate"][sl])
     g.close()
+
+
+@pytest.mark.parametrize("algo", [9, 8])
+@pytest.mark.parametrize("layout", [0, 2])
+def test_fixed_shape_equals_dynamic(algo, layout):
+    """The headline cell runs a compile-time-shape instantiation of the TTI kernel; RS_NO_FIXED_SHAPE keeps a handle on
+    the general one.  Same inputs, 70 TTIs in 16-TTI launches (streamed CQI and trace replay): every output and the
+    whole state are identical, and both equal the oracle."""
+    import os
+    from oracle.pyoracle import OracleScheduler
+    S, n, B, T = 20, 5, 40, 70
+    w = np.full(S, 0.05)
+    p = np.tile(PF, (S, 1))
+    p[1::3] = MT
+    u2s = np.repeat(np.arange(S), n).astype(np.int32)
+    U, G = len(u2s), 64
+    fixed = sched.Scheduler(algo, w, p, u2s, B, cqi_per_rb=layout)
+    os.environ["RS_NO_FIXED_SHAPE"] = "1"
+    try:
+        dyn = sched.Scheduler(algo, w, p, u2s, B, cqi_per_rb=layout)
+    finally:
+        del os.environ["RS_NO_FIXED_SHAPE"]
+    assert sched.lib().rs_fixed_shape(fixed._h) >= 0 and sched.lib().rs_fixed_shape(dyn._h) == -1
+    odd = sched.Scheduler(algo, w, p, np.repeat(np.arange(S), n)[::-1].astype(np.int32).copy(), B, cqi_per_rb=layout)
+    assert sched.lib().rs_fixed_shape(odd._h) == -1          # same sizes, another UE -> slice map: general kernel
+    odd.close()
+    cqi = workload.synth_cqi(77, 0, B, 0, T, U, G)
+    r2 = workload.synth_rand2(77, 0, B, 0, T, S)
+    _, dts = workload.tti_clock(T)
+    feed = sched.pack_cqi(cqi) if layout == 2 else cqi
+    a = fixed.run_host(feed, r2, dts, want_aux=True, ttis_per_launch=16)
+    b = dyn.run_host(feed, r2, dts, want_aux=True, ttis_per_launch=16)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    sa, sb = fixed.get_state(), dyn.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    o = OracleScheduler(algo, w, p, u2s, B, n_threads=8)
+    for t in range(T):
+        r = o.step(cqi[t], r2[t], dt=float(dts[t]))
+        assert np.array_equal(r["rbg_to_ue"], a["rbg_to_ue"][t]) and np.array_equal(r["tbs_bits"], a["tbs_bits"][t]), t
+    assert np.array_equal(o.get_state()["avg_rate"], sa["avg_rate"])
+    # trace replay through both
+    rng = np.random.default_rng(5)
+    traces = np.repeat(workload.histogram_cqi(rng, (12, 30, G)), 8, axis=2)
+    ue_trace = rng.integers(0, 12, (B, U)).astype(np.int32)
+    now, _ = workload.tti_clock(T)
+    rows = sched.trace_rows_for_run(now, 0, n_rows=30)
+    outs = []
+    for g in (fixed, dyn):
+        g.reset_state()
+        g.set_traces(traces, ue_trace)
+        outs.append((g.run_traces_host(rows, r2, dts, want_aux=True, ttis_per_launch=16), g.get_state()))
+    for k in outs[0][0]:
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), ("trace", k)
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), ("trace", k)
+    fixed.close()
+    dyn.close()
