@@ -64,8 +64,8 @@ typedef struct rs_config {
                                bearer container.  Per-bearer arrays (rates, byte counters, queues, delays) are then
                                [B][U][2], every run call needs rs_set_queues, and the kernels do what
                                SelectFlowsToSchedule / ComputeSchedulingMetric / DoStopSchedule do with two bearers
-                               (downlink-transport-scheduler.cpp:115-146, 179-191, 683-711).  Ids 7/8/9/10/101/103; id 1
-                               schedules flows, not users: give it one user per bearer instead */
+                               (downlink-transport-scheduler.cpp:115-146, 179-191, 683-711).  Every id but 1, which schedules
+                               flows, not users: give it one user per bearer (same CQI row) instead */
   const double* weight;       /* [S] slice_weights_ */
   const int32_t* params;      /* [S][4] alpha,beta,epsilon,psi (SchedulerAlgoParam, packet-scheduler.h:31-49) */
   const int32_t* ue_to_slice; /* [U] user_to_slice_ */

@@ -85,6 +85,7 @@ static long g_rand_script_pos = -1;            /* >= 0 while inside a recorded D
 static int g_rand_in_call = 0;
 static double g_stop_seconds = 0;   /* time inside DoStopSchedule (RLC, packets, cerr lines) of the recorded TTIs */
 static bool g_in_recorded_call = false;
+static double g_abi_seconds = 0;   /* --gpu: time inside rs_step_cell, read from the plug-in */
 
 static uint64_t SplitMix64() {
   uint64_t z = (g_rand_state += 0x9E3779B97F4A7C15ull);
@@ -289,8 +290,8 @@ static void ObservedSchedule(Sched* self, int S, const std::vector<int>& user_to
   g_sched_seconds += std::chrono::duration<double>(t1 - t0).count();
   g_sched_calls++;
   if (g_opt.time_every > 0 && g_sched_calls % g_opt.time_every == 0) {
-    fprintf(stdout, "{\"sched_calls\": %ld, \"sched_seconds\": %.6f, \"stop_seconds\": %.6f}\n", g_sched_calls, g_sched_seconds,
-            g_stop_seconds);
+    fprintf(stdout, "{\"sched_calls\": %ld, \"sched_seconds\": %.6f, \"stop_seconds\": %.6f, \"abi_seconds\": %.6f}\n", g_sched_calls,
+            g_sched_seconds, g_stop_seconds, g_abi_seconds);
     fflush(stdout);
   }
   g_rand_script_pos = -1;
@@ -465,7 +466,7 @@ class ObservedGpu : public RsGpuScheduler {
   void DoSchedule() override {
     ObservedSchedule(
         this, num_slices_, user_to_slice_, &slice_weights_, &slice_algo_params_,
-        [this]() { RsGpuScheduler::DoSchedule(); },
+        [this]() { RsGpuScheduler::DoSchedule(); g_abi_seconds = step_seconds_; },
         [this](std::vector<double>& st) { for (int s = 0; s < num_slices_; ++s) st[s] = slice_state_[s]; },
         [this](std::vector<uint8_t>& active, std::vector<int16_t>& r2u, std::vector<int32_t>& bits, int32_t& nvs, int rbg) {
           CollectUsers(GetUsersToSchedule(), active, r2u, bits, rbg);

@@ -112,6 +112,12 @@ struct DevCfg {
   double* offset; double* ewma;
 };
 
+/* The dimensions of a cell as the device code reads them (see rs_tti_kernel and the shape policies below). */
+struct Dims {
+  int S, U, G, R, rbg, cqi_per_rb, cqi_row, n_chunks, m_cap, sort_n, sort_depth, nb;
+  Layout lay;
+};
+
 struct RunArgs {
   const uint8_t* cqi; long long cqi_tti_stride;   /* TTI t reads slab (t0 + t) / cqi_refresh */
   int t0, cqi_refresh;
@@ -600,19 +606,19 @@ __device__ __forceinline__ void mbar_wait(void* mbar, unsigned parity) {
 /* Where UE u's CQI vector of this TTI starts: row u of the [U][cqi_row] slab, or (trace mode) the
  * current row of the trace the UE replays (cqi then points at that row of trace 0). */
 template <bool TRACE>
-__device__ __forceinline__ const uint8_t* ue_cqi(const DevCfg& d, const Cell& c, const uint8_t* cqi, int u) {
-  return TRACE ? cqi + c.utr[u] : cqi + (size_t)u * d.cqi_row;
+__device__ __forceinline__ const uint8_t* ue_cqi(const DevCfg& d, const Dims& dm, const Cell& c, const uint8_t* cqi, int u) {
+  return TRACE ? cqi + c.utr[u] : cqi + (size_t)u * dm.cqi_row;
 }
 /* CQI on the first RB of RBG g (the RB the metric is evaluated on, transport.cpp:536); p = ue_cqi() */
-__device__ __forceinline__ int cqi_first_rb(const DevCfg& d, const uint8_t* p, int g) {
-  if (d.cqi_per_rb == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
-  return d.cqi_per_rb ? (p[(size_t)g * d.rbg] & 15) : (p[g] & 15);
+__device__ __forceinline__ int cqi_first_rb(const Dims& dm, const uint8_t* p, int g) {
+  if (dm.cqi_per_rb == 2) return (p[g >> 1] >> (4 * (g & 1))) & 15;
+  return dm.cqi_per_rb ? (p[(size_t)g * dm.rbg] & 15) : (p[g] & 15);
 }
 
 /* Slice targets and RBG quotas, transport.cpp:463-521, by one warp (lane s and lane s+32). */
-__device__ __forceinline__ void slice_quotas(const DevCfg& d, const Cell& c, int r0, int r1, int lane, int* g_target, int* g_quota) {
-  const int S = d.S;
-  const int nb_rbs = d.G * d.rbg;
+__device__ __forceinline__ void slice_quotas(const DevCfg& d, const Dims& dm, const Cell& c, int r0, int r1, int lane, int* g_target, int* g_quota) {
+  const int S = dm.S;
+  const int nb_rbs = dm.G * dm.rbg;
   int tgt[2], wd[2];
   int sum = 0, nonempty = 0;
 #pragma unroll
@@ -657,11 +663,11 @@ __device__ __forceinline__ void slice_quotas(const DevCfg& d, const Cell& c, int
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int s = lane + 32 * h;
-    q[h] = (s < S) ? tgt[h] / d.rbg : 0;
+    q[h] = (s < S) ? tgt[h] / dm.rbg : 0;
     qsum += q[h];
   }
   qsum = __reduce_add_sync(kFull, qsum);
-  const int extra_rbgs = d.G - qsum;
+  const int extra_rbgs = dm.G - qsum;
   const int b1 = r1 % S;
   best = 0xffffffffu;
 #pragma unroll
@@ -693,9 +699,9 @@ __device__ __forceinline__ void slice_quotas(const DevCfg& d, const Cell& c, int
  * of its own entry's slice in a register, one redux.sync(min) finds the lowest feasible lane and
  * broadcasts its (rbg,slice), and the other lanes drop out if they lost their RBG or their slice
  * ran out.  c.quota is consumed (the host-visible quotas were written by slice_quotas). */
-__device__ __forceinline__ void greedy_maxcell(const DevCfg& d, const Cell& c, const unsigned short* sorted, int lane) {
-  const int n = d.sort_n;
-  int nfree = d.G;
+__device__ __forceinline__ void greedy_maxcell(const DevCfg& d, const Dims& dm, const Cell& c, const unsigned short* sorted, int lane) {
+  const int n = dm.sort_n;
+  int nfree = dm.G;
   for (int base = 0; base < n && nfree > 0; base += 32) {
     const int i = base + lane;
     const unsigned e = (i < n) ? sorted[i] : 0u;
@@ -721,11 +727,11 @@ __device__ __forceinline__ void greedy_maxcell(const DevCfg& d, const Cell& c, c
 }
 
 /* GreedyByRow, transport.cpp:249-272, by one warp. a[] holds the unsorted (rbg-major) entries. */
-__device__ __forceinline__ void greedy_by_row(const DevCfg& d, const Cell& c, const unsigned short* a, int lane) {
-  const int S = d.S;
+__device__ __forceinline__ void greedy_by_row(const DevCfg& d, const Dims& dm, const Cell& c, const unsigned short* a, int lane) {
+  const int S = dm.S;
   int rem_a = (lane < S) ? c.quota[lane] : 0;
   int rem_b = (lane + 32 < S) ? c.quota[lane + 32] : 0;
-  for (int g = 0; g < d.G; ++g) {
+  for (int g = 0; g < dm.G; ++g) {
     unsigned v = 0;
     if (lane < S && rem_a > 0) v = ((unsigned)(a[g * S + lane] >> 12) << 8 | (unsigned)(63 - lane)) + 1u;
     if (lane + 32 < S && rem_b > 0) {
@@ -743,7 +749,7 @@ __device__ __forceinline__ void greedy_by_row(const DevCfg& d, const Cell& c, co
 
 /* Link adaptation + accounting for UE u holding the RBGs in mask (transport.cpp:632-660 and 170-199;
  * dl-pf-packet-scheduler.cpp:64-96 for id 1). */
-__device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, const uint8_t* row, int u,
+__device__ __forceinline__ void finalize_ue(const DevCfg& d, const Dims& dm, const Cell& c, const uint8_t* row, int u,
                                             unsigned m_lo, unsigned m_hi, int* o_bits, uint8_t* o_mcs, uint8_t* o_fc,
                                             int data_u, const double* presum = nullptr, const int* qd2 = nullptr) {
   int bits = 0, mcs = 0xff, fc = 0;
@@ -758,15 +764,15 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Cell& c, cons
     while (m) {
       const int g = __ffsll((long long)m) - 1;
       m &= m - 1;
-      if (d.cqi_per_rb == 1) {
-        const uint8_t* p = row + (size_t)g * d.rbg;
-        for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, c.tval[p[r] & 15]);
+      if (dm.cqi_per_rb == 1) {
+        const uint8_t* p = row + (size_t)g * dm.rbg;
+        for (int r = 0; r < dm.rbg; ++r) sum = __dadd_rn(sum, c.tval[p[r] & 15]);
       } else {
-        const double t = c.tval[cqi_first_rb(d, row, g)];
-        for (int r = 0; r < d.rbg; ++r) sum = __dadd_rn(sum, t);
+        const double t = c.tval[cqi_first_rb(dm, row, g)];
+        for (int r = 0; r < dm.rbg; ++r) sum = __dadd_rn(sum, t);
       }
     }
-    const int nrb = nrbg * d.rbg;
+    const int nrb = nrbg * dm.rbg;
     const double mean = __ddiv_rn(sum, (double)nrb);
     fc = cqi_from_mean(mean);
     mcs = 2 * (fc - 1);                        /* MapCQIToMCS, AMCModule.cpp:36-40 */
@@ -816,19 +822,19 @@ struct InterScratch {
   unsigned char* nxt;      /* [S + 1] singly linked list of the emulated hashtable, S = before-begin */
   unsigned char* bkt;      /* [128] node before the first node of each bucket, 0xff = empty bucket */
 };
-__device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Cell& c) {
+__device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Dims& dm, const Cell& c) {
   InterScratch x;
   unsigned char* p = (unsigned char*)c.sb.posl;
-  const int n = d.G + d.S;
+  const int n = dm.G + dm.S;
   x.eff = (double*)p;
   p += 128;
   x.val = (double*)p;
   x.pick = (int*)(p + 8 * n);
   x.over = x.pick + n;
-  x.under = x.over + d.S;
-  x.order = (unsigned char*)(x.under + d.S);
-  x.nxt = x.order + d.S;
-  x.bkt = x.nxt + d.S + 1;
+  x.under = x.over + dm.S;
+  x.order = (unsigned char*)(x.under + dm.S);
+  x.nxt = x.order + dm.S;
+  x.bkt = x.nxt + dm.S + 1;
   return x;
 }
 /* efficiency of the (rbg, slice) pair: the slice winner's, 0 for a slice without a listed user */
@@ -840,9 +846,9 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  * quota left (thread G + s) reports the gap between its best and its "second" efficiency, then one thread walks
  * the candidates in the reference's order with the reference's int-truncated running maximum.  Result in
  * c.outsl. */
-__device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
-  const int tid = threadIdx.x, G = d.G, S = d.S;
-  const InterScratch x = inter_scratch(d, c);
+__device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
+  const int tid = threadIdx.x, G = dm.G, S = dm.S;
+  const InterScratch x = inter_scratch(d, dm, c);
   int* held = c.wd;   /* free once the quotas exist; cleared again at the end of the TTI */
   for (int s = tid; s < S; s += kThreads) held[s] = 0;
   if (tid < 16) x.eff[tid] = c_tab.eff[tid];
@@ -915,9 +921,9 @@ __device__ void vogel_approximate(const DevCfg& d, const Cell& c) {
  * the iteration order of the reference's std::unordered_map of the slices below quota, which is emulated:
  * libstdc++'s hashtable with its prime bucket counts 13 / 29 / 59 / 127, nodes of an empty bucket go to the
  * front of the list, a rehash re-links the nodes in list order).  Result in c.outsl. */
-__device__ void sub_opt(const DevCfg& d, const Cell& c) {
-  const int tid = threadIdx.x, G = d.G, S = d.S;
-  const InterScratch x = inter_scratch(d, c);
+__device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
+  const int tid = threadIdx.x, G = dm.G, S = dm.S;
+  const InterScratch x = inter_scratch(d, dm, c);
   int* held = c.wd;
   for (int s = tid; s < S; s += kThreads) held[s] = 0;
   if (tid < 16) x.eff[tid] = c_tab.eff[tid];
@@ -1034,33 +1040,42 @@ __device__ void sub_opt(const DevCfg& d, const Cell& c) {
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
 template <int ALGO, bool TRACE, bool QUEUE, class SH = DynShape>
-__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d_in, const RunArgs r) {
+__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DevCfg d = d_in;
-  if constexpr (SH::kStatic) {   /* the dimensions and the layout become compile-time constants of this instantiation */
-    d.S = SH::S; d.U = SH::U; d.G = SH::G; d.R = SH::R; d.rbg = SH::RBG;
-    d.cqi_per_rb = SH::LAY; d.cqi_row = SH::kCqiRow;
+  /* The dimensions and the layout (Dims) are compile-time constants of a FixedShape instantiation and copies of the
+   * launch parameters otherwise; pointers are always read from the parameter block itself (a local copy of the
+   * whole DevCfg would cost them their "global memory" provenance: generic LD/ST instead of LDG/STG). */
+  Dims dm;
+  if constexpr (SH::kStatic) {
     constexpr Layout kLay = SH::layout();
-    d.lay = kLay;
-    d.n_chunks = SH::kChunks; d.m_cap = SH::kMCap; d.sort_n = SH::kSortN; d.sort_depth = SH::kSortDepth;
-    d.nb = 1;
+    dm.S = SH::S; dm.U = SH::U; dm.G = SH::G; dm.R = SH::R; dm.rbg = SH::RBG;
+    dm.cqi_per_rb = SH::LAY; dm.cqi_row = SH::kCqiRow;
+    dm.lay = kLay;
+    dm.n_chunks = SH::kChunks; dm.m_cap = SH::kMCap; dm.sort_n = SH::kSortN; dm.sort_depth = SH::kSortDepth;
+    dm.nb = 1;
+  } else {
+    dm.S = d.S; dm.U = d.U; dm.G = d.G; dm.R = d.R; dm.rbg = d.rbg;
+    dm.cqi_per_rb = d.cqi_per_rb; dm.cqi_row = d.cqi_row;
+    dm.lay = d.lay;
+    dm.n_chunks = d.n_chunks; dm.m_cap = d.m_cap; dm.sort_n = d.sort_n; dm.sort_depth = d.sort_depth;
+    dm.nb = d.nb;
   }
-  Cell c = carve(smem, d.lay);
+  Cell c = carve(smem, dm.lay);
   c.sb.eq_tab = d.eq_tab;
   c.sb.eq_max = d.eq_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int S = d.S, U = d.U, G = d.G;
+  const int S = dm.S, U = dm.U, G = dm.G;
   const int b = blockIdx.x;
   constexpr bool NVS = ALGO == 7 || ALGO == 11;   /* DownlinkNVSScheduler, greedy and non-greedy */
   /* DownlinkTransportScheduler with one of its inter-slice algorithms: GreedyByRow (8), MaximizeCell (9),
    * UpperBound (10), SubOpt (101), VogelApproximate (103) */
   constexpr bool TRANSPORT = ALGO == 8 || ALGO == 9 || ALGO == 10 || ALGO == 101 || ALGO == 103;
   if (b >= d.n_cells) return;
-  c.cumb = d.cum_bytes + (size_t)b * U * (QUEUE ? d.nb : 1);
-  c.cumr = d.cum_rbs + (size_t)b * U * (QUEUE ? d.nb : 1);
+  c.cumb = d.cum_bytes + (size_t)b * U * (QUEUE ? dm.nb : 1);
+  c.cumr = d.cum_rbs + (size_t)b * U * (QUEUE ? dm.nb : 1);
 
   /* cell state -> shared memory */
-  const int nb = QUEUE ? d.nb : 1;   /* bearers per UE: the backlogged instantiations know one */
+  const int nb = QUEUE ? dm.nb : 1;   /* bearers per UE: the backlogged instantiations know one */
   for (int u = tid; u < U; u += kThreads) {
     const size_t i = (size_t)b * U + u;
     for (int k = 0; k < nb; ++k) {
@@ -1102,15 +1117,15 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 #ifdef RS_NO_BULK
   auto stage_cqi = [&](int t) {
     if (TRACE) {
-      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row;
-      const int cpr = d.cqi_row >> 4;
+      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * dm.cqi_row;
+      const int cpr = dm.cqi_row >> 4;
       for (int q = tid; q < U * cpr; q += kThreads) {
         const int u = q / cpr, part = (q - u * cpr) << 4;
-        cp_async16(c.cq + u * d.cqi_row + part, base + c.utr[u] + part);
+        cp_async16(c.cq + u * dm.cqi_row + part, base + c.utr[u] + part);
       }
     } else {
-      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * d.cqi_row;
-      const int n16 = (U * d.cqi_row) >> 4;
+      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * dm.cqi_row;
+      const int n16 = (U * dm.cqi_row) >> 4;
       for (int q = tid; q < n16; q += kThreads) cp_async16(c.cq + (q << 4), src + ((size_t)q << 4));
     }
     cp_async_commit();
@@ -1126,13 +1141,13 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     __syncthreads();
   }
   auto stage_cqi = [&](int t) {
-    const unsigned total = (unsigned)(U * d.cqi_row);
+    const unsigned total = (unsigned)(U * dm.cqi_row);
     if (TRACE) {
       if (tid == 0) mbar_expect_tx(c.mbar, total);
-      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row;
-      for (int u = tid; u < U; u += kThreads) bulk_g2s(c.cq + u * d.cqi_row, base + c.utr[u], (unsigned)d.cqi_row, c.mbar);
+      const uint8_t* base = d.trace_tab + (size_t)r.trace_row[t] * dm.cqi_row;
+      for (int u = tid; u < U; u += kThreads) bulk_g2s(c.cq + u * dm.cqi_row, base + c.utr[u], (unsigned)dm.cqi_row, c.mbar);
     } else if (tid == 0) {
-      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * d.cqi_row;
+      const uint8_t* src = r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride + (size_t)b * U * dm.cqi_row;
       mbar_expect_tx(c.mbar, total);
       bulk_g2s(c.cq, src, total, c.mbar);
     }
@@ -1153,9 +1168,9 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   long long last_ = clock64();
 #endif
   for (int t = 0; t < r.T; ++t) {
-    const uint8_t* cqi = TRACE ? d.trace_tab + (size_t)r.trace_row[t] * d.cqi_row
+    const uint8_t* cqi = TRACE ? d.trace_tab + (size_t)r.trace_row[t] * dm.cqi_row
                                : r.cqi + (size_t)((r.t0 + t) / r.cqi_refresh) * r.cqi_tti_stride +
-                                     (size_t)b * U * d.cqi_row;
+                                     (size_t)b * U * dm.cqi_row;
     const uint8_t* act = r.active ? r.active + (size_t)t * r.active_tti_stride + (size_t)b * U : nullptr;
     const double dt = r.dt[t];
     const size_t tb = (size_t)t * d.n_cells + b;
@@ -1186,7 +1201,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       if (hm == 2 && hl && hl[u] < 0.0) return 0.0;          /* the bearer of the slice's priority is empty, :696-698 */
       return e;
     };
-    auto row_of = [&](int u) -> const uint8_t* { return stage ? c.cq + u * d.cqi_row : ue_cqi<TRACE>(d, c, cqi, u); };
+    auto row_of = [&](int u) -> const uint8_t* { return stage ? c.cq + u * dm.cqi_row : ue_cqi<TRACE>(d, dm, c, cqi, u); };
     short* o_rbg = r.rbg_to_ue ? r.rbg_to_ue + tb * G : nullptr;
     int* o_bits = r.tbs_bits ? r.tbs_bits + tb * U : nullptr;
     uint8_t* o_mcs = r.mcs ? r.mcs + tb * U : nullptr;
@@ -1262,25 +1277,27 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     RS_TICK(0);
     if (TRANSPORT) {
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
-      for (int ch = 0; ch < d.n_chunks; ++ch) {
+      for (int ch = 0; ch < dm.n_chunks; ++ch) {
         const int s0 = chunk_lo(ch), s1 = chunk_lo(ch + 1);
         const int j0 = sptr_of(s0), j1 = sptr_of(s1);
         if (ch == 0 && warp == (rot + kWarps - 1) % kWarps)
-          slice_quotas(d, c, r.rand2[tb * d.rand_stride], r.rand2[tb * d.rand_stride + 1], lane, o_tgt, o_quo);
+          slice_quotas(d, dm, c, r.rand2[tb * d.rand_stride], r.rand2[tb * d.rand_stride + 1], lane, o_tgt, o_quo);
         for (int q = tid; q < (j1 - j0) * kMStride; q += kThreads) {
           const int j = j0 + (q >> 4), cq = q & 15;
           const int u = sue_of(j);
           const int su = slice_of(u);
           double e = d.epow[su * 16 + cq];
           const int hm = d.holmul[su];
-          if (QUEUE && hm) e = prio_gate(u, su, hm, e);
+          /* alpha slices: gate / head-of-line delay of the prioritised bearer; without queue state (backlogged
+           * instantiation) the delay of an infinite buffer is 0, so an alpha+beta slice's metric is 0 */
+          if (hm) e = QUEUE ? prio_gate(u, su, hm, e) : (hm == 1 ? __dmul_rn(0.0, e) : e);
           c.mtab[q] = cq ? __ddiv_rn(e, c.den[u]) : 0.0;
         }
         __syncthreads();
         /* four RBGs per item (one 32-bit CQI load per UE) while that still gives every thread an item;
          * fewer, bigger slices on a wide CTA go one RBG per item */
-        const bool vec4 = d.cqi_per_rb != 1 && (G % 4 == 0) && (kThreads <= 128 || (s1 - s0) * (G >> 2) >= kThreads);
-        const bool nib = d.cqi_per_rb == 2;
+        const bool vec4 = dm.cqi_per_rb != 1 && (G % 4 == 0) && (kThreads <= 128 || (s1 - s0) * (G >> 2) >= kThreads);
+        const bool nib = dm.cqi_per_rb == 2;
         if (vec4) {
           const int g4 = G >> 2;
           const int items = (s1 - s0) * g4;
@@ -1324,7 +1341,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             for (int j = sptr_of(s); j < sptr_of(s + 1); ++j) {
               const int u = sue_of(j);
               if (!listed(u)) continue;
-              const int cq = cqi_first_rb(d, row_of(u), g);
+              const int cq = cqi_first_rb(dm, row_of(u), g);
               const double m = c.mtab[(j - j0) * kMStride + cq];
               if (m > best) { best = m; bu = u; bc = cq; }
             }
@@ -1380,18 +1397,18 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             cnt++;
             double sum = c.den[ue];
             const uint8_t* row = row_of(ue);
-            if (d.cqi_per_rb == 1) {
-              const uint8_t* p = row + (size_t)g * d.rbg;
-              for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+            if (dm.cqi_per_rb == 1) {
+              const uint8_t* p = row + (size_t)g * dm.rbg;
+              for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
             } else {
-              const double tv = c.tval[cqi_first_rb(d, row, g)];
-              for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+              const double tv = c.tval[cqi_first_rb(dm, row, g)];
+              for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, tv);
             }
             c.den[ue] = sum;
             c.mask[2 * ue + (g >> 5)] |= 1u << (g & 31);   /* a UE belongs to one slice: no other thread touches it */
           }
           c.frb[s] = cnt;
-          if (c.misc[14]) c.off[s] = (double)(c.target[s] - cnt * d.rbg);   /* :618-620 */
+          if (c.misc[14]) c.off[s] = (double)(c.target[s] - cnt * dm.rbg);   /* :618-620 */
           else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
         }
         __syncthreads();
@@ -1410,20 +1427,20 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           if (o_rbg) o_rbg[g] = (short)ue;
         }
       } else if (ALGO == 103) {
-        vogel_approximate(d, c);
+        vogel_approximate(d, dm, c);
       } else if (ALGO == 101) {
-        sub_opt(d, c);
+        sub_opt(d, dm, c);
       } else if (ALGO == 9) {
 #ifndef RS_SKIP_SORT
-        sort_desc(c.sb, d.sort_n, d.sort_depth, kWarps - rot);
+        sort_desc(c.sb, dm.sort_n, dm.sort_depth, kWarps - rot);
 #endif
         RS_TICK(2);
 #ifndef RS_SKIP_GREEDY
-        if (warp == rot) greedy_maxcell(d, c, c.sb.out, lane);
+        if (warp == rot) greedy_maxcell(d, dm, c, c.sb.out, lane);
 #endif
         RS_TICK(3);
       } else {
-        if (warp == rot) greedy_by_row(d, c, c.sb.a, lane);
+        if (warp == rot) greedy_by_row(d, dm, c, c.sb.a, lane);
       }
       __syncthreads();
 
@@ -1448,7 +1465,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       /* slice_rbs_offset_ update (:618-620); only when RBsAllocation ran (>= 1 user) */
       if (ALGO != 10)
       for (int s = tid; s < S; s += kThreads) {
-        if (c.misc[14]) c.off[s] = (double)(c.target[s] - c.frb[s] * d.rbg);
+        if (c.misc[14]) c.off[s] = (double)(c.target[s] - c.frb[s] * dm.rbg);
         else { if (o_tgt) o_tgt[s] = 0; if (o_quo) o_quo[s] = 0; }
       }
     } else if (ALGO == 11) {
@@ -1473,12 +1490,20 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       for (int q = tid; q < Ua; q += kThreads) {   /* user_highest_cqi, nvs.cpp:416-425 */
         const uint8_t* row = row_of(c.ng_list[q]);
         int hc = 0;
-        for (int g = 0; g < G; ++g) hc = max(hc, cqi_first_rb(d, row, g));
+        for (int g = 0; g < G; ++g) hc = max(hc, cqi_first_rb(dm, row, g));
         c.ng_hc[q] = (unsigned char)hc;
       }
       for (int q = tid; q < Ua * kMStride; q += kThreads) {   /* sEff * 180000 / (1 + avg), nvs.cpp:512-513 */
         const int cq = q & 15;
-        c.mtab[q] = cq ? __ddiv_rn(d.epow[cq], __dadd_rn(1.0, c.avg[c.ng_list[q >> 4]])) : 0.0;
+        /* UserToSchedule::GetAverageTransmissionRate: 1 + the listed bearers' rates in slot order (packet-scheduler.cpp:423-433) */
+        const int un = c.ng_list[q >> 4];
+        double rate = __dadd_rn(1.0, c.avg[nb * un]);
+        if (two) {
+          rate = 1.0;
+          if (qd[2 * un] > 0) rate = __dadd_rn(rate, c.avg[2 * un]);
+          if (qd[2 * un + 1] > 0) rate = __dadd_rn(rate, c.avg[2 * un + 1]);
+        }
+        c.mtab[q] = cq ? __ddiv_rn(d.epow[cq], rate) : 0.0;
       }
       __syncthreads();
       const int* draws = r.rand2 + tb * d.rand_stride;
@@ -1493,7 +1518,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             double highest = -1.0;
             for (int q = 0; q < Ua; ++q) {
               const int mcs = my[q];
-              const double m = (mcs <= cqi_first_rb(d, row_of(c.ng_list[q]), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
+              const double m = (mcs <= cqi_first_rb(dm, row_of(c.ng_list[q]), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
               if (highest < m) highest = m;
             }
             pf = __dadd_rn(pf, highest);
@@ -1526,7 +1551,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
           for (int q = 0; q < Ua; ++q) {
             const int mcs = max((int)c.ng_hc[q] - draws[best_i * Ua + q] % 4, 1);
             const int u = c.ng_list[q];
-            const double m = (mcs <= cqi_first_rb(d, row_of(u), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
+            const double m = (mcs <= cqi_first_rb(dm, row_of(u), g)) ? c.mtab[q * kMStride + mcs] : 0.0;
             if (highest < m) { highest = m; bu = u; }
           }
         }
@@ -1556,15 +1581,15 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             const uint8_t* row = row_of(u);
             double sum = 0;   /* EESM over every RB of the band, RB order */
             for (int g = 0; g < G; ++g) {
-              if (d.cqi_per_rb == 1) {
-                const uint8_t* p = row + (size_t)g * d.rbg;
-                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+              if (dm.cqi_per_rb == 1) {
+                const uint8_t* p = row + (size_t)g * dm.rbg;
+                for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
               } else {
-                const double tv = c.tval[cqi_first_rb(d, row, g)];
-                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+                const double tv = c.tval[cqi_first_rb(dm, row, g)];
+                for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, tv);
               }
             }
-            const int wide = cqi_from_mean(__ddiv_rn(sum, (double)(G * d.rbg)));
+            const int wide = cqi_from_mean(__ddiv_rn(sum, (double)(G * dm.rbg)));
             need = min(data_of(u), kMaxQueueBytes) * 8 / d.tbs1[wide];
           }
           req[j - j0] = need;
@@ -1578,7 +1603,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             for (int j = j0 + lane; j < j1; j += 32) {
               const int u = sue_of(j);
               if (!listed(u) || alc[j - j0] >= req[j - j0]) continue;
-              const double m = c.mtab[(j - j0) * kMStride + cqi_first_rb(d, row_of(u), g)];
+              const double m = c.mtab[(j - j0) * kMStride + cqi_first_rb(dm, row_of(u), g)];
               if (m > best) { best = m; bj = j; }
             }
 #pragma unroll
@@ -1591,7 +1616,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               int bu = -1;
               if (bj != 0x7fffffff) {
                 bu = sue_of(bj);
-                alc[bj - j0] += d.rbg;
+                alc[bj - j0] += dm.rbg;
                 c.mask[2 * bu + (g >> 5)] |= 1u << (g & 31);
               }
               if (o_rbg) o_rbg[g] = (short)bu;
@@ -1607,7 +1632,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         for (int j = j0; j < j1; ++j) {
           const int u = sue_of(j);
           if (!listed(u)) continue;
-          const int cq = cqi_first_rb(d, row_of(u), g);
+          const int cq = cqi_first_rb(dm, row_of(u), g);
           const double m = c.mtab[(j - j0) * kMStride + cq];
           if (m > best) { best = m; bu = u; }
         }
@@ -1632,7 +1657,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
             double best = 0.0;
             for (int u = lane; u < U; u += 32) {
               if (!listed(u) || c.done[u]) continue;
-              const double m = __ddiv_rn(d.epow[cqi_first_rb(d, row_of(u), g)], c.den[u]);
+              const double m = __ddiv_rn(d.epow[cqi_first_rb(dm, row_of(u), g)], c.den[u]);
               if (m > best) { best = m; bu = u; }
             }
 #pragma unroll
@@ -1648,16 +1673,16 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
               c.mask[2 * bu + (g >> 5)] |= 1u << (g & 31);
               const uint8_t* row = row_of(bu);
               double sum = fsum[bu];
-              if (d.cqi_per_rb == 1) {
-                const uint8_t* p = row + (size_t)g * d.rbg;
-                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
+              if (dm.cqi_per_rb == 1) {
+                const uint8_t* p = row + (size_t)g * dm.rbg;
+                for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, c.tval[p[rr] & 15]);
               } else {
-                const double tv = c.tval[cqi_first_rb(d, row, g)];
-                for (int rr = 0; rr < d.rbg; ++rr) sum = __dadd_rn(sum, tv);
+                const double tv = c.tval[cqi_first_rb(dm, row, g)];
+                for (int rr = 0; rr < dm.rbg; ++rr) sum = __dadd_rn(sum, tv);
               }
               fsum[bu] = sum;
               const int nrbg = __popc(c.mask[2 * bu]) + __popc(c.mask[2 * bu + 1]);
-              const int fc = cqi_from_mean(__ddiv_rn(sum, (double)(nrbg * d.rbg)));
+              const int fc = cqi_from_mean(__ddiv_rn(sum, (double)(nrbg * dm.rbg)));
               if (d.tbs_n[nrbg * 16 + fc] >= min(qd[bu], kMaxQueueBytes) * 8) {   /* dlps.cpp:264-269 */
                 c.done[bu] = 1;
                 finished = 1;
@@ -1676,7 +1701,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
         int bu = 0x7fffffff;
         for (int u = lane; u < U; u += 32) {
           if (!listed(u)) continue;
-          const int cq = cqi_first_rb(d, row_of(u), g);
+          const int cq = cqi_first_rb(dm, row_of(u), g);
           const double m = __ddiv_rn(d.epow[cq], c.den[u]);
           if (m > best) { best = m; bu = u; }
         }
@@ -1699,7 +1724,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     /* ---- P6: link adaptation, accounting, outputs; reset per-TTI scratch ---------------------- */
     for (int u = tid; u < U; u += kThreads) {
       const unsigned m_lo = c.mask[2 * u], m_hi = c.mask[2 * u + 1];
-      finalize_ue(d, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, data_of(u), ALGO == 10 ? c.den : nullptr,
+      finalize_ue(d, dm, c, row_of(u), u, m_lo, m_hi, o_bits, o_mcs, o_fc, data_of(u), ALGO == 10 ? c.den : nullptr,
                   two ? qd : nullptr);
       c.mask[2 * u] = 0;
       c.mask[2 * u + 1] = 0;

@@ -448,8 +448,8 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     return fail(RS_ERR_ARG, "rs_create: weight/params/ue_to_slice missing");
   const int nb = cfg->n_bearers == 2 ? 2 : 1;
   if (cfg->n_bearers < 0 || cfg->n_bearers > 2) return fail(RS_ERR_ARG, "n_bearers %d outside 0..2 (MAX_BEARERS = 2)", cfg->n_bearers);
-  if (nb == 2 && (algo == 1 || algo == 11))
-    return fail(RS_ERR_UNSUPPORTED, "two bearers per UE: id 1 schedules flows (give it one user per bearer), id 11 is not covered");
+  if (nb == 2 && algo == 1)
+    return fail(RS_ERR_UNSUPPORTED, "two bearers per UE: id 1 schedules flows, not users -- give it one user per bearer");
   if (cfg->data_to_transmit < 0 || cfg->data_to_transmit > 268435455)
     return fail(RS_ERR_ARG, "data_to_transmit %d outside 0..2^28-1 (data*8 is an int in the reference)", cfg->data_to_transmit);
   for (int u = 0; u < U; ++u)

@@ -34,6 +34,7 @@
 #include <iostream>
 #include <list>
 #include <stdexcept>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,8 @@ class RsGpuScheduler : public PacketScheduler {
   std::vector<double> slice_weights_;
   std::vector<SchedulerAlgoParam> slice_algo_params_;
   std::vector<double> slice_state_; /* slice_rbs_offset_ (ids 8/9) or slice_ewma_time_ (id 7) */
+  double step_seconds_ = 0;         /* wall time spent inside rs_step_cell (copy up, launch, copy down, sync) */
+  long step_calls_ = 0;
 
   /* scheduler_id: 1 No-Slicing PF, 7 NVS, 8 Sequential, 9 RadioSaber, 10 UpperBound (single-cell-with-interference.h:95-110),
    * and 101 SubOpt / 103 VogelApproximate, the two inter-slice algorithms ENodeB.cpp:363-379 can install.
@@ -340,7 +343,10 @@ class RsGpuScheduler : public PacketScheduler {
       io.out.alloc_ue = grant_ue_.data();
       io.out.alloc_rbg = grant_rbg_.data();
     }
+    const auto c0 = std::chrono::steady_clock::now();
     Check(rs_step_cell(h_, &io), "rs_step_cell");
+    step_seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+    step_calls_++;
     if (id_ == 11 && nvs_slice != host_slice) throw std::runtime_error("RsGpuScheduler: host and device disagree on the NVS slice");
 
     UsersToSchedule* users = GetUsersToSchedule();

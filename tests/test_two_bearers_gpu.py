@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 DIR = os.path.join(ROOT, "tests", "golden", "two_bearers")
 
 
-@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103])
+@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103, 11])
 @pytest.mark.parametrize("mode", ["step", "run_host"])
 def test_batch_path_reproduces_the_reference_with_two_bearers(algo, mode):
     rec = golden_io.load_npz(os.path.join(DIR, f"a{algo}.npz"))
@@ -27,6 +27,8 @@ def test_batch_path_reproduces_the_reference_with_two_bearers(algo, mode):
     cqi1 = workload.synth_cqi(seed, 0, 1, 0, T, U, G)[:, 0]
     cqi = np.repeat(cqi1[:, None], B, axis=1)
     r2 = np.repeat(rec["rand2"][:, None], B, axis=1)
+    if algo == 11:   # every rand() value the reference's 300-sample search drew (cell 3 has the reference's listed users)
+        r2 = np.repeat(rec["rand_ng"][:, None], B, axis=1)
     queue = np.stack([rec["queue"][rng.permutation(T)] if b != CELL else rec["queue"] for b in range(B)], axis=1)
     hol = np.repeat(rec["hol"][:, None], B, axis=1)
     avg0 = np.repeat(rec["avg_before"][0][None], B, axis=0)
@@ -78,9 +80,41 @@ def test_batch_path_reproduces_the_reference_with_two_bearers(algo, mode):
     g.close()
 
 
+def test_id1_schedules_flows_one_user_per_bearer():
+    """DL_PF_PacketScheduler lists FLOWS (one per bearer, downlink-packet-scheduler.cpp:48-94), so a cell with two
+    bearers per UE is a cell of one "user" per bearer for id 1: flow f = the f-th bearer of the eNB's container, with
+    its UE's CQI row.  Per-bearer rates and counters of the unmodified reference, TTI by TTI."""
+    rec = golden_io.load_npz(os.path.join(DIR, "a1.npz"))
+    T, U, S, G, seed = int(rec["T"]), int(rec["U"]), int(rec["S"]), int(rec["G"]), int(rec["seed"])
+    app = rec["app_id"]
+    F = int(app.max()) + 1
+    fu = np.zeros(F, np.int32)
+    fi = np.zeros(F, np.int32)
+    for u in range(U):
+        for i in range(2):
+            if app[u, i] >= 0:
+                fu[app[u, i]], fi[app[u, i]] = u, i
+    g = sched.Scheduler(1, rec["weight"], rec["params"], rec["ue_to_slice"][fu], 2)
+    cqi = workload.synth_cqi(seed, 0, 1, 0, T, U, G)[:, 0]
+    g.set_state(avg_rate=np.repeat(rec["avg_before"][0][fu, fi][None], 2, axis=0),
+                tx_bytes=np.repeat(rec["tx_before"][0][fu, fi][None], 2, axis=0))
+    served = 0
+    for t in range(T):
+        q = np.repeat(rec["queue"][t][fu, fi][None], 2, axis=0)
+        out = g.step(np.repeat(cqi[t][fu][None], 2, axis=0), None, dt=float(rec["dt"][t]), queue=q)
+        st = g.get_state()
+        for k, gk in (("avg_rate", "avg_after"), ("tx_bytes", "tx_after"), ("cum_bytes", "cum_bytes"), ("cum_rbs", "cum_rbs")):
+            assert np.array_equal(st[k][1], rec[gk][t][fu, fi]), (t, k)
+        flows = out["rbg_to_ue"][1]
+        assert np.array_equal(np.where(flows >= 0, fu[np.maximum(flows, 0)], -1), rec["rbg_to_ue"][t]), (t, "rbg_to_ue")
+        served += int((flows >= 0).sum())
+    assert served > 1000
+    g.close()
+
+
 def test_two_bearers_need_queues_and_refuse_flow_level_ids():
     rec = golden_io.load_npz(os.path.join(DIR, "a9.npz"))
-    for algo in (1, 11):
+    for algo in (1,):
         with pytest.raises(sched.RsError, match="two bearers"):
             sched.Scheduler(algo, rec["weight"], rec["params"], rec["ue_to_slice"], 1, n_bearers=2)
     g = sched.Scheduler(9, rec["weight"], rec["params"], rec["ue_to_slice"], 1, n_bearers=2)

@@ -30,13 +30,17 @@ def run(binary, algo, tmp, gpu):
     n = marks[-1]["sched_calls"] - marks[0]["sched_calls"]
     tot = marks[-1]["sched_seconds"] - marks[0]["sched_seconds"]
     stop = marks[-1]["stop_seconds"] - marks[0]["stop_seconds"]
-    return {"do_schedule_ms": 1e3 * tot / n, "do_stop_schedule_ms": 1e3 * stop / n, "ewma_select_alloc_ms": 1e3 * (tot - stop) / n}
+    res = {"do_schedule_ms": 1e3 * tot / n, "do_stop_schedule_ms": 1e3 * stop / n, "ewma_select_alloc_ms": 1e3 * (tot - stop) / n}
+    if gpu:
+        res["rs_step_cell_ms"] = 1e3 * (marks[-1].get("abi_seconds", 0.0) - marks[0].get("abi_seconds", 0.0)) / n
+    return res
 
 
 def main():
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     ref_o2 = os.path.join(ROOT, "oracle", "_ref", "O2", "ref_harness")
     gpu = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu")
+    gpu_o2 = os.path.join(ROOT, "oracle", "_ref", "O2", "ref_harness_gpu")
     with tempfile.TemporaryDirectory() as tmp:
         json.dump({"slices": [{"n_slices": S, "weight": 1.0 / S, "video_app": 0, "video_bitrate": 0, "internet_flow": 0,
                                "if_bitrate": 0, "backlog_flow": 1, "algo_alpha": 0, "algo_beta": 0, "algo_epsilon": 1,
@@ -47,7 +51,8 @@ def main():
             line = {"scheduler_id": algo, "cell": "20 slices x 5 UEs, 100 MHz, backlogged", "ttis": T,
                     "reference_O0": run(ref, algo, tmp, False),
                     "reference_O2": run(ref_o2, algo, tmp, False) if os.path.exists(ref_o2) else None,
-                    "plugin_gpu": run(gpu, algo, tmp, True)}
+                    "plugin_gpu_hostO0": run(gpu, algo, tmp, True),
+                    "plugin_gpu_hostO2": run(gpu_o2, algo, tmp, True) if os.path.exists(gpu_o2) else None}
             print(json.dumps(line), flush=True)
 
 

@@ -20,7 +20,7 @@ from tools.make_golden_logs_two_bearers import CFG, HARNESS, n_bearers  # noqa: 
 
 OUT = os.path.join(ROOT, "tests", "golden", "two_bearers")
 TTIS, SEED = 200, 43
-IDS = (9, 8, 7, 10, 101, 103)
+IDS = (9, 8, 7, 10, 101, 103, 11, 1)
 
 
 def main():
@@ -38,6 +38,9 @@ def main():
                    "--rand", rnd, "--bearers", str(nbr), "--out", rec_path, "--bearer-log", bl]
             if algo == 10:
                 cmd += ["--alloc-log", al]
+            rl = os.path.join(tmp, f"a{algo}.rlog")
+            if algo == 11:
+                cmd += ["--rand-log", rl]
             subprocess.run(cmd, check=True, capture_output=True)
             rec = golden_io.parse_record_stream(rec_path)
             T = rec["T"]
@@ -92,6 +95,17 @@ def main():
                     cnt[t] = k
                     ue[t, :k], rb[t, :k] = pairs[:, 0], pairs[:, 1]
                 g["alloc_n"], g["alloc_ue"], g["alloc_rbg"] = cnt, ue, rb
+            if algo == 11:   # every rand() value of the 300-sample search, TTI by TTI (downlink-nvs-scheduler.cpp:437-446)
+                rawr = np.fromfile(rl, dtype="<i4")
+                draws, p3 = [], 0
+                for _ in range(T):
+                    k = int(rawr[p3])
+                    draws.append(rawr[p3 + 1:p3 + 1 + k])
+                    p3 += 1 + k
+                assert p3 == len(rawr)
+                width = max(len(x) for x in draws)
+                g["rand_ng_n"] = np.array([len(x) for x in draws], dtype=np.int32)
+                g["rand_ng"] = np.stack([np.pad(x, (0, width - len(x))) for x in draws]).astype(np.int32)
             both = int(((out["queue"][:, :, 0] > 0) & (out["queue"][:, :, 1] > 0)).sum())
             handover = int(((out["queue"][:, :, 1] == 0) & (out["queue"][:, :, 0] > 0) & exists[None, :, 1].astype(bool)).sum())
             path = os.path.join(OUT, f"a{algo}.npz")

@@ -25,12 +25,13 @@ from radiosaber_b200 import sched, workload  # noqa: E402
 G = 64
 
 
-def measure(algo, w, p, u2s, B, ttis, launches, label):
+def measure(algo, w, p, u2s, B, ttis, launches, label, warm=14):
     import torch
     dev = torch.device("cuda", 0)
     S, U = len(w), len(u2s)
     g = sched.Scheduler(algo, w, p, u2s, B)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)   # a real stream: handle 0 (the default stream) means "the handle's own" to rs_set_stream
+    torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
     d_cqi = torch.empty((ttis, B, U, G), dtype=torch.uint8, device=dev)
     d_r2 = torch.empty((ttis, B, max(g.rand_stride, 2)), dtype=torch.int32, device=dev)
@@ -39,19 +40,19 @@ def measure(algo, w, p, u2s, B, ttis, launches, label):
     d_rbg = torch.empty((ttis, B, G), dtype=torch.int16, device=dev)
     d_bits = torch.empty((ttis, B, U), dtype=torch.int32, device=dev)
     outs = {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr()}
-    _, dts = workload.tti_clock(ttis * (launches + 2))
+    _, dts = workload.tti_clock(ttis * (launches + warm))
 
     def step(k):
         g.run_device(ttis, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts[k * ttis:(k + 1) * ttis], outs,
                      ttis_per_launch=ttis)
 
-    step(0)
-    step(1)
+    for k in range(warm):     # past the start-up transient (all bearers begin at the same average rate): steady state
+        step(k)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(launches):
-        step(2 + k)
+        step(warm + k)
     e1.record(stream)
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
@@ -59,7 +60,7 @@ def measure(algo, w, p, u2s, B, ttis, launches, label):
     value = B * ttis * launches / (ms * 1e-3)
     rbg = d_rbg.cpu().numpy()
     line = {"label": label, "scheduler_id": algo, "slices": S, "ues_per_slice": U // S, "ues": U, "cells": B,
-            "ttis_per_launch": ttis, "launches": launches, "cell_ttis_per_s": value, "ue_ttis_per_s": value * U,
+            "ttis_per_launch": ttis, "launches": launches, "warmup_ttis": ttis * warm, "cell_ttis_per_s": value, "ue_ttis_per_s": value * U,
             "smem_bytes_per_cta": g.smem_bytes, "algorithmic_bytes_per_cell_tti": alg,
             "algorithmic_GBps": value * alg / 1e9, "rbgs_allocated_frac": float((rbg >= 0).mean())}
     g.close()
@@ -74,6 +75,8 @@ def main():
     ap.add_argument("--ttis", type=int, default=16)
     ap.add_argument("--launches", type=int, default=6)
     ap.add_argument("--only", default=None, choices=[None, "ids", "sweep"])
+    ap.add_argument("--points", default=None, help='sweep points "S,n;S,n;..." instead of the full grid')
+    ap.add_argument("--ids", default=None, help='scheduler ids "9,8,..." instead of all')
     args = ap.parse_args()
     lines = []
 
@@ -88,13 +91,16 @@ def main():
         pf = np.tile(np.array([0, 0, 1, 1], dtype=np.int32), (S, 1))
         mix = pf.copy()
         mix[1::2, 3] = 0      # every other slice MT (max-CI): eps 1, psi 0
-        for algo in (9, 8, 7, 1, 11, 10, 101, 103):
+        for algo in ([int(x) for x in args.ids.split(",")] if args.ids else (9, 8, 7, 1, 11, 10, 101, 103)):
             emit(measure(algo, w, pf, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF"))
             if algo not in (1, 11, 10, 101, 103):
                 emit(measure(algo, w, mix, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF/MT mix"))
     if args.only in (None, "sweep"):
-        for S in (5, 10, 15, 20, 30, 40, 50):
-            for n in (2, 5, 10, 15, 20, 30, 40):
+        grid = [(S, n) for S in (5, 10, 15, 20, 30, 40, 50) for n in (2, 5, 10, 15, 20, 30, 40)]
+        if args.points:
+            grid = [tuple(int(x) for x in pt.split(",")) for pt in args.points.split(";")]
+        for S, n in grid:
+            if True:
                 U = S * n
                 B = max(148, int(round(409600 / U)))
                 w = 1.0 + (np.arange(S) % 3)
