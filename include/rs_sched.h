@@ -321,6 +321,9 @@ int32_t rs_threads_per_cta(const rs_handle* h);
 /* >= 0: the handle's backlogged launches run a compile-time-shape instantiation of the TTI kernel (the headline cell,
  * 20 slices x 5 UEs x 64 RBGs); -1: the general kernel.  Same results either way. */
 int32_t rs_fixed_shape(const rs_handle* h);
+/* 1: big slices -- the per-slice argmax divides its metrics where it compares them instead of tabulating them per chunk of
+ * slices (same doubles, same winners). */
+int32_t rs_direct_metric(const rs_handle* h);
 int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h); /* U(G+20)+16S+2G+8, SURVEY 8(d) */
 
 /* Device test hook: libstdc++ std::sort order (key descending, comparator of

@@ -105,6 +105,8 @@ struct DevCfg {
                                   when alpha and beta are set; nvs.cpp:384-386 whenever alpha is set) */
   const int* tbs1;             /* [16] GetTBSizeFromMCS(mcs(cqi)) for one RB: m_requiredRBs, packet-scheduler.cpp:334 */
   int sort_depth_g;        /* id 10: 2*floor(log2(G)), the depth limit of a per-slice sort of G entries */
+  int direct;              /* 1: big slices, the per-slice argmax divides its metrics on the fly instead of tabulating them per
+                              chunk (rs_tti_kernel, "P2 for big slices"); the table area then holds Epow's S rows */
   int nb;                  /* bearers per UE (MAX_BEARERS, packet-scheduler.h:31): 1, or 2 = slot i holds the bearer of priority i;
                               state arrays are then [B][U][2] and the queue-aware kernels (QUEUE) are the only ones used */
   /* state, [B][U][nb] / [B][S] */
@@ -114,7 +116,7 @@ struct DevCfg {
 
 /* The dimensions of a cell as the device code reads them (see rs_tti_kernel and the shape policies below). */
 struct Dims {
-  int S, U, G, R, rbg, cqi_per_rb, cqi_row, n_chunks, m_cap, sort_n, sort_depth, nb;
+  int S, U, G, R, rbg, cqi_per_rb, cqi_row, n_chunks, m_cap, sort_n, sort_depth, nb, direct;
   Layout lay;
 };
 
@@ -1053,12 +1055,14 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
     dm.lay = kLay;
     dm.n_chunks = SH::kChunks; dm.m_cap = SH::kMCap; dm.sort_n = SH::kSortN; dm.sort_depth = SH::kSortDepth;
     dm.nb = 1;
+    dm.direct = 0;
   } else {
     dm.S = d.S; dm.U = d.U; dm.G = d.G; dm.R = d.R; dm.rbg = d.rbg;
     dm.cqi_per_rb = d.cqi_per_rb; dm.cqi_row = d.cqi_row;
     dm.lay = d.lay;
     dm.n_chunks = d.n_chunks; dm.m_cap = d.m_cap; dm.sort_n = d.sort_n; dm.sort_depth = d.sort_depth;
     dm.nb = d.nb;
+    dm.direct = d.direct;
   }
   Cell c = carve(smem, dm.lay);
   c.sb.eq_tab = d.eq_tab;
@@ -1276,6 +1280,63 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
 
     RS_TICK(0);
     if (TRANSPORT) {
+      if (dm.direct) {
+        /* ---- P2 for big slices: the per-chunk metric table leaves most of the CTA idle when a chunk holds one or two
+         * slices of dozens of UEs (20 x 40 UEs: 16 items per chunk for 512 threads, 20 chunks one after the other).
+         * Here every (slice, RBG quad) of the cell is an item at once and the metric of a (UE, RBG) pair is divided
+         * where it is compared: Epow[s][cqi] / den[u], the same two doubles and the same IEEE divide as a table
+         * entry, so the winners are the same.  Epow's rows are staged in the (otherwise unused) table area. */
+        if (warp == (rot + kWarps - 1) % kWarps)
+          slice_quotas(d, dm, c, r.rand2[tb * d.rand_stride], r.rand2[tb * d.rand_stride + 1], lane, o_tgt, o_quo);
+        double* ep = c.mtab;
+        for (int q = tid; q < S * kMStride; q += kThreads) ep[q] = d.epow[q];
+        __syncthreads();
+        const bool nib = dm.cqi_per_rb == 2;   /* the host enables this path for one-CQI-per-RBG layouts and G % 4 == 0 */
+        const int per = G >> 2;
+        for (int q = tid; q < S * per; q += kThreads) {
+          const int s = q / per, g0 = (q % per) * 4;
+          const int hm = d.holmul[s];
+          double best[4] = {-1.0, -1.0, -1.0, -1.0};
+          unsigned bu01 = 0xffffffffu, bu23 = 0xffffffffu;   /* winners of RBGs g0..g0+3, 16 bits each (kNoUe = none) */
+          auto quad_of = [&](int u) -> unsigned {   /* the CQIs of UE u on the four RBGs, one per byte */
+            const uint8_t* row_u = row_of(u);
+            if (nib) {
+              const unsigned h = *(const unsigned short*)(row_u + (g0 >> 1));
+              return (h & 0xfu) | ((h & 0xf0u) << 4) | ((h & 0xf00u) << 8) | ((h & 0xf000u) << 12);
+            }
+            return *(const unsigned*)(row_u + g0);
+          };
+          for (int j = sptr_of(s); j < sptr_of(s + 1); ++j) {
+            const int u = sue_of(j);
+            if (!listed(u)) continue;
+            const unsigned w = quad_of(u);
+            const double den_u = c.den[u];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const int cq = (w >> (8 * x)) & 15;
+              double e = ep[s * kMStride + cq];
+              if (hm) e = QUEUE ? prio_gate(u, s, hm, e) : (hm == 1 ? __dmul_rn(0.0, e) : e);
+              const double mv = cq ? __ddiv_rn(e, den_u) : 0.0;
+              if (mv > best[x]) {
+                best[x] = mv;
+                if (x == 0) bu01 = (bu01 & 0xffff0000u) | (unsigned)u;
+                else if (x == 1) bu01 = (bu01 & 0x0000ffffu) | ((unsigned)u << 16);
+                else if (x == 2) bu23 = (bu23 & 0xffff0000u) | (unsigned)u;
+                else bu23 = (bu23 & 0x0000ffffu) | ((unsigned)u << 16);
+              }
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int g = g0 + x;
+            const unsigned wu = ((x < 2 ? bu01 : bu23) >> (16 * (x & 1))) & 0xffffu;
+            const int wc = wu == kNoUe ? 0 : (int)((quad_of((int)wu) >> (8 * x)) & 15);   /* the sort key: the winner's CQI */
+            c.sb.a[g * S + s] = (unsigned short)((wc << 12) | (g << 6) | s);
+            c.win[g * S + s] = (unsigned short)wu;
+          }
+        }
+        __syncthreads();
+      } else
       /* ---- P1/P2: metric table per chunk of slices, per-(rbg,slice) argmax; quotas by the last warp */
       for (int ch = 0; ch < dm.n_chunks; ++ch) {
         const int s0 = chunk_lo(ch), s1 = chunk_lo(ch + 1);

@@ -286,7 +286,7 @@ bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
   const rs::DevCfg& d = h->d;
   if (h->wide || d.nb != 1 || d.S != SH::S || d.U != SH::U || d.G != SH::G || d.rbg != SH::RBG || d.cqi_per_rb != SH::LAY ||
       d.n_chunks != SH::kChunks || d.m_cap != SH::kMCap || d.sort_n != SH::kSortN || d.sort_depth != SH::kSortDepth ||
-      !h->stage_ok)
+      !h->stage_ok || d.direct)
     return false;
   for (int u = 0; u < d.U; ++u)
     if (u2s[(size_t)u] != u / SH::UPS) return false;
@@ -572,6 +572,15 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     chunks = {0, 1};
   }
   d.n_chunks = (int)chunks.size() - 1;
+  /* Big slices (a chunk of the metric table would give the CTA fewer (slice, RBG quad) items than it has threads,
+   * and there are several chunks): divide the metrics on the fly over all slices at once; the table area only has
+   * to hold Epow's S rows.  RS_NO_DIRECT=1 keeps the table (A/B and the equality test). */
+  d.direct = 0;
+  if (is_transport(algo) && d.n_chunks > 1 && max_slice >= 8 && d.cqi_per_rb != 1 && G % 4 == 0 && !getenv("RS_NO_DIRECT")) {
+    const int threads = (U >= RS_WIDE_MIN_UES) ? rsw::kThreads : rs::kThreads;
+    const int per_chunk = std::max(1, (S + d.n_chunks - 1) / d.n_chunks) * std::max(1, G / 4);
+    if (per_chunk < threads) { d.direct = 1; m_cap = std::max(S, 1); }
+  }
   d.m_cap = m_cap;
   /* Stage a TTI's CQI in shared memory (cp.async) when the layout is one value per RBG, rows are 16-byte
    * multiples and the staged cell does not cost occupancy the batch could use: eight cells per SM for
@@ -1473,6 +1482,7 @@ int64_t rs_launch_count(const rs_handle* h) { return h ? h->launches : 0; }
 int32_t rs_smem_bytes(const rs_handle* h) { return h ? h->layout.total : 0; }
 int32_t rs_threads_per_cta(const rs_handle* h) { return (h && h->wide) ? rsw::kThreads : rs::kThreads; }
 int32_t rs_fixed_shape(const rs_handle* h) { return h ? h->fixed : -1; }
+int32_t rs_direct_metric(const rs_handle* h) { return h ? h->d.direct : 0; }
 int64_t rs_algorithmic_bytes_per_cell_tti(const rs_handle* h) {
   if (!h) return 0;
   const int64_t U = h->d.U, G = h->d.G, S = h->d.S;

@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti", "rs_log_tti_grants",
     "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues",
     "rs_get_stream", "rs_host_alloc", "rs_host_free", "rs_step_cell", "rs_run_host_async", "rs_run_traces_host_async",
-    "rs_wait", "rs_dims", "rs_fixed_shape",
+    "rs_wait", "rs_dims", "rs_fixed_shape", "rs_direct_metric",
 )
 
 
@@ -143,6 +143,8 @@ def lib():
         L.rs_wait.argtypes = [C.c_void_p, C.c_int64]
         L.rs_fixed_shape.argtypes = [C.c_void_p]
         L.rs_fixed_shape.restype = C.c_int32
+        L.rs_direct_metric.argtypes = [C.c_void_p]
+        L.rs_direct_metric.restype = C.c_int32
         _lib = L
     return _lib
 

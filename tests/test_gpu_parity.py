@@ -470,3 +470,45 @@ def test_fixed_shape_equals_dynamic(algo, layout):
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), ("trace", k)
     fixed.close()
     dyn.close()
+
+
+@pytest.mark.parametrize("algo,S,n,queue", [(9, 20, 20, False), (8, 12, 40, False), (9, 12, 40, True), (10, 6, 24, False),
+                                            (101, 10, 10, True), (9, 50, 10, False)])
+def test_direct_metric_equals_table(algo, S, n, queue):
+    """Big slices divide their metrics on the fly (rs_direct_metric); RS_NO_DIRECT keeps the per-chunk table.  Same
+    inputs, every output and the state identical (and both equal the oracle: the shapes of test_sweep_shapes_* and
+    test_wide_cells_* run the direct path against it)."""
+    import os
+    B, T = 6, 10
+    rng = np.random.default_rng(S * n)
+    w = rng.dirichlet(np.ones(S))
+    p = np.array([PF if s % 3 else MT for s in range(S)], dtype=np.int32)
+    if queue:
+        p[1] = [1, 1, 1, 1]
+        p[2] = [1, 0, 1, 1]
+    u2s = np.repeat(np.arange(S), n).astype(np.int32)
+    U, G = len(u2s), 64
+    direct = sched.Scheduler(algo, w, p, u2s, B)
+    os.environ["RS_NO_DIRECT"] = "1"
+    try:
+        table = sched.Scheduler(algo, w, p, u2s, B)
+    finally:
+        del os.environ["RS_NO_DIRECT"]
+    assert sched.lib().rs_direct_metric(direct._h) == 1 and sched.lib().rs_direct_metric(table._h) == 0
+    _, dts = workload.tti_clock(T)
+    for t in range(T):
+        cqi = workload.synth_cqi(9, 0, B, t, 1, U, G)[0]
+        r2 = workload.synth_rand_draws(9, 0, B, t, 1, S, max(direct.rand_stride, 2))[0]
+        kw = {}
+        if queue:
+            kw = {"queue": rng.choice([0, 500, 100000000], size=(B, U)).astype(np.int32), "hol": rng.random((B, U)) * 0.03}
+        act = (rng.random((B, U)) < 0.85).astype(np.uint8)
+        a = direct.step(cqi, r2, dt=float(dts[t]), active=act, want_aux=True, **kw)
+        b = table.step(cqi, r2, dt=float(dts[t]), active=act, want_aux=True, **kw)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (t, k)
+    sa, sb = direct.get_state(), table.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    direct.close()
+    table.close()
