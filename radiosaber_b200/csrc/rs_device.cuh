@@ -146,8 +146,8 @@ __host__ __device__ constexpr inline int rs_align(int x, int a) { return (x + a 
 /* cq_bytes: room for one TTI of the cell's CQI ([U][cqi_row], staged with cp.async); 0 = CQI is read
  * from global memory where it lies. */
 /* ng_ues: id 11 only, the largest number of UEs in a slice (scratch of the 300-sample search). */
-/* min_sort_n: id 10 sorts one slice's G entries at a time and parks the grants next to them: it needs
- * the slot arrays at least 8 G entries long whatever S is. */
+/* min_sort_n: id 10 sorts its slices' G entries on up to five warps at a time next to the parked grants: it needs
+ * the slot arrays at least max(16 G, 1024) entries long whatever S is (rs_sched.cu). */
 __host__ __device__ constexpr inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
                                                         int min_sort_n = 0, int nb = 1) {
   Layout L{};
@@ -487,6 +487,77 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
     }
   }
   __syncthreads();
+}
+
+/* The same sort by ONE warp on private buffers, for short arrays (n <= 64: UpperBound sorts one slice's G entries,
+ * several slices at a time on different warps).  Ranges are taken depth first from a small stack -- the order in
+ * which disjoint ranges are partitioned does not change the result, only a range's depth matters (the heap-sort
+ * fallback at the depth limit).  stack: >= 16 entries of this warp; b.cnt: >= 32 entries; b.out = b.posr. */
+__device__ __forceinline__ void warp_sort_desc(const SortBufs& b, unsigned* stack, int n, int depth_limit, int lane) {
+  int sp = 0;
+  if (n > kSortThreshold) {
+    if (lane == 0) stack[0] = (unsigned)n << 12;   /* f | l << 12 | depth << 24 */
+    sp = 1;
+  }
+  __syncwarp();
+  while (sp > 0) {
+    const unsigned e = stack[--sp];
+    const int f = e & 0xfff, l = (e >> 12) & 0xfff, depth = (int)(e >> 24);
+    __syncwarp();
+    if (depth >= depth_limit) {
+      if (lane == 0) heap_sort(b.a + f, l - f);
+      __syncwarp();
+      continue;
+    }
+    const int cut = warp_partition(b, f, l, lane, depth_limit - depth);
+    if (cut >= 0) {
+      if (l - cut > kSortThreshold) {
+        if (lane == 0) stack[sp] = (unsigned)cut | ((unsigned)l << 12) | ((unsigned)(depth + 1) << 24);
+        sp++;
+      }
+      if (cut - f > kSortThreshold) {
+        if (lane == 0) stack[sp] = (unsigned)f | ((unsigned)cut << 12) | ((unsigned)(depth + 1) << 24);
+        sp++;
+      }
+    }
+    __syncwarp();
+  }
+  /* __final_insertion_sort == stable counting sort on the 4-bit key, two 32-entry chunks at most */
+  const int nw = (n + 31) >> 5;
+  b.cnt[lane] = 0;
+  __syncwarp();
+  for (int w = 0; w < nw; ++w) {
+    const int i = w * 32 + lane;
+    const bool valid = i < n;
+    const int k = valid ? (b.a[i] >> 12) : 16;
+    const unsigned mm = __match_any_sync(kFull, k);
+    const int rk = __popc(mm & ((1u << lane) - 1u));
+    if (valid) {
+      b.posl[i] = (unsigned short)rk;
+      if (rk == 0) b.cnt[(15 - k) * nw + w] = (unsigned short)__popc(mm);
+    }
+  }
+  __syncwarp();
+  {
+    const int mine = lane < 16 * nw ? (int)b.cnt[lane] : 0;   /* 16 * nw <= 32 counters: one per lane */
+    int incl = mine;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const int v = __shfl_up_sync(kFull, incl, dd);
+      if (lane >= dd) incl += v;
+    }
+    __syncwarp();
+    b.cnt[lane] = (unsigned short)(incl - mine);
+  }
+  __syncwarp();
+  for (int w = 0; w < nw; ++w) {
+    const int i = w * 32 + lane;
+    if (i < n) {
+      const unsigned short e = b.a[i];
+      b.out[b.cnt[(15 - (e >> 12)) * nw + w] + b.posl[i]] = e;
+    }
+  }
+  __syncwarp();
 }
 
 /* ================================================================================================
@@ -1418,33 +1489,45 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
       if (ALGO == 10) {
         /* UpperBound (transport.cpp:223-246, 603-616): every slice with a positive quota takes the first
          * quota entries of ITS OWN std::sort of the G (rbg, efficiency) pairs, so an RBG can be granted
-         * to several slices.  One sort of G entries per slice, by the whole CTA; the grants are parked in
+         * to several slices.  One sort of G entries per slice (warp_sort_desc); the grants are parked in
          * shared memory (slice-major, sorted order) next to the sort buffers. */
-        SortBufs s2 = c.sb;
-        s2.a = c.sb.posl;
-        s2.posl = c.sb.posl + G;
-        s2.posr = c.sb.posl + 2 * G;
-        s2.out = s2.posr;
-        unsigned short* g_ue = c.sb.posl + 4 * G;    /* [2G] */
-        unsigned short* g_rbg = c.sb.posl + 6 * G;   /* [2G] */
+        /* up to five slices at a time, one warp each, on private buffers in the (dead) right slot array; the grant
+         * lists g_ue / g_rbg [2G] sit in the left one */
+        unsigned short* g_ue = c.sb.posl;            /* [2G] */
+        unsigned short* g_rbg = c.sb.posl + 2 * G;   /* [2G] */
+        constexpr int kSorters = kWarps < 5 ? kWarps : 5;
         int base = 0;
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < S; ++s) {   /* every thread: where each slice's grants start */
           const int q = min(c.quota[s], G);
-          if (q <= 0) { if (tid == 0) c.frb[s] = 0; continue; }
-          for (int i = tid; i < G; i += kThreads) s2.a[i] = (unsigned short)((c.sb.a[i * S + s] & 0xf000u) | (unsigned)i);
-          __syncthreads();
-          sort_desc(s2, G, d.sort_depth_g, kWarps - rot);
-          for (int k = tid; k < q; k += kThreads) {
-            const int g = s2.out[k] & 0xfff;
-            if (base + k < 2 * G) {
-              g_ue[base + k] = c.win[g * S + s];
-              g_rbg[base + k] = (unsigned short)g;
-            }
-          }
-          if (tid == 0) { c.frb[s] = q; c.wd[s] = base; }   /* wd is free once the quotas exist: first grant of the slice */
-          base += q;
-          __syncthreads();
+          if (tid == 0) { c.frb[s] = max(q, 0); c.wd[s] = base; }   /* wd is free once the quotas exist: first grant of the slice */
+          if (q > 0) base += q;
         }
+        __syncthreads();
+        if (warp < kSorters) {
+          SortBufs s2 = c.sb;
+          s2.a = c.sb.posr + warp * 3 * G;
+          s2.posl = s2.a + G;
+          s2.posr = s2.a + 2 * G;
+          s2.out = s2.posr;
+          s2.cnt = c.sb.cnt + warp * 32;
+          unsigned* stack = c.sb.seg0 + warp * 16;
+          for (int s = warp; s < S; s += kSorters) {
+            const int q = c.frb[s], b0 = c.wd[s];
+            if (q <= 0) continue;
+            for (int i = lane; i < G; i += 32) s2.a[i] = (unsigned short)((c.sb.a[i * S + s] & 0xf000u) | (unsigned)i);
+            __syncwarp();
+            warp_sort_desc(s2, stack, G, d.sort_depth_g, lane);
+            for (int k = lane; k < q; k += 32) {
+              const int g = s2.out[k] & 0xfff;
+              if (b0 + k < 2 * G) {
+                g_ue[b0 + k] = c.win[g * S + s];
+                g_rbg[b0 + k] = (unsigned short)g;
+              }
+            }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
         const int n_grants = min(base, 2 * G);
         for (int u = tid; u < U; u += kThreads) c.den[u] = 0.0;   /* the metric denominators are dead: EESM sums */
         __syncthreads();

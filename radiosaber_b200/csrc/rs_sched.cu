@@ -576,10 +576,10 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
    * and there are several chunks): divide the metrics on the fly over all slices at once; the table area only has
    * to hold Epow's S rows.  RS_NO_DIRECT=1 keeps the table (A/B and the equality test). */
   d.direct = 0;
-  if (is_transport(algo) && d.n_chunks > 1 && max_slice >= 8 && d.cqi_per_rb != 1 && G % 4 == 0 && !getenv("RS_NO_DIRECT")) {
+  if (is_transport(algo) && d.n_chunks > 1 && d.cqi_per_rb != 1 && G % 4 == 0 && !getenv("RS_NO_DIRECT")) {
     const int threads = (U >= RS_WIDE_MIN_UES) ? rsw::kThreads : rs::kThreads;
     const int per_chunk = std::max(1, (S + d.n_chunks - 1) / d.n_chunks) * std::max(1, G / 4);
-    if (per_chunk < threads) { d.direct = 1; m_cap = std::max(S, 1); }
+    if ((per_chunk < threads && max_slice >= 8) || getenv("RS_FORCE_DIRECT")) { d.direct = 1; m_cap = std::max(S, 1); }
   }
   d.m_cap = m_cap;
   /* Stage a TTI's CQI in shared memory (cp.async) when the layout is one value per RBG, rows are 16-byte
@@ -593,7 +593,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
    * 300 x users of the served slice (id 11; the stride is sized for the largest slice) */
   d.rand_stride = (algo == 11) ? 300 * max_slice : (is_transport(algo) ? 2 : 0);
   /* id 10 sorts G entries at a time next to the parked grants; ids 101/103 keep their scratch in the slot arrays */
-  const int min_sort_n = (algo == 10) ? 8 * G
+  /* id 10: left slot array = the grant lists [4G]; right = five warps x 3G sort buffers; 1024 entries also make the
+   * range lists (5 x 16 stack entries) and the counters (5 x 32) of those warps fit whatever G is */
+  const int min_sort_n = (algo == 10) ? std::max(16 * G, 1024)
                          : ((algo == 101 || algo == 103) ? (rs::inter_scratch_bytes(G, S) + 3) / 4 : 0);   /* posl + posr = 4 n bytes */
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
   h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb)))
@@ -609,7 +611,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
      * alone on its SM with its CQI staged than sharing it unstaged (tools/sweep_bench.py) */
     const int floor_fit = h->wide ? 1 : 2;
     const int wanted = std::min(floor_fit, (n_cells + kSms - 1) / kSms);
-    if (staged.total <= RS_STAGE_MAX_SMEM || (fit >= 1 && fit >= wanted)) { h->layout = staged; h->stage_ok = true; }
+    if ((staged.total <= RS_STAGE_MAX_SMEM || (fit >= 1 && fit >= wanted)) && !getenv("RS_NO_STAGE")) { h->layout = staged; h->stage_ok = true; }
   }
   d.lay = h->layout;
 
