@@ -1082,12 +1082,23 @@ __device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
       x.pick[g] = to;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+      /* the first RBG (in RBG order) with the strictly smallest loss: lanes take g = tid, tid + 32, ..., then a
+       * butterfly on (loss, rbg) */
       double least = 1.7976931348623157e308;
-      int rbg = -1;
-      for (int g = 0; g < G; ++g)
+      int rbg = 0x7fffffff;
+      for (int g = tid; g < G; g += 32)
         if (x.pick[g] >= 0 && x.val[g] < least) { least = x.val[g]; rbg = g; }
-      if (rbg < 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ol = __shfl_xor_sync(kFull, least, o);
+        const int og = __shfl_xor_sync(kFull, rbg, o);
+        if (og != 0x7fffffff && (rbg == 0x7fffffff || ol < least || (ol == least && og < rbg))) { least = ol; rbg = og; }
+      }
+      if (rbg == 0x7fffffff) rbg = -1;
+      if (tid != 0) {
+        /* lane 0 applies the move */
+      } else if (rbg < 0) {
         c.misc[11] = 0;   /* the reference asserts a move exists */
       } else {
         const int from = c.outsl[rbg], to = x.pick[rbg];

@@ -167,8 +167,8 @@ constexpr int kEqMax = 2048;
 #ifndef RS_WIDE_MIN_UES
 #define RS_WIDE_MIN_UES 480   /* cells with at least this many UEs run 512 threads wide (tools/sweep_bench.py) */
 #endif
-#ifndef RS_STAGE_MAX_SMEM
-#define RS_STAGE_MAX_SMEM (27 * 1024)   /* staging must leave room for eight cells per SM */
+#ifndef RS_STAGE_MIN_FIT
+#define RS_STAGE_MIN_FIT 8   /* narrow cells: staging the CQI must leave room for this many cells per SM (or all the batch offers) */
 #endif
 
 template <typename T>
@@ -606,12 +606,18 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     const rs::Layout staged = h->wide ? reinterpret_cast<const rs::Layout&>(staged_w)
                                       : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb);
     const int kSmemPerSm = 227 * 1024, kSms = 148;
-    const int fit = kSmemPerSm / (staged.total + 1024);
-    /* big cells: two staged cells per SM beat more unstaged ones, and a 512-thread cell is better off
-     * alone on its SM with its CQI staged than sharing it unstaged (tools/sweep_bench.py) */
-    const int floor_fit = h->wide ? 1 : 2;
-    const int wanted = std::min(floor_fit, (n_cells + kSms - 1) / kSms);
-    if ((staged.total <= RS_STAGE_MAX_SMEM || (fit >= 1 && fit >= wanted)) && !getenv("RS_NO_STAGE")) { h->layout = staged; h->stage_ok = true; }
+    /* Staging pays as long as it does not cost residency: cells an SM can hold = min(register limit of the
+     * instantiation, shared memory, what the batch offers).  Measured (profiles/r02_configs3_sweep.jsonl): 20 x 20 UEs
+     * 4 staged cells per SM 6.3 M vs 8 unstaged 7.9 M cell-TTIs/s; 50 x 40 UEs 1 staged 0.97 M vs 2 unstaged 1.32 M;
+     * same residency either way (20 x 40, 40 x 20, 50 x 10: two 512-thread cells per SM) staged wins by 10-23 %.
+     * Narrow cells may give up residency down to RS_STAGE_MIN_FIT cells per SM. */
+    const int reg_limit = h->wide ? RS_WIDE_MIN_BLOCKS : 8;
+    const int offered = std::max(1, (n_cells + kSms - 1) / kSms);
+    const int fit_staged = std::min({reg_limit, kSmemPerSm / (staged.total + 1024), offered});
+    const int fit_plain = std::min({reg_limit, kSmemPerSm / (h->layout.total + 1024), offered});
+    int min_fit = h->wide ? fit_plain : std::min(fit_plain, RS_STAGE_MIN_FIT);
+    if (const char* e = getenv("RS_STAGE_MIN_FIT")) min_fit = std::min(fit_plain, std::max(1, atoi(e)));
+    if (fit_staged >= 1 && fit_staged >= min_fit && !getenv("RS_NO_STAGE")) { h->layout = staged; h->stage_ok = true; }
   }
   d.lay = h->layout;
 
