@@ -883,12 +883,14 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Dims& dm, con
 
 /* Scratch of ids 101 / 103 in the (dead) slot arrays of the sort; inter_scratch_bytes() of it
  * (make_layout's min_sort_n). */
-__host__ __device__ inline int inter_scratch_bytes(int G, int S) { return 128 + 12 * (G + S) + 8 * S + S + (S + 1) + 128 + 16; }
+__host__ __device__ inline int inter_scratch_bytes(int G, int S) { return 128 + 20 * (G + S) + 8 * S + S + (S + 1) + 128 + 16; }
 struct InterScratch {
   double* eff;             /* [16] AMC efficiency per CQI: lanes index it with different CQIs, which the constant
                               cache would serialise */
   double* val;             /* [G + S] candidate gap / loss */
   int* pick;               /* [G + S] */
+  int* k2;                 /* [G + S] id 103: CQI key of a candidate's "second" efficiency, -1 = none */
+  int* todo;               /* [G + S] id 103: candidates to recompute this round */
   int* over;               /* [S] RBGs above quota, 0 = not in the map */
   int* under;              /* [S] RBGs below quota */
   unsigned char* order;    /* [S] the slices below quota in std::unordered_map iteration order */
@@ -903,7 +905,9 @@ __device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Dim
   p += 128;
   x.val = (double*)p;
   x.pick = (int*)(p + 8 * n);
-  x.over = x.pick + n;
+  x.k2 = x.pick + n;
+  x.todo = x.k2 + n;
+  x.over = x.todo + n;
   x.under = x.over + dm.S;
   x.order = (unsigned char*)(x.under + dm.S);
   x.nxt = x.order + dm.S;
@@ -915,41 +919,71 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
   return x.eff[c.sb.a[g * S + s] >> 12];
 }
 
-/* VogelApproximate, transport.cpp:378-451: G rounds; in each, every free RBG (thread g) and every slice with
- * quota left (thread G + s) reports the gap between its best and its "second" efficiency, then one thread walks
- * the candidates in the reference's order with the reference's int-truncated running maximum.  Result in
- * c.outsl. */
+/* VogelApproximate, transport.cpp:378-451: up to G rounds; in each, every free RBG (candidate g: a row over the slices
+ * with quota left) and every slice with quota left (candidate G + s: a column over the free RBGs) reports the gap
+ * between its best and its "second" efficiency exactly as the reference computes them, then the candidates are walked
+ * in the reference's order with its int-truncated running maximum, and the last one taken is granted.
+ *
+ * The reference scans a line in order with   if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
+ *                                            if (e2 == -1 || e > e2) e2 = e;
+ * i.e. e1 / first = the first maximum, and e2 = the largest element that was NOT a new strict maximum when it was
+ * visited (a displaced maximum is not demoted).  Efficiency is strictly increasing in the CQI, so a line is scanned on
+ * its 4-bit CQI keys by one warp: an inclusive prefix maximum marks the "records", the last record is (e1, first), a
+ * redux.max over the non-records is e2.
+ *
+ * Between rounds only two things change: the granted RBG leaves every column, and a slice that reached its quota
+ * leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is no
+ * e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So every round
+ * re-scans just the lines that pass that test (a handful of the G + S).  Result in c.outsl. */
+__device__ __forceinline__ void vogel_scan_line(const Cell& c, const InterScratch& x, const int* held, int S, int G, int q,
+                                                int lane) {
+  const bool is_row = q < G;
+  const int n = is_row ? S : G;
+  int run = -1, k1 = -1, first = -1, k2 = -1;
+  const bool live = is_row ? (c.outsl[q] == 0xff) : (held[q - G] < c.quota[q - G]);
+  if (live)
+    for (int h0 = 0; h0 < n; h0 += 32) {
+      const int i = h0 + lane;
+      bool v = i < n;
+      if (v) v = is_row ? (held[i] < c.quota[i]) : (c.outsl[i] == 0xff);
+      const int key = v ? (int)((is_row ? c.sb.a[q * S + i] : c.sb.a[i * S + (q - G)]) >> 12) : -1;
+      int inc = key;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, dd);
+        if (lane >= dd) inc = max(inc, t);
+      }
+      int exc = __shfl_up_sync(kFull, inc, 1);
+      if (lane == 0) exc = -1;
+      exc = max(exc, run);
+      const bool rec = v && key > exc;
+      const unsigned recm = __ballot_sync(kFull, rec);
+      if (recm) {
+        const int last = 31 - __clz(recm);
+        k1 = __shfl_sync(kFull, key, last);
+        first = h0 + last;
+      }
+      k2 = max(k2, __reduce_max_sync(kFull, (v && !rec) ? key : -1));
+      run = max(run, __shfl_sync(kFull, inc, 31));
+    }
+  if (lane == 0) {
+    const double e1 = k1 < 0 ? -1.0 : x.eff[k1], e2 = k2 < 0 ? -1.0 : x.eff[k2];
+    x.val[q] = __dsub_rn(e1, e2);
+    x.pick[q] = first;
+    x.k2[q] = k2;
+  }
+}
+
 __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
-  const int tid = threadIdx.x, G = dm.G, S = dm.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = dm.G, S = dm.S;
   const InterScratch x = inter_scratch(d, dm, c);
   int* held = c.wd;   /* free once the quotas exist; cleared again at the end of the TTI */
   for (int s = tid; s < S; s += kThreads) held[s] = 0;
   if (tid < 16) x.eff[tid] = c_tab.eff[tid];
   __syncthreads();
+  for (int q = warp; q < G + S; q += kWarps) vogel_scan_line(c, x, held, S, G, q, lane);
+  __syncthreads();
   for (int round = 0; round < G; ++round) {
-    for (int q = tid; q < G + S; q += kThreads) {
-      double e1 = -1, e2 = -1;
-      int first = -1;
-      if (q < G) {
-        if (c.outsl[q] == 0xff)
-          for (int k = 0; k < S; ++k) {
-            if (held[k] >= c.quota[k]) continue;
-            const double e = pair_eff(c, x, S, q, k);
-            if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
-            if (e2 == -1 || e > e2) e2 = e;
-          }
-      } else if (held[q - G] < c.quota[q - G]) {
-        for (int j = 0; j < G; ++j) {
-          if (c.outsl[j] != 0xff) continue;
-          const double e = pair_eff(c, x, S, j, q - G);
-          if (e1 == -1 || e > e1) { first = j; e1 = e; continue; }
-          if (e2 == -1 || e > e2) e2 = e;
-        }
-      }
-      x.val[q] = __dsub_rn(e1, e2);
-      x.pick[q] = first;
-    }
-    __syncthreads();
     if (tid < 32) {
       /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int
        * that is set to the (truncated) gap whenever a candidate is taken.  max_diff is therefore always the
@@ -980,12 +1014,30 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
           const int gr = win < G ? win : x.pick[win], gs = win < G ? x.pick[win] : win - G;
           c.outsl[gr] = (unsigned char)gs;
           held[gs] += 1;
+          c.misc[11] = (unsigned)gr | ((unsigned)gs << 8) | (held[gs] >= c.quota[gs] ? 0x10000u : 0u);
         }
         c.misc[12] = (win >= 0) ? 1u : 0u;
+        c.misc[13] = 0;
       }
     }
     __syncthreads();
     if (!c.misc[12]) break;
+    {   /* which lines does the grant touch? */
+      const unsigned gm = c.misc[11];
+      const int gr = gm & 0xff, gs = (gm >> 8) & 0xff;
+      const bool full = (gm & 0x10000u) != 0;
+      for (int q = tid; q < G + S; q += kThreads) {
+        if (x.pick[q] < 0) continue;            /* already out */
+        bool redo;
+        if (q < G) redo = (q == gr) || (full && (int)(c.sb.a[q * S + gs] >> 12) >= x.k2[q]);
+        else redo = (q - G == gs && full) || (int)(c.sb.a[gr * S + (q - G)] >> 12) >= x.k2[q];
+        if (redo) x.todo[atomicAdd(&c.misc[13], 1u)] = q;
+      }
+    }
+    __syncthreads();
+    const int n_todo = (int)c.misc[13];
+    for (int i = warp; i < n_todo; i += kWarps) vogel_scan_line(c, x, held, S, G, x.todo[i], lane);
+    __syncthreads();
   }
 }
 
