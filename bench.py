@@ -646,8 +646,8 @@ def main():
     ap.add_argument("--cells-total", type=int, default=0, help="BASELINE configs[4]: total cells, sharded over the ranks")
     ap.add_argument("--no-parity-spot", action="store_true")
     ap.add_argument("--e2e-trace-ttis-per-launch", type=int, default=16)
-    ap.add_argument("--e2e-refresh-ttis-per-launch", type=int, default=20, help="headline e2e leg (a CQI slab every 40 TTIs)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-refresh-ttis-per-launch", type=int, default=10, help="headline e2e leg (a CQI slab every 40 TTIs)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-ttis-per-step", type=int, default=10)
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-opt", default="O0", choices=["O0", "O2"], help="reference build: -O0 as shipped, or oracle/_ref/O2")
