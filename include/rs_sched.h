@@ -192,14 +192,14 @@ int rs_set_queues(rs_handle* h, const int32_t* queue_bytes, const double* hol_de
  *   dt      HOST array [T]
  *   d_out   device pointers, arrays [T][B][...]; NULL members are skipped
  *   ttis_per_launch  TTIs handled by one kernel launch with the cell state held on chip
- *                    (<= 0: library default 16; at most 32: the TTIs' dt / trace rows ride in the kernel parameters)
+ *                    (<= 0: library default 16; at most 64: the TTIs' dt / trace rows ride in the kernel parameters)
  * Asynchronous on the handle's stream; rs_sync() waits. */
 int rs_run_device(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t cqi_tti_stride, int32_t cqi_refresh,
                   const int32_t* d_rand2, const uint8_t* d_active, int64_t active_tti_stride,
                   const double* dt, const rs_outputs* d_out, int32_t ttis_per_launch);
 
 /* Same, HOST buffers in and out ([T][B][...]): the library moves them in chunks of ttis_per_launch TTIs (at most
- * 32; <= 0: library default) through a ring of device slots and overlaps the copies with the kernels on three
+ * 64; <= 0: library default) through a ring of device slots and overlaps the copies with the kernels on three
  * streams.  Page-locked buffers (rs_host_alloc) make the copies asynchronous.  Synchronous: returns when the
  * results are in `out`. */
 int rs_run_host(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_refresh, const int32_t* rand2,

@@ -1,7 +1,9 @@
 /* include/rs_sched_nccl.h -- the multi-GPU end-of-run reduce of the per-slice statistics, from C/C++.
  *
  * Lives in its own small library (radiosaber_b200/librs_nccl.so = this header's entry points, linked against
- * libnccl.so.2 and librs_sched.so) so that librs_sched.so itself carries no NCCL dependency.
+ * libnccl.so.2 and librs_sched.so) so that librs_sched.so itself carries no NCCL dependency.  In a process that also
+ * uses PyTorch, import torch BEFORE loading this library: both then share torch's bundled NCCL (the loader resolves
+ * libnccl.so.2 to the copy already in the process); the other way round torch finds the system's older NCCL and fails.
  *
  * What this replaces.  The reference runs ONE cell per process (nbCells = 1,
  * src/scenarios/single-cell-with-interference.h:74), one process per seed

@@ -55,7 +55,7 @@ constexpr int kMStride = 16;           /* metric table row: entries for CQI 0..1
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned short kNoUe = 0xffff;
 constexpr int kMaxQueueBytes = 268435455;  /* queue sizes saturate here: data * 8 is an int in the reference (2^31 overflows there) */
-constexpr int kMaxTtisPerLaunch = 32;  /* TTIs one launch can take (their dt / trace row ride in the kernel parameters) */
+constexpr int kMaxTtisPerLaunch = 64;  /* TTIs one launch can take (their dt / trace row ride in the kernel parameters) */
 
 /* ---- tables that are the same for every handle (set once per device) ------------------------- */
 struct ConstTables {
@@ -104,6 +104,7 @@ struct DevCfg {
   const unsigned char* holmul; /* [S] 1: the slice's metric carries the head-of-line delay (transport.cpp:702-706
                                   when alpha and beta are set; nvs.cpp:384-386 whenever alpha is set) */
   const int* tbs1;             /* [16] GetTBSizeFromMCS(mcs(cqi)) for one RB: m_requiredRBs, packet-scheduler.cpp:334 */
+  const short* vogel_tab;      /* id 103: [kVogelTab] built on the host from the doubles the reference subtracts (rs_sched.cu build_vogel_tab) */
   int sort_depth_g;        /* id 10: 2*floor(log2(G)), the depth limit of a per-slice sort of G entries */
   int direct;              /* 1: big slices, the per-slice argmax divides its metrics on the fly instead of tabulating them per
                               chunk (rs_tti_kernel, "P2 for big slices"); the table area then holds Epow's S rows */
@@ -881,16 +882,18 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Dims& dm, con
   if (o_fc) o_fc[u] = (uint8_t)fc;
 }
 
+constexpr int kVogelTab = 16 * 17 + 16 * 17 + 2;   /* id 103: gap ranks [16][17] + acceptance thresholds [ranks + 1], int16 each */
 /* Scratch of ids 101 / 103 in the (dead) slot arrays of the sort; inter_scratch_bytes() of it
  * (make_layout's min_sort_n). */
-__host__ __device__ inline int inter_scratch_bytes(int G, int S) { return 128 + 20 * (G + S) + 8 * S + S + (S + 1) + 128 + 16; }
+__host__ __device__ inline int inter_scratch_bytes(int G, int S) { return 128 + 20 * (G + S) + 8 * S + S + (S + 1) + 128 + 16 + 2 * kVogelTab; }
 struct InterScratch {
   double* eff;             /* [16] AMC efficiency per CQI: lanes index it with different CQIs, which the constant
                               cache would serialise */
   double* val;             /* [G + S] candidate gap / loss */
   int* pick;               /* [G + S] */
-  int* k2;                 /* [G + S] id 103: CQI key of a candidate's "second" efficiency, -1 = none */
-  int* todo;               /* [G + S] id 103: candidates to recompute this round */
+  int* k2;                 /* id 103 re-uses val / pick / k2 / todo (20 (G + S) bytes) as six int16 arrays, see vogel_approximate */
+  int* todo;
+  short* vtab;             /* [kVogelTab] id 103: gap rank of (k1, k2 + 1), then the acceptance threshold of a running maximum */
   int* over;               /* [S] RBGs above quota, 0 = not in the map */
   int* under;              /* [S] RBGs below quota */
   unsigned char* order;    /* [S] the slices below quota in std::unordered_map iteration order */
@@ -912,6 +915,7 @@ __device__ __forceinline__ InterScratch inter_scratch(const DevCfg& d, const Dim
   x.order = (unsigned char*)(x.under + dm.S);
   x.nxt = x.order + dm.S;
   x.bkt = x.nxt + dm.S + 1;
+  x.vtab = (short*)(((size_t)(x.bkt + 128) + 1) & ~(size_t)1);   /* the 16 spare bytes of inter_scratch_bytes cover the alignment */
   return x;
 }
 /* efficiency of the (rbg, slice) pair: the slice winner's, 0 for a slice without a listed user */
@@ -924,29 +928,49 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  * between its best and its "second" efficiency exactly as the reference computes them, then the candidates are walked
  * in the reference's order with its int-truncated running maximum, and the last one taken is granted.
  *
- * The reference scans a line in order with   if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
- *                                            if (e2 == -1 || e > e2) e2 = e;
+ * Lines.  The reference scans a line in order with   if (e1 == -1 || e > e1) { first = k; e1 = e; continue; }
+ *                                                    if (e2 == -1 || e > e2) e2 = e;
  * i.e. e1 / first = the first maximum, and e2 = the largest element that was NOT a new strict maximum when it was
  * visited (a displaced maximum is not demoted).  Efficiency is strictly increasing in the CQI, so a line is scanned on
  * its 4-bit CQI keys by one warp: an inclusive prefix maximum marks the "records", the last record is (e1, first), a
  * redux.max over the non-records is e2.
  *
- * Between rounds only two things change: the granted RBG leaves every column, and a slice that reached its quota
- * leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is no
- * e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So every round
- * re-scans just the lines that pass that test (a handful of the G + S).  Result in c.outsl. */
-__device__ __forceinline__ void vogel_scan_line(const Cell& c, const InterScratch& x, const int* held, int S, int G, int q,
-                                                int lane) {
+ * Gaps.  e1 - e2 is one of 16 x 17 doubles (e2 = -1 when there is no second); the host subtracts them and hands down
+ * their dense ranks and, for every possible running maximum, the rank of the largest gap not above its truncation
+ * (vogel_tab): the walk -- "taken iff gap > (int) largest gap so far", the grant is the last one taken -- is then an
+ * integer prefix maximum.
+ *
+ * Rounds.  Between rounds only two things change: the granted RBG leaves every column, and a slice that reached its
+ * quota leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is
+ * no e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So a round
+ * re-scans just the lines that pass that test.  Every warp walks the candidates itself (same data, same grant), keeps
+ * the slices' fill and the free-RBG mask in registers, owns the candidates q = warp + kWarps * lane, and writes their
+ * next-round values into the other half of a double buffer: ONE CTA barrier per round.  Result in c.outsl. */
+struct VogelBufs {
+  short* rk;     /* [2][n] rank of the candidate's gap */
+  short* pick;   /* [2][n] the RBG / slice it would grant, -1 = candidate out */
+  short* k2;     /* [2][n] CQI key of its second efficiency, -1 = none */
+  const short* rank_of;   /* [16][17] */
+  const short* thr;       /* [ranks + 1], index = running maximum's rank + 1 */
+  int n;
+};
+__device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& v, int buf, int S, int G, int q, int lane,
+                                                int ha, int qa, int hb, int qb, unsigned long long free_m) {
   const bool is_row = q < G;
   const int n = is_row ? S : G;
   int run = -1, k1 = -1, first = -1, k2 = -1;
-  const bool live = is_row ? (c.outsl[q] == 0xff) : (held[q - G] < c.quota[q - G]);
+  bool live;
+  if (is_row) live = ((free_m >> q) & 1ull) != 0;
+  else {
+    const int s = q - G;
+    live = __shfl_sync(kFull, s < 32 ? (ha < qa) : (hb < qb), s & 31);
+  }
   if (live)
     for (int h0 = 0; h0 < n; h0 += 32) {
       const int i = h0 + lane;
-      bool v = i < n;
-      if (v) v = is_row ? (held[i] < c.quota[i]) : (c.outsl[i] == 0xff);
-      const int key = v ? (int)((is_row ? c.sb.a[q * S + i] : c.sb.a[i * S + (q - G)]) >> 12) : -1;
+      bool ok = i < n;
+      if (ok) ok = is_row ? (h0 == 0 ? ha < qa : hb < qb) : (((free_m >> i) & 1ull) != 0);
+      const int key = ok ? (int)((is_row ? c.sb.a[q * S + i] : c.sb.a[i * S + (q - G)]) >> 12) : -1;
       int inc = key;
 #pragma unroll
       for (int dd = 1; dd < 32; dd <<= 1) {
@@ -956,87 +980,93 @@ __device__ __forceinline__ void vogel_scan_line(const Cell& c, const InterScratc
       int exc = __shfl_up_sync(kFull, inc, 1);
       if (lane == 0) exc = -1;
       exc = max(exc, run);
-      const bool rec = v && key > exc;
+      const bool rec = ok && key > exc;
       const unsigned recm = __ballot_sync(kFull, rec);
       if (recm) {
         const int last = 31 - __clz(recm);
         k1 = __shfl_sync(kFull, key, last);
         first = h0 + last;
       }
-      k2 = max(k2, __reduce_max_sync(kFull, (v && !rec) ? key : -1));
+      k2 = max(k2, __reduce_max_sync(kFull, (ok && !rec) ? key : -1));
       run = max(run, __shfl_sync(kFull, inc, 31));
     }
   if (lane == 0) {
-    const double e1 = k1 < 0 ? -1.0 : x.eff[k1], e2 = k2 < 0 ? -1.0 : x.eff[k2];
-    x.val[q] = __dsub_rn(e1, e2);
-    x.pick[q] = first;
-    x.k2[q] = k2;
+    v.rk[buf * v.n + q] = k1 < 0 ? (short)0 : v.rank_of[k1 * 17 + k2 + 1];
+    v.pick[buf * v.n + q] = (short)first;
+    v.k2[buf * v.n + q] = (short)k2;
   }
 }
 
 __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = dm.G, S = dm.S;
   const InterScratch x = inter_scratch(d, dm, c);
-  int* held = c.wd;   /* free once the quotas exist; cleared again at the end of the TTI */
-  for (int s = tid; s < S; s += kThreads) held[s] = 0;
-  if (tid < 16) x.eff[tid] = c_tab.eff[tid];
+  VogelBufs v;
+  v.n = G + S;
+  v.rk = (short*)x.val;
+  v.pick = v.rk + 2 * v.n;
+  v.k2 = v.pick + 2 * v.n;
+  v.rank_of = x.vtab;
+  v.thr = x.vtab + 16 * 17;
+  for (int i = tid; i < kVogelTab; i += kThreads) x.vtab[i] = d.vogel_tab[i];
+  /* every warp's own copy of the state: lane s / s + 32 hold slice s's quota and fill, free_m the RBGs not yet granted */
+  const int qa = lane < S ? c.quota[lane] : 0, qb = lane + 32 < S ? c.quota[lane + 32] : 0;
+  int ha = 0, hb = 0;
+  unsigned long long free_m = G >= 64 ? ~0ull : ((1ull << G) - 1ull);
   __syncthreads();
-  for (int q = warp; q < G + S; q += kWarps) vogel_scan_line(c, x, held, S, G, q, lane);
+  for (int q = warp; q < v.n; q += kWarps) vogel_scan_line(c, v, 0, S, G, q, lane, ha, qa, hb, qb, free_m);
   __syncthreads();
   for (int round = 0; round < G; ++round) {
-    if (tid < 32) {
-      /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int
-       * that is set to the (truncated) gap whenever a candidate is taken.  max_diff is therefore always the
-       * truncated largest gap seen so far (-1 before the first), so q is taken iff gap_q > trunc(max of the gaps
-       * before q) and the grant is the LAST candidate taken: a prefix maximum per 32 candidates. */
-      double run = -1.0;   /* largest gap so far; -1 = none (gaps are >= 0) */
-      int win = -1;
-      for (int q0 = 0; q0 < G + S; q0 += 32) {
-        const int q = q0 + tid;
-        const bool valid = q < G + S && x.pick[q] >= 0;   /* allocated RBGs / slices at their quota are skipped */
-        const double v = valid ? x.val[q] : -1.0;
-        double incl = v;
+    const int cur = round & 1, nxt = cur ^ 1;
+    /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int that is
+     * set to the (truncated) gap whenever a candidate is taken.  max_diff is therefore always the truncated largest gap
+     * seen so far (-1 before the first), so q is taken iff gap_q > trunc(max of the gaps before q) and the grant is the
+     * LAST candidate taken: a prefix maximum per 32 candidates, on the gaps' ranks. */
+    int run = -1, win = -1;
+    for (int q0 = 0; q0 < v.n; q0 += 32) {
+      const int q = q0 + lane;
+      const bool valid = q < v.n && v.pick[cur * v.n + q] >= 0;   /* allocated RBGs / slices at their quota are skipped */
+      const int rkq = valid ? (int)v.rk[cur * v.n + q] : -1;
+      int incl = rkq;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(kFull, incl, o);
-          if (tid >= o && up > incl) incl = up;
-        }
-        double before = __shfl_up_sync(kFull, incl, 1);
-        if (tid == 0 || before < run) before = run;
-        const bool taken = valid && v > (double)(int)before;
-        const unsigned bal = __ballot_sync(kFull, taken);
-        if (bal) win = q0 + 31 - __clz(bal);
-        const double last = __shfl_sync(kFull, incl, 31);
-        if (last > run) run = last;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl = max(incl, up);
       }
-      if (tid == 0) {
-        if (win >= 0) {
-          const int gr = win < G ? win : x.pick[win], gs = win < G ? x.pick[win] : win - G;
-          c.outsl[gr] = (unsigned char)gs;
-          held[gs] += 1;
-          c.misc[11] = (unsigned)gr | ((unsigned)gs << 8) | (held[gs] >= c.quota[gs] ? 0x10000u : 0u);
-        }
-        c.misc[12] = (win >= 0) ? 1u : 0u;
-        c.misc[13] = 0;
+      int before = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) before = -1;
+      before = max(before, run);
+      const bool taken = valid && rkq > (int)v.thr[before + 1];
+      const unsigned bal = __ballot_sync(kFull, taken);
+      if (bal) win = q0 + 31 - __clz(bal);
+      run = max(run, __shfl_sync(kFull, incl, 31));
+    }
+    if (win < 0) break;   /* the same in every warp */
+    const int pk = v.pick[cur * v.n + win];
+    const int gr = win < G ? win : pk, gs = win < G ? pk : win - G;
+    if (lane == (gs & 31)) { if (gs < 32) ha++; else hb++; }
+    const bool full = __shfl_sync(kFull, gs < 32 ? (ha >= qa) : (hb >= qb), gs & 31);
+    free_m &= ~(1ull << gr);
+    if (tid == 0) c.outsl[gr] = (unsigned char)gs;
+    /* this warp's candidates: carry them over, re-scan the ones the grant can have changed */
+    const int qq = warp + kWarps * lane;
+    bool redo = false;
+    if (qq < v.n) {
+      const short p_ = v.pick[cur * v.n + qq], k_ = v.k2[cur * v.n + qq];
+      v.pick[nxt * v.n + qq] = p_;
+      v.k2[nxt * v.n + qq] = k_;
+      v.rk[nxt * v.n + qq] = v.rk[cur * v.n + qq];
+      if (p_ >= 0) {
+        if (qq < G) redo = (qq == gr) || (full && (int)(c.sb.a[qq * S + gs] >> 12) >= (int)k_);
+        else redo = (qq - G == gs && full) || (int)(c.sb.a[gr * S + (qq - G)] >> 12) >= (int)k_;
       }
     }
-    __syncthreads();
-    if (!c.misc[12]) break;
-    {   /* which lines does the grant touch? */
-      const unsigned gm = c.misc[11];
-      const int gr = gm & 0xff, gs = (gm >> 8) & 0xff;
-      const bool full = (gm & 0x10000u) != 0;
-      for (int q = tid; q < G + S; q += kThreads) {
-        if (x.pick[q] < 0) continue;            /* already out */
-        bool redo;
-        if (q < G) redo = (q == gr) || (full && (int)(c.sb.a[q * S + gs] >> 12) >= x.k2[q]);
-        else redo = (q - G == gs && full) || (int)(c.sb.a[gr * S + (q - G)] >> 12) >= x.k2[q];
-        if (redo) x.todo[atomicAdd(&c.misc[13], 1u)] = q;
-      }
+    __syncwarp();
+    unsigned rm = __ballot_sync(kFull, redo);
+    while (rm) {
+      const int l = __ffs(rm) - 1;
+      rm &= rm - 1;
+      vogel_scan_line(c, v, nxt, S, G, warp + kWarps * l, lane, ha, qa, hb, qb, free_m);
     }
-    __syncthreads();
-    const int n_todo = (int)c.misc[13];
-    for (int i = warp; i < n_todo; i += kWarps) vogel_scan_line(c, x, held, S, G, x.todo[i], lane);
     __syncthreads();
   }
 }

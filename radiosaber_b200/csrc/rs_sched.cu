@@ -163,6 +163,32 @@ void build_eq_table(int nmax, std::vector<unsigned short>* tab) {
     }
   }
 }
+/* VogelApproximate's gaps (transport.cpp:378-451): e1 - e2 over the AMC efficiencies of CQI 0..15 (0 = a slice without a
+ * listed user) with e2 = -1 when a line has no second element.  tab[k1 * 17 + k2 + 1] = dense rank of that double among
+ * all 272 (equal doubles, equal ranks); tab[272 + r + 1] = rank of the largest gap <= (double)(int)gap_r, -1 if none:
+ * "candidate gap > (int) running maximum" is then a comparison of ranks.  Index 272 (running maximum "none") holds the
+ * threshold of max_diff's initial -1. */
+void build_vogel_tab(std::vector<short>* tab) {
+  double eff[17];
+  eff[0] = -1.0;   /* k2 = -1 */
+  eff[1] = 0.0;    /* CQI 0 */
+  for (int c = 1; c <= 15; ++c) eff[c + 1] = eff_from_cqi(c);
+  std::vector<double> gaps;
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int k2 = -1; k2 < 16; ++k2) { volatile double g = eff[k1 + 1] - eff[k2 + 1]; const double gv = g; gaps.push_back(gv); }
+  std::vector<double> uniq(gaps);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  tab->assign(rs::kVogelTab, 0);
+  for (size_t i = 0; i < gaps.size(); ++i)
+    (*tab)[i] = (short)(std::lower_bound(uniq.begin(), uniq.end(), gaps[i]) - uniq.begin());
+  auto thr_of = [&](double running_max) {   /* rank of the largest gap <= (double)(int)running_max */
+    const double t = (double)(int)running_max;
+    return (short)((std::upper_bound(uniq.begin(), uniq.end(), t) - uniq.begin()) - 1);
+  };
+  (*tab)[272] = thr_of(-1.0);
+  for (size_t r = 0; r < uniq.size(); ++r) (*tab)[272 + 1 + r] = thr_of(uniq[r]);
+}
 constexpr int kEqMax = 2048;
 #ifndef RS_WIDE_MIN_UES
 #define RS_WIDE_MIN_UES 480   /* cells with at least this many UEs run 512 threads wide (tools/sweep_bench.py) */
@@ -219,6 +245,7 @@ struct rs_handle {
   const double* hol_next = nullptr;
   DevBuf<unsigned char> holmul;
   DevBuf<int> tbs1;
+  DevBuf<short> vogel_tab;
   DevBuf<unsigned long long> stats;
   /* staging for rs_step / rs_run_host*: a ring of slots that stays in flight across calls.  Chunk n of the
    * handle's lifetime uses slot n % kSlots; a slot is refilled once the kernel that read it is done (k_done) and
@@ -424,7 +451,7 @@ void rs_destroy(rs_handle* h) {
   if (h->mb_host) cudaFreeHost(h->mb_host);
   h->mb_dev.release();
   h->trace_tab.release(); h->ue_trace_off.release();
-  h->holmul.release(); h->tbs1.release();
+  h->holmul.release(); h->tbs1.release(); h->vogel_tab.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_in) cudaStreamDestroy(h->copy_in);
   if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -659,6 +686,12 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   BAIL(upload(h->tbs1, tbs1));
   d.holmul = h->holmul.p;
   d.tbs1 = h->tbs1.p;
+  if (algo == 103) {
+    std::vector<short> vt;
+    build_vogel_tab(&vt);
+    BAIL(upload(h->vogel_tab, vt));
+    d.vogel_tab = h->vogel_tab.p;
+  }
   if ((algo == 9 && d.sort_n > 16) || (algo == 10 && G > 16)) {
     std::vector<unsigned short> eq;
     d.eq_max = std::min(algo == 10 ? G : d.sort_n, kEqMax);

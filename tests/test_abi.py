@@ -100,6 +100,7 @@ def test_batch_runner_fails_loudly_without_a_gpu(tmp_path):
 
 def test_nccl_library_exports_every_declared_symbol():
     """include/rs_sched_nccl.h -> radiosaber_b200/librs_nccl.so (loads without a GPU; no calls made)."""
+    import torch  # noqa: F401  -- before the library: a process that loads the system libnccl first cannot import torch later
     src = open(os.path.join(ROOT, "include", "rs_sched_nccl.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", src)))

@@ -143,6 +143,8 @@ def test_headline_shape_long_run_against_the_oracle():
 
 
 def _nccl():
+    import torch  # noqa: F401  -- first: librs_nccl.so binds to whichever libnccl.so.2 the process has loaded, and torch
+    #                              must get its own bundled one (the system's is older and lacks symbols torch needs)
     L = C.CDLL(os.path.join(ROOT, "radiosaber_b200", "librs_nccl.so"))
     L.rs_nccl_last_error.restype = C.c_char_p
     L.rs_reduce_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
