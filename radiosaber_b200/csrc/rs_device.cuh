@@ -134,6 +134,7 @@ struct RunArgs {
   double dt[kMaxTtisPerLaunch];       /* Now - lastUpdate of the EWMA at TTI t (flows/radio-bearer.cpp:150) */
   int trace_row[kMaxTtisPerLaunch];   /* trace mode: row of every UE's trace in force at TTI t */
   int T;
+  int cell_off;            /* first cell of this launch (the host may run the two halves of a batch on two streams) */
   short* rbg_to_ue; int* tbs_bits; uint8_t* mcs; uint8_t* final_cqi;
   int* slice_target; int* slice_quota; int* nvs_slice;
   int* alloc_n; short* alloc_ue; short* alloc_rbg;   /* id 10: [T][B], [T][B][2G], [T][B][2G] */
@@ -1233,7 +1234,7 @@ __global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const D
   c.sb.eq_max = d.eq_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = dm.S, U = dm.U, G = dm.G;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x + r.cell_off;   /* a launch covers the cells [cell_off, cell_off + gridDim.x) of the batch */
   constexpr bool NVS = ALGO == 7 || ALGO == 11;   /* DownlinkNVSScheduler, greedy and non-greedy */
   /* DownlinkTransportScheduler with one of its inter-slice algorithms: GreedyByRow (8), MaximizeCell (9),
    * UpperBound (10), SubOpt (101), VogelApproximate (103) */

@@ -222,6 +222,12 @@ struct rs_handle {
   rs::Layout layout{};
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  /* Big batches run as two half-batches on two streams: each half's launches are chained on its own stream, so the
+   * partial last wave of one half's launch is filled by CTAs of the other half's next launch instead of leaving SMs
+   * idle until the grid drains (4096 cells = 3.46 waves of 1184 resident cells: +5-10 %, profiles/README.md). */
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int parts = 1;
   int64_t launches = 0;
   int32_t row_m1[27];
   /* static tables */
@@ -258,7 +264,7 @@ struct rs_handle {
     DevBuf<short> rbg_to_ue, alloc_ue, alloc_rbg;
     DevBuf<int> alloc_n, queue;
     DevBuf<double> hol;
-    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, k_done2 = nullptr, out_done = nullptr;
     bool k_rec = false, out_rec = false;   /* the events have been recorded at least once */
   } slot[kSlots];
   uint64_t chunk_seq = 0;
@@ -266,7 +272,7 @@ struct rs_handle {
    * before last must be done before it is overwritten */
   struct Slab {
     DevBuf<uint8_t> cqi;
-    cudaEvent_t used = nullptr;   /* recorded after the last kernel that read the slab */
+    cudaEvent_t used = nullptr, used2 = nullptr;   /* recorded after the last kernel (of each half) that read the slab */
     bool used_rec = false;
     int index = -1;               /* slab of the CURRENT call resident here */
   } slab[2];
@@ -329,14 +335,25 @@ const void* fixed_kernel(int algo, int which, bool trace) {
   return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<8, false, false, FixedNib>;
 }
 
-int launch_ttis(rs_handle* h, const rs::RunArgs& a, bool trace, const rs::DevCfg* cfg = nullptr) {
-  const dim3 grid(h->B), block(h->wide ? rsw::kThreads : rs::kThreads);
+/* part < 0: the whole batch on the handle's stream; part 0 / 1: the first / second half on stream / stream2 */
+int launch_ttis(rs_handle* h, const rs::RunArgs& a0, bool trace, const rs::DevCfg* cfg = nullptr, int part = -1) {
+  rs::RunArgs a = a0;
+  int n = h->B;
+  cudaStream_t st = h->stream;
+  if (part >= 0) {
+    const int half = (h->B + 1) / 2;
+    a.cell_off = part == 0 ? 0 : half;
+    n = part == 0 ? half : h->B - half;
+    if (part == 1) st = h->stream2;
+    if (n <= 0) return RS_OK;
+  }
+  const dim3 grid(n), block(h->wide ? rsw::kThreads : rs::kThreads);
   const size_t sm = (size_t)h->layout.total;
   /* by address: the rsw:: kernels take rsw::DevCfg / rsw::RunArgs, the same bytes as the rs:: structs */
   const void* fn = (h->fixed >= 0 && !a.queue) ? fixed_kernel(h->d.algo, h->fixed, trace)
                                                : tti_kernel_any(h->d.algo, trace, a.queue != nullptr, h->wide);
   void* args[2] = {(void*)(cfg ? cfg : &h->d), (void*)&a};
-  CU(cudaLaunchKernel(fn, grid, block, args, sm, h->stream));
+  CU(cudaLaunchKernel(fn, grid, block, args, sm, st));
   CU(cudaGetLastError());
   h->launches++;
   return RS_OK;
@@ -404,6 +421,7 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
   if (!s.in_done) {
     CU(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.k_done2, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
   }
   return RS_OK;
@@ -431,6 +449,7 @@ void rs_destroy(rs_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->copy_in) cudaStreamSynchronize(h->copy_in);
   if (h->copy_out) cudaStreamSynchronize(h->copy_out);
   h->ue_to_slice.release(); h->slice_ptr.release(); h->slice_ues.release(); h->chunk_slice.release();
@@ -444,9 +463,13 @@ void rs_destroy(rs_handle* h) {
     s.queue.release(); s.hol.release();
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.k_done) cudaEventDestroy(s.k_done);
+    if (s.k_done2) cudaEventDestroy(s.k_done2);
     if (s.out_done) cudaEventDestroy(s.out_done);
   }
-  for (auto& sl : h->slab) { sl.cqi.release(); if (sl.used) cudaEventDestroy(sl.used); }
+  for (auto& sl : h->slab) { sl.cqi.release(); if (sl.used) cudaEventDestroy(sl.used); if (sl.used2) cudaEventDestroy(sl.used2); }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   for (auto& e : h->call_done) if (e) cudaEventDestroy(e);
   if (h->mb_host) cudaFreeHost(h->mb_host);
   h->mb_dev.release();
@@ -672,8 +695,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e))); }
   h->stream = h->own_stream;
+  /* two half-batches once each half still fills the GPU (RS_NO_SPLIT=1: one launch per step of TTIs, as in round 1) */
+  h->parts = (n_cells >= 2 * 148 * (h->wide ? RS_WIDE_MIN_BLOCKS : 8) && !getenv("RS_NO_SPLIT")) ? 2 : 1;
   BAIL(upload(h->ue_to_slice, u2s));
   BAIL(upload(h->slice_ptr, ptr));
   BAIL(upload(h->slice_ues, ues));
@@ -732,6 +760,7 @@ int rs_sync(rs_handle* h) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->copy_in));
   CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->stream2));
   CU(cudaStreamSynchronize(h->copy_out));
   return RS_OK;
 }
@@ -799,6 +828,7 @@ namespace {
 void drain(rs_handle* h) {
   cudaStreamSynchronize(h->copy_in);
   cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->stream2);
   cudaStreamSynchronize(h->copy_out);
 }
 #define CU_DRAIN(call)                                                                             \
@@ -850,6 +880,13 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   if (ttis_per_launch <= 0) ttis_per_launch = 16;
   ttis_per_launch = std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch);
   const size_t B = h->B, U = h->d.U;
+  /* more than one launch in this call and a big batch: the two halves of the batch go down two streams (forked
+   * here, joined at the end of the call), so the tail of one launch overlaps the head of the next */
+  const bool split = h->parts == 2 && n_ttis > ttis_per_launch;
+  if (split) {
+    CU(cudaEventRecord(h->fork_ev, h->stream));
+    CU(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+  }
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
     a.T = std::min(ttis_per_launch, n_ttis - t0);
@@ -865,8 +902,13 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.hol = d_hol ? d_hol + (size_t)t0 * B * U * h->d.nb : nullptr;
     a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
     point_outputs(h, &a, d_out, (size_t)t0);
-    const int rc = launch_ttis(h, a, trace_row != nullptr);
-    if (rc != RS_OK) return rc;
+    int rc = launch_ttis(h, a, trace_row != nullptr, nullptr, split ? 0 : -1);
+    if (rc == RS_OK && split) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, 1);
+    if (rc != RS_OK) { if (split) cudaStreamSynchronize(h->stream2); return rc; }
+  }
+  if (split) {
+    CU(cudaEventRecord(h->join_ev, h->stream2));
+    CU(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
   }
   return RS_OK;
 }
@@ -896,6 +938,11 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   const int TC = std::max(1, std::min(std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch), n_ttis));
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   const bool slabs = !trace_row && cqi_refresh > 1;   /* consecutive chunks share a CQI slab */
+  const bool split = h->parts == 2;
+  if (split) {   /* stream2 joins whatever the caller's stream has seen so far (state uploads, earlier device calls) */
+    CU(cudaEventRecord(h->fork_ev, h->stream));
+    CU(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+  }
   for (auto& s : h->slot) {
     const int rc = alloc_slot(h, s, TC, out, active != nullptr, !trace_row && !slabs, queue != nullptr, hol != nullptr);
     if (rc != RS_OK) { drain(h); return rc; }
@@ -904,6 +951,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     for (auto& sl : h->slab) {
       CU_DRAIN(sl.cqi.alloc(B * U * C));
       if (!sl.used) CU_DRAIN(cudaEventCreateWithFlags(&sl.used, cudaEventDisableTiming));
+      if (!sl.used2) CU_DRAIN(cudaEventCreateWithFlags(&sl.used2, cudaEventDisableTiming));
       sl.index = -1;   /* slab numbers are relative to this call's cqi pointer */
     }
   for (auto& e : h->call_done)
@@ -916,7 +964,10 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     if (slabs) T = std::min(T, (t0 / cqi_refresh + 1) * cqi_refresh - t0);
     const int slab0 = t0 / cqi_refresh;
     /* inputs: the slot's previous kernel must be done with them */
-    if (s.k_rec) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
+    if (s.k_rec) {
+      CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
+      if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done2, 0));
+    }
     const uint8_t* d_cqi = nullptr;
     rs_handle::Slab* sl = nullptr;
     if (slabs) {
@@ -924,7 +975,10 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
       if (!sl) {
         sl = &h->slab[next_slab_buf];
         next_slab_buf ^= 1;
-        if (sl->used_rec) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used, 0));
+        if (sl->used_rec) {
+          CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used, 0));
+          if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used2, 0));
+        }
         CU_DRAIN(cudaMemcpyAsync(sl->cqi.p, cqi + (size_t)slab0 * B * U * C, B * U * C, cudaMemcpyHostToDevice, h->copy_in));
         sl->index = slab0;
       }
@@ -939,9 +993,14 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     if (queue) CU_DRAIN(cudaMemcpyAsync(s.queue.p, queue + (size_t)t0 * B * U * NB, (size_t)T * B * U * NB * 4, cudaMemcpyHostToDevice, h->copy_in));
     if (hol) CU_DRAIN(cudaMemcpyAsync(s.hol.p, hol + (size_t)t0 * B * U * NB, (size_t)T * B * U * NB * 8, cudaMemcpyHostToDevice, h->copy_in));
     CU_DRAIN(cudaEventRecord(s.in_done, h->copy_in));
-    /* kernel: inputs in, and the slot's previous outputs drained */
+    /* kernel(s): inputs in, and the slot's previous outputs drained; a big batch runs as two half-batches, each half
+     * chained on its own stream from chunk to chunk (the copies wait for both) */
     CU_DRAIN(cudaStreamWaitEvent(h->stream, s.in_done, 0));
     if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->stream, s.out_done, 0));
+    if (split) {
+      CU_DRAIN(cudaStreamWaitEvent(h->stream2, s.in_done, 0));
+      if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->stream2, s.out_done, 0));
+    }
     rs::RunArgs a{};
     a.T = T;
     a.cqi = d_cqi; a.cqi_tti_stride = (long long)(B * U * C);
@@ -966,13 +1025,20 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
       so.alloc_rbg = out->alloc_rbg ? s.alloc_rbg.p : nullptr;
       point_outputs(h, &a, &so, 0);
     }
-    const int rc = launch_ttis(h, a, trace_row != nullptr);
+    int rc = launch_ttis(h, a, trace_row != nullptr, nullptr, split ? 0 : -1);
+    if (rc == RS_OK && split) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, 1);
     if (rc != RS_OK) { drain(h); return rc; }
     CU_DRAIN(cudaEventRecord(s.k_done, h->stream));
+    if (split) CU_DRAIN(cudaEventRecord(s.k_done2, h->stream2));
     s.k_rec = true;
-    if (sl) { CU_DRAIN(cudaEventRecord(sl->used, h->stream)); sl->used_rec = true; }
+    if (sl) {
+      CU_DRAIN(cudaEventRecord(sl->used, h->stream));
+      if (split) CU_DRAIN(cudaEventRecord(sl->used2, h->stream2));
+      sl->used_rec = true;
+    }
     /* outputs */
     CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done, 0));
+    if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done2, 0));
     if (out) {
       if (a.rbg_to_ue) CU_DRAIN(cudaMemcpyAsync(out->rbg_to_ue + (size_t)t0 * B * G, s.rbg_to_ue.p, (size_t)T * B * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
       if (a.tbs_bits) CU_DRAIN(cudaMemcpyAsync(out->tbs_bits + (size_t)t0 * B * U, s.tbs_bits.p, (size_t)T * B * U * 4, cudaMemcpyDeviceToHost, h->copy_out));
@@ -988,6 +1054,10 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     CU_DRAIN(cudaEventRecord(s.out_done, h->copy_out));
     s.out_rec = true;
     h->chunk_seq++;
+  }
+  if (split) {   /* the handle's stream is behind the second half's kernels again (rs_get_state, the next device call) */
+    CU_DRAIN(cudaEventRecord(h->join_ev, h->stream2));
+    CU_DRAIN(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
   }
   /* copy_out is behind every kernel of the call (it waited on each k_done), and every kernel is behind its inputs */
   const int64_t tk = h->calls++;

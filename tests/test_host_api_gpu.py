@@ -188,3 +188,46 @@ def test_rs_batch_two_gpus_equal_one(tmp_path):
     assert sum(runs[0]["slice_bytes"]) > 0 and runs[1]["gpus"] == 2
     assert (tmp_path / "c1.stderr").read_text() == (tmp_path / "c2.stderr").read_text()   # cell 200 lives on GPU 1
     assert (tmp_path / "c1.stdout").read_text() == (tmp_path / "c2.stdout").read_text()
+
+
+def test_two_half_batches_equal_one_launch():
+    """A big batch runs as two half-batches on two streams (each half's launches chained, the tail of one launch
+    overlapping the head of the next); RS_NO_SPLIT=1 keeps one launch per step.  Same results, both through the
+    host-buffer path and with everything resident on the device."""
+    import torch
+    S, n, B, T = 20, 5, 2400, 11
+    w, p, u2s = _cfg(S, n, mix=True)
+    U, G = len(u2s), 64
+    cqi = workload.synth_cqi(21, 0, B, 0, T, U, G)
+    r2 = workload.synth_rand2(21, 0, B, 0, T, S)
+    _, dts = workload.tti_clock(T)
+    res = []
+    for no_split in (False, True):
+        if no_split:
+            os.environ["RS_NO_SPLIT"] = "1"
+        try:
+            g = sched.Scheduler(9, w, p, u2s, B)
+        finally:
+            os.environ.pop("RS_NO_SPLIT", None)
+        a = g.run_host(cqi, r2, dts, want_aux=True, ttis_per_launch=4)
+        st_host = g.get_state()
+        g.reset_state()
+        dev = torch.device("cuda", 0)
+        d_cqi = torch.from_numpy(cqi).to(dev)
+        d_r2 = torch.from_numpy(r2).to(dev)
+        d_rbg = torch.empty((T, B, G), dtype=torch.int16, device=dev)
+        d_bits = torch.empty((T, B, U), dtype=torch.int32, device=dev)
+        g.run_device(T, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts, {"rbg_to_ue": d_rbg.data_ptr(), "tbs_bits": d_bits.data_ptr()},
+                     ttis_per_launch=4)
+        st_dev = g.get_state()            # synchronises the handle's stream: must be behind BOTH halves
+        res.append((a, st_host, d_rbg.cpu().numpy(), d_bits.cpu().numpy(), st_dev))
+        g.close()
+    (a0, s0, r0, b0, t0), (a1, s1, r1, b1, t1) = res
+    for k in a0:
+        assert np.array_equal(a0[k], a1[k]), k
+    for k in s0:
+        assert np.array_equal(s0[k], s1[k]), k
+        assert np.array_equal(t0[k], t1[k]), k
+        assert np.array_equal(s0[k], t0[k]), k         # host-buffer path == device-resident path
+    assert np.array_equal(r0, r1) and np.array_equal(b0, b1)
+    assert np.array_equal(r0, a0["rbg_to_ue"]) and np.array_equal(b0, a0["tbs_bits"])
