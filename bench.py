@@ -638,7 +638,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cells", type=int, default=4096, help="cells per GPU")
     ap.add_argument("--algo", type=int, default=9)
-    ap.add_argument("--ttis-per-step", type=int, default=48)
+    ap.add_argument("--ttis-per-step", type=int, default=96)
     ap.add_argument("--ttis-per-launch", type=int, default=16)
     ap.add_argument("--e2e-ttis", type=int, default=80)
     ap.add_argument("--e2e-ttis-per-launch", type=int, default=8)
