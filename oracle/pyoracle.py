@@ -21,7 +21,7 @@ class _Cfg(C.Structure):
     _fields_ = [
         ("algo", C.c_int32), ("n_slices", C.c_int32), ("n_ues", C.c_int32), ("n_rbs", C.c_int32),
         ("rbg_size", C.c_int32), ("cqi_per_rb", C.c_int32), ("data_to_transmit", C.c_int32),
-        ("dead_work", C.c_int32),
+        ("dead_work", C.c_int32), ("n_bearers", C.c_int32), ("reserved", C.c_int32),
         ("weight", C.c_void_p), ("params", C.c_void_p), ("ue_to_slice", C.c_void_p), ("tbs_row_m1", C.c_void_p),
     ]
 
@@ -83,7 +83,7 @@ class OracleScheduler:
     """
 
     def __init__(self, algo, weight, params, ue_to_slice, n_cells, n_rbs=512, rbg_size=8, cqi_per_rb=0,
-                 data_to_transmit=100000000, dead_work=0, tbs_row_m1=None, n_threads=1):
+                 data_to_transmit=100000000, dead_work=0, tbs_row_m1=None, n_threads=1, n_bearers=1):
         self.algo = int(algo)
         self.ue_to_slice = np.ascontiguousarray(ue_to_slice, dtype=np.int32)
         self.U = int(self.ue_to_slice.shape[0])
@@ -97,14 +97,16 @@ class OracleScheduler:
         self.cqi_per_rb = int(cqi_per_rb)
         self.n_threads = int(n_threads)
         self._row_m1 = None if tbs_row_m1 is None else np.ascontiguousarray(tbs_row_m1, dtype=np.int32)
+        self.nb = 2 if int(n_bearers) == 2 else 1
         self._cfg = _Cfg(self.algo, self.S, self.U, self.R, self.rbg_size, self.cqi_per_rb,
-                         int(data_to_transmit), int(dead_work),
+                         int(data_to_transmit), int(dead_work), int(n_bearers), 0,
                          _ptr(self.weight), _ptr(self.params), _ptr(self.ue_to_slice), _ptr(self._row_m1))
         B, U, S = self.B, self.U, self.S
-        self.avg_rate = np.full((B, U), 100000.0, dtype=np.float64)   # radio-bearer.cpp:54
-        self.tx_bytes = np.zeros((B, U), dtype=np.int32)
-        self.cum_bytes = np.zeros((B, U), dtype=np.uint64)
-        self.cum_rbs = np.zeros((B, U), dtype=np.uint64)
+        BU = (B, U) if self.nb == 1 else (B, U, 2)   # per-bearer state
+        self.avg_rate = np.full(BU, 100000.0, dtype=np.float64)   # radio-bearer.cpp:54
+        self.tx_bytes = np.zeros(BU, dtype=np.int32)
+        self.cum_bytes = np.zeros(BU, dtype=np.uint64)
+        self.cum_rbs = np.zeros(BU, dtype=np.uint64)
         self.slice_offset = np.zeros((B, S), dtype=np.float64)
         self.nvs_ewma = np.zeros((B, S), dtype=np.float64)
 
@@ -128,8 +130,9 @@ class OracleScheduler:
             rand2 = np.zeros((B, 2), dtype=np.int32)
         rand2 = np.ascontiguousarray(rand2, dtype=np.int32).reshape(B, -1)   # [B][2]; id 11: [B][300 * users]
         act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).reshape(B, U)
-        q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32).reshape(B, U)
-        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(B, U)
+        per = (B, U) if self.nb == 1 else (B, U, 2)
+        q = None if queue is None else np.ascontiguousarray(queue, dtype=np.int32).reshape(per)
+        h = None if hol is None else np.ascontiguousarray(hol, dtype=np.float64).reshape(per)
         out = {
             "rbg_to_ue": np.empty((B, G), dtype=np.int16),
             "tbs_bits": np.empty((B, U), dtype=np.int32),

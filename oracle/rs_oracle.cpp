@@ -104,6 +104,9 @@ struct User {          /* PacketScheduler::UserToSchedule, ps.h:88-123 */
   int bits = 0;
   int data = 0;
   double hol = 0;   /* RadioBearer::GetHeadOfLinePacketDelay of the (single) bearer */
+  /* two bearers per UE (m_bearers[MAX_BEARERS], m_dataToTransmit[MAX_BEARERS], ps.h:101-102): slot = bearer priority */
+  int data2[2] = {0, 0};
+  double hol2[2] = {0, 0};
 };
 
 struct CellView {
@@ -130,13 +133,14 @@ struct CellView {
   int16_t* alloc_rbg;
   const int32_t* queue;   /* [U] bytes queued per bearer this TTI, NULL = cfg->data_to_transmit for everyone */
   const double* hol;      /* [U] head-of-line delay, NULL = 0 */
+  int nb = 1;             /* bearers per UE; per-bearer arrays are [U][nb] */
 };
 
 /* RadioBearer::UpdateAverageTransmissionRate, flows/radio-bearer.cpp:138-164,
  * looped over every bearer (transport.cpp:715-727, nvs.cpp:392-403, dlps.cpp:503-514). */
 void UpdateAverages(const CellView& c) {
   if (c.dt == 0) return; /* Now == lastUpdate */
-  for (int u = 0; u < c.cfg->n_ues; ++u) {
+  for (int u = 0; u < c.cfg->n_ues * c.nb; ++u) {   /* every bearer */
     double rate = (c.tx[u] * 8) / c.dt;
     double beta = 0.02;
     c.avg[u] = ((1 - beta) * c.avg[u]) + (beta * rate);
@@ -159,9 +163,20 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
     usr.slice = cfg->ue_to_slice[u];
     /* transport.cpp:119-128: only bearers with packets are listed; dataToTransmit = 100000000 for an
      * infinite buffer, else the queue size */
+    if (c.nb == 2) {
+      /* both bearers of the UE join one UserToSchedule (InsertFlowToUser, ps.cpp:304-318); the bearer that comes first
+       * in the container (slot 0, then slot 1) creates the record and sets m_requiredRBs (:333) */
+      for (int i = 0; i < 2; ++i) {
+        usr.data2[i] = std::max(c.queue[2 * u + i], 0);
+        usr.hol2[i] = c.hol ? c.hol[2 * u + i] : 0.0;
+      }
+      if (usr.data2[0] <= 0 && usr.data2[1] <= 0) continue;
+      usr.data = usr.data2[0] > 0 ? usr.data2[0] : usr.data2[1];
+    } else {
     usr.data = c.queue ? c.queue[u] : cfg->data_to_transmit;
     if (c.queue && usr.data <= 0) continue;
     usr.hol = c.hol ? c.hol[u] : 0.0;
+    }
     usr.cqi.resize(R);
     usr.eff.resize(R);
     for (int r = 0; r < R; ++r) {
@@ -185,19 +200,50 @@ std::vector<User> SelectUsers(const CellView& c, int only_slice) {
 
 /* ComputeSchedulingMetric, transport.cpp:677-713; nvs = the copy in nvs.cpp:360-390, which multiplies
  * the head-of-line delay in whenever alpha != 0 (the transport version only when beta != 0). */
-double TransportMetric(const rso_config* cfg, const User& usr, double avg, double eff, bool nvs = false) {
+/* 1 + the rates of the user's LISTED bearers in slot order (transport.cpp:680-687, ps.cpp:423-433) */
+double RateSum(const CellView& c, const User& usr) {
+  double sum_rate = 1;
+  if (c.nb == 2) {
+    for (int i = 0; i < 2; ++i)
+      if (usr.data2[i] > 0) sum_rate += c.avg[2 * usr.id + i];
+  } else {
+    sum_rate += c.avg[usr.id];
+  }
+  return sum_rate;
+}
+
+/* slice_priority_ (transport.cpp:115, 143-146): the highest priority among the listed bearers of each slice */
+std::vector<int> SlicePriority(const CellView& c, const std::vector<User>& users) {
+  std::vector<int> prio(c.cfg->n_slices, 0);
+  if (c.nb == 2)
+    for (const User& u : users)
+      if (u.data2[1] > 0) prio[u.slice] = 1;
+  return prio;
+}
+
+double TransportMetric(const CellView& c, const User& usr, const std::vector<int>& slice_prio, double eff, bool nvs = false) {
+  const rso_config* cfg = c.cfg;
   double metric = 0;
-  double average_rate = 1;
-  average_rate += avg; /* one bearer per UE */
+  double average_rate = RateSum(c, usr);
   eff = eff * 180000 / 1000;
   average_rate /= 1000.0;
   const int32_t* p = cfg->params + 4 * usr.slice;
   int alpha = p[0], beta = p[1], epsilon = p[2], psi = p[3];
   if (alpha == 0) {
     metric = pow(eff, epsilon) / pow(average_rate, psi);
+  } else if (c.nb == 2) {
+    /* the prioritized flow has no packet, set metric to 0 (:696-698); else its head-of-line delay (:700-706) */
+    const int pr = slice_prio[usr.slice];
+    if (usr.data2[pr] == 0) {
+      metric = 0;
+    } else if (beta || nvs) {
+      metric = usr.hol2[pr] * pow(eff, epsilon) / pow(average_rate, psi);
+    } else {
+      metric = pow(eff, epsilon) / pow(average_rate, psi);
+    }
   } else {
-    /* two bearers per UE: the caller marks "the bearer of the slice's priority is empty" (:696-698) with a head-of-line
-     * delay of 0 where the delay multiplies the metric anyway, and with a negative one where it does not */
+    /* one entry per UE: a caller that folds two bearers marks "the bearer of the slice's priority is empty" (:696-698)
+     * with a head-of-line delay of 0 where the delay multiplies the metric anyway, and with a negative one where it does not */
     if (usr.data == 0 || (!(beta || nvs) && usr.hol < 0)) {
       metric = 0;
     } else {
@@ -382,6 +428,17 @@ void FinalizeUser(const CellView& c, User& usr, const int32_t* row_m1) {
 void AccountUser(const CellView& c, const User& usr) {
   int available = usr.bits / 8;
   if (available <= 0) return;
+  if (c.nb == 2) {   /* priority 1 first, what is left to priority 0; every bearer that sends is booked the user's RBs */
+    for (int i = 1; i >= 0 && available > 0; --i) {
+      if (usr.data2[i] <= 0) continue;
+      const int sent = std::min(available, usr.data2[i]);
+      available -= sent;
+      c.tx[2 * usr.id + i] += sent;
+      c.cum_bytes[2 * usr.id + i] += sent;
+      c.cum_rbs[2 * usr.id + i] += usr.rbs.size();
+    }
+    return;
+  }
   if (usr.data > 0) {
     int sent = std::min(available, usr.data);
     c.tx[usr.id] += sent;        /* RadioBearer::UpdateTransmittedBytes, radio-bearer.cpp:118-123 */
@@ -421,6 +478,7 @@ void StepTransport(const CellView& c, const int32_t* row_m1) {
   UpdateAverages(c);
   std::vector<User> users = SelectUsers(c, -1);
   if (users.empty()) return;
+  const std::vector<int> slice_prio = SlicePriority(c, users);
 
   /* RBsAllocation, transport.cpp:453-675 */
   int nb_rbs = cfg->n_rbs;
@@ -475,7 +533,7 @@ void StepTransport(const CellView& c, const int32_t* row_m1) {
   std::vector<std::vector<double>> metrics(G, std::vector<double>(n));
   for (int i = 0; i < G; ++i)
     for (size_t j = 0; j < n; ++j)
-      metrics[i][j] = TransportMetric(cfg, users[j], c.avg[users[j].id], users[j].eff[i * rbg_size]);
+      metrics[i][j] = TransportMetric(c, users[j], slice_prio, users[j].eff[i * rbg_size]);
 
   std::vector<std::vector<int>> user_index(G, std::vector<int>(S, -1));   /* :543-567 */
   std::vector<std::vector<double>> se(G, std::vector<double>(S, 0));
@@ -560,8 +618,7 @@ double AssignRbsGivenMcs(const CellView& c, const std::vector<User>& users, cons
       if (assigned_mcs[index] <= cqi) {
         double sEff = EffFromCqi(assigned_mcs[index]);
         /* UserToSchedule::GetAverageTransmissionRate, ps.cpp:423-433: 1 + sum of the bearers' rates */
-        double sum_rate = 1;
-        sum_rate += c.avg[users[index].id];
+        double sum_rate = RateSum(c, users[index]);
         metric = sEff * 180000 / sum_rate;
       }
       if (highest_metric < metric) {
@@ -625,7 +682,8 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   std::vector<bool> with_queue(S, false);
   for (int u = 0; u < cfg->n_ues; ++u) {
     if (c.active && !c.active[u]) continue;
-    if ((c.queue ? c.queue[u] : cfg->data_to_transmit) > 0) with_queue[cfg->ue_to_slice[u]] = true;
+    const bool queued = c.nb == 2 ? (c.queue[2 * u] > 0 || c.queue[2 * u + 1] > 0) : ((c.queue ? c.queue[u] : cfg->data_to_transmit) > 0);
+    if (queued) with_queue[cfg->ue_to_slice[u]] = true;
   }
   for (int i = 0; i < S; ++i) {
     if (!with_queue[i]) continue;
@@ -650,6 +708,7 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   UpdateAverages(c);
   std::vector<User> users = SelectUsers(c, slice_id);
   if (users.empty()) return;
+  const std::vector<int> slice_prio = SlicePriority(c, users);
 
   if (cfg->algo == 11) {
     AllocateNonGreedy(c, users, c.rand2);
@@ -666,7 +725,7 @@ void StepNvs(const CellView& c, const int32_t* row_m1) {
   std::vector<std::vector<double>> metrics(G, std::vector<double>(n));
   for (int i = 0; i < G; ++i)
     for (size_t j = 0; j < n; ++j)
-      metrics[i][j] = TransportMetric(cfg, users[j], c.avg[users[j].id], users[j].eff[i * rbg_size], true);
+      metrics[i][j] = TransportMetric(c, users[j], slice_prio, users[j].eff[i * rbg_size], true);
   for (int i = 0; i < G; ++i) {
     double target_metric = std::numeric_limits<double>::lowest();
     int pick = -1;
@@ -744,10 +803,12 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   const size_t cqi_stride = (size_t)U * (cfg->cqi_per_rb ? cfg->n_rbs : G);
   CellView c;
   c.cfg = cfg;
-  c.avg = io->avg_rate + (size_t)b * U;
-  c.tx = io->tx_bytes + (size_t)b * U;
-  c.cum_bytes = io->cum_bytes + (size_t)b * U;
-  c.cum_rbs = io->cum_rbs + (size_t)b * U;
+  const int nb = cfg->n_bearers == 2 ? 2 : 1;
+  c.nb = nb;
+  c.avg = io->avg_rate + (size_t)b * U * nb;
+  c.tx = io->tx_bytes + (size_t)b * U * nb;
+  c.cum_bytes = io->cum_bytes + (size_t)b * U * nb;
+  c.cum_rbs = io->cum_rbs + (size_t)b * U * nb;
   c.offset = io->slice_offset ? io->slice_offset + (size_t)b * S : nullptr;
   c.ewma = io->nvs_ewma ? io->nvs_ewma + (size_t)b * S : nullptr;
   c.cqi = io->cqi + (size_t)b * cqi_stride;
@@ -764,8 +825,8 @@ void StepCell(const rso_config* cfg, rso_io* io, int b, const int32_t* row_m1) {
   c.alloc_n = io->alloc_n ? io->alloc_n + b : nullptr;
   c.alloc_ue = (io->alloc_ue && io->alloc_rbg) ? io->alloc_ue + (size_t)b * 2 * G : nullptr;
   c.alloc_rbg = (io->alloc_ue && io->alloc_rbg) ? io->alloc_rbg + (size_t)b * 2 * G : nullptr;
-  c.queue = io->queue_bytes ? io->queue_bytes + (size_t)b * U : nullptr;
-  c.hol = io->hol_delay ? io->hol_delay + (size_t)b * U : nullptr;
+  c.queue = io->queue_bytes ? io->queue_bytes + (size_t)b * U * nb : nullptr;
+  c.hol = io->hol_delay ? io->hol_delay + (size_t)b * U * nb : nullptr;
   ClearOutputs(c);
   switch (cfg->algo) {
     case 1: StepPf(c, row_m1); break;
@@ -866,6 +927,7 @@ int rso_step(const rso_config* cfg, int32_t n_cells, rso_io* io, int32_t n_threa
   if (transport && (!io->rand2 || !io->slice_offset)) return 3;
   if ((cfg->algo == 7 || cfg->algo == 11) && !io->nvs_ewma) return 3;
   if (cfg->algo == 11 && (!io->rand2 || io->rand_stride < 300)) return 3;
+  if (cfg->n_bearers == 2 && (cfg->algo == 1 || !io->queue_bytes)) return 4;   /* id 1 schedules flows: one user per bearer */
   int32_t row_m1[27];
   if (cfg->tbs_row_m1) std::memcpy(row_m1, cfg->tbs_row_m1, sizeof(row_m1));
   else DefaultRowM1(row_m1);

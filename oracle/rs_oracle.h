@@ -31,6 +31,9 @@ typedef struct rso_config {
   int32_t data_to_transmit; /* 100000000 for infinite buffer (transport.cpp:123-125) */
   int32_t dead_work;        /* 1: also do the reference's wideband-CQI EESM per user
                                (packet-scheduler.cpp:321-334); results never change */
+  int32_t n_bearers;        /* bearers per UE: 0 / 1 = one; 2 = MAX_BEARERS (packet-scheduler.h:31): slot i of a UE = its bearer
+                               of priority i; avg_rate / tx_bytes / cum_* / queue_bytes / hol_delay are then [B][U][2] */
+  int32_t reserved;
   const double* weight;     /* [S] slice_weights_ */
   const int32_t* params;    /* [S][4] alpha,beta,epsilon,psi */
   const int32_t* ue_to_slice; /* [U] user_to_slice_ */

@@ -86,7 +86,8 @@ def test_trace_replay_batch_equals_python_mirror(algo, tmp_path):
     B, T, seed = 29, 90, 9
     path = _config(tmp_path, [(4, 0.25, (0, 0, 1, 1))], [3, 5, 2, 4])
     got = _run("--algo", algo, "--config", path, "--cells", B, "--ttis", T, "--seed", seed,
-               "--traces", tdir, "--mapping", tmp_path / "mapping.config", "--trace-rows", n_rows)
+               "--traces", tdir, "--mapping", tmp_path / "mapping.config", "--trace-rows", n_rows,
+               "--log-cell", 5, "--log-prefix", tmp_path / "cell5")
     assert got["cqi"] == "trace replay"
     w, p, u2s = sched.load_slice_config(path)
     S, U = len(w), len(u2s)
@@ -99,12 +100,30 @@ def test_trace_replay_batch_equals_python_mirror(algo, tmp_path):
     g.set_traces(traces, ue_trace)
     now, dts = workload.tti_clock(T)
     tr = sched.trace_rows_for_run(now, 0, n_rows=n_rows)
-    g.run_traces_host(tr, workload.synth_rand2(seed, 0, B, 0, T, S), dts, ttis_per_launch=16)
+    res = g.run_traces_host(tr, workload.synth_rand2(seed, 0, B, 0, T, S), dts, want_aux=True, ttis_per_launch=16)
     st = g.get_stats()
     assert got["slice_bytes"] == [int(x) for x in st[0]]
     assert got["slice_rbs"] == [int(x) for x in st[1]]
     assert int(st[0].sum()) > 0
+    # the reference's log text of cell 5 in replay mode (the flag used to be accepted and ignored): the
+    # runner rebuilds the cell's CQI rows from the traces; here they come from the same arrays
+    lw = sched.LogWriter(algo, u2s, S, cqi_per_rb=2)
+    for t in range(T):
+        rows_t = np.stack([traces[ue_trace[5, u], tr[t], ::8] if tr[t] >= 0 else np.full(64, 10, np.uint8) for u in range(U)])
+        lw.tti(100 + t, sched.pack_cqi(rows_t), res["rbg_to_ue"][t, 5], res["tbs_bits"][t, 5], res["final_cqi"][t, 5],
+               res["slice_target"][t, 5] if algo == 9 else None, res["slice_quota"][t, 5] if algo == 9 else None)
+    assert (tmp_path / "cell5.stdout").read_text() == lw.stdout
+    assert (tmp_path / "cell5.stderr").read_text() == lw.stderr
+    assert lw.stderr.count("\n") > T
     g.close()
+
+
+def test_mapping_with_a_bad_trace_id_is_refused(tmp_path):
+    path = _config(tmp_path, [(2, 0.5, (0, 0, 1, 1))], [2, 2])
+    (tmp_path / "mapping.config").write_text("0 -3\n1 2\n")
+    r = subprocess.run([BIN, "--algo", "9", "--config", path, "--cells", "4", "--ttis", "2", "--traces", str(tmp_path),
+                        "--mapping", str(tmp_path / "mapping.config")], capture_output=True, text=True)
+    assert r.returncode == 1 and "trace id -3" in r.stderr
 
 
 def test_errors_are_loud(tmp_path):

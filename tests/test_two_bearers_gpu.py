@@ -122,3 +122,39 @@ def test_two_bearers_need_queues_and_refuse_flow_level_ids():
     with pytest.raises(sched.RsError, match="rs_set_queues"):
         g.step(workload.synth_cqi(1, 0, 1, 0, 1, U, 64)[0], np.zeros((1, 2), np.int32))
     g.close()
+
+
+@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103, 11])
+def test_two_bearers_random_cells_against_the_oracle(algo):
+    """Beyond the reference's records: random slice parameters, queues and delays, two bearers per UE, 30 TTIs of 12
+    cells, CUDA against the oracle (outputs every TTI, the per-bearer state at the end)."""
+    from oracle.pyoracle import OracleScheduler
+    rng = np.random.default_rng(2000 + algo)
+    S, B, T = 7, 12, 30
+    ues = rng.integers(1, 7, S)
+    u2s = np.repeat(np.arange(S), ues).astype(np.int32)
+    U, G = len(u2s), 64
+    w = rng.dirichlet(np.ones(S))
+    p = np.zeros((S, 4), dtype=np.int32)
+    p[:, 0] = rng.integers(0, 2, S)
+    p[:, 1] = rng.integers(0, 2, S)
+    p[:, 2] = rng.choice([0, 1, 1, 2], S)
+    p[:, 3] = rng.integers(0, 2, S)
+    g = sched.Scheduler(algo, w, p, u2s, B, n_bearers=2)
+    o = OracleScheduler(algo, w, p, u2s, B, n_bearers=2, n_threads=4)
+    _, dts = workload.tti_clock(T)
+    for t in range(T):
+        cqi = workload.synth_cqi(algo, 0, B, t, 1, U, G)[0]
+        draws = workload.synth_rand_draws(algo, 0, B, t, 1, S, max(g.rand_stride, 2))[0]
+        kind = rng.random((B, U, 2))
+        queue = np.where(kind < 0.35, 0, np.where(kind < 0.8, rng.integers(20, 5000, (B, U, 2)), 100000000)).astype(np.int32)
+        hol = np.where(rng.random((B, U, 2)) < 0.1, 0.0, rng.random((B, U, 2)) * 0.05)
+        act = (rng.random((B, U)) < 0.9).astype(np.uint8)
+        a = o.step(cqi, draws, dt=float(dts[t]), active=act, want_aux=True, queue=queue, hol=hol)
+        b = g.step(cqi, draws, dt=float(dts[t]), active=act, want_aux=True, queue=queue, hol=hol)
+        for k in b:
+            assert np.array_equal(a[k], b[k]), (t, k)
+    sa, sb = o.get_state(), g.get_state()
+    for k in ("avg_rate", "tx_bytes", "cum_bytes", "cum_rbs"):
+        assert np.array_equal(sa[k], sb[k]), k
+    g.close()
