@@ -701,7 +701,8 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e))); }
   h->stream = h->own_stream;
   /* two half-batches once each half still fills the GPU (RS_NO_SPLIT=1: one launch per step of TTIs, as in round 1) */
-  h->parts = (n_cells >= 2 * 148 * (h->wide ? RS_WIDE_MIN_BLOCKS : 8) && !getenv("RS_NO_SPLIT")) ? 2 : 1;
+  { const int resident = std::max(1, std::min(h->wide ? RS_WIDE_MIN_BLOCKS : 8, (227 * 1024) / (h->layout.total + 1024)));
+    h->parts = (n_cells >= 2 * 148 * resident && !getenv("RS_NO_SPLIT")) ? 2 : 1; }
   BAIL(upload(h->ue_to_slice, u2s));
   BAIL(upload(h->slice_ptr, ptr));
   BAIL(upload(h->slice_ues, ues));
