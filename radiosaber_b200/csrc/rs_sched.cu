@@ -222,10 +222,12 @@ struct rs_handle {
   rs::Layout layout{};
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
-  /* Big batches run as two half-batches on two streams: each half's launches are chained on its own stream, so the
-   * partial last wave of one half's launch is filled by CTAs of the other half's next launch instead of leaving SMs
+  /* Big batches run as up to four part-batches on as many streams: each part's launches are chained on its own stream,
+   * so the partial last wave of one part's launch is filled by CTAs of another part's launch instead of leaving SMs
    * idle until the grid drains (4096 cells = 3.46 waves of 1184 resident cells: +5-10 %, profiles/README.md). */
-  cudaStream_t stream2 = nullptr;
+  static constexpr int kMaxParts = 4;
+  cudaStream_t xs[kMaxParts - 1] = {};    /* streams of parts 1.. (part 0 runs on `stream`) */
+  cudaEvent_t join_evs[kMaxParts - 1] = {};
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   int parts = 1;
   int64_t launches = 0;
@@ -264,7 +266,8 @@ struct rs_handle {
     DevBuf<short> rbg_to_ue, alloc_ue, alloc_rbg;
     DevBuf<int> alloc_n, queue;
     DevBuf<double> hol;
-    cudaEvent_t in_done = nullptr, k_done = nullptr, k_done2 = nullptr, out_done = nullptr;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    cudaEvent_t k_done_x[3] = {};   /* kernel-done events of parts 1.. */
     bool k_rec = false, out_rec = false;   /* the events have been recorded at least once */
   } slot[kSlots];
   uint64_t chunk_seq = 0;
@@ -272,7 +275,7 @@ struct rs_handle {
    * before last must be done before it is overwritten */
   struct Slab {
     DevBuf<uint8_t> cqi;
-    cudaEvent_t used = nullptr, used2 = nullptr;   /* recorded after the last kernel (of each half) that read the slab */
+    cudaEvent_t used = nullptr, used_x[3] = {};   /* recorded after the last kernel (of each part) that read the slab */
     bool used_rec = false;
     int index = -1;               /* slab of the CURRENT call resident here */
   } slab[2];
@@ -335,16 +338,16 @@ const void* fixed_kernel(int algo, int which, bool trace) {
   return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<8, false, false, FixedNib>;
 }
 
-/* part < 0: the whole batch on the handle's stream; part 0 / 1: the first / second half on stream / stream2 */
+/* part < 0: the whole batch on the handle's stream; part p of h->parts: cells [p B / P, (p + 1) B / P) on stream / xs[p-1] */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a0, bool trace, const rs::DevCfg* cfg = nullptr, int part = -1) {
   rs::RunArgs a = a0;
   int n = h->B;
   cudaStream_t st = h->stream;
   if (part >= 0) {
-    const int half = (h->B + 1) / 2;
-    a.cell_off = part == 0 ? 0 : half;
-    n = part == 0 ? half : h->B - half;
-    if (part == 1) st = h->stream2;
+    const long long lo = (long long)h->B * part / h->parts, hi = (long long)h->B * (part + 1) / h->parts;
+    a.cell_off = (int)lo;
+    n = (int)(hi - lo);
+    if (part > 0) st = h->xs[part - 1];
     if (n <= 0) return RS_OK;
   }
   const dim3 grid(n), block(h->wide ? rsw::kThreads : rs::kThreads);
@@ -421,7 +424,7 @@ int alloc_slot(rs_handle* h, rs_handle::Slot& s, int T, const rs_outputs* out, b
   if (!s.in_done) {
     CU(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s.k_done2, cudaEventDisableTiming));
+    for (auto& e : s.k_done_x) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
   }
   return RS_OK;
@@ -449,7 +452,7 @@ void rs_destroy(rs_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->stream2) cudaStreamSynchronize(h->stream2);
+  for (auto st : h->xs) if (st) cudaStreamSynchronize(st);
   if (h->copy_in) cudaStreamSynchronize(h->copy_in);
   if (h->copy_out) cudaStreamSynchronize(h->copy_out);
   h->ue_to_slice.release(); h->slice_ptr.release(); h->slice_ues.release(); h->chunk_slice.release();
@@ -463,13 +466,14 @@ void rs_destroy(rs_handle* h) {
     s.queue.release(); s.hol.release();
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.k_done) cudaEventDestroy(s.k_done);
-    if (s.k_done2) cudaEventDestroy(s.k_done2);
+    for (auto e : s.k_done_x) if (e) cudaEventDestroy(e);
     if (s.out_done) cudaEventDestroy(s.out_done);
   }
-  for (auto& sl : h->slab) { sl.cqi.release(); if (sl.used) cudaEventDestroy(sl.used); if (sl.used2) cudaEventDestroy(sl.used2); }
+  for (auto& sl : h->slab) { sl.cqi.release(); if (sl.used) cudaEventDestroy(sl.used); for (auto e : sl.used_x) if (e) cudaEventDestroy(e); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->join_ev) cudaEventDestroy(h->join_ev);
-  if (h->stream2) cudaStreamDestroy(h->stream2);
+  for (auto e : h->join_evs) if (e) cudaEventDestroy(e);
+  for (auto st : h->xs) if (st) cudaStreamDestroy(st);
   for (auto& e : h->call_done) if (e) cudaEventDestroy(e);
   if (h->mb_host) cudaFreeHost(h->mb_host);
   h->mb_dev.release();
@@ -695,14 +699,18 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    for (auto& st : h->xs) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (auto& ev : h->join_evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e))); }
   h->stream = h->own_stream;
   /* two half-batches once each half still fills the GPU (RS_NO_SPLIT=1: one launch per step of TTIs, as in round 1) */
+  /* parts: as many as leave every part at least one full GPU of resident cells, at most RS_PARTS (default 4) */
   { const int resident = std::max(1, std::min(h->wide ? RS_WIDE_MIN_BLOCKS : 8, (227 * 1024) / (h->layout.total + 1024)));
-    h->parts = (n_cells >= 2 * 148 * resident && !getenv("RS_NO_SPLIT")) ? 2 : 1; }
+    h->parts = std::max(1, std::min(rs_handle::kMaxParts, n_cells / (148 * resident)));
+    if (const char* e = getenv("RS_PARTS")) h->parts = std::max(1, std::min({rs_handle::kMaxParts, atoi(e), n_cells}));   /* experiments */
+    if (getenv("RS_NO_SPLIT")) h->parts = 1; }
   BAIL(upload(h->ue_to_slice, u2s));
   BAIL(upload(h->slice_ptr, ptr));
   BAIL(upload(h->slice_ues, ues));
@@ -761,7 +769,7 @@ int rs_sync(rs_handle* h) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->copy_in));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaStreamSynchronize(h->stream2));
+  for (auto st : h->xs) CU(cudaStreamSynchronize(st));
   CU(cudaStreamSynchronize(h->copy_out));
   return RS_OK;
 }
@@ -829,7 +837,7 @@ namespace {
 void drain(rs_handle* h) {
   cudaStreamSynchronize(h->copy_in);
   cudaStreamSynchronize(h->stream);
-  cudaStreamSynchronize(h->stream2);
+  for (auto st : h->xs) cudaStreamSynchronize(st);
   cudaStreamSynchronize(h->copy_out);
 }
 #define CU_DRAIN(call)                                                                             \
@@ -883,10 +891,11 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
   const size_t B = h->B, U = h->d.U;
   /* more than one launch in this call and a big batch: the two halves of the batch go down two streams (forked
    * here, joined at the end of the call), so the tail of one launch overlaps the head of the next */
-  const bool split = h->parts == 2 && n_ttis > ttis_per_launch;
+  const bool split = h->parts > 1 && n_ttis > ttis_per_launch;
+  const int P = split ? h->parts : 1;
   if (split) {
     CU(cudaEventRecord(h->fork_ev, h->stream));
-    CU(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+    for (int q = 1; q < P; ++q) CU(cudaStreamWaitEvent(h->xs[q - 1], h->fork_ev, 0));
   }
   for (int t0 = 0; t0 < n_ttis; t0 += ttis_per_launch) {
     rs::RunArgs a{};
@@ -904,12 +913,12 @@ int run_device_impl(rs_handle* h, int32_t n_ttis, const uint8_t* d_cqi, int64_t 
     a.stage = h->stage_ok && (trace_row || ((((uintptr_t)d_cqi) & 15) == 0 && (cqi_tti_stride & 15) == 0)) ? 1 : 0;
     point_outputs(h, &a, d_out, (size_t)t0);
     int rc = launch_ttis(h, a, trace_row != nullptr, nullptr, split ? 0 : -1);
-    if (rc == RS_OK && split) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, 1);
-    if (rc != RS_OK) { if (split) cudaStreamSynchronize(h->stream2); return rc; }
+    for (int q = 1; q < P && rc == RS_OK; ++q) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, q);
+    if (rc != RS_OK) { for (auto st : h->xs) cudaStreamSynchronize(st); return rc; }
   }
-  if (split) {
-    CU(cudaEventRecord(h->join_ev, h->stream2));
-    CU(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+  for (int q = 1; q < P; ++q) {
+    CU(cudaEventRecord(h->join_evs[q - 1], h->xs[q - 1]));
+    CU(cudaStreamWaitEvent(h->stream, h->join_evs[q - 1], 0));
   }
   return RS_OK;
 }
@@ -939,10 +948,11 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
   const int TC = std::max(1, std::min(std::min<int>(ttis_per_launch, rs::kMaxTtisPerLaunch), n_ttis));
   const size_t B = h->B, U = h->d.U, S = h->d.S, G = h->d.G, C = h->cqi_cols;
   const bool slabs = !trace_row && cqi_refresh > 1;   /* consecutive chunks share a CQI slab */
-  const bool split = h->parts == 2;
-  if (split) {   /* stream2 joins whatever the caller's stream has seen so far (state uploads, earlier device calls) */
+  const bool split = h->parts > 1;
+  const int P = h->parts;
+  if (split) {   /* the extra streams join whatever the caller's stream has seen so far (state uploads, earlier device calls) */
     CU(cudaEventRecord(h->fork_ev, h->stream));
-    CU(cudaStreamWaitEvent(h->stream2, h->fork_ev, 0));
+    for (int q = 1; q < P; ++q) CU(cudaStreamWaitEvent(h->xs[q - 1], h->fork_ev, 0));
   }
   for (auto& s : h->slot) {
     const int rc = alloc_slot(h, s, TC, out, active != nullptr, !trace_row && !slabs, queue != nullptr, hol != nullptr);
@@ -952,7 +962,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     for (auto& sl : h->slab) {
       CU_DRAIN(sl.cqi.alloc(B * U * C));
       if (!sl.used) CU_DRAIN(cudaEventCreateWithFlags(&sl.used, cudaEventDisableTiming));
-      if (!sl.used2) CU_DRAIN(cudaEventCreateWithFlags(&sl.used2, cudaEventDisableTiming));
+      for (auto& e : sl.used_x) if (!e) CU_DRAIN(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       sl.index = -1;   /* slab numbers are relative to this call's cqi pointer */
     }
   for (auto& e : h->call_done)
@@ -967,7 +977,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     /* inputs: the slot's previous kernel must be done with them */
     if (s.k_rec) {
       CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done, 0));
-      if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done2, 0));
+      for (int q = 1; q < P; ++q) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, s.k_done_x[q - 1], 0));
     }
     const uint8_t* d_cqi = nullptr;
     rs_handle::Slab* sl = nullptr;
@@ -978,7 +988,7 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
         next_slab_buf ^= 1;
         if (sl->used_rec) {
           CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used, 0));
-          if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used2, 0));
+          for (int q = 1; q < P; ++q) CU_DRAIN(cudaStreamWaitEvent(h->copy_in, sl->used_x[q - 1], 0));
         }
         CU_DRAIN(cudaMemcpyAsync(sl->cqi.p, cqi + (size_t)slab0 * B * U * C, B * U * C, cudaMemcpyHostToDevice, h->copy_in));
         sl->index = slab0;
@@ -998,9 +1008,9 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
      * chained on its own stream from chunk to chunk (the copies wait for both) */
     CU_DRAIN(cudaStreamWaitEvent(h->stream, s.in_done, 0));
     if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->stream, s.out_done, 0));
-    if (split) {
-      CU_DRAIN(cudaStreamWaitEvent(h->stream2, s.in_done, 0));
-      if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->stream2, s.out_done, 0));
+    for (int q = 1; q < P; ++q) {
+      CU_DRAIN(cudaStreamWaitEvent(h->xs[q - 1], s.in_done, 0));
+      if (s.out_rec) CU_DRAIN(cudaStreamWaitEvent(h->xs[q - 1], s.out_done, 0));
     }
     rs::RunArgs a{};
     a.T = T;
@@ -1027,19 +1037,19 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
       point_outputs(h, &a, &so, 0);
     }
     int rc = launch_ttis(h, a, trace_row != nullptr, nullptr, split ? 0 : -1);
-    if (rc == RS_OK && split) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, 1);
+    for (int q = 1; q < P && rc == RS_OK; ++q) rc = launch_ttis(h, a, trace_row != nullptr, nullptr, q);
     if (rc != RS_OK) { drain(h); return rc; }
     CU_DRAIN(cudaEventRecord(s.k_done, h->stream));
-    if (split) CU_DRAIN(cudaEventRecord(s.k_done2, h->stream2));
+    for (int q = 1; q < P; ++q) CU_DRAIN(cudaEventRecord(s.k_done_x[q - 1], h->xs[q - 1]));
     s.k_rec = true;
     if (sl) {
       CU_DRAIN(cudaEventRecord(sl->used, h->stream));
-      if (split) CU_DRAIN(cudaEventRecord(sl->used2, h->stream2));
+      for (int q = 1; q < P; ++q) CU_DRAIN(cudaEventRecord(sl->used_x[q - 1], h->xs[q - 1]));
       sl->used_rec = true;
     }
     /* outputs */
     CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done, 0));
-    if (split) CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done2, 0));
+    for (int q = 1; q < P; ++q) CU_DRAIN(cudaStreamWaitEvent(h->copy_out, s.k_done_x[q - 1], 0));
     if (out) {
       if (a.rbg_to_ue) CU_DRAIN(cudaMemcpyAsync(out->rbg_to_ue + (size_t)t0 * B * G, s.rbg_to_ue.p, (size_t)T * B * G * 2, cudaMemcpyDeviceToHost, h->copy_out));
       if (a.tbs_bits) CU_DRAIN(cudaMemcpyAsync(out->tbs_bits + (size_t)t0 * B * U, s.tbs_bits.p, (size_t)T * B * U * 4, cudaMemcpyDeviceToHost, h->copy_out));
@@ -1056,9 +1066,9 @@ int run_host_impl(rs_handle* h, int32_t n_ttis, const uint8_t* cqi, int32_t cqi_
     s.out_rec = true;
     h->chunk_seq++;
   }
-  if (split) {   /* the handle's stream is behind the second half's kernels again (rs_get_state, the next device call) */
-    CU_DRAIN(cudaEventRecord(h->join_ev, h->stream2));
-    CU_DRAIN(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+  for (int q = 1; q < P; ++q) {   /* the handle's stream is behind every part's kernels again (rs_get_state, the next device call) */
+    CU_DRAIN(cudaEventRecord(h->join_evs[q - 1], h->xs[q - 1]));
+    CU_DRAIN(cudaStreamWaitEvent(h->stream, h->join_evs[q - 1], 0));
   }
   /* copy_out is behind every kernel of the call (it waited on each k_done), and every kernel is behind its inputs */
   const int64_t tk = h->calls++;

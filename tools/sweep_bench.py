@@ -25,7 +25,7 @@ from radiosaber_b200 import sched, workload  # noqa: E402
 G = 64
 
 
-def measure(algo, w, p, u2s, B, ttis, launches, label, warm=14):
+def measure(algo, w, p, u2s, B, ttis, launches, label, warm=5, per_launch=16):
     import torch
     dev = torch.device("cuda", 0)
     S, U = len(w), len(u2s)
@@ -44,7 +44,7 @@ def measure(algo, w, p, u2s, B, ttis, launches, label, warm=14):
 
     def step(k):
         g.run_device(ttis, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts[k * ttis:(k + 1) * ttis], outs,
-                     ttis_per_launch=ttis)
+                     ttis_per_launch=per_launch)
 
     for k in range(warm):     # past the start-up transient (all bearers begin at the same average rate): steady state
         step(k)
@@ -60,7 +60,7 @@ def measure(algo, w, p, u2s, B, ttis, launches, label, warm=14):
     value = B * ttis * launches / (ms * 1e-3)
     rbg = d_rbg.cpu().numpy()
     line = {"label": label, "scheduler_id": algo, "slices": S, "ues_per_slice": U // S, "ues": U, "cells": B,
-            "ttis_per_launch": ttis, "launches": launches, "warmup_ttis": ttis * warm, "cell_ttis_per_s": value, "ue_ttis_per_s": value * U,
+            "ttis_per_call": ttis, "ttis_per_launch": per_launch, "calls": launches, "warmup_ttis": ttis * warm, "cell_ttis_per_s": value, "ue_ttis_per_s": value * U,
             "smem_bytes_per_cta": g.smem_bytes, "algorithmic_bytes_per_cell_tti": alg,
             "algorithmic_GBps": value * alg / 1e9, "rbgs_allocated_frac": float((rbg >= 0).mean())}
     g.close()
@@ -72,8 +72,8 @@ def measure(algo, w, p, u2s, B, ttis, launches, label, warm=14):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
-    ap.add_argument("--ttis", type=int, default=16)
-    ap.add_argument("--launches", type=int, default=6)
+    ap.add_argument("--ttis", type=int, default=48, help="TTIs per call (three 16-TTI launches: part-batches overlap inside a call)")
+    ap.add_argument("--launches", type=int, default=3, help="timed calls")
     ap.add_argument("--only", default=None, choices=[None, "ids", "sweep"])
     ap.add_argument("--points", default=None, help='sweep points "S,n;S,n;..." instead of the full grid')
     ap.add_argument("--ids", default=None, help='scheduler ids "9,8,..." instead of all')
