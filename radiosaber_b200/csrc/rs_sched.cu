@@ -706,9 +706,9 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e))); }
   h->stream = h->own_stream;
   /* two half-batches once each half still fills the GPU (RS_NO_SPLIT=1: one launch per step of TTIs, as in round 1) */
-  /* parts: as many as leave every part at least one full GPU of resident cells, at most RS_PARTS (default 4) */
+  /* two part-batches once each still fills the GPU's resident cells; RS_PARTS = 1..4 for experiments */
   { const int resident = std::max(1, std::min(h->wide ? RS_WIDE_MIN_BLOCKS : 8, (227 * 1024) / (h->layout.total + 1024)));
-    h->parts = std::max(1, std::min(rs_handle::kMaxParts, n_cells / (148 * resident)));
+    h->parts = n_cells >= 2 * 148 * resident ? 2 : 1;   /* measured: 1 part 17.9 M, 2 parts 20.3 M, 3 and 4 parts 20.3 M */
     if (const char* e = getenv("RS_PARTS")) h->parts = std::max(1, std::min({rs_handle::kMaxParts, atoi(e), n_cells}));   /* experiments */
     if (getenv("RS_NO_SPLIT")) h->parts = 1; }
   BAIL(upload(h->ue_to_slice, u2s));
