@@ -933,8 +933,9 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  *                                                    if (e2 == -1 || e > e2) e2 = e;
  * i.e. e1 / first = the first maximum, and e2 = the largest element that was NOT a new strict maximum when it was
  * visited (a displaced maximum is not demoted).  Efficiency is strictly increasing in the CQI, so a line is scanned on
- * its 4-bit CQI keys by one warp: an inclusive prefix maximum marks the "records", the last record is (e1, first), a
- * redux.max over the non-records is e2.
+ * its 4-bit CQI keys by one warp, two keys per lane, with redux.max and ballots only: the first maximum is (e1, first);
+ * everything behind it is a non-record; in front of it the largest key is a non-record iff it occurs twice, else the
+ * search repeats in front of that key (vogel_scan_line).
  *
  * Gaps.  e1 - e2 is one of 16 x 17 doubles (e2 = -1 when there is no second); the host subtracts them and hands down
  * their dense ranks and, for every possible running maximum, the rank of the largest gap not above its truncation
@@ -958,39 +959,50 @@ struct VogelBufs {
 __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& v, int buf, int S, int G, int q, int lane,
                                                 int ha, int qa, int hb, int qb, unsigned long long free_m) {
   const bool is_row = q < G;
-  const int n = is_row ? S : G;
-  int run = -1, k1 = -1, first = -1, k2 = -1;
+  const int n = is_row ? S : G;   /* <= 64: two keys per lane */
+  int k1 = -1, first = -1, k2 = -1;
   bool live;
   if (is_row) live = ((free_m >> q) & 1ull) != 0;
   else {
     const int s = q - G;
     live = __shfl_sync(kFull, s < 32 ? (ha < qa) : (hb < qb), s & 31);
   }
-  if (live)
-    for (int h0 = 0; h0 < n; h0 += 32) {
-      const int i = h0 + lane;
-      bool ok = i < n;
-      if (ok) ok = is_row ? (h0 == 0 ? ha < qa : hb < qb) : (((free_m >> i) & 1ull) != 0);
-      const int key = ok ? (int)((is_row ? c.sb.a[q * S + i] : c.sb.a[i * S + (q - G)]) >> 12) : -1;
-      int inc = key;
+  if (live) {
+    int key[2];
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        const int t = __shfl_up_sync(kFull, inc, dd);
-        if (lane >= dd) inc = max(inc, t);
-      }
-      int exc = __shfl_up_sync(kFull, inc, 1);
-      if (lane == 0) exc = -1;
-      exc = max(exc, run);
-      const bool rec = ok && key > exc;
-      const unsigned recm = __ballot_sync(kFull, rec);
-      if (recm) {
-        const int last = 31 - __clz(recm);
-        k1 = __shfl_sync(kFull, key, last);
-        first = h0 + last;
-      }
-      k2 = max(k2, __reduce_max_sync(kFull, (ok && !rec) ? key : -1));
-      run = max(run, __shfl_sync(kFull, inc, 31));
+    for (int h = 0; h < 2; ++h) {
+      const int i = 32 * h + lane;
+      bool ok = i < n;
+      if (ok) ok = is_row ? (h == 0 ? ha < qa : hb < qb) : (((free_m >> i) & 1ull) != 0);
+      key[h] = ok ? (int)((is_row ? c.sb.a[q * S + i] : c.sb.a[i * S + (q - G)]) >> 12) : -1;
     }
+    /* e1 / first: the first maximum (the last "record" of the reference's scan) */
+    const int M = __reduce_max_sync(kFull, max(key[0], key[1]));
+    if (M >= 0) {
+      const unsigned b0 = __ballot_sync(kFull, key[0] == M), b1 = __ballot_sync(kFull, key[1] == M);
+      const int m = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+      k1 = M;
+      first = m;
+      /* e2 = the largest NON-record.  Everything behind the first maximum is one ... */
+      int e2 = __reduce_max_sync(kFull, max(lane > m ? key[0] : -1, 32 + lane > m ? key[1] : -1));
+      /* ... and in front of it: M1 = the largest key before `end`; if it occurs twice its second occurrence is a
+       * non-record (and nothing in front can be larger); if once, it is a record, everything between it and `end` is a
+       * non-record, and the search goes on in front of it.  Keys fall strictly from one trip to the next. */
+      int end = m;
+      while (true) {
+        const int c0 = lane < end ? key[0] : -1, c1 = 32 + lane < end ? key[1] : -1;
+        const int M1 = __reduce_max_sync(kFull, max(c0, c1));
+        if (M1 <= e2) break;   /* nothing in front of `end` can raise e2 (also: nothing valid there) */
+        const unsigned e0 = __ballot_sync(kFull, c0 == M1), e1 = __ballot_sync(kFull, c1 == M1);
+        if (__popc(e0) + __popc(e1) >= 2) { e2 = M1; break; }
+        const int m1 = e0 ? __ffs(e0) - 1 : 32 + __ffs(e1) - 1;
+        e2 = max(e2, __reduce_max_sync(kFull, max((lane > m1 && lane < end) ? key[0] : -1,
+                                                   (32 + lane > m1 && 32 + lane < end) ? key[1] : -1)));
+        end = m1;
+      }
+      k2 = e2;
+    }
+  }
   if (lane == 0) {
     v.rk[buf * v.n + q] = k1 < 0 ? (short)0 : v.rank_of[k1 * 17 + k2 + 1];
     v.pick[buf * v.n + q] = (short)first;
@@ -1019,27 +1031,33 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
   for (int round = 0; round < G; ++round) {
     const int cur = round & 1, nxt = cur ^ 1;
     /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int that is
-     * set to the (truncated) gap whenever a candidate is taken.  max_diff is therefore always the truncated largest gap
-     * seen so far (-1 before the first), so q is taken iff gap_q > trunc(max of the gaps before q) and the grant is the
-     * LAST candidate taken: a prefix maximum per 32 candidates, on the gaps' ranks. */
-    int run = -1, win = -1;
-    for (int q0 = 0; q0 < v.n; q0 += 32) {
-      const int q = q0 + lane;
-      const bool valid = q < v.n && v.pick[cur * v.n + q] >= 0;   /* allocated RBGs / slices at their quota are skipped */
-      const int rkq = valid ? (int)v.rk[cur * v.n + q] : -1;
-      int incl = rkq;
+     * set to the (truncated) gap whenever a candidate is taken; the grant is the LAST candidate taken.  max_diff is
+     * always the truncated largest gap seen so far, so q is taken iff rank_q > thr[largest rank before q].  Let M be the
+     * largest rank and m its first position: thr[x] <= x < M for every x seen before m, so m itself is always taken,
+     * and behind m the running maximum is M: the grant is the last q > m with rank_q > thr[M], else m.  No scan. */
+    int rkq[4], best = -1;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl = max(incl, up);
+    for (int j = 0; j < 4; ++j) {   /* n = G + S <= 128 candidates, four per lane */
+      const int q = 32 * j + lane;
+      rkq[j] = (q < v.n && v.pick[cur * v.n + q] >= 0) ? (int)v.rk[cur * v.n + q] : -1;   /* -1: candidate out */
+      best = max(best, rkq[j]);
+    }
+    const int M = __reduce_max_sync(kFull, best);
+    int win = -1;
+    if (M >= 0) {
+      const int T = (int)v.thr[M + 1];
+      int m = 0x7fffffff, last = -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned is_max = __ballot_sync(kFull, rkq[j] == M);
+        if (is_max && m == 0x7fffffff) m = 32 * j + __ffs(is_max) - 1;
       }
-      int before = __shfl_up_sync(kFull, incl, 1);
-      if (lane == 0) before = -1;
-      before = max(before, run);
-      const bool taken = valid && rkq > (int)v.thr[before + 1];
-      const unsigned bal = __ballot_sync(kFull, taken);
-      if (bal) win = q0 + 31 - __clz(bal);
-      run = max(run, __shfl_sync(kFull, incl, 31));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned over = __ballot_sync(kFull, rkq[j] > T && 32 * j + lane > m);
+        if (over) last = 32 * j + 31 - __clz(over);
+      }
+      win = last >= 0 ? last : m;
     }
     if (win < 0) break;   /* the same in every warp */
     const int pk = v.pick[cur * v.n + win];
