@@ -311,8 +311,8 @@ const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
     default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
   }
 }
-/* The headline cell -- 20 slices x 5 UEs, 64 RBGs of 8 RBs, one CQI value per RBG (u8 or 4-bit), backlogged, ids 9
- * and 8 -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
+/* The headline cell -- 20 slices x 5 UEs, 64 RBGs of 8 RBs, one CQI value per RBG (u8 or 4-bit), backlogged, ids 9,
+ 8, 10, 101 and 103 (the transport ids: same layout) -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
  * layout known at compile time.  A handle uses one only if its configuration and its host-computed layout match the
  * instantiation exactly; RS_NO_FIXED_SHAPE=1 in the environment keeps every handle on the general kernel. */
 using FixedU8 = rs::FixedShape<20, 5, 64, 8, 0>;
@@ -329,13 +329,18 @@ bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
   const rs::Layout want = SH::layout();
   return memcmp(&want, &h->layout, sizeof want) == 0;
 }
+#define RS_FIXED_PICK(A)                                                                                                   \
+  (which == 0 ? (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<A, false, false, FixedU8>) \
+              : (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<A, false, false, FixedNib>))
+bool has_fixed_kernel(int algo) { return algo == 9 || algo == 8 || algo == 10 || algo == 101 || algo == 103; }
 const void* fixed_kernel(int algo, int which, bool trace) {
-  if (algo == 9) {
-    if (which == 0) return trace ? (const void*)rs::rs_tti_kernel<9, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<9, false, false, FixedU8>;
-    return trace ? (const void*)rs::rs_tti_kernel<9, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<9, false, false, FixedNib>;
+  switch (algo) {
+    case 8: return RS_FIXED_PICK(8);
+    case 10: return RS_FIXED_PICK(10);
+    case 101: return RS_FIXED_PICK(101);
+    case 103: return RS_FIXED_PICK(103);
+    default: return RS_FIXED_PICK(9);
   }
-  if (which == 0) return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<8, false, false, FixedU8>;
-  return trace ? (const void*)rs::rs_tti_kernel<8, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<8, false, false, FixedNib>;
 }
 
 /* part < 0: the whole batch on the handle's stream; part p of h->parts: cells [p B / P, (p + 1) B / P) on stream / xs[p-1] */
@@ -685,7 +690,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     if (h->layout.total > max_optin)
       BAIL(fail(RS_ERR_UNSUPPORTED, "cell needs %d B of shared memory, device allows %d", h->layout.total, max_optin));
   }
-  if ((algo == 9 || algo == 8) && !getenv("RS_NO_FIXED_SHAPE")) {
+  if (has_fixed_kernel(algo) && !getenv("RS_NO_FIXED_SHAPE")) {
     if (shape_matches<FixedU8>(h, u2s)) h->fixed = 0;
     else if (shape_matches<FixedNib>(h, u2s)) h->fixed = 1;
   }

@@ -413,7 +413,7 @@ def test_full_size_batch_invariants():
     g.close()
 
 
-@pytest.mark.parametrize("algo", [9, 8])
+@pytest.mark.parametrize("algo", [9, 8, 10, 101, 103])
 @pytest.mark.parametrize("layout", [0, 2])
 def test_fixed_shape_equals_dynamic(algo, layout):
     """The headline cell runs a compile-time-shape instantiation of the TTI kernel; RS_NO_FIXED_SHAPE keeps a handle on
