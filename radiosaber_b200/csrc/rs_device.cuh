@@ -400,6 +400,13 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
   return cut;
 }
 
+#ifdef RS_SORT_TIMING   /* tools/sort_prof.cu: clock64() per level, thread 0 of CTA 0 (each tick is a global read-modify-write:
+                           compare builds, not absolute cycles) */
+__device__ long long g_sort_prof[64];
+#define RS_STICK(slot) do { if (tid == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_sort_prof[slot] += now_ - slast_; slast_ = now_; } } while (0)
+#else
+#define RS_STICK(slot) do {} while (0)
+#endif
 /* All kThreads threads of the CTA call this. On return b.out[0..n) holds the entries in the order
  * std::sort leaves them.  Ranges of one recursion depth are independent, so each level hands the
  * ranges longer than _S_threshold to the warps, one range per warp at a time. */
@@ -408,6 +415,9 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
 __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_limit, int rot) {
   const int tid = threadIdx.x, lane = tid & 31, warp = ((tid >> 5) + rot) % kWarps;
   const int nw = (n + 31) >> 5;
+#ifdef RS_SORT_TIMING
+  long long slast_ = clock64();
+#endif
   if (tid == 0) {
     b.seg0[0] = (unsigned)n << 16;
     b.misc[8] = (n > kSortThreshold) ? 1u : 0u;
@@ -415,6 +425,7 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
     b.misc[10] = 0;
   }
   __syncthreads();
+  RS_STICK(0);
   for (int level = 0;; ++level) {
     unsigned* cur = (level & 1) ? b.seg1 : b.seg0;
     unsigned* nxt = (level & 1) ? b.seg0 : b.seg1;
@@ -438,9 +449,12 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
         if (l - cut > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)cut | ((unsigned)l << 16);
       }
     }
+    RS_STICK(1 + 4 * (level < 12 ? level : 12));
     __syncthreads();
+    RS_STICK(4 + 4 * (level < 12 ? level : 12));
   }
   __syncthreads();
+  RS_STICK(60);
 
   /* __final_insertion_sort == stable sort by key of what is in a[] now: counting sort, 16 keys */
   for (int q = tid; q < 16 * nw; q += kThreads) b.cnt[q] = 0;
@@ -489,6 +503,7 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
     }
   }
   __syncthreads();
+  RS_STICK(61);
 }
 
 /* The same sort by ONE warp on private buffers, for short arrays (n <= 64: UpperBound sorts one slice's G entries,
@@ -945,17 +960,19 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  * Rounds.  Between rounds only two things change: the granted RBG leaves every column, and a slice that reached its
  * quota leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is
  * no e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So a round
- * re-scans just the lines that pass that test.  Every warp walks the candidates itself (same data, same grant), keeps
+ * re-scans just the lines that pass that test.  One warp walks the candidates and posts the grant (a CTA barrier); every warp keeps
  * the slices' fill and the free-RBG mask in registers, owns the candidates q = warp + kWarps * lane, and writes their
- * next-round values into the other half of a double buffer: ONE CTA barrier per round.  Result in c.outsl. */
+ * next-round values (one packed word per candidate) into the other half of a double buffer; a second barrier ends
+ * the round.  Result in c.outsl. */
 struct VogelBufs {
-  short* rk;     /* [2][n] rank of the candidate's gap */
-  short* pick;   /* [2][n] the RBG / slice it would grant, -1 = candidate out */
-  short* k2;     /* [2][n] CQI key of its second efficiency, -1 = none */
+  unsigned* cand;   /* [2][n] candidate = gap rank | (grant + 1) << 9 | (CQI key of the second efficiency + 1) << 16; grant: the
+                       RBG / slice it would grant, 0 in that field = candidate out */
   const short* rank_of;   /* [16][17] */
   const short* thr;       /* [ranks + 1], index = running maximum's rank + 1 */
   int n;
 };
+__device__ __forceinline__ int vogel_pick(unsigned w) { return (int)((w >> 9) & 0x7fu) - 1; }
+__device__ __forceinline__ int vogel_k2(unsigned w) { return (int)(w >> 16) - 1; }
 __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& v, int buf, int S, int G, int q, int lane,
                                                 int ha, int qa, int hb, int qb, unsigned long long free_m) {
   const bool is_row = q < G;
@@ -1003,11 +1020,8 @@ __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& 
       k2 = e2;
     }
   }
-  if (lane == 0) {
-    v.rk[buf * v.n + q] = k1 < 0 ? (short)0 : v.rank_of[k1 * 17 + k2 + 1];
-    v.pick[buf * v.n + q] = (short)first;
-    v.k2[buf * v.n + q] = (short)k2;
-  }
+  if (lane == 0)
+    v.cand[buf * v.n + q] = (k1 < 0 ? 0u : (unsigned)v.rank_of[k1 * 17 + k2 + 1]) | ((unsigned)(first + 1) << 9) | ((unsigned)(k2 + 1) << 16);
 }
 
 __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
@@ -1015,9 +1029,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
   const InterScratch x = inter_scratch(d, dm, c);
   VogelBufs v;
   v.n = G + S;
-  v.rk = (short*)x.val;
-  v.pick = v.rk + 2 * v.n;
-  v.k2 = v.pick + 2 * v.n;
+  v.cand = (unsigned*)x.val;
   v.rank_of = x.vtab;
   v.thr = x.vtab + 16 * 17;
   for (int i = tid; i < kVogelTab; i += kThreads) x.vtab[i] = d.vogel_tab[i];
@@ -1034,33 +1046,40 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
      * set to the (truncated) gap whenever a candidate is taken; the grant is the LAST candidate taken.  max_diff is
      * always the truncated largest gap seen so far, so q is taken iff rank_q > thr[largest rank before q].  Let M be the
      * largest rank and m its first position: thr[x] <= x < M for every x seen before m, so m itself is always taken,
-     * and behind m the running maximum is M: the grant is the last q > m with rank_q > thr[M], else m.  No scan. */
-    int rkq[4], best = -1;
+     * and behind m the running maximum is M: the grant is the last q > m with rank_q > thr[M], else m.  No scan.
+     * One warp walks and posts the grant; the others wait for it at the barrier. */
+    if (warp == 0) {
+      int rkq[4], best = -1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {   /* n = G + S <= 128 candidates, four per lane */
-      const int q = 32 * j + lane;
-      rkq[j] = (q < v.n && v.pick[cur * v.n + q] >= 0) ? (int)v.rk[cur * v.n + q] : -1;   /* -1: candidate out */
-      best = max(best, rkq[j]);
-    }
-    const int M = __reduce_max_sync(kFull, best);
-    int win = -1;
-    if (M >= 0) {
-      const int T = (int)v.thr[M + 1];
-      int m = 0x7fffffff, last = -1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned is_max = __ballot_sync(kFull, rkq[j] == M);
-        if (is_max && m == 0x7fffffff) m = 32 * j + __ffs(is_max) - 1;
+      for (int j = 0; j < 4; ++j) {   /* n = G + S <= 128 candidates, four per lane */
+        const int q = 32 * j + lane;
+        const unsigned w = q < v.n ? v.cand[cur * v.n + q] : 0u;
+        rkq[j] = (w & 0xfe00u) ? (int)(w & 0x1ffu) : -1;   /* -1: candidate out */
+        best = max(best, rkq[j]);
       }
+      const int M = __reduce_max_sync(kFull, best);
+      int win = -1;
+      if (M >= 0) {
+        const int T = (int)v.thr[M + 1];
+        int m = 0x7fffffff, last = -1;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned over = __ballot_sync(kFull, rkq[j] > T && 32 * j + lane > m);
-        if (over) last = 32 * j + 31 - __clz(over);
+        for (int j = 0; j < 4; ++j) {
+          const unsigned is_max = __ballot_sync(kFull, rkq[j] == M);
+          if (is_max && m == 0x7fffffff) m = 32 * j + __ffs(is_max) - 1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned over = __ballot_sync(kFull, rkq[j] > T && 32 * j + lane > m);
+          if (over) last = 32 * j + 31 - __clz(over);
+        }
+        win = last >= 0 ? last : m;
       }
-      win = last >= 0 ? last : m;
+      if (lane == 0) c.misc[13] = (unsigned)win;
     }
-    if (win < 0) break;   /* the same in every warp */
-    const int pk = v.pick[cur * v.n + win];
+    __syncthreads();
+    const int win = (int)c.misc[13];
+    if (win < 0) break;
+    const int pk = vogel_pick(v.cand[cur * v.n + win]);
     const int gr = win < G ? win : pk, gs = win < G ? pk : win - G;
     if (lane == (gs & 31)) { if (gs < 32) ha++; else hb++; }
     const bool full = __shfl_sync(kFull, gs < 32 ? (ha >= qa) : (hb >= qb), gs & 31);
@@ -1070,13 +1089,12 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
     const int qq = warp + kWarps * lane;
     bool redo = false;
     if (qq < v.n) {
-      const short p_ = v.pick[cur * v.n + qq], k_ = v.k2[cur * v.n + qq];
-      v.pick[nxt * v.n + qq] = p_;
-      v.k2[nxt * v.n + qq] = k_;
-      v.rk[nxt * v.n + qq] = v.rk[cur * v.n + qq];
-      if (p_ >= 0) {
-        if (qq < G) redo = (qq == gr) || (full && (int)(c.sb.a[qq * S + gs] >> 12) >= (int)k_);
-        else redo = (qq - G == gs && full) || (int)(c.sb.a[gr * S + (qq - G)] >> 12) >= (int)k_;
+      const unsigned w = v.cand[cur * v.n + qq];
+      v.cand[nxt * v.n + qq] = w;
+      if (w & 0xfe00u) {
+        const int k_ = vogel_k2(w);
+        if (qq < G) redo = (qq == gr) || (full && (int)(c.sb.a[qq * S + gs] >> 12) >= k_);
+        else redo = (qq - G == gs && full) || (int)(c.sb.a[gr * S + (qq - G)] >> 12) >= k_;
       }
     }
     __syncwarp();
