@@ -961,11 +961,11 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  * quota leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is
  * no e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So a round
  * re-scans just the lines that pass that test.  One warp walks the candidates and posts the grant (a CTA barrier); every warp keeps
- * the slices' fill and the free-RBG mask in registers, owns the candidates q = warp + kWarps * lane, and writes their
- * next-round values (one packed word per candidate) into the other half of a double buffer; a second barrier ends
- * the round.  Result in c.outsl. */
+ * the slices' fill and the free-RBG mask in registers, owns the candidates q = warp + kWarps * lane (one packed word each) and re-scans
+ * them in place -- the walk lies between the barrier that ends a round and the one that posts the grant, the re-scans
+ * between that one and the end of the round.  Result in c.outsl. */
 struct VogelBufs {
-  unsigned* cand;   /* [2][n] candidate = gap rank | (grant + 1) << 9 | (CQI key of the second efficiency + 1) << 16; grant: the
+  unsigned* cand;   /* [n] candidate = gap rank | (grant + 1) << 9 | (CQI key of the second efficiency + 1) << 16; grant: the
                        RBG / slice it would grant, 0 in that field = candidate out */
   const short* rank_of;   /* [16][17] */
   const short* thr;       /* [ranks + 1], index = running maximum's rank + 1 */
@@ -1041,7 +1041,6 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
   for (int q = warp; q < v.n; q += kWarps) vogel_scan_line(c, v, 0, S, G, q, lane, ha, qa, hb, qb, free_m);
   __syncthreads();
   for (int round = 0; round < G; ++round) {
-    const int cur = round & 1, nxt = cur ^ 1;
     /* The reference walks the candidates in order and takes candidate q when its gap exceeds max_diff, an int that is
      * set to the (truncated) gap whenever a candidate is taken; the grant is the LAST candidate taken.  max_diff is
      * always the truncated largest gap seen so far, so q is taken iff rank_q > thr[largest rank before q].  Let M be the
@@ -1053,7 +1052,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
 #pragma unroll
       for (int j = 0; j < 4; ++j) {   /* n = G + S <= 128 candidates, four per lane */
         const int q = 32 * j + lane;
-        const unsigned w = q < v.n ? v.cand[cur * v.n + q] : 0u;
+        const unsigned w = q < v.n ? v.cand[q] : 0u;
         rkq[j] = (w & 0xfe00u) ? (int)(w & 0x1ffu) : -1;   /* -1: candidate out */
         best = max(best, rkq[j]);
       }
@@ -1074,12 +1073,13 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
         }
         win = last >= 0 ? last : m;
       }
-      if (lane == 0) c.misc[13] = (unsigned)win;
+      /* the grant travels with the candidate: the candidate's owner may re-scan it while the others still read */
+      if (lane == 0) c.misc[13] = win < 0 ? 0xffffffffu : ((unsigned)win | ((unsigned)vogel_pick(v.cand[win]) << 8));
     }
     __syncthreads();
-    const int win = (int)c.misc[13];
-    if (win < 0) break;
-    const int pk = vogel_pick(v.cand[cur * v.n + win]);
+    const unsigned posted = c.misc[13];
+    if (posted == 0xffffffffu) break;
+    const int win = (int)(posted & 0xffu), pk = (int)(posted >> 8);
     const int gr = win < G ? win : pk, gs = win < G ? pk : win - G;
     if (lane == (gs & 31)) { if (gs < 32) ha++; else hb++; }
     const bool full = __shfl_sync(kFull, gs < 32 ? (ha >= qa) : (hb >= qb), gs & 31);
@@ -1089,8 +1089,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
     const int qq = warp + kWarps * lane;
     bool redo = false;
     if (qq < v.n) {
-      const unsigned w = v.cand[cur * v.n + qq];
-      v.cand[nxt * v.n + qq] = w;
+      const unsigned w = v.cand[qq];
       if (w & 0xfe00u) {
         const int k_ = vogel_k2(w);
         if (qq < G) redo = (qq == gr) || (full && (int)(c.sb.a[qq * S + gs] >> 12) >= k_);
@@ -1102,7 +1101,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
     while (rm) {
       const int l = __ffs(rm) - 1;
       rm &= rm - 1;
-      vogel_scan_line(c, v, nxt, S, G, warp + kWarps * l, lane, ha, qa, hb, qb, free_m);
+      vogel_scan_line(c, v, 0, S, G, warp + kWarps * l, lane, ha, qa, hb, qb, free_m);
     }
     __syncthreads();
   }
@@ -1242,8 +1241,22 @@ __device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
+/* Cells per SM the kernel is compiled for, i.e. its register cap (65536 / kThreads / cells).  The compile-time-shape
+ * instantiations of Sequential (8) and of SubOpt / VogelApproximate with streamed CQI (101, 103) fit 48 registers without
+ * spilling, so ten of their cells fit an SM when the shared memory allows it -- the packed CQI layout: 19.8 KB per cell;
+ * one byte per RBG: 23 KB, nine cells.  Measured (packed / u8, cell-TTIs/s): id 8 65.2 -> 70.2 / 67.1 M, id 101 18.5 ->
+ * 22.9 / 21.2 M (63 registers uncapped: eight cells), id 103 9.8 -> 10.1 M packed but 9.9 -> 9.5 M u8 (52 registers
+ * uncapped already give nine cells), hence the layout test.  RadioSaber's (9) needs 53 and loses 3 % to spills at 48;
+ * UpperBound's (10) spills too. */
+template <int ALGO, bool TRACE, class SH>
+constexpr int min_cells_per_sm() {
+  if constexpr (SH::kStatic && RS_MIN_BLOCKS == 8) {
+    if (ALGO == 8 || (ALGO == 101 && !TRACE) || (ALGO == 103 && !TRACE && SH::LAY == 2)) return 10;
+  }
+  return RS_MIN_BLOCKS;
+}
 template <int ALGO, bool TRACE, bool QUEUE, class SH = DynShape>
-__global__ void __launch_bounds__(kThreads, RS_MIN_BLOCKS) rs_tti_kernel(const DevCfg d, const RunArgs r) {
+__global__ void __launch_bounds__(kThreads, min_cells_per_sm<ALGO, TRACE, SH>()) rs_tti_kernel(const DevCfg d, const RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
   /* The dimensions and the layout (Dims) are compile-time constants of a FixedShape instantiation and copies of the
    * launch parameters otherwise; pointers are always read from the parameter block itself (a local copy of the

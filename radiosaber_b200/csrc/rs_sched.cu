@@ -10,7 +10,10 @@
  * rsw:: = 512 threads per cell, two per SM, for cells with hundreds of UEs */
 #define RS_NS rs
 #define RS_THREADS 128
-#define RS_MIN_BLOCKS 8
+#ifndef RS_NARROW_MIN_BLOCKS
+#define RS_NARROW_MIN_BLOCKS 8   /* cells per SM the 128-thread kernels are compiled for (register cap 65536 / 128 / this) */
+#endif
+#define RS_MIN_BLOCKS RS_NARROW_MIN_BLOCKS
 #include "rs_device.cuh"
 #undef RS_NS
 #undef RS_THREADS

@@ -25,15 +25,16 @@ from radiosaber_b200 import sched, workload  # noqa: E402
 G = 64
 
 
-def measure(algo, w, p, u2s, B, ttis, launches, label, warm=5, per_launch=16):
+def measure(algo, w, p, u2s, B, ttis, launches, label, warm=5, per_launch=16, layout=0):
     import torch
     dev = torch.device("cuda", 0)
     S, U = len(w), len(u2s)
-    g = sched.Scheduler(algo, w, p, u2s, B)
+    g = sched.Scheduler(algo, w, p, u2s, B, cqi_per_rb=layout)
+    row = G // 2 if layout == 2 else G   # bytes of CQI per UE: one value per RBG, or two RBGs per byte
     stream = torch.cuda.Stream(dev)   # a real stream: handle 0 (the default stream) means "the handle's own" to rs_set_stream
     torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
-    d_cqi = torch.empty((ttis, B, U, G), dtype=torch.uint8, device=dev)
+    d_cqi = torch.empty((ttis, B, U, row), dtype=torch.uint8, device=dev)
     d_r2 = torch.empty((ttis, B, max(g.rand_stride, 2)), dtype=torch.int32, device=dev)
     g.synth_cqi(1, 0, 0, ttis, d_cqi.data_ptr())
     g.synth_rand2(1, 0, 0, ttis, d_r2.data_ptr())
@@ -43,7 +44,7 @@ def measure(algo, w, p, u2s, B, ttis, launches, label, warm=5, per_launch=16):
     _, dts = workload.tti_clock(ttis * (launches + warm))
 
     def step(k):
-        g.run_device(ttis, d_cqi.data_ptr(), B * U * G, d_r2.data_ptr(), dts[k * ttis:(k + 1) * ttis], outs,
+        g.run_device(ttis, d_cqi.data_ptr(), B * U * row, d_r2.data_ptr(), dts[k * ttis:(k + 1) * ttis], outs,
                      ttis_per_launch=per_launch)
 
     for k in range(warm):     # past the start-up transient (all bearers begin at the same average rate): steady state
@@ -61,7 +62,7 @@ def measure(algo, w, p, u2s, B, ttis, launches, label, warm=5, per_launch=16):
     rbg = d_rbg.cpu().numpy()
     line = {"label": label, "scheduler_id": algo, "slices": S, "ues_per_slice": U // S, "ues": U, "cells": B,
             "ttis_per_call": ttis, "ttis_per_launch": per_launch, "calls": launches, "warmup_ttis": ttis * warm, "cell_ttis_per_s": value, "ue_ttis_per_s": value * U,
-            "smem_bytes_per_cta": g.smem_bytes, "algorithmic_bytes_per_cell_tti": alg,
+            "smem_bytes_per_cta": g.smem_bytes, "cqi_layout": layout, "algorithmic_bytes_per_cell_tti": alg,
             "algorithmic_GBps": value * alg / 1e9, "rbgs_allocated_frac": float((rbg >= 0).mean())}
     g.close()
     del d_cqi, d_r2, d_rbg, d_bits
@@ -77,6 +78,7 @@ def main():
     ap.add_argument("--only", default=None, choices=[None, "ids", "sweep"])
     ap.add_argument("--points", default=None, help='sweep points "S,n;S,n;..." instead of the full grid')
     ap.add_argument("--ids", default=None, help='scheduler ids "9,8,..." instead of all')
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 2], help="CQI layout: 0 = u8 per RBG, 2 = two RBGs per byte")
     args = ap.parse_args()
     lines = []
 
@@ -92,7 +94,7 @@ def main():
         mix = pf.copy()
         mix[1::2, 3] = 0      # every other slice MT (max-CI): eps 1, psi 0
         for algo in ([int(x) for x in args.ids.split(",")] if args.ids else (9, 8, 7, 1, 11, 10, 101, 103)):
-            emit(measure(algo, w, pf, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF"))
+            emit(measure(algo, w, pf, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF", layout=args.layout))
             if algo not in (1, 11, 10, 101, 103):
                 emit(measure(algo, w, mix, u2s, 4096, args.ttis, args.launches, f"configs[2] id {algo} PF/MT mix"))
     if args.only in (None, "sweep"):
