@@ -285,6 +285,14 @@ __device__ __forceinline__ void median_to_first(unsigned short* a, int first, in
   a[pick] = t;
 }
 
+/* atomicAdd on shared memory as ONE instruction: around a one-lane atomicAdd the compiler builds its warp aggregation
+ * (vote, popc, leader election) for nothing. */
+__device__ __forceinline__ unsigned smem_add(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
 struct SortBufs {
   unsigned short* a;     /* [n] in: entries in insertion order; scratch afterwards */
   unsigned short* out;   /* [n] result, sorted (== posr) */
@@ -353,10 +361,19 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
    * running the same loop, rs_sched.cu build_eq_table).  Apply it in one gather. */
   if (nl == m && nr == m && l - f <= b.eq_max && 32 - __clz(l - f) <= levels_left) {
     const int len = l - f;
-    for (int i = lane; i < len; i += 32) b.posl[f + i] = a[f + i];
-    __syncwarp();
     const unsigned short* tab = b.eq_tab + eq_offset(len);
-    for (int i = lane; i < len; i += 32) a[f + i] = b.posl[f + tab[i]];
+    if (len <= 64) {   /* two entries per lane: permute through registers */
+      const bool h0 = lane < len, h1 = lane + 32 < len;
+      const unsigned short v0 = h0 ? a[f + tab[lane]] : (unsigned short)0;
+      const unsigned short v1 = h1 ? a[f + tab[lane + 32]] : (unsigned short)0;
+      __syncwarp();
+      if (h0) a[f + lane] = v0;
+      if (h1) a[f + lane + 32] = v1;
+    } else {
+      for (int i = lane; i < len; i += 32) b.posl[f + i] = a[f + i];
+      __syncwarp();
+      for (int i = lane; i < len; i += 32) a[f + i] = b.posl[f + tab[i]];
+    }
     __syncwarp();
     return -1;
   }
@@ -426,10 +443,10 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
   }
   __syncthreads();
   RS_STICK(0);
+  int c_cur = 8, c_nxt = 9, c_old = 10;   /* misc[8..10]: range counters of this level, the next, the one after (rotating) */
   for (int level = 0;; ++level) {
     unsigned* cur = (level & 1) ? b.seg1 : b.seg0;
     unsigned* nxt = (level & 1) ? b.seg0 : b.seg1;
-    const int c_cur = 8 + level % 3, c_nxt = 8 + (level + 1) % 3, c_old = 8 + (level + 2) % 3;
     const int nseg = (int)b.misc[c_cur];
     if (nseg == 0) break;
     if (level >= depth_limit) {      /* __introsort_loop's depth_limit == 0: heap sort what is left */
@@ -444,14 +461,19 @@ __device__ __forceinline__ void sort_desc(const SortBufs& b, int n, int depth_li
       const unsigned sg = cur[s];
       const int f = sg & 0xffff, l = sg >> 16;
       const int cut = warp_partition(b, f, l, lane, depth_limit - level);
-      if (lane == 0 && cut >= 0) {
-        if (cut - f > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)f | ((unsigned)cut << 16);
-        if (l - cut > kSortThreshold) nxt[atomicAdd(&b.misc[c_nxt], 1u)] = (unsigned)cut | ((unsigned)l << 16);
+      if (lane == 0 && cut >= 0) {   /* one slot request for both parts */
+        const int nl_ = cut - f > kSortThreshold, nr_ = l - cut > kSortThreshold;
+        if (nl_ + nr_) {
+          unsigned at = smem_add(&b.misc[c_nxt], (unsigned)(nl_ + nr_));
+          if (nl_) nxt[at++] = (unsigned)f | ((unsigned)cut << 16);
+          if (nr_) nxt[at] = (unsigned)cut | ((unsigned)l << 16);
+        }
       }
     }
     RS_STICK(1 + 4 * (level < 12 ? level : 12));
     __syncthreads();
     RS_STICK(4 + 4 * (level < 12 ? level : 12));
+    { const int t = c_cur; c_cur = c_nxt; c_nxt = c_old; c_old = t; }
   }
   __syncthreads();
   RS_STICK(60);
@@ -1252,6 +1274,7 @@ template <int ALGO, bool TRACE, class SH>
 constexpr int min_cells_per_sm() {
   if constexpr (SH::kStatic && RS_MIN_BLOCKS == 8) {
     if (ALGO == 8 || (ALGO == 101 && !TRACE) || (ALGO == 103 && !TRACE && SH::LAY == 2)) return 10;
+    return 9;   /* 56 registers: what these instantiations take anyway (53-54), pinned -- at 57 the ninth cell is gone */
   }
   return RS_MIN_BLOCKS;
 }
