@@ -150,14 +150,19 @@ __host__ __device__ constexpr inline int rs_align(int x, int a) { return (x + a 
 /* ng_ues: id 11 only, the largest number of UEs in a slice (scratch of the 300-sample search). */
 /* min_sort_n: id 10 sorts its slices' G entries on up to five warps at a time next to the parked grants: it needs
  * the slot arrays at least max(16 G, 1024) entries long whatever S is (rs_sched.cu). */
+/* den_in_cnt: the metric denominators (written in P0, last read by the per-slice argmax) share the bytes of the sort's
+ * counters (first written by the sort) -- every id but 10, whose EESM sums reuse `den` while its warp sorts count
+ * (den_shares_cnt below).  The 800 B are what lets a tenth headline cell (one CQI byte per RBG) fit an SM. */
+__host__ __device__ constexpr inline bool den_shares_cnt(int algo) { return algo != 10; }
 __host__ __device__ constexpr inline Layout make_layout(int S, int U, int G, int m_cap, int cq_bytes = 0, int ng_ues = 0,
-                                                        int min_sort_n = 0, int nb = 1) {
+                                                        int min_sort_n = 0, int nb = 1, bool den_in_cnt = false) {
   Layout L{};
   const int n = (S * G > min_sort_n) ? S * G : min_sort_n;
   const int nw = (n + 31) / 32;
   int o = 0;
   L.avg = o;  o += 8 * U * nb;
-  L.den = o;  o += 8 * U;
+  const bool share_den = den_in_cnt && 8 * U <= 2 * 16 * nw;
+  L.den = o;  o += share_den ? 0 : 8 * U;
   L.off = o;  o += 8 * S;
   L.tval = o; o += 8 * 16;
   L.posl = o; o += 2 * n;
@@ -180,7 +185,9 @@ __host__ __device__ constexpr inline Layout make_layout(int S, int U, int G, int
   L.misc = o;   o += 4 * 48;
   L.a = o;    o += 2 * n;
   L.win = o;  o += 2 * n;
+  o = rs_align(o, 8);
   L.cnt = o;  o += 2 * 16 * nw;
+  if (share_den) L.den = L.cnt;
   L.outsl = o; o += G;
   L.sptr = rs_align(o, 4); o = L.sptr + 4 * (S + 1);
   L.sues = o; o += 2 * U;
@@ -219,7 +226,7 @@ struct FixedShape {
   static constexpr int kSortN = G_ * S_;
   __host__ __device__ static constexpr int log2_floor(int v) { int lg = 0; while (v > 1) { v >>= 1; ++lg; } return lg; }
   static constexpr int kSortDepth = 2 * log2_floor(kSortN);
-  __host__ __device__ static constexpr Layout layout() { return make_layout(S_, U, G_, kMCap, U * kCqiRow, 0, 0, 1); }
+  __host__ __device__ static constexpr Layout layout(int algo) { return make_layout(S_, U, G_, kMCap, U * kCqiRow, 0, 0, 1, den_shares_cnt(algo)); }
 };
 
 /* ================================================================================================
@@ -1265,16 +1272,18 @@ __device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
  * ============================================================================================== */
 /* Cells per SM the kernel is compiled for, i.e. its register cap (65536 / kThreads / cells).  The compile-time-shape
  * instantiations of Sequential (8) and of SubOpt / VogelApproximate with streamed CQI (101, 103) fit 48 registers without
- * spilling, so ten of their cells fit an SM when the shared memory allows it -- the packed CQI layout: 19.8 KB per cell;
- * one byte per RBG: 23 KB, nine cells.  Measured (packed / u8, cell-TTIs/s): id 8 65.2 -> 70.2 / 67.1 M, id 101 18.5 ->
- * 22.9 / 21.2 M (63 registers uncapped: eight cells), id 103 9.8 -> 10.1 M packed but 9.9 -> 9.5 M u8 (52 registers
- * uncapped already give nine cells), hence the layout test.  RadioSaber's (9) needs 53 and loses 3 % to spills at 48;
- * UpperBound's (10) spills too. */
+ * spilling, so ten of their cells fit an SM (shared memory: 19.8 KB per cell with the packed CQI layout, 22.2 KB with one
+ * byte per RBG now that the metric denominators share the sort counters' bytes -- make_layout).  Measured with the packed
+ * layout (cell-TTIs/s): id 8 65.2 -> 70.2 M, id 101 18.5 -> 22.9 M (63 registers uncapped: eight cells), id 103 9.8 -> 10.1 M.
+ * RadioSaber's kernel (9) is slower with ten cells at 48 registers (19.5 vs 20.25 M: 32 B of cold spills and tighter
+ * scheduling cost more than the tenth cell brings) and UpperBound's (10) spills, so those are pinned to nine cells (56
+ * registers; they take 50-56) -- pinned, because at 57 the ninth cell is gone (an unrelated edit once cost the headline 7 %
+ * that way). */
 template <int ALGO, bool TRACE, class SH>
 constexpr int min_cells_per_sm() {
   if constexpr (SH::kStatic && RS_MIN_BLOCKS == 8) {
-    if (ALGO == 8 || (ALGO == 101 && !TRACE) || (ALGO == 103 && !TRACE && SH::LAY == 2)) return 10;
-    return 9;   /* 56 registers: what these instantiations take anyway (53-54), pinned -- at 57 the ninth cell is gone */
+    if (ALGO == 8 || ((ALGO == 101 || ALGO == 103) && !TRACE)) return 10;
+    return 9;
   }
   return RS_MIN_BLOCKS;
 }
@@ -1286,7 +1295,7 @@ __global__ void __launch_bounds__(kThreads, min_cells_per_sm<ALGO, TRACE, SH>())
    * whole DevCfg would cost them their "global memory" provenance: generic LD/ST instead of LDG/STG). */
   Dims dm;
   if constexpr (SH::kStatic) {
-    constexpr Layout kLay = SH::layout();
+    constexpr Layout kLay = SH::layout(ALGO);
     dm.S = SH::S; dm.U = SH::U; dm.G = SH::G; dm.R = SH::R; dm.rbg = SH::RBG;
     dm.cqi_per_rb = SH::LAY; dm.cqi_row = SH::kCqiRow;
     dm.lay = kLay;

@@ -329,7 +329,7 @@ bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
     return false;
   for (int u = 0; u < d.U; ++u)
     if (u2s[(size_t)u] != u / SH::UPS) return false;
-  const rs::Layout want = SH::layout();
+  const rs::Layout want = SH::layout(h->d.algo);
   return memcmp(&want, &h->layout, sizeof want) == 0;
 }
 #define RS_FIXED_PICK(A)                                                                                                   \
@@ -660,13 +660,13 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   const int min_sort_n = (algo == 10) ? std::max(16 * G, 1024)
                          : ((algo == 101 || algo == 103) ? (rs::inter_scratch_bytes(G, S) + 3) / 4 : 0);   /* posl + posr = 4 n bytes */
   { int lg = 0; for (int m = G; m > 1; m >>= 1) lg++; d.sort_depth_g = 2 * lg; }
-  h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb)))
-                      : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb);
+  h->layout = h->wide ? reinterpret_cast<const rs::Layout&>(static_cast<const rsw::Layout&>(rsw::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb, rs::den_shares_cnt(algo))))
+                      : rs::make_layout(S, U, G, m_cap, 0, d.ng_ues, min_sort_n, nb, rs::den_shares_cnt(algo));
   h->stage_ok = false;
   if (d.cqi_per_rb != 1 && d.cqi_row % 16 == 0) {
-    const rsw::Layout staged_w = rsw::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb);
+    const rsw::Layout staged_w = rsw::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb, rs::den_shares_cnt(algo));
     const rs::Layout staged = h->wide ? reinterpret_cast<const rs::Layout&>(staged_w)
-                                      : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb);
+                                      : rs::make_layout(S, U, G, m_cap, U * d.cqi_row, d.ng_ues, min_sort_n, nb, rs::den_shares_cnt(algo));
     const int kSmemPerSm = 227 * 1024, kSms = 148;
     /* Staging pays as long as it does not cost residency: cells an SM can hold = min(register limit of the
      * instantiation, shared memory, what the batch offers).  Measured (profiles/r02_configs3_sweep.jsonl): 20 x 20 UEs
