@@ -1267,6 +1267,68 @@ __device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
   }
 }
 
+/* NVS non-greedy, the 300-sample search (nvs.cpp:436-470) for a served slice of at most NU listed users, one sample per
+ * thread at a time.  A sample gives user q the MCS hc_q - rand() % 4 (at least 1); on RBG g the user's metric is
+ * mtab[q][mcs_q] if mcs_q <= its CQI there, else 0; the sample's score is the sum over the RBGs, in RBG order, of the
+ * largest metric.  "mcs_q <= CQI on g" is bit g of ok[q][mcs_q], and the metric does not depend on g: sort the users by
+ * metric (registers, odd-even transposition), give every RBG to the first user in that order whose bit is set, and add
+ * the RBGs' values in order -- the same doubles in the same order as the reference adds them (an RBG nobody can use
+ * adds 0.0).  The first sample with the largest score wins: this thread's samples come in increasing order. */
+template <int NU>
+__device__ __forceinline__ void ng_search(const Cell& c, const unsigned* ok, const int* draws, int Ua, int G, int tid,
+                                          double& best_pf, int& best_i) {
+  for (int i = tid; i < 300; i += kThreads) {
+    double M[NU];
+    unsigned lo[NU], hi[NU];
+#pragma unroll
+    for (int q = 0; q < NU; ++q) {
+      M[q] = -1.0;
+      lo[q] = 0;
+      hi[q] = 0;
+      if (q < Ua) {
+        const int mcs = max((int)c.ng_hc[q] - draws[i * Ua + q] % 4, 1);
+        M[q] = c.mtab[q * kMStride + mcs];
+        lo[q] = ok[(q * 16 + mcs) * 2];
+        hi[q] = ok[(q * 16 + mcs) * 2 + 1];
+      }
+    }
+#pragma unroll
+    for (int pass = 0; pass < NU; ++pass)
+#pragma unroll
+      for (int j = pass & 1; j + 1 < NU; j += 2)
+        if (M[j] < M[j + 1]) {
+          const double tm = M[j]; M[j] = M[j + 1]; M[j + 1] = tm;
+          const unsigned tl = lo[j]; lo[j] = lo[j + 1]; lo[j + 1] = tl;
+          const unsigned th = hi[j]; hi[j] = hi[j + 1]; hi[j + 1] = th;
+        }
+    unsigned seen_lo = 0, seen_hi = 0;
+#pragma unroll
+    for (int q = 0; q < NU; ++q) {   /* an RBG belongs to the first user (largest metric) that can use it */
+      const unsigned l = lo[q] & ~seen_lo, h = hi[q] & ~seen_hi;
+      seen_lo |= lo[q];
+      seen_hi |= hi[q];
+      lo[q] = l;
+      hi[q] = h;
+    }
+    double pf = 0.0;
+    unsigned bit = 1u;
+    for (int g = 0; g < min(G, 32); ++g, bit <<= 1) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NU; ++q) if (lo[q] & bit) v = M[q];
+      pf = __dadd_rn(pf, v);
+    }
+    bit = 1u;
+    for (int g = 32; g < G; ++g, bit <<= 1) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NU; ++q) if (hi[q] & bit) v = M[q];
+      pf = __dadd_rn(pf, v);
+    }
+    if (best_pf < pf) { best_pf = pf; best_i = i; }
+  }
+}
+
 /* ================================================================================================
  * The TTI kernel: grid = cells, block = kThreads, T TTIs per launch with the cell state on chip.
  * ============================================================================================== */
@@ -1806,11 +1868,30 @@ __global__ void __launch_bounds__(kThreads, min_cells_per_sm<ALGO, TRACE, SH>())
       }
       __syncthreads();
       const int Ua = (int)c.misc[13];
-      for (int q = tid; q < Ua; q += kThreads) {   /* user_highest_cqi, nvs.cpp:416-425 */
-        const uint8_t* row = row_of(c.ng_list[q]);
-        int hc = 0;
-        for (int g = 0; g < G; ++g) hc = max(hc, cqi_first_rb(dm, row, g));
-        c.ng_hc[q] = (unsigned char)hc;
+      const bool few = Ua <= 8 && G <= 64;   /* the search on RBG bitmasks (ng_search), else entry by entry */
+      unsigned* ok = (unsigned*)c.ng_mcs;    /* few: ok[(q * 16 + t) * 2 + w] = RBGs 32 w .. 32 w + 31 of user q with CQI >= t */
+      if (few) {
+        for (int q = warp; q < Ua; q += kWarps) {   /* one warp per listed user: a ballot per threshold and half */
+          const uint8_t* row = row_of(c.ng_list[q]);
+          const int c0 = lane < G ? cqi_first_rb(dm, row, lane) : 0, c1 = lane + 32 < G ? cqi_first_rb(dm, row, lane + 32) : 0;
+          int hc = 0;
+          for (int t = 1; t < 16; ++t) {
+            const unsigned b0 = __ballot_sync(kFull, c0 >= t), b1 = __ballot_sync(kFull, c1 >= t);
+            if (lane == 0) {
+              ok[(q * 16 + t) * 2] = b0;
+              ok[(q * 16 + t) * 2 + 1] = b1;
+            }
+            if (b0 | b1) hc = t;
+          }
+          if (lane == 0) c.ng_hc[q] = (unsigned char)hc;   /* user_highest_cqi, nvs.cpp:416-425 */
+        }
+      } else {
+        for (int q = tid; q < Ua; q += kThreads) {   /* user_highest_cqi, nvs.cpp:416-425 */
+          const uint8_t* row = row_of(c.ng_list[q]);
+          int hc = 0;
+          for (int g = 0; g < G; ++g) hc = max(hc, cqi_first_rb(dm, row, g));
+          c.ng_hc[q] = (unsigned char)hc;
+        }
       }
       for (int q = tid; q < Ua * kMStride; q += kThreads) {   /* sEff * 180000 / (1 + avg), nvs.cpp:512-513 */
         const int cq = q & 15;
@@ -1829,7 +1910,10 @@ __global__ void __launch_bounds__(kThreads, min_cells_per_sm<ALGO, TRACE, SH>())
       unsigned char* my = c.ng_mcs + tid * d.ng_ues;
       double best_pf = 0.0;
       int best_i = 0x7fffffff;
-      if (Ua > 0) {
+      if (Ua > 0 && few) {
+        if (Ua <= 5) ng_search<5>(c, ok, draws, Ua, G, tid, best_pf, best_i);
+        else ng_search<8>(c, ok, draws, Ua, G, tid, best_pf, best_i);
+      } else if (Ua > 0) {
         for (int i = tid; i < 300; i += kThreads) {
           for (int q = 0; q < Ua; ++q) my[q] = (unsigned char)max((int)c.ng_hc[q] - draws[i * Ua + q] % 4, 1);
           double pf = 0.0;

@@ -138,6 +138,16 @@ def test_headline_shape_20x5(algo):
     _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
 
 
+@pytest.mark.parametrize("layout", [0, 1])
+def test_nvs_nongreedy_slice_sizes_around_the_bitmask_search(layout):
+    """Id 11 scores its 300 samples on RBG bitmasks when the served slice lists at most 8 users (two instantiations: up
+    to 5, up to 8) and entry by entry otherwise; inactive bearers move a slice between the three.  NVS serves one slice
+    per TTI, so 60 TTIs visit every size."""
+    ups = [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 5, 8]
+    S = len(ups)
+    _mk(11, S, ups, np.full(S, 1.0 / S), np.tile(PF, (S, 1)), B=12, seed=1100 + layout, T=60, cqi_per_rb=layout, with_active=True)
+
+
 @pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103])
 def test_mixed_enterprise_schedulers_diff_weights(algo):
     S = 20
