@@ -988,25 +988,28 @@ __device__ __forceinline__ double pair_eff(const Cell& c, const InterScratch& x,
  *
  * Rounds.  Between rounds only two things change: the granted RBG leaves every column, and a slice that reached its
  * quota leaves every row.  Removing element x from a line changes (e1, first, e2) only if key(x) >= key(e2) (or there is
- * no e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  So a round
- * re-scans just the lines that pass that test.  One warp walks the candidates and posts the grant (a CTA barrier); every warp keeps
+ * no e2): a record below e2 can only promote elements below e2, a non-record below e2 changes nothing.  And a line whose
+ * maximum occurs three times or more keeps all three when it loses a maximum other than the first one (e2 IS the maximum
+ * then; the candidate carries a count of its maxima).  So a round re-scans just the lines that pass both tests -- with
+ * winner CQIs of 12-15 all over a column, the second test is what spares most of them.  One warp walks the candidates and posts the grant (a CTA barrier); every warp keeps
  * the slices' fill and the free-RBG mask in registers, owns the candidates q = warp + kWarps * lane (one packed word each) and re-scans
  * them in place -- the walk lies between the barrier that ends a round and the one that posts the grant, the re-scans
  * between that one and the end of the round.  Result in c.outsl. */
 struct VogelBufs {
-  unsigned* cand;   /* [n] candidate = gap rank | (grant + 1) << 9 | (CQI key of the second efficiency + 1) << 16; grant: the
-                       RBG / slice it would grant, 0 in that field = candidate out */
+  unsigned* cand;   /* [n] candidate = gap rank | (grant + 1) << 9 | (CQI key of the second efficiency + 1) << 16 | key of the best
+                       << 21 | min(7, how often that key occurs in the line) << 25; grant: the RBG / slice it would grant,
+                       0 in that field = candidate out */
   const short* rank_of;   /* [16][17] */
   const short* thr;       /* [ranks + 1], index = running maximum's rank + 1 */
   int n;
 };
 __device__ __forceinline__ int vogel_pick(unsigned w) { return (int)((w >> 9) & 0x7fu) - 1; }
-__device__ __forceinline__ int vogel_k2(unsigned w) { return (int)(w >> 16) - 1; }
+__device__ __forceinline__ int vogel_k2(unsigned w) { return (int)((w >> 16) & 0x1fu) - 1; }
 __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& v, int buf, int S, int G, int q, int lane,
                                                 int ha, int qa, int hb, int qb, unsigned long long free_m) {
   const bool is_row = q < G;
   const int n = is_row ? S : G;   /* <= 64: two keys per lane */
-  int k1 = -1, first = -1, k2 = -1;
+  int k1 = -1, first = -1, k2 = -1, n_max = 0;
   bool live;
   if (is_row) live = ((free_m >> q) & 1ull) != 0;
   else {
@@ -1029,6 +1032,7 @@ __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& 
       const int m = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
       k1 = M;
       first = m;
+      n_max = min(__popc(b0) + __popc(b1), 7);
       /* e2 = the largest NON-record.  Everything behind the first maximum is one ... */
       int e2 = __reduce_max_sync(kFull, max(lane > m ? key[0] : -1, 32 + lane > m ? key[1] : -1));
       /* ... and in front of it: M1 = the largest key before `end`; if it occurs twice its second occurrence is a
@@ -1050,7 +1054,8 @@ __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& 
     }
   }
   if (lane == 0)
-    v.cand[buf * v.n + q] = (k1 < 0 ? 0u : (unsigned)v.rank_of[k1 * 17 + k2 + 1]) | ((unsigned)(first + 1) << 9) | ((unsigned)(k2 + 1) << 16);
+    v.cand[buf * v.n + q] = (k1 < 0 ? 0u : (unsigned)v.rank_of[k1 * 17 + k2 + 1] | ((unsigned)k1 << 21) | ((unsigned)n_max << 25)) |
+                            ((unsigned)(first + 1) << 9) | ((unsigned)(k2 + 1) << 16);
 }
 
 __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
@@ -1120,9 +1125,21 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
     if (qq < v.n) {
       const unsigned w = v.cand[qq];
       if (w & 0xfe00u) {
-        const int k_ = vogel_k2(w);
-        if (qq < G) redo = (qq == gr) || (full && (int)(c.sb.a[qq * S + gs] >> 12) >= k_);
-        else redo = (qq - G == gs && full) || (int)(c.sb.a[gr * S + (qq - G)] >> 12) >= k_;
+        /* the line dies, or loses one element x: row qq loses slice gs when that slice is full now, column qq - G loses RBG gr */
+        const bool row = qq < G;
+        const bool dies = row ? qq == gr : (qq - G == gs && full);
+        const bool loses = row ? full : true;
+        if (dies) redo = true;
+        else if (loses) {
+          const int kx = (int)((row ? c.sb.a[qq * S + gs] : c.sb.a[gr * S + (qq - G)]) >> 12);
+          if (kx >= vogel_k2(w)) {
+            /* x is a maximum behind the first one and at least two maxima stay: first, e1 and e2 (= the maximum) stand;
+             * the count is a lower bound (it saturates at 7), so it is simply taken down */
+            const int n_max = (int)((w >> 25) & 7u);
+            if (kx == (int)((w >> 21) & 15u) && vogel_pick(w) != (row ? gs : gr) && n_max >= 3) v.cand[qq] = w - (1u << 25);
+            else redo = true;
+          }
+        }
       }
     }
     __syncwarp();
