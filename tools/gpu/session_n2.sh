@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, 2-GPU session: rs_batch --gpus 2 == --gpus 1, bench at N=2 (weak) and BASELINE configs[4] (--cells-total 65536)
-O=gpurun_out/n2
+O=gpurun_out/n2_final
 mkdir -p $O
 nvidia-smi -L > $O/gpus.txt
 timeout 900 python -m pytest tests/test_host_api_gpu.py -m gpu -q -k "two_gpus or reduce" > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
