@@ -138,6 +138,16 @@ def test_headline_shape_20x5(algo):
     _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=48, seed=algo, T=25)
 
 
+@pytest.mark.parametrize("algo", [10, 11, 101, 103])
+def test_f4_ids_steady_state_on_the_headline_cell(algo):
+    """The f4 schedulers far past the start-up transient (every bearer starts at the same average rate, so the first TTIs
+    are full of ties): 300 TTIs of the headline cell on the compile-time-shape kernels against the oracle, state
+    compared after every TTI.  Pins the incremental re-scans of id 103 (three-maxima rule included) and the bitmask search
+    of id 11 where the bench-shaped sweeps time them."""
+    S = 20
+    _mk(algo, S, [5] * S, np.full(S, 0.05), np.tile(PF, (S, 1)), B=8, seed=500 + algo, T=300)
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 def test_nvs_nongreedy_slice_sizes_around_the_bitmask_search(layout):
     """Id 11 scores its 300 samples on RBG bitmasks when the served slice lists at most 8 users (two instantiations: up
