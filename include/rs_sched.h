@@ -290,9 +290,15 @@ int rs_get_stats(rs_handle* h, uint64_t* stats);
 typedef struct rs_log rs_log;
 int rs_log_create(const rs_config* cfg, rs_log** out);
 void rs_log_destroy(rs_log* lg);
-int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes /*[U]*/, const uint64_t* cum_rbs /*[U]*/);
+/* Per-bearer arrays of an rs_log are [U][nb] with nb = 2 when cfg->n_bearers == 2 (slot i = the bearer of priority i,
+ * as in the device state), else [U].  Not for id 1 with two bearers (id 1 schedules flows: one user per bearer). */
+int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes /*[U][nb]*/, const uint64_t* cum_rbs /*[U][nb]*/);
 int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs);
-/* Queue state of the cell for the NEXT rs_log_tti (same meaning as rs_set_queues, [U] each, either may be NULL):
+/* Application id printed for every bearer ([U][nb]; < 0 = the UE has no such bearer).  Default: bearer u * nb + i is
+ * application u * nb + i -- the ids SingleCellWithI hands out when every UE has nb flows
+ * (single-cell-with-interference.h:411-426: applications are created UE by UE, flow by flow). */
+int rs_log_set_app_ids(rs_log* lg, const int32_t* app_ids);
+/* Queue state of the cell for the NEXT rs_log_tti (same meaning as rs_set_queues, [U][nb] each, either may be NULL):
  * bytes credited are capped by the queue and the hol_delay field prints the bearer's delay. */
 int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_delay);
 /* Appends one TTI of one cell.  cqi [U][row] in cfg's CQI layout; rbg_to_ue [G]; tbs_bits [U];

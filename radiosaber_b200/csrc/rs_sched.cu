@@ -1238,9 +1238,11 @@ int rs_set_traces(rs_handle* h, const uint8_t* traces, int32_t n_traces, int32_t
  * (NSDI23-radiosaber-experiments/ ... /plot_throughput.py:35-47) work unchanged. */
 struct rs_log {
   int algo = 9, S = 0, U = 0, G = 0, R = 0, rbg = 0, layout = 0, row = 0, data = 0;
+  int nb = 1;                   /* bearers per UE; the per-bearer arrays below are [U][nb], slot i = the bearer of priority i */
   std::vector<int> u2s;
+  std::vector<int32_t> app;     /* application id of every bearer (rs_log_set_app_ids; default u * nb + i), < 0 = no such bearer */
   std::vector<uint64_t> cum_bytes, cum_rbs;
-  std::vector<int32_t> queue;   /* per-UE dataToTransmit for the next rs_log_tti (rs_log_set_queues), empty = cfg's */
+  std::vector<int32_t> queue;   /* per-bearer dataToTransmit for the next rs_log_tti (rs_log_set_queues), empty = cfg's */
   std::vector<double> hol;
   double eff[16];
   std::string out, err;
@@ -1256,9 +1258,16 @@ int rs_log_create(const rs_config* cfg, rs_log** out) {
   lg->algo = cfg->algo; lg->S = cfg->n_slices; lg->U = cfg->n_ues; lg->R = cfg->n_rbs; lg->rbg = cfg->rbg_size;
   lg->G = lg->R / lg->rbg; lg->layout = cfg->cqi_per_rb; lg->data = cfg->data_to_transmit;
   lg->row = lg->layout == 1 ? lg->R : (lg->layout == 2 ? lg->G / 2 : lg->G);
+  lg->nb = cfg->n_bearers == 2 ? 2 : 1;
+  if (lg->nb == 2 && lg->algo == 1) {   /* id 1 schedules flows: log a two-bearer cell as one user per bearer */
+    delete lg;
+    return fail(RS_ERR_UNSUPPORTED, "rs_log_create: id 1 schedules flows; give it one user per bearer");
+  }
   lg->u2s.assign(cfg->ue_to_slice, cfg->ue_to_slice + lg->U);
-  lg->cum_bytes.assign(lg->U, 0);
-  lg->cum_rbs.assign(lg->U, 0);
+  lg->app.resize((size_t)lg->U * lg->nb);
+  for (size_t k = 0; k < lg->app.size(); ++k) lg->app[k] = (int32_t)k;
+  lg->cum_bytes.assign((size_t)lg->U * lg->nb, 0);
+  lg->cum_rbs.assign((size_t)lg->U * lg->nb, 0);
   lg->eff[0] = 0.0;
   for (int c = 1; c <= 15; ++c) lg->eff[c] = eff_from_cqi(c);
   *out = lg;
@@ -1269,15 +1278,21 @@ void rs_log_destroy(rs_log* lg) { delete lg; }
 
 int rs_log_set_counters(rs_log* lg, const uint64_t* cum_bytes, const uint64_t* cum_rbs) {
   if (!lg) return fail(RS_ERR_ARG, "null log");
-  if (cum_bytes) lg->cum_bytes.assign(cum_bytes, cum_bytes + lg->U);
-  if (cum_rbs) lg->cum_rbs.assign(cum_rbs, cum_rbs + lg->U);
+  if (cum_bytes) lg->cum_bytes.assign(cum_bytes, cum_bytes + (size_t)lg->U * lg->nb);
+  if (cum_rbs) lg->cum_rbs.assign(cum_rbs, cum_rbs + (size_t)lg->U * lg->nb);
+  return RS_OK;
+}
+
+int rs_log_set_app_ids(rs_log* lg, const int32_t* app_ids) {
+  if (!lg || !app_ids) return fail(RS_ERR_ARG, "rs_log_set_app_ids: bad argument");
+  lg->app.assign(app_ids, app_ids + (size_t)lg->U * lg->nb);
   return RS_OK;
 }
 
 int rs_log_set_queues(rs_log* lg, const int32_t* queue_bytes, const double* hol_delay) {
   if (!lg) return fail(RS_ERR_ARG, "null log");
-  if (queue_bytes) lg->queue.assign(queue_bytes, queue_bytes + lg->U); else lg->queue.clear();
-  if (hol_delay) lg->hol.assign(hol_delay, hol_delay + lg->U); else lg->hol.clear();
+  if (queue_bytes) lg->queue.assign(queue_bytes, queue_bytes + (size_t)lg->U * lg->nb); else lg->queue.clear();
+  if (hol_delay) lg->hol.assign(hol_delay, hol_delay + (size_t)lg->U * lg->nb); else lg->hol.clear();
   return RS_OK;
 }
 
@@ -1330,23 +1345,31 @@ static int log_tti_core(rs_log* lg, uint64_t timestamp, const uint8_t* cqi, cons
     }
   }
   /* stderr, DoStopSchedule: transport.cpp:177-199, nvs.cpp:226-251, dl-pf-packet-scheduler.cpp:80-96.
-   * Application id == user id (one bearer per UE); the head-of-line delay (0 for an infinite buffer) is printed
-   * the way operator<< prints a double, i.e. %g. */
+   * Application id: rs_log_set_app_ids, by default bearer k = u * nb + i is application k (== the user id with one bearer
+   * per UE); the head-of-line delay (0 for an infinite buffer) is printed the way operator<< prints a double, i.e. %g. */
+  const int nb = lg->nb;
   for (int u = 0; u < U; ++u) {
-    const int avail = tbs_bits[u] / 8;
-    if (avail <= 0) continue;
-    int sent = avail;
-    if (algo != 1) {
-      const int data = lg->queue.empty() ? lg->data : lg->queue[u];
-      if (data <= 0) continue;
-      sent = std::min(avail, data);
+    int avail = tbs_bits[u] / 8;
+    /* the bearer of priority 1 is served first, what is left goes to the other one; every bearer that sends is booked
+     * the user's whole RB count (transport.cpp:179-191, nvs.cpp:231-243) */
+    for (int i = nb - 1; i >= 0; --i) {
+      if (avail <= 0) break;
+      const size_t k = (size_t)u * nb + i;
+      if (lg->app[k] < 0) continue;
+      int sent = avail;
+      if (algo != 1) {
+        const int data = lg->queue.empty() ? lg->data : lg->queue[k];
+        if (data <= 0) continue;
+        sent = std::min(avail, data);
+      }
+      avail -= sent;
+      lg->cum_bytes[k] += (uint64_t)sent;
+      lg->cum_rbs[k] += (uint64_t)rbgs[u].size() * lg->rbg;
+      snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: %g user: %d slice: %d\n",
+               (unsigned long long)timestamp, (int)lg->app[k], (unsigned long long)lg->cum_bytes[k],
+               (unsigned long long)lg->cum_rbs[k], lg->hol.empty() ? 0.0 : lg->hol[k], u, lg->u2s[u]);
+      lg->err += buf;
     }
-    lg->cum_bytes[u] += (uint64_t)sent;
-    lg->cum_rbs[u] += (uint64_t)rbgs[u].size() * lg->rbg;
-    snprintf(buf, sizeof buf, "%llu app: %d cumu_bytes: %llu cumu_rbs: %llu hol_delay: %g user: %d slice: %d\n",
-             (unsigned long long)timestamp, u, (unsigned long long)lg->cum_bytes[u],
-             (unsigned long long)lg->cum_rbs[u], lg->hol.empty() ? 0.0 : lg->hol[u], u, lg->u2s[u]);
-    lg->err += buf;
   }
   lg->queue.clear();
   lg->hol.clear();
@@ -1413,8 +1436,8 @@ void rs_log_clear(rs_log* lg) {
 }
 int rs_log_get_counters(rs_log* lg, uint64_t* cum_bytes, uint64_t* cum_rbs) {
   if (!lg) return fail(RS_ERR_ARG, "null log");
-  if (cum_bytes) memcpy(cum_bytes, lg->cum_bytes.data(), sizeof(uint64_t) * lg->U);
-  if (cum_rbs) memcpy(cum_rbs, lg->cum_rbs.data(), sizeof(uint64_t) * lg->U);
+  if (cum_bytes) memcpy(cum_bytes, lg->cum_bytes.data(), sizeof(uint64_t) * lg->U * lg->nb);
+  if (cum_rbs) memcpy(cum_rbs, lg->cum_rbs.data(), sizeof(uint64_t) * lg->U * lg->nb);
   return RS_OK;
 }
 

@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "rs_parse_trace_file", "rs_parse_mapping_file", "rs_trace_row", "rs_set_traces",
     "rs_run_traces_device", "rs_run_traces_host",
     "rs_log_create", "rs_log_destroy", "rs_log_set_counters", "rs_log_get_counters", "rs_log_tti", "rs_log_tti_grants",
-    "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues",
+    "rs_log_stdout", "rs_log_stderr", "rs_log_clear", "rs_log_set_queues", "rs_log_set_app_ids",
     "rs_get_stream", "rs_host_alloc", "rs_host_free", "rs_step_cell", "rs_run_host_async", "rs_run_traces_host_async",
     "rs_wait", "rs_dims", "rs_fixed_shape", "rs_direct_metric",
 )
@@ -124,6 +124,7 @@ def lib():
         L.rs_log_set_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rs_log_set_queues.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rs_log_set_app_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.rs_log_tti.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
         L.rs_log_tti_grants.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_void_p] * 6
         L.rs_log_stdout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -446,13 +447,18 @@ class LogWriter:
     (downlink-transport-scheduler.cpp:192-199, 523-527, 631-649; host only)."""
 
     def __init__(self, algo, ue_to_slice, n_slices, n_rbs=512, rbg_size=8, cqi_per_rb=0,
-                 data_to_transmit=100000000):
+                 data_to_transmit=100000000, n_bearers=1, app_ids=None):
         self._u2s = np.ascontiguousarray(ue_to_slice, dtype=np.int32)
         self.U, self.S, self.G = int(self._u2s.shape[0]), int(n_slices), int(n_rbs) // int(rbg_size)
-        cfg = _Cfg(int(algo), self.S, self.U, int(n_rbs), int(rbg_size), int(cqi_per_rb), int(data_to_transmit), 0,
+        self.nb = 2 if int(n_bearers) == 2 else 1   # per-bearer arrays (queue, hol, counters, app ids) are [U] or [U][2]
+        cfg = _Cfg(int(algo), self.S, self.U, int(n_rbs), int(rbg_size), int(cqi_per_rb), int(data_to_transmit), int(n_bearers),
                    None, None, _ptr(self._u2s), None)
         self._h = C.c_void_p()
         _check(lib().rs_log_create(C.byref(cfg), C.byref(self._h)))
+        if app_ids is not None:
+            a = np.ascontiguousarray(app_ids, dtype=np.int32)
+            assert a.size == self.U * self.nb
+            _check(lib().rs_log_set_app_ids(self._h, _ptr(a)))
 
     def tti(self, timestamp, cqi, rbg_to_ue, tbs_bits, final_cqi=None, slice_target=None, slice_quota=None,
             queue=None, hol=None):
@@ -487,7 +493,8 @@ class LogWriter:
         _check(lib().rs_log_set_counters(self._h, _ptr(cb), _ptr(cr)))
 
     def counters(self):
-        cb, cr = np.empty(self.U, np.uint64), np.empty(self.U, np.uint64)
+        shape = (self.U,) if self.nb == 1 else (self.U, 2)
+        cb, cr = np.empty(shape, np.uint64), np.empty(shape, np.uint64)
         _check(lib().rs_log_get_counters(self._h, _ptr(cb), _ptr(cr)))
         return cb, cr
 

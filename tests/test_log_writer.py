@@ -57,6 +57,48 @@ def test_writer_reproduces_reference_text_from_reference_results(name):
     assert lw.stdout == "" and lw.stderr == ""
 
 
+@pytest.mark.parametrize("algo", [9, 8, 7, 10, 101, 103, 11])
+def test_writer_two_bearers_per_ue_batch_mode(algo):
+    """A cell whose internet-flow slices carry two bearers per UE (MAX_BEARERS = 2): per-bearer queues, head-of-line
+    delays and application ids in, the unmodified reference's text of the same 200-TTI run out
+    (tools/make_golden_logs_two_bearers_batch.py; the per-bearer record is tests/golden/two_bearers/a<id>.npz)."""
+    import gzip
+    from radiosaber_b200 import workload
+    d = os.path.join(GOLDEN, "two_bearers")
+    rec = np.load(os.path.join(d, f"a{algo}.npz"))
+    T, U, S, G = int(rec["T"]), int(rec["U"]), int(rec["S"]), int(rec["G"])
+    cqi = workload.synth_cqi(int(rec["seed"]), 0, 1, 0, T, U, G)[:, 0]
+    lw = sched.LogWriter(algo, rec["ue_to_slice"], S, n_bearers=2, app_ids=rec["app_id"])
+    tq = algo in (8, 9, 101, 103)
+    for t in range(T):
+        kw = {"queue": rec["queue"][t], "hol": rec["hol"][t]}
+        if algo == 10:
+            lw.tti_grants(FIRST_TS + t, cqi[t], int(rec["alloc_n"][t]), rec["alloc_ue"][t], rec["alloc_rbg"][t],
+                          rec["bits"][t], rec["final_cqi"][t], rec["target"][t], rec["quota"][t], **kw)
+        else:
+            lw.tti(FIRST_TS + t, cqi[t], rec["rbg_to_ue"][t], rec["bits"][t], rec["final_cqi"][t],
+                   rec["target"][t] if tq else None, rec["quota"][t] if tq else None, **kw)
+    out = gzip.open(os.path.join(d, f"a{algo}.stdout.gz"), "rt").read()
+    err = gzip.open(os.path.join(d, f"a{algo}.stderr.gz"), "rt").read()
+    err = "".join(l for l in err.splitlines(keepends=True) if not l.startswith("ipflow "))
+    assert lw.stdout == out
+    assert lw.stderr == err
+    cb, cr = lw.counters()
+    assert np.array_equal(cb, rec["cum_bytes"][T - 1]) and np.array_equal(cr, rec["cum_rbs"][T - 1])
+    # some TTI served both bearers of a UE, and some bearer was served while the other one had nothing queued
+    both = {}
+    for l in err.splitlines():
+        f = l.split()
+        if len(f) > 10 and f[1] == "app:":
+            both[(f[0], f[10])] = both.get((f[0], f[10]), 0) + 1
+    assert max(both.values()) == 2
+
+
+def test_writer_rejects_two_bearers_for_flow_level_pf():
+    with pytest.raises(Exception):
+        sched.LogWriter(1, np.zeros(4, np.int32), 1, n_bearers=2)
+
+
 def test_writer_layouts_agree():
     rec = load_golden("a9_fix20x5_synth")
     texts = []
