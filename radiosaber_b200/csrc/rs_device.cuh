@@ -213,13 +213,21 @@ __host__ __device__ constexpr inline Layout make_layout(int S, int U, int G, int
 struct DynShape {
   static constexpr bool kStatic = false;
 };
+/* UEs one chunk of the per-slice metric table holds: at least the largest slice; otherwise as many as still fit the
+ * bytes of the sort's slot arrays, which the table borrows (make_layout: 8 * 16 * cap <= 4 * n), and at least 32.  The
+ * headline cell: 40 UEs = 8 slices per chunk, 128 (slice, RBG quad) items per chunk for 128 threads, three chunks. */
+__host__ __device__ constexpr inline int metric_table_cap(int max_slice, int U, int sort_n) {
+  const int fit = sort_n / 32 > 32 ? sort_n / 32 : 32;
+  const int want = U < fit ? U : fit;
+  return max_slice > want ? max_slice : want;
+}
 template <int S_, int UPS_, int G_, int RBG_, int LAY_>
 struct FixedShape {
   static constexpr bool kStatic = true;
   static constexpr int S = S_, UPS = UPS_, U = S_ * UPS_, G = G_, RBG = RBG_, R = G_ * RBG_, LAY = LAY_;
   static constexpr int kCqiRow = LAY_ == 1 ? R : (LAY_ == 2 ? G_ / 2 : G_);
-  /* metric-table chunks as rs_create packs them: consecutive slices while their UEs fit max(UPS, min(U, 32)) */
-  static constexpr int kCap = UPS_ > (U < 32 ? U : 32) ? UPS_ : (U < 32 ? U : 32);
+  /* metric-table chunks as rs_create packs them: consecutive slices while their UEs fit metric_table_cap() */
+  static constexpr int kCap = metric_table_cap(UPS_, U, S_ * G_);
   static constexpr int kSlicesPerChunk = kCap / UPS_;
   static constexpr int kChunks = (S_ + kSlicesPerChunk - 1) / kSlicesPerChunk;
   static constexpr int kMCap = (S_ < kSlicesPerChunk ? S_ : kSlicesPerChunk) * UPS_;

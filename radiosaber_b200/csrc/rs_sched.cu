@@ -616,7 +616,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   std::vector<int> chunks;
   int m_cap = 0;
   if (is_transport(algo)) {
-    const int cap = std::max(max_slice, std::min(U, 32));   /* small table: more cells resident per SM */
+    const int cap = rs::metric_table_cap(max_slice, U, S * G);   /* small table: it lives in the sort's slot arrays */
     chunks.push_back(0);
     int cur = 0;
     for (int s = 0; s < S; ++s) {
