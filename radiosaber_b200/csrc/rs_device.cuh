@@ -908,8 +908,8 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Dims& dm, con
     if (avail > 0) {
       if (d.algo == 1) {
         c.tx[u] += avail;
-        c.cumb[u] += (unsigned long long)avail;
-        c.cumr[u] += (unsigned long long)nrb;
+        atomicAdd(&c.cumb[u], (unsigned long long)avail);   /* no value comes back: a fire-and-forget RED instead of a load the TTI would wait for */
+        atomicAdd(&c.cumr[u], (unsigned long long)nrb);
       } else if (qd2) {
         /* two bearers: the bearer of the higher priority is served first and what is left goes to the other one;
          * every bearer that sends is booked the user's whole RB count (transport.cpp:179-191, nvs.cpp:229-243) */
@@ -919,14 +919,14 @@ __device__ __forceinline__ void finalize_ue(const DevCfg& d, const Dims& dm, con
           const int sent = min(avail, data_i);
           avail -= sent;
           c.tx[2 * u + i] += sent;
-          c.cumb[2 * u + i] += (unsigned long long)sent;
-          c.cumr[2 * u + i] += (unsigned long long)nrb;
+          atomicAdd(&c.cumb[2 * u + i], (unsigned long long)sent);
+          atomicAdd(&c.cumr[2 * u + i], (unsigned long long)nrb);
         }
       } else if (data_u > 0) {
         const int sent = min(avail, data_u);
         c.tx[u] += sent;
-        c.cumb[u] += (unsigned long long)sent;
-        c.cumr[u] += (unsigned long long)nrb;
+        atomicAdd(&c.cumb[u], (unsigned long long)sent);
+        atomicAdd(&c.cumr[u], (unsigned long long)nrb);
       }
     }
   }
