@@ -9,7 +9,10 @@
 /* the device code twice: rs:: = 128 threads per cell, eight cells per SM (the headline shape);
  * rsw:: = 512 threads per cell, two per SM, for cells with hundreds of UEs */
 #define RS_NS rs
-#define RS_THREADS 128
+#ifndef RS_NARROW_THREADS
+#define RS_NARROW_THREADS 128   /* experiments: -DRS_NARROW_THREADS=256 -DRS_NARROW_MIN_BLOCKS=4 */
+#endif
+#define RS_THREADS RS_NARROW_THREADS
 #ifndef RS_NARROW_MIN_BLOCKS
 #define RS_NARROW_MIN_BLOCKS 8   /* cells per SM the 128-thread kernels are compiled for (register cap 65536 / 128 / this) */
 #endif
