@@ -65,7 +65,7 @@ struct ConstTables {
   double cut[16];    /* cut[k], k=1..14: largest mean with 10*log10(-log(mean)) >= SINRForCQIIndex[k]
                         (AMCModule.cpp:252-261 expressed on the EESM mean) */
 };
-__constant__ ConstTables c_tab;
+static __constant__ ConstTables c_tab;   /* one copy per translation unit that holds kernels (rs_kernels.cu sets its own) */
 
 /* ---- per-handle description (lives in kernel parameter space) -------------------------------- */
 struct Layout {
@@ -246,7 +246,7 @@ __device__ __forceinline__ bool before(unsigned short x, unsigned short y) { ret
 
 /* std::__partial_sort(first,last,last): __make_heap + __sort_heap (bits/stl_heap.h), comp = before.
  * Sequential; reached only when the depth limit runs out (never seen on real inputs). */
-__device__ void heap_adjust(unsigned short* f, int hole, int len, unsigned short v) {
+static __device__ void heap_adjust(unsigned short* f, int hole, int len, unsigned short v) {
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
@@ -268,7 +268,7 @@ __device__ void heap_adjust(unsigned short* f, int hole, int len, unsigned short
   }
   f[hole] = v;
 }
-__device__ void heap_sort(unsigned short* f, int len) {
+static __device__ void heap_sort(unsigned short* f, int len) {
   if (len >= 2) {
     int parent = (len - 2) / 2;
     while (true) {
@@ -1066,7 +1066,7 @@ __device__ __forceinline__ void vogel_scan_line(const Cell& c, const VogelBufs& 
                             ((unsigned)(first + 1) << 9) | ((unsigned)(k2 + 1) << 16);
 }
 
-__device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
+static __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = dm.G, S = dm.S;
   const InterScratch x = inter_scratch(d, dm, c);
   VogelBufs v;
@@ -1166,7 +1166,7 @@ __device__ void vogel_approximate(const DevCfg& d, const Dims& dm, const Cell& c
  * the iteration order of the reference's std::unordered_map of the slices below quota, which is emulated:
  * libstdc++'s hashtable with its prime bucket counts 13 / 29 / 59 / 127, nodes of an empty bucket go to the
  * front of the list, a rehash re-links the nodes in list order).  Result in c.outsl. */
-__device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
+static __device__ void sub_opt(const DevCfg& d, const Dims& dm, const Cell& c) {
   const int tid = threadIdx.x, G = dm.G, S = dm.S;
   const InterScratch x = inter_scratch(d, dm, c);
   int* held = c.wd;

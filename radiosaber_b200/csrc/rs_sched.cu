@@ -6,6 +6,7 @@
  * lives here: without a CUDA device every compute entry point fails with RS_ERR_CUDA.
  */
 #include "../../include/rs_sched.h"
+#include "rs_kernels.h"
 /* the device code twice: rs:: = 128 threads per cell, eight cells per SM (the headline shape);
  * rsw:: = 512 threads per cell, two per SM, for cells with hundreds of UEs */
 #define RS_NS rs
@@ -301,21 +302,12 @@ static_assert(sizeof(rs::DevCfg) == sizeof(rsw::DevCfg) && sizeof(rs::RunArgs) =
                   sizeof(rs::ConstTables) == sizeof(rsw::ConstTables),
               "the two instantiations of rs_device.cuh share their parameter structs");
 
-/* one kernel per (scheduler id, CQI source, backlogged / queue-aware, CTA width) */
-#define RS_TTI_PICK(NS, A)                                                                           \
-  (queue ? (trace ? (const void*)NS::rs_tti_kernel<A, true, true> : (const void*)NS::rs_tti_kernel<A, false, true>) \
-         : (trace ? (const void*)NS::rs_tti_kernel<A, true, false> : (const void*)NS::rs_tti_kernel<A, false, false>))
+/* one kernel per (scheduler id, CQI source, backlogged / queue-aware, CTA width); the instantiations live in five
+ * translation units of their own (rs_kernels.cu) */
 const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
-  switch (algo) {
-    case 1: return wide ? RS_TTI_PICK(rsw, 1) : RS_TTI_PICK(rs, 1);
-    case 7: return wide ? RS_TTI_PICK(rsw, 7) : RS_TTI_PICK(rs, 7);
-    case 8: return wide ? RS_TTI_PICK(rsw, 8) : RS_TTI_PICK(rs, 8);
-    case 10: return wide ? RS_TTI_PICK(rsw, 10) : RS_TTI_PICK(rs, 10);
-    case 101: return wide ? RS_TTI_PICK(rsw, 101) : RS_TTI_PICK(rs, 101);
-    case 103: return wide ? RS_TTI_PICK(rsw, 103) : RS_TTI_PICK(rs, 103);
-    case 11: return wide ? RS_TTI_PICK(rsw, 11) : RS_TTI_PICK(rs, 11);
-    default: return wide ? RS_TTI_PICK(rsw, 9) : RS_TTI_PICK(rs, 9);
-  }
+  const bool first = algo == 9 || algo == 8 || algo == 10 || algo == 1;
+  if (wide) return first ? rs_kernel_tu3(algo, trace, queue) : rs_kernel_tu4(algo, trace, queue);
+  return first ? rs_kernel_tu1(algo, trace, queue) : rs_kernel_tu2(algo, trace, queue);
 }
 /* The headline cell -- 20 slices x 5 UEs, 64 RBGs of 8 RBs, one CQI value per RBG (u8 or 4-bit), backlogged, ids 9,
  8, 10, 101 and 103 (the transport ids: same layout) -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
@@ -335,19 +327,8 @@ bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
   const rs::Layout want = SH::layout(h->d.algo);
   return memcmp(&want, &h->layout, sizeof want) == 0;
 }
-#define RS_FIXED_PICK(A)                                                                                                   \
-  (which == 0 ? (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<A, false, false, FixedU8>) \
-              : (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<A, false, false, FixedNib>))
 bool has_fixed_kernel(int algo) { return algo == 9 || algo == 8 || algo == 10 || algo == 101 || algo == 103; }
-const void* fixed_kernel(int algo, int which, bool trace) {
-  switch (algo) {
-    case 8: return RS_FIXED_PICK(8);
-    case 10: return RS_FIXED_PICK(10);
-    case 101: return RS_FIXED_PICK(101);
-    case 103: return RS_FIXED_PICK(103);
-    default: return RS_FIXED_PICK(9);
-  }
-}
+const void* fixed_kernel(int algo, int which, bool trace) { return rs_kernel_tu5(algo, which, trace); }
 
 /* part < 0: the whole batch on the handle's stream; part p of h->parts: cells [p B / P, (p + 1) B / P) on stream / xs[p-1] */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a0, bool trace, const rs::DevCfg* cfg = nullptr, int part = -1) {
@@ -703,8 +684,11 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
   rs::ConstTables ct;
   { std::string why;
     if (!build_const_tables(&ct, &why)) BAIL(fail(RS_ERR_UNSUPPORTED, "host libm: %s", why.c_str())); }
-  { cudaError_t e = cudaMemcpyToSymbol(rs::c_tab, &ct, sizeof ct);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(rsw::c_tab, &ct, sizeof ct);
+  { cudaError_t e = rs_tables_tu1(&ct);   /* every unit that holds kernels has its own copy of the constant tables */
+    if (e == cudaSuccess) e = rs_tables_tu2(&ct);
+    if (e == cudaSuccess) e = rs_tables_tu3(&ct);
+    if (e == cudaSuccess) e = rs_tables_tu4(&ct);
+    if (e == cudaSuccess) e = rs_tables_tu5(&ct);
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e))); }
   BAIL(set_smem_attr(h));
   { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
