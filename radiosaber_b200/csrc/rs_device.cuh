@@ -234,7 +234,13 @@ struct FixedShape {
   static constexpr int kSortN = G_ * S_;
   __host__ __device__ static constexpr int log2_floor(int v) { int lg = 0; while (v > 1) { v >>= 1; ++lg; } return lg; }
   static constexpr int kSortDepth = 2 * log2_floor(kSortN);
-  __host__ __device__ static constexpr Layout layout(int algo) { return make_layout(S_, U, G_, kMCap, U * kCqiRow, 0, 0, 1, den_shares_cnt(algo)); }
+  /* NVS (ids 7, 11) tabulates the served slice only: one "chunk" of UPS UEs, plus the scratch of the served slice's users */
+  __host__ __device__ static constexpr bool nvs(int algo) { return algo == 7 || algo == 11; }
+  __host__ __device__ static constexpr int chunks(int algo) { return nvs(algo) ? 1 : kChunks; }
+  __host__ __device__ static constexpr int mcap(int algo) { return nvs(algo) ? UPS_ : kMCap; }
+  __host__ __device__ static constexpr Layout layout(int algo) {
+    return make_layout(S_, U, G_, mcap(algo), U * kCqiRow, nvs(algo) ? UPS_ : 0, 0, 1, den_shares_cnt(algo));
+  }
 };
 
 /* ================================================================================================
@@ -1370,6 +1376,7 @@ template <int ALGO, bool TRACE, class SH>
 constexpr int min_cells_per_sm() {
   if constexpr (SH::kStatic && RS_MIN_BLOCKS == 8) {
     if (ALGO == 8 || ((ALGO == 101 || ALGO == 103) && !TRACE)) return 10;
+    if (ALGO == 11) return 8;   /* the sample search keeps five (metric, mask) pairs in registers: it spills at 56 */
     return 9;
   }
   return RS_MIN_BLOCKS;
@@ -1386,7 +1393,7 @@ __global__ void __launch_bounds__(kThreads, min_cells_per_sm<ALGO, TRACE, SH>())
     dm.S = SH::S; dm.U = SH::U; dm.G = SH::G; dm.R = SH::R; dm.rbg = SH::RBG;
     dm.cqi_per_rb = SH::LAY; dm.cqi_row = SH::kCqiRow;
     dm.lay = kLay;
-    dm.n_chunks = SH::kChunks; dm.m_cap = SH::kMCap; dm.sort_n = SH::kSortN; dm.sort_depth = SH::kSortDepth;
+    dm.n_chunks = SH::chunks(ALGO); dm.m_cap = SH::mcap(ALGO); dm.sort_n = SH::kSortN; dm.sort_depth = SH::kSortDepth;
     dm.nb = 1;
     dm.direct = 0;
   } else {

@@ -1,9 +1,9 @@
-/* rs_kernels.cu -- one of the five translation units that hold the rs_tti_kernel instantiations (rs_kernels.h);
- * -DRS_TU=1..5 picks which.  No host logic here: rs_sched.cu asks for kernel addresses and launches them. */
+/* rs_kernels.cu -- one of the six translation units that hold the rs_tti_kernel instantiations (rs_kernels.h);
+ * -DRS_TU=1..6 picks which.  No host logic here: rs_sched.cu asks for kernel addresses and launches them. */
 #include "rs_kernels.h"
 
 #ifndef RS_TU
-#error "compile with -DRS_TU=1..5"
+#error "compile with -DRS_TU=1..6"
 #endif
 #ifndef RS_NARROW_THREADS
 #define RS_NARROW_THREADS 128
@@ -59,6 +59,7 @@ using FixedNib = rs::FixedShape<20, 5, 64, 8, 2>;
 #define RS_FIXED_PICK(A)                                                                                                   \
   (which == 0 ? (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedU8> : (const void*)rs::rs_tti_kernel<A, false, false, FixedU8>) \
               : (trace ? (const void*)rs::rs_tti_kernel<A, true, false, FixedNib> : (const void*)rs::rs_tti_kernel<A, false, false, FixedNib>))
+#if RS_TU == 5
 const void* rs_kernel_tu5(int algo, int which, bool trace) {
   switch (algo) {
     case 8: return RS_FIXED_PICK(8);
@@ -68,6 +69,12 @@ const void* rs_kernel_tu5(int algo, int which, bool trace) {
     default: return RS_FIXED_PICK(9);
   }
 }
+#else
+const void* rs_kernel_tu6(int algo, int which, bool trace) {
+  if (algo == 11) return RS_FIXED_PICK(11);
+  return RS_FIXED_PICK(7);
+}
+#endif
 #endif
 
 cudaError_t RS_CAT(rs_tables_tu, RS_TU)(const void* ct) { return cudaMemcpyToSymbol(RS_NS::c_tab, ct, sizeof(RS_NS::ConstTables)); }

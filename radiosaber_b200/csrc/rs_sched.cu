@@ -310,7 +310,7 @@ const void* tti_kernel_any(int algo, bool trace, bool queue, bool wide) {
   return first ? rs_kernel_tu1(algo, trace, queue) : rs_kernel_tu2(algo, trace, queue);
 }
 /* The headline cell -- 20 slices x 5 UEs, 64 RBGs of 8 RBs, one CQI value per RBG (u8 or 4-bit), backlogged, ids 9,
- 8, 10, 101 and 103 (the transport ids: same layout) -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
+ 8, 10, 101 and 103 (the transport ids: same layout) and the NVS ids 7 and 11 -- has FixedShape instantiations of the TTI kernel (rs_device.cuh): same code, dimensions and shared-memory
  * layout known at compile time.  A handle uses one only if its configuration and its host-computed layout match the
  * instantiation exactly; RS_NO_FIXED_SHAPE=1 in the environment keeps every handle on the general kernel. */
 using FixedU8 = rs::FixedShape<20, 5, 64, 8, 0>;
@@ -319,7 +319,7 @@ template <class SH>
 bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
   const rs::DevCfg& d = h->d;
   if (h->wide || d.nb != 1 || d.S != SH::S || d.U != SH::U || d.G != SH::G || d.rbg != SH::RBG || d.cqi_per_rb != SH::LAY ||
-      d.n_chunks != SH::kChunks || d.m_cap != SH::kMCap || d.sort_n != SH::kSortN || d.sort_depth != SH::kSortDepth ||
+      d.n_chunks != SH::chunks(d.algo) || d.m_cap != SH::mcap(d.algo) || d.sort_n != SH::kSortN || d.sort_depth != SH::kSortDepth ||
       !h->stage_ok || d.direct)
     return false;
   for (int u = 0; u < d.U; ++u)
@@ -327,8 +327,10 @@ bool shape_matches(const rs_handle* h, const std::vector<int>& u2s) {
   const rs::Layout want = SH::layout(h->d.algo);
   return memcmp(&want, &h->layout, sizeof want) == 0;
 }
-bool has_fixed_kernel(int algo) { return algo == 9 || algo == 8 || algo == 10 || algo == 101 || algo == 103; }
-const void* fixed_kernel(int algo, int which, bool trace) { return rs_kernel_tu5(algo, which, trace); }
+bool has_fixed_kernel(int algo) { return algo == 9 || algo == 8 || algo == 10 || algo == 101 || algo == 103 || algo == 7 || algo == 11; }
+const void* fixed_kernel(int algo, int which, bool trace) {
+  return (algo == 7 || algo == 11) ? rs_kernel_tu6(algo, which, trace) : rs_kernel_tu5(algo, which, trace);
+}
 
 /* part < 0: the whole batch on the handle's stream; part p of h->parts: cells [p B / P, (p + 1) B / P) on stream / xs[p-1] */
 int launch_ttis(rs_handle* h, const rs::RunArgs& a0, bool trace, const rs::DevCfg* cfg = nullptr, int part = -1) {
@@ -689,6 +691,7 @@ int rs_create(const rs_config* cfg, int32_t n_cells, int32_t device, rs_handle**
     if (e == cudaSuccess) e = rs_tables_tu3(&ct);
     if (e == cudaSuccess) e = rs_tables_tu4(&ct);
     if (e == cudaSuccess) e = rs_tables_tu5(&ct);
+    if (e == cudaSuccess) e = rs_tables_tu6(&ct);
     if (e != cudaSuccess) BAIL(fail(RS_ERR_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e))); }
   BAIL(set_smem_attr(h));
   { cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);

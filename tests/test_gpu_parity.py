@@ -433,7 +433,7 @@ def test_full_size_batch_invariants():
     g.close()
 
 
-@pytest.mark.parametrize("algo", [9, 8, 10, 101, 103])
+@pytest.mark.parametrize("algo", [9, 8, 10, 101, 103, 7, 11])
 @pytest.mark.parametrize("layout", [0, 2])
 def test_fixed_shape_equals_dynamic(algo, layout):
     """The headline cell runs a compile-time-shape instantiation of the TTI kernel; RS_NO_FIXED_SHAPE keeps a handle on
@@ -458,7 +458,7 @@ def test_fixed_shape_equals_dynamic(algo, layout):
     assert sched.lib().rs_fixed_shape(odd._h) == -1          # same sizes, another UE -> slice map: general kernel
     odd.close()
     cqi = workload.synth_cqi(77, 0, B, 0, T, U, G)
-    r2 = workload.synth_rand2(77, 0, B, 0, T, S)
+    r2 = workload.synth_rand_draws(77, 0, B, 0, T, S, max(fixed.rand_stride, 2))   # id 11: 300 draws per user of the largest slice
     _, dts = workload.tti_clock(T)
     feed = sched.pack_cqi(cqi) if layout == 2 else cqi
     a = fixed.run_host(feed, r2, dts, want_aux=True, ttis_per_launch=16)
