@@ -625,6 +625,8 @@ def run_cuda_arm(args, n_gpus):
                          "note": "path is bound by shared-memory sort/scan and FP64 issue, not HBM (DESIGN.md)"},
             "clocks": sampler.result(),
             "smem_bytes_per_cta": g.smem_bytes,
+            "kernel_instantiation": ("FixedShape<20,5,64,8,%d>" % (0 if sched.lib().rs_fixed_shape(g._h) == 0 else 2))
+            if sched.lib().rs_fixed_shape(g._h) >= 0 else "DynShape (general kernel)",
             "stats_reduce": stats_how,
             "slice_bytes_total": [int(x) for x in stats[0]],
             "jain_fairness_per_slice_mean": float(np.mean(sched.jain_index(stats, np.full(S, UES_PER_SLICE * total_cells)))),
