@@ -440,7 +440,7 @@ __device__ __forceinline__ int warp_partition(const SortBufs& b, int f, int l, i
 
 #ifdef RS_SORT_TIMING   /* tools/sort_prof.cu: clock64() per level, thread 0 of CTA 0 (each tick is a global read-modify-write:
                            compare builds, not absolute cycles) */
-__device__ long long g_sort_prof[64];
+static __device__ long long g_sort_prof[64];
 #define RS_STICK(slot) do { if (tid == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_sort_prof[slot] += now_ - slast_; slast_ = now_; } } while (0)
 #else
 #define RS_STICK(slot) do {} while (0)
